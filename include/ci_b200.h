@@ -1,0 +1,173 @@
+/* ci_b200.h -- C ABI of the B200-native state-space engine for CausalImpact.
+ *
+ * This is the drop-in boundary for ONE path of google/tfp-causalimpact: the
+ * model-fit + posterior-predictive path that the reference runs through
+ * TensorFlow Probability.  Each entry point names the reference interface it
+ * replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 (CI_OK) or a negative ci_status; none throws or
+ *     aborts; ci_last_error() gives the thread-local message of the last failure.
+ *   - buffers are CALLER-OWNED, contiguous, row-major.  Pointers are HOST
+ *     pointers unless the function name ends in _d, in which case they are
+ *     DEVICE pointers on the context's device and `stream` is a cudaStream_t
+ *     (passed as void*) the work is enqueued on; _d calls do not synchronise.
+ *   - `dtype` (ci_problem.dtype) selects the element type of every `void*`
+ *     buffer: 0 = float32, 1 = float64  (reference: DataOptions.dtype,
+ *     causalimpact/causalimpact_lib.py:155-159).
+ *   - theta layout, one row per chain / draw, all unconstrained:
+ *       [ w_0 .. w_{p-1}, log sigma_obs^2, log sigma_level^2 (, log sigma_slope^2) ]
+ *     dim = p + 1 + d,  d = 1 (local level) or 2 (local linear trend).
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef CI_B200_H_
+#define CI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CI_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum {
+  CI_OK = 0,
+  CI_ERR_INVALID = -1,     /* bad argument / shape / unsupported size        */
+  CI_ERR_CUDA = -2,        /* CUDA runtime error (message has the details)   */
+  CI_ERR_NO_DEVICE = -3,   /* no usable CUDA device                          */
+  CI_ERR_STATE = -4,       /* call order (e.g. compute before ci_set_data)   */
+  CI_ERR_UNSUPPORTED = -5  /* feature outside this path (seasonal, ...)      */
+} ci_status;
+
+enum { CI_MODEL_LOCAL_LEVEL = 0, CI_MODEL_LOCAL_LINEAR_TREND = 1 };
+enum { CI_F32 = 0, CI_F64 = 1 };
+/* ci_logprob*: which filter kernel runs */
+enum { CI_VARIANT_SEQ = 0,   /* per-timestep recursion, state in registers   */
+       CI_VARIANT_SCAN = 1   /* time-parallel associative scan (warp shuffles) */ };
+/* ci_logprob* flags */
+enum { CI_WITH_PRIOR = 1     /* add log prior + Jacobian: value is the HMC target */ };
+
+/* The model + priors.  Replaces the TFP StructuralTimeSeries object built by
+ * _build_default_gibbs_model (causalimpact/causalimpact_lib.py:398-500):
+ *   obs_*   InverseGamma(conc, scale) on sigma_obs^2, obs_ub bounds the SCALE
+ *           sigma_obs                                   (lib.py:434-443)
+ *   lvl_*   same for the local-level random walk        (lib.py:424-432)
+ *   slope_* same for the trend slope (extension; the reference has no slope,
+ *           lib.py:496) -- ignored when model == 0
+ *   m0, P0  initial level ~ N(m0, P0)                   (lib.py:467-469)
+ */
+typedef struct {
+  int32_t model;    /* CI_MODEL_*                                            */
+  int32_t dtype;    /* CI_F32 / CI_F64                                       */
+  int32_t T;        /* length of the extended series: pre + after-pre
+                       (lib.py:548-562)                                      */
+  int32_t p;        /* covariates + intercept (data.py:129-135); 0 = none    */
+  double obs_conc, obs_scale, obs_ub;
+  double lvl_conc, lvl_scale, lvl_ub;
+  double slope_conc, slope_scale, slope_ub;
+  double m0, P0;
+  double m0_slope, P0_slope;
+} ci_problem;
+
+/* HMC driver options (replaces num_results / num_warmup_steps handed to
+ * gibbs_sampler.fit_with_gibbs_sampling, lib.py:365-388). */
+typedef struct {
+  int32_t n_warmup;       /* adaptation iterations (discarded)               */
+  int32_t n_results;      /* kept iterations per chain                       */
+  int32_t max_leapfrog;   /* integration length is U{1..max_leapfrog} per
+                             iteration (same for every chain)                */
+  int32_t adapt_mass;     /* 1 = adapt a diagonal mass matrix in warm-up     */
+  double init_step;       /* initial leapfrog step size                      */
+  double target_accept;   /* dual-averaging target (0.8)                     */
+} ci_hmc_opts;
+
+typedef struct {
+  float accept_rate;      /* mean acceptance probability over kept iterations */
+  float step_size;        /* final adapted step size                          */
+  int32_t n_divergent;    /* kept iterations with non-finite / exploding H    */
+  int32_t n_leapfrog;     /* total gradient evaluations of this chain         */
+} ci_hmc_stats;
+
+typedef struct ci_ctx ci_ctx;
+
+/* ---- library / context ------------------------------------------------- */
+int ci_version(void);
+const char* ci_last_error(void);
+int ci_device_count(void);                 /* < 0 on error                   */
+int ci_ctx_create(int device, ci_ctx** out);
+int ci_ctx_destroy(ci_ctx* ctx);
+/* Number of kernel launches this context has enqueued so far. */
+int64_t ci_launch_count(const ci_ctx* ctx);
+
+/* Upload one problem: replaces the tensors _train_causalimpact_sts hands to the
+ * sampler (lib.py:545-581).
+ *   y     [T]    standardized outcome, NaN = missing (pre-period NaNs and the
+ *                whole after-pre range, lib.py:548-562)
+ *   X     [T,p]  standardized design matrix incl. intercept (NULL when p == 0)
+ *   Omega [p,p]  slab precision (lib.py:451-453)          (NULL when p == 0)
+ */
+int ci_set_data(ci_ctx* ctx, const ci_problem* prob, const void* y,
+                const void* X, const void* Omega);
+
+/* ---- K1/K2/K3: Kalman log-prob (+ gradient) for a batch of chains -------
+ * Replaces tfd.LinearGaussianStateSpaceModel(...).log_prob as it would be
+ * evaluated under tfp.sts.fit_with_hmc (north_star); the reference call site
+ * being replaced is the sampler loop at lib.py:365-388.
+ *   theta [C,dim] in;  value [C] out;  grad [C,dim] out (may be NULL).
+ */
+int ci_logprob(ci_ctx* ctx, const void* theta, int n_chains, void* value,
+               int variant, int flags);
+int ci_logprob_grad(ci_ctx* ctx, const void* theta, int n_chains, void* value,
+                    void* grad, int variant, int flags);
+int ci_logprob_grad_d(ci_ctx* ctx, const void* theta_d, int n_chains,
+                      void* value_d, void* grad_d, int variant, int flags,
+                      void* stream);
+
+/* ---- K6: batched-chain HMC over the filter kernel ------------------------
+ * Replaces gibbs_sampler.fit_with_gibbs_sampling (lib.py:365-388).
+ *   theta0 [C,dim]  initial points
+ *   draws  [n_results, C, dim] out;  stats [C] out.
+ * RNG is Philox4x32-10 keyed by (seed, chain_id0 + c): results do not depend
+ * on how chains are split across devices (causalimpact_lib_test.py:493-502).
+ */
+int ci_hmc_run(ci_ctx* ctx, const ci_hmc_opts* opts, uint64_t seed,
+               uint64_t chain_id0, const void* theta0, int n_chains,
+               void* draws, ci_hmc_stats* stats);
+int ci_hmc_run_d(ci_ctx* ctx, const ci_hmc_opts* opts, uint64_t seed,
+                 uint64_t chain_id0, const void* theta0_d, int n_chains,
+                 void* draws_d, ci_hmc_stats* stats_d, void* stream);
+
+/* ---- K4: simulation smoother + one-step predictive draw ------------------
+ * Replaces _resample_latents' LGSSM posterior_sample (inside the sampler,
+ * lib.py:365-388) and _get_posterior_means_and_trajectories (lib.py:609-632).
+ *   theta_draws [S,dim] in
+ *   level [S,T] out  (may be NULL) posterior sample of the level path
+ *   traj  [S,T] out  level + X.w + sigma_obs * N(0,1)      (lib.py:629-631)
+ *   mean  [T]   out  average over draws of level + X.w     (lib.py:627)
+ * RNG keyed by (seed, draw_id0 + s).
+ */
+int ci_posterior_predict(ci_ctx* ctx, const void* theta_draws, int S,
+                         uint64_t seed, uint64_t draw_id0, void* level,
+                         void* traj, void* mean);
+int ci_posterior_predict_d(ci_ctx* ctx, const void* theta_draws_d, int S,
+                           uint64_t seed, uint64_t draw_id0, void* level_d,
+                           void* traj_d, void* mean_sum_d, void* stream);
+
+/* ---- K5: per-time quantiles across draws ---------------------------------
+ * Replaces posterior_processing.calculate_trajectory_quantiles
+ * (causalimpact/posterior_processing.py:25-60): pandas
+ * DataFrame.quantile(axis=1), i.e. linear interpolation at q*(S-1), NaNs
+ * skipped.   a [S,T] (draw-major, as _get_posterior_means_and_trajectories
+ * returns it) -> out [T,nq].  dtype: CI_F32 / CI_F64.
+ */
+int ci_row_quantiles(ci_ctx* ctx, const void* a, int S, int T, int dtype,
+                     const double* q, int nq, void* out);
+int ci_row_quantiles_d(ci_ctx* ctx, const void* a_d, int S, int T, int dtype,
+                       const double* q, int nq, void* out_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CI_B200_H_ */

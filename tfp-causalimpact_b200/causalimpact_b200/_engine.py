@@ -1,0 +1,266 @@
+"""ctypes binding of the C ABI in include/ci_b200.h (libci_b200.so).
+
+This is the only place Python touches the native library.  There is no CPU
+fallback: if the shared library is missing or no B200 is visible the calls
+raise ``EngineError`` -- loudly, never silently.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _build
+
+F32, F64 = 0, 1
+MODEL_LOCAL_LEVEL, MODEL_LOCAL_LINEAR_TREND = 0, 1
+VARIANT_SEQ, VARIANT_SCAN = 0, 1
+WITH_PRIOR = 1
+
+
+class EngineError(RuntimeError):
+  """A C-ABI call failed (message comes from ci_last_error())."""
+
+
+class CiProblem(C.Structure):
+  _fields_ = [("model", C.c_int32), ("dtype", C.c_int32), ("T", C.c_int32), ("p", C.c_int32),
+              ("obs_conc", C.c_double), ("obs_scale", C.c_double), ("obs_ub", C.c_double),
+              ("lvl_conc", C.c_double), ("lvl_scale", C.c_double), ("lvl_ub", C.c_double),
+              ("slope_conc", C.c_double), ("slope_scale", C.c_double), ("slope_ub", C.c_double),
+              ("m0", C.c_double), ("P0", C.c_double),
+              ("m0_slope", C.c_double), ("P0_slope", C.c_double)]
+
+
+class CiHmcOpts(C.Structure):
+  _fields_ = [("n_warmup", C.c_int32), ("n_results", C.c_int32), ("max_leapfrog", C.c_int32),
+              ("adapt_mass", C.c_int32), ("init_step", C.c_double), ("target_accept", C.c_double)]
+
+
+class CiHmcStats(C.Structure):
+  _fields_ = [("accept_rate", C.c_float), ("step_size", C.c_float),
+              ("n_divergent", C.c_int32), ("n_leapfrog", C.c_int32)]
+
+
+HMC_STATS_DTYPE = np.dtype([("accept_rate", np.float32), ("step_size", np.float32),
+                            ("n_divergent", np.int32), ("n_leapfrog", np.int32)])
+
+# every symbol include/ci_b200.h declares
+EXPORTS = (
+    "ci_version", "ci_last_error", "ci_device_count", "ci_ctx_create", "ci_ctx_destroy",
+    "ci_launch_count", "ci_set_data", "ci_logprob", "ci_logprob_grad", "ci_logprob_grad_d",
+    "ci_hmc_run", "ci_hmc_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
+    "ci_row_quantiles", "ci_row_quantiles_d",
+)
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+  """dlopen the in-tree libci_b200.so (built by __graft_entry__.build())."""
+  global _lib
+  if _lib is not None and path is None:
+    return _lib
+  path = path or os.environ.get("CI_B200_LIB") or _build.LIB_PATH
+  if not os.path.exists(path):
+    raise EngineError(
+        f"{path} not found: the CUDA extension is not built. Run "
+        "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+        "There is no CPU fallback.")
+  lib = C.CDLL(path)
+  vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+  lib.ci_version.restype = i32
+  lib.ci_last_error.restype = C.c_char_p
+  lib.ci_device_count.restype = i32
+  lib.ci_ctx_create.argtypes = [i32, C.POINTER(vp)]
+  lib.ci_ctx_destroy.argtypes = [vp]
+  lib.ci_launch_count.argtypes = [vp]
+  lib.ci_launch_count.restype = C.c_int64
+  lib.ci_set_data.argtypes = [vp, C.POINTER(CiProblem), vp, vp, vp]
+  lib.ci_logprob.argtypes = [vp, vp, i32, vp, i32, i32]
+  lib.ci_logprob_grad.argtypes = [vp, vp, i32, vp, vp, i32, i32]
+  lib.ci_logprob_grad_d.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp]
+  lib.ci_hmc_run.argtypes = [vp, C.POINTER(CiHmcOpts), u64, u64, vp, i32, vp, vp]
+  lib.ci_hmc_run_d.argtypes = [vp, C.POINTER(CiHmcOpts), u64, u64, vp, i32, vp, vp, vp]
+  lib.ci_posterior_predict.argtypes = [vp, vp, i32, u64, u64, vp, vp, vp]
+  lib.ci_posterior_predict_d.argtypes = [vp, vp, i32, u64, u64, vp, vp, vp, vp]
+  lib.ci_row_quantiles.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_double), i32, vp]
+  lib.ci_row_quantiles_d.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_double), i32, vp, vp]
+  _lib = lib
+  return lib
+
+
+@dataclasses.dataclass
+class ProblemSpec:
+  """Host-side twin of ``ci_problem`` plus the arrays ci_set_data uploads."""
+  model: int
+  dtype: int
+  y: np.ndarray                       # [T], NaN == masked
+  X: Optional[np.ndarray]             # [T, p] or None
+  Omega: Optional[np.ndarray]         # [p, p] or None
+  m0: float
+  P0: float
+  obs_conc: float
+  obs_scale: float
+  obs_ub: float
+  lvl_conc: float
+  lvl_scale: float
+  lvl_ub: float
+  slope_conc: float = 16.0
+  slope_scale: float = 0.0
+  slope_ub: float = float("inf")
+  m0_slope: float = 0.0
+  P0_slope: float = 1.0
+
+  @property
+  def T(self) -> int:
+    return int(self.y.shape[0])
+
+  @property
+  def p(self) -> int:
+    return 0 if self.X is None else int(self.X.shape[1])
+
+  @property
+  def d(self) -> int:
+    return 2 if self.model == MODEL_LOCAL_LINEAR_TREND else 1
+
+  @property
+  def dim(self) -> int:
+    return self.p + 1 + self.d
+
+  @property
+  def np_dtype(self):
+    return np.float64 if self.dtype == F64 else np.float32
+
+
+def _ptr(a: Optional[np.ndarray]):
+  return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+  """One ``ci_ctx``: a device, its uploaded problem and workspaces."""
+
+  def __init__(self, device: int = 0):
+    self._lib = load_library()
+    self._ctx = C.c_void_p()
+    self.device = device
+    self.spec: Optional[ProblemSpec] = None
+    self._check(self._lib.ci_ctx_create(device, C.byref(self._ctx)))
+
+  # -- plumbing ------------------------------------------------------------
+  def _check(self, rc: int):
+    if rc != 0:
+      msg = self._lib.ci_last_error()
+      raise EngineError(f"ci_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+  def close(self):
+    if self._ctx:
+      self._lib.ci_ctx_destroy(self._ctx)
+      self._ctx = C.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:   # pylint: disable=broad-except
+      pass
+
+  @property
+  def launch_count(self) -> int:
+    return int(self._lib.ci_launch_count(self._ctx))
+
+  def _arr(self, a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=self.spec.np_dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+      raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+  # -- problem -------------------------------------------------------------
+  def set_data(self, spec: ProblemSpec):
+    self.spec = spec
+    dt = spec.np_dtype
+    y = np.ascontiguousarray(spec.y, dtype=dt)
+    X = None if spec.X is None else np.ascontiguousarray(spec.X, dtype=dt)
+    Om = None if spec.Omega is None else np.ascontiguousarray(spec.Omega, dtype=dt)
+    pb = CiProblem(model=spec.model, dtype=spec.dtype, T=spec.T, p=spec.p,
+                   obs_conc=spec.obs_conc, obs_scale=spec.obs_scale, obs_ub=spec.obs_ub,
+                   lvl_conc=spec.lvl_conc, lvl_scale=spec.lvl_scale, lvl_ub=spec.lvl_ub,
+                   slope_conc=spec.slope_conc, slope_scale=spec.slope_scale,
+                   slope_ub=min(spec.slope_ub, 1e300), m0=spec.m0, P0=spec.P0,
+                   m0_slope=spec.m0_slope, P0_slope=spec.P0_slope)
+    self._check(self._lib.ci_set_data(self._ctx, C.byref(pb), _ptr(y), _ptr(X), _ptr(Om)))
+
+  # -- K1/K2/K3 --------------------------------------------------------------
+  def logprob(self, theta, variant: int = VARIANT_SCAN, with_prior: bool = False) -> np.ndarray:
+    theta = self._arr(np.atleast_2d(theta))
+    n = theta.shape[0]
+    if theta.shape[1] != self.spec.dim:
+      raise ValueError(f"theta must be [C,{self.spec.dim}]")
+    val = np.empty(n, dtype=self.spec.np_dtype)
+    self._check(self._lib.ci_logprob(self._ctx, _ptr(theta), n, _ptr(val), variant,
+                                     WITH_PRIOR if with_prior else 0))
+    return val
+
+  def logprob_grad(self, theta, variant: int = VARIANT_SCAN,
+                   with_prior: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    theta = self._arr(np.atleast_2d(theta))
+    n = theta.shape[0]
+    if theta.shape[1] != self.spec.dim:
+      raise ValueError(f"theta must be [C,{self.spec.dim}]")
+    val = np.empty(n, dtype=self.spec.np_dtype)
+    grad = np.empty_like(theta)
+    self._check(self._lib.ci_logprob_grad(self._ctx, _ptr(theta), n, _ptr(val), _ptr(grad),
+                                          variant, WITH_PRIOR if with_prior else 0))
+    return val, grad
+
+  def logprob_grad_ptr(self, theta_ptr: int, n_chains: int, value_ptr: int, grad_ptr: int,
+                       variant: int = VARIANT_SCAN, flags: int = 0, stream: int = 0,
+                       host: bool = False):
+    """Raw-pointer entry (device pointers + stream, or pinned host pointers)."""
+    if host:
+      self._check(self._lib.ci_logprob_grad(self._ctx, theta_ptr, n_chains, value_ptr,
+                                            grad_ptr or None, variant, flags))
+    else:
+      self._check(self._lib.ci_logprob_grad_d(self._ctx, theta_ptr, n_chains, value_ptr,
+                                              grad_ptr or None, variant, flags, stream or None))
+
+  # -- K6 --------------------------------------------------------------------
+  def hmc_run(self, theta0, *, n_warmup: int, n_results: int, seed: int, chain_id0: int = 0,
+              max_leapfrog: int = 8, init_step: float = 0.05, target_accept: float = 0.8,
+              adapt_mass: bool = True):
+    theta0 = self._arr(np.atleast_2d(theta0))
+    n = theta0.shape[0]
+    draws = np.empty((n_results, n, self.spec.dim), dtype=self.spec.np_dtype)
+    stats = np.zeros(n, dtype=HMC_STATS_DTYPE)
+    opts = CiHmcOpts(n_warmup=n_warmup, n_results=n_results, max_leapfrog=max_leapfrog,
+                     adapt_mass=int(adapt_mass), init_step=init_step,
+                     target_accept=target_accept)
+    self._check(self._lib.ci_hmc_run(self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0,
+                                     _ptr(theta0), n, _ptr(draws), _ptr(stats)))
+    return draws, stats
+
+  # -- K4 --------------------------------------------------------------------
+  def posterior_predict(self, theta_draws, *, seed: int, draw_id0: int = 0,
+                        want_level: bool = True):
+    th = self._arr(np.atleast_2d(theta_draws))
+    S, T = th.shape[0], self.spec.T
+    level = np.empty((S, T), dtype=self.spec.np_dtype) if want_level else None
+    traj = np.empty((S, T), dtype=self.spec.np_dtype)
+    mean = np.empty(T, dtype=self.spec.np_dtype)
+    self._check(self._lib.ci_posterior_predict(self._ctx, _ptr(th), S, seed & (2**64 - 1),
+                                               draw_id0, _ptr(level), _ptr(traj), _ptr(mean)))
+    return level, traj, mean
+
+  # -- K5 --------------------------------------------------------------------
+  def row_quantiles(self, a, q) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    if a.dtype not in (np.float32, np.float64):
+      a = a.astype(np.float64)
+    S, T = a.shape
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.empty((T, q.shape[0]), dtype=a.dtype)
+    self._check(self._lib.ci_row_quantiles(
+        self._ctx, _ptr(a), S, T, F64 if a.dtype == np.float64 else F32,
+        q.ctypes.data_as(C.POINTER(C.c_double)), q.shape[0], _ptr(out)))
+    return out

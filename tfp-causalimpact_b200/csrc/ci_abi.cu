@@ -1,0 +1,323 @@
+// ci_abi.cu -- the C ABI declared in include/ci_b200.h.
+// Plain pointers and sizes only; no torch types.  There is no CPU fallback:
+// every compute entry point fails with CI_ERR_NO_DEVICE / CI_ERR_CUDA when no
+// sm_100 device is usable.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ci_b200.h"
+#include "ci_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                   \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(CI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct ci_ctx {
+  int device = -1;
+  int sm_count = 0;
+  int smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool has_data = false;
+  ci_problem prob{};
+  int NB = 0, ld = 0, dim = 0;
+  size_t esz = 4;
+  DevBuf tiles, omega;
+  DevBuf w_theta, w_value, w_grad;   // workspaces of the host-pointer entry points
+  int64_t launches = 0;
+  int force_G = 0;                   // CI_B200_G env override (tuning)
+};
+
+namespace {
+
+using namespace ci;
+
+template <typename R> ProbDev<R> make_probdev(const ci_ctx* c) {
+  ProbDev<R> pr;
+  pr.tiles = static_cast<const R*>(c->tiles.p);
+  pr.omega = static_cast<const R*>(c->omega.p);
+  pr.T = c->prob.T; pr.p = c->prob.p; pr.ld = c->ld; pr.NB = c->NB; pr.dim = c->dim;
+  pr.model = c->prob.model;
+  pr.m0 = (R)c->prob.m0; pr.P0 = (R)c->prob.P0;
+  pr.obs_conc = (R)c->prob.obs_conc; pr.obs_scale = (R)c->prob.obs_scale;
+  pr.obs_ub = (R)c->prob.obs_ub;
+  pr.lvl_conc = (R)c->prob.lvl_conc; pr.lvl_scale = (R)c->prob.lvl_scale;
+  pr.lvl_ub = (R)c->prob.lvl_ub;
+  return pr;
+}
+
+inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+// Shared-memory plan for a kernel with G consumer warps and `extra_elems`
+// kernel-specific per-warp scratch elements.
+int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out) {
+  const uint32_t esz = (uint32_t)c->esz;
+  const int p = c->prob.p, NB = c->NB;
+  SmemCfg cfg{};
+  cfg.stage_elems = (uint32_t)tile_elems(p);
+  const uint32_t stage_bytes = cfg.stage_elems * esz;
+  // per-warp scratch
+  uint32_t e = 0;
+  cfg.w_off = e;     e += align_up((uint32_t)(p > 0 ? p : 1), 4);
+  cfg.rbuf_off = e;  e += TB + 8;
+  cfg.ckpt_off = e;  e += align_up(2u * (uint32_t)NB, 4);
+  cfg.extra_off = e; e += align_up(extra_elems, 4);
+  cfg.warp_bytes = align_up(e * esz, 16);
+  const uint32_t omega_bytes = align_up((uint32_t)(p * p) * esz, 16);
+  const uint32_t fixed = omega_bytes + (uint32_t)G * cfg.warp_bytes;
+  const uint32_t budget = (uint32_t)c->smem_optin;
+  // stages: as many as fit (each stage also needs 16 bytes of barriers)
+  if (fixed + 2u * (stage_bytes + 16u) + 128u > budget)
+    return fail(CI_ERR_UNSUPPORTED,
+                "problem too wide for the tile pipeline: p=%d needs %u B per stage", p,
+                stage_bytes);
+  uint32_t nst = (budget - fixed - 128u) / (stage_bytes + 16u);
+  if (nst >= (uint32_t)NB) { nst = (uint32_t)NB; cfg.resident = 1; }
+  else { cfg.resident = 0; if (nst > 8) nst = 8; }
+  cfg.nstage = nst;
+  uint32_t off = align_up(nst * stage_bytes, 128);
+  cfg.off_full = off;   off += nst * 8;
+  cfg.off_empty = off;  off += nst * 8;
+  off = align_up(off, 16);
+  cfg.off_omega = off;  off += omega_bytes;
+  cfg.off_warp = off;   off += (uint32_t)G * cfg.warp_bytes;
+  cfg.total_bytes = off;
+  *out = cfg;
+  return CI_OK;
+}
+
+int pick_G(const ci_ctx* c, int C) {
+  if (c->force_G > 0) return c->force_G > MAXG ? MAXG : c->force_G;
+  int G = (C + c->sm_count - 1) / c->sm_count;
+  if (G < 1) G = 1;
+  if (G > MAXG) G = MAXG;
+  return G;
+}
+
+template <typename R>
+int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* grad_d, int variant,
+                   int flags, cudaStream_t st) {
+  if (variant != CI_VARIANT_SCAN)
+    return fail(CI_ERR_UNSUPPORTED, "variant %d not available for this model", variant);
+  const int G = pick_G(c, C);
+  SmemCfg cfg;
+  int rc = plan_smem(c, G, 0, &cfg);
+  if (rc) return rc;
+  auto kern = k_logpost_scan<R>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)cfg.total_bytes));
+  const int grid = (C + G - 1) / G;
+  kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(
+      make_probdev<R>(c), cfg, static_cast<const R*>(theta_d), C, static_cast<R*>(value_d),
+      static_cast<R*>(grad_d), flags);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+template <typename R>
+void build_tiles(const ci_problem* pb, const void* y_, const void* X_, int NB, int ld,
+                 std::vector<R>& out) {
+  const R* y = static_cast<const R*>(y_);
+  const R* X = static_cast<const R*>(X_);
+  const int T = pb->T, p = pb->p;
+  const size_t te = (size_t)tile_elems(p);
+  out.assign((size_t)NB * te, (R)0);
+  const R qnan = std::numeric_limits<R>::quiet_NaN();
+  for (int b = 0; b < NB; ++b) {
+    R* tile = out.data() + (size_t)b * te;
+    for (int tl = 0; tl < TB; ++tl) {
+      const int t = b * TB + tl;
+      R* row = tile + tile_off(tl, ld);
+      if (t < T) {
+        for (int j = 0; j < p; ++j) row[j] = X[(size_t)t * p + j];
+        row[p] = y[t];
+      } else {
+        row[p] = qnan;   // padded step == masked step
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int ci_version(void) { return CI_B200_VERSION; }
+const char* ci_last_error(void) { return g_err.c_str(); }
+
+int ci_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { fail(CI_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); return CI_ERR_NO_DEVICE; }
+  return n;
+}
+
+int ci_ctx_create(int device, ci_ctx** out) {
+  if (!out) return fail(CI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(CI_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(CI_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(CI_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  ci_ctx* c = new ci_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) { delete c; return fail(CI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
+  if (const char* g = getenv("CI_B200_G")) c->force_G = atoi(g);
+  *out = c;
+  return CI_OK;
+}
+
+int ci_ctx_destroy(ci_ctx* c) {
+  if (!c) return CI_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  c->tiles.release(); c->omega.release();
+  c->w_theta.release(); c->w_value.release(); c->w_grad.release();
+  delete c;
+  return CI_OK;
+}
+
+int64_t ci_launch_count(const ci_ctx* c) { return c ? c->launches : 0; }
+
+int ci_set_data(ci_ctx* c, const ci_problem* pb, const void* y, const void* X, const void* Omega) {
+  if (!c || !pb || !y) return fail(CI_ERR_INVALID, "null argument");
+  if (pb->T < 1) return fail(CI_ERR_INVALID, "T must be >= 1 (got %d)", pb->T);
+  if (pb->p < 0) return fail(CI_ERR_INVALID, "p must be >= 0 (got %d)", pb->p);
+  if (pb->p > 0 && (!X || !Omega)) return fail(CI_ERR_INVALID, "X and Omega are required when p > 0");
+  if (pb->dtype != CI_F32 && pb->dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  if (pb->model != CI_MODEL_LOCAL_LEVEL && pb->model != CI_MODEL_LOCAL_LINEAR_TREND)
+    return fail(CI_ERR_INVALID, "unknown model %d", pb->model);
+  if (pb->model == CI_MODEL_LOCAL_LINEAR_TREND)
+    return fail(CI_ERR_UNSUPPORTED, "local linear trend kernels are not built yet");
+  const int d = pb->model == CI_MODEL_LOCAL_LINEAR_TREND ? 2 : 1;
+  if (pb->p + 1 + d > ci::MAX_DIM)
+    return fail(CI_ERR_UNSUPPORTED, "p=%d exceeds the supported maximum %d", pb->p, ci::MAX_DIM - 1 - d);
+  if (!(pb->P0 > 0)) return fail(CI_ERR_INVALID, "P0 must be positive");
+  CU_TRY(cudaSetDevice(c->device));
+  c->has_data = false;
+  c->prob = *pb;
+  c->esz = pb->dtype == CI_F64 ? 8 : 4;
+  c->NB = (pb->T + ci::TB - 1) / ci::TB;
+  c->ld = ci::tile_ld(pb->p);
+  c->dim = pb->p + 1 + d;
+  const size_t te = (size_t)ci::tile_elems(pb->p);
+  const size_t tile_bytes = (size_t)c->NB * te * c->esz;
+  CU_TRY(c->tiles.reserve(tile_bytes));
+  if (pb->dtype == CI_F64) {
+    std::vector<double> h; build_tiles<double>(pb, y, X, c->NB, c->ld, h);
+    CU_TRY(cudaMemcpyAsync(c->tiles.p, h.data(), tile_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  } else {
+    std::vector<float> h; build_tiles<float>(pb, y, X, c->NB, c->ld, h);
+    CU_TRY(cudaMemcpyAsync(c->tiles.p, h.data(), tile_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  const size_t ob = (size_t)pb->p * pb->p * c->esz;
+  CU_TRY(c->omega.reserve(ob > 0 ? ob : 16));
+  if (ob) {
+    CU_TRY(cudaMemcpyAsync(c->omega.p, Omega, ob, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  // validate that the pipeline fits before accepting the problem
+  ci::SmemCfg cfg;
+  int rc = plan_smem(c, 1, 0, &cfg);
+  if (rc) return rc;
+  c->has_data = true;
+  return CI_OK;
+}
+
+int ci_logprob_grad_d(ci_ctx* c, const void* theta_d, int C, void* value_d, void* grad_d,
+                      int variant, int flags, void* stream) {
+  if (!c || !theta_d || !value_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (C < 1) return fail(CI_ERR_INVALID, "n_chains must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prob.dtype == CI_F64)
+    return launch_logpost<double>(c, theta_d, C, value_d, grad_d, variant, flags, st);
+  return launch_logpost<float>(c, theta_d, C, value_d, grad_d, variant, flags, st);
+}
+
+int ci_logprob_grad(ci_ctx* c, const void* theta, int C, void* value, void* grad, int variant,
+                    int flags) {
+  if (!c || !theta || !value) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (C < 1) return fail(CI_ERR_INVALID, "n_chains must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t tb = (size_t)C * c->dim * c->esz, vb = (size_t)C * c->esz;
+  CU_TRY(c->w_theta.reserve(tb));
+  CU_TRY(c->w_value.reserve(vb));
+  if (grad) CU_TRY(c->w_grad.reserve(tb));
+  CU_TRY(cudaMemcpyAsync(c->w_theta.p, theta, tb, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_logprob_grad_d(c, c->w_theta.p, C, c->w_value.p, grad ? c->w_grad.p : nullptr,
+                             variant, flags, c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(value, c->w_value.p, vb, cudaMemcpyDeviceToHost, c->stream));
+  if (grad) CU_TRY(cudaMemcpyAsync(grad, c->w_grad.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_logprob(ci_ctx* c, const void* theta, int C, void* value, int variant, int flags) {
+  return ci_logprob_grad(c, theta, C, value, nullptr, variant, flags);
+}
+
+// ---- not built yet (placeholders keep the ABI complete) -------------------
+int ci_hmc_run(ci_ctx*, const ci_hmc_opts*, uint64_t, uint64_t, const void*, int, void*, ci_hmc_stats*) { return fail(CI_ERR_UNSUPPORTED, "ci_hmc_run: not built yet"); }
+int ci_hmc_run_d(ci_ctx*, const ci_hmc_opts*, uint64_t, uint64_t, const void*, int, void*, ci_hmc_stats*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_hmc_run_d: not built yet"); }
+int ci_posterior_predict(ci_ctx*, const void*, int, uint64_t, uint64_t, void*, void*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_posterior_predict: not built yet"); }
+int ci_posterior_predict_d(ci_ctx*, const void*, int, uint64_t, uint64_t, void*, void*, void*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_posterior_predict_d: not built yet"); }
+int ci_row_quantiles(ci_ctx*, const void*, int, int, int, const double*, int, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles: not built yet"); }
+int ci_row_quantiles_d(ci_ctx*, const void*, int, int, int, const double*, int, void*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles_d: not built yet"); }
+
+}  // extern "C"

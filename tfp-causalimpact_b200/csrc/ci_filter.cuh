@@ -1,0 +1,294 @@
+// ci_filter.cuh -- warp-cooperative, time-parallel Kalman filter for the local
+// level model: value, adjoint gradient, and the pieces the simulation smoother
+// reuses.  ONE WARP PER CHAIN; within a tile of TB = 256 steps lane L owns the
+// KS = 8 consecutive steps 8L..8L+7.
+//
+// Replaces (reference, relative to /root/reference): the LGSSM arithmetic TFP
+// performs inside gibbs_sampler.fit_with_gibbs_sampling, call site
+// causalimpact/causalimpact_lib.py:365-388.  Conventions follow TFP's
+// LinearGaussianStateSpaceModel: N(m0,P0) is the prior of the state AT t=0,
+// every step updates with y_t (unless masked) and then predicts.
+//
+// Time-parallel formulation (restated in oracle/scan_np.py):
+//   variance  P' = (aP+b)/(cP+d)   -> 2x2 Moebius matrices, warp scan
+//   mean      a' = (1-K)a + K r     -> affine maps, warp scan
+//   adjoints  abar, Pbar            -> affine maps, reverse warp scans
+// State that crosses tiles (a, P, abar, Pbar) is carried in registers; the
+// forward pass checkpoints (a,P) per tile and the backward pass recomputes the
+// tile from its checkpoint, so [X|y] is streamed exactly twice per
+// value+gradient evaluation and nothing per-step is ever written to HBM.
+#pragma once
+#include "ci_common.cuh"
+
+namespace ci {
+
+template <typename R> struct Mob { R a, b, c, d; };
+
+template <typename R> __device__ __forceinline__ Mob<R> mob_shfl_up(const Mob<R>& m, int off) {
+  Mob<R> o;
+  o.a = __shfl_up_sync(FULL, m.a, off); o.b = __shfl_up_sync(FULL, m.b, off);
+  o.c = __shfl_up_sync(FULL, m.c, off); o.d = __shfl_up_sync(FULL, m.d, off);
+  return o;
+}
+// later * earlier, rescaled (a Moebius map is projective: any scale is the same map)
+template <typename R> __device__ __forceinline__ Mob<R> mob_mul(const Mob<R>& L, const Mob<R>& E) {
+  Mob<R> o;
+  o.a = L.a * E.a + L.b * E.c; o.b = L.a * E.b + L.b * E.d;
+  o.c = L.c * E.a + L.d * E.c; o.d = L.c * E.b + L.d * E.d;
+  const R s = Num<R>::rcp_fast(o.a + o.b + o.c + o.d);
+  o.a *= s; o.b *= s; o.c *= s; o.d *= s;
+  return o;
+}
+
+// ---------------------------------------------------------------------------
+// consumer side of the tile pipeline
+// ---------------------------------------------------------------------------
+template <typename R> struct TilePipe {
+  const R* stage0;
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t stage_elems;
+  uint32_t nstage;
+  uint32_t it;        // tiles consumed so far (streaming mode)
+  uint32_t cur;
+  bool resident;      // all tiles fit: loaded once, never released
+
+  __device__ __forceinline__ const R* acquire(int tile) {
+    uint32_t par;
+    if (resident) { cur = (uint32_t)tile; par = 0u; }
+    else { cur = it % nstage; par = (it / nstage) & 1u; }
+    mbar_wait(&full[cur], par);
+    return stage0 + (size_t)cur * stage_elems;
+  }
+  __device__ __forceinline__ void release(int lane) {
+    if (!resident) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[cur]);
+    }
+    ++it;
+  }
+};
+
+// Producer (one elected thread): issues the bulk copies for `n_pass` sweeps.
+// Sweep s walks tiles 0..NB-1 when dir[s] > 0 and NB-1..0 otherwise; the
+// caller describes the schedule through the functor `sweep_dir(s)`.
+template <typename R, typename DirFn>
+__device__ void tile_producer(const R* gtiles, R* stage0, uint64_t* full, uint64_t* empty,
+                              uint32_t stage_elems, uint32_t nstage, int NB, bool resident,
+                              long long n_sweeps, DirFn sweep_dir) {
+  const uint32_t bytes = stage_elems * (uint32_t)sizeof(R);
+  if (resident) {
+    for (int b = 0; b < NB; ++b) {
+      mbar_expect_tx(&full[b], bytes);
+      bulk_g2s(stage0 + (size_t)b * stage_elems, gtiles + (size_t)b * stage_elems, bytes, &full[b]);
+    }
+    return;
+  }
+  uint32_t it = 0;
+  for (long long s = 0; s < n_sweeps; ++s) {
+    const bool fwd = sweep_dir(s);
+    for (int i = 0; i < NB; ++i, ++it) {
+      const int b = fwd ? i : NB - 1 - i;
+      const uint32_t st = it % nstage;
+      if (it >= nstage) mbar_wait(&empty[st], ((it / nstage) - 1u) & 1u);
+      mbar_expect_tx(&full[st], bytes);
+      bulk_g2s(stage0 + (size_t)st * stage_elems, gtiles + (size_t)b * stage_elems, bytes,
+               &full[st]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// one tile's worth of per-lane filter state
+// ---------------------------------------------------------------------------
+template <typename R> struct Blk {
+  R r[KS];    // residual y - x.w   (0 where masked)
+  R P[KS];    // predicted variance at the step
+  R K[KS];    // gain               (0 where masked)
+  R rF[KS];   // 1/F                (0 where masked)
+  R v[KS];    // innovation         (0 where masked)
+  uint32_t obs;
+};
+
+// r_k = y_k - sum_j x_kj w_j for the lane's KS rows; conflict-free shared reads.
+template <typename R>
+__device__ __forceinline__ void blk_residuals(Blk<R>& B, const R* __restrict__ tile,
+                                              const R* __restrict__ w_s, int p, int ld, int lane) {
+  const R* row0 = tile + tile_off(lane * KS, ld);
+  R acc[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) acc[k] = row0[k * ld + p];
+  for (int j = 0; j < p; ++j) {
+    const R wj = w_s[j];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) acc[k] = fma(-row0[k * ld + j], wj, acc[k]);
+  }
+  uint32_t obs = 0;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const bool o = (acc[k] == acc[k]);
+    obs |= (o ? 1u : 0u) << k;
+    B.r[k] = o ? acc[k] : (R)0;
+  }
+  B.obs = obs;
+}
+
+// Forward over one tile.  (a_c, P_c) carry the predicted moments in and out.
+template <typename R>
+__device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& P_c, int lane) {
+  // ---- variance path: Moebius scan ----
+  const R alpha = s_e + s_h, beta = s_e * s_h;
+  Mob<R> M{(R)1, (R)0, (R)0, (R)1};
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    Mob<R> N;
+    if ((B.obs >> k) & 1u) {
+      N.a = alpha * M.a + beta * M.c; N.b = alpha * M.b + beta * M.d;
+      N.c = M.a + s_e * M.c;          N.d = M.b + s_e * M.d;
+    } else {
+      N.a = M.a + s_h * M.c; N.b = M.b + s_h * M.d; N.c = M.c; N.d = M.d;
+    }
+    M = N;
+  }
+  {
+    const R s = Num<R>::rcp_fast(M.a + M.b + M.c + M.d);
+    M.a *= s; M.b *= s; M.c *= s; M.d *= s;
+  }
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const Mob<R> O = mob_shfl_up(M, off);
+    if (lane >= off) M = mob_mul(M, O);
+  }
+  Mob<R> E = mob_shfl_up(M, 1);
+  if (lane == 0) { E.a = 1; E.b = 0; E.c = 0; E.d = 1; }
+  R Pc = (E.a * P_c + E.b) / (E.c * P_c + E.d);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    B.P[k] = Pc;
+    if ((B.obs >> k) & 1u) {
+      const R rF = Num<R>::rcp(Pc + s_e);
+      const R K = Pc * rF;
+      B.rF[k] = rF; B.K[k] = K;
+      Pc = fma(-K, Pc, Pc);
+    } else {
+      B.rF[k] = 0; B.K[k] = 0;
+    }
+    Pc += s_h;
+  }
+  P_c = __shfl_sync(FULL, Pc, 31);
+  // ---- mean path: affine scan ----
+  R m = 1, c = 0;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const R omk = (R)1 - B.K[k];
+    c = fma(omk, c, B.K[k] * B.r[k]);
+    m = omk * m;
+  }
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const R mo = __shfl_up_sync(FULL, m, off), co = __shfl_up_sync(FULL, c, off);
+    if (lane >= off) { c = fma(m, co, c); m = m * mo; }
+  }
+  R me = __shfl_up_sync(FULL, m, 1), ce = __shfl_up_sync(FULL, c, 1);
+  if (lane == 0) { me = 1; ce = 0; }
+  R ac = fma(me, a_c, ce);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const R v = ((B.obs >> k) & 1u) ? (B.r[k] - ac) : (R)0;
+    B.v[k] = v;
+    ac = fma(B.K[k], v, ac);
+  }
+  a_c = __shfl_sync(FULL, ac, 31);
+}
+
+// sum over the lane's observed steps of  log F + v^2/F
+template <typename R> __device__ __forceinline__ R blk_loglik_terms(const Blk<R>& B, R s_e) {
+  R s = 0;
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    if ((B.obs >> k) & 1u) s += Num<R>::log(B.P[k] + s_e) + B.v[k] * B.v[k] * B.rF[k];
+  return s;
+}
+
+// Reverse (adjoint) sweep over one tile.  (ab_c, pb_c) carry d ll/d a, d ll/d P
+// of the step just after the tile in, and of the tile's first step out.
+// rbar[k] = d ll / d r_k.
+template <typename R>
+__device__ __forceinline__ void blk_backward(const Blk<R>& B, R s_e, R& ab_c, R& pb_c, int lane,
+                                             R& ge, R& gh, R* rbar) {
+  // ---- abar: abar_t = (1-K) abar_{t+1} + v/F ----
+  R m = 1, c = 0;
+#pragma unroll
+  for (int k = KS - 1; k >= 0; --k) {
+    const R omk = (R)1 - B.K[k];
+    c = fma(omk, c, B.v[k] * B.rF[k]);
+    m = omk * m;
+  }
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const R mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
+    if (lane + off < 32) { c = fma(m, co, c); m = m * mo; }
+  }
+  R me = __shfl_down_sync(FULL, m, 1), ce = __shfl_down_sync(FULL, c, 1);
+  if (lane == 31) { me = 1; ce = 0; }
+  R ab = fma(me, ab_c, ce);
+  R abn[KS];
+#pragma unroll
+  for (int k = KS - 1; k >= 0; --k) {
+    abn[k] = ab;
+    ab = fma((R)1 - B.K[k], ab, B.v[k] * B.rF[k]);
+  }
+  ab_c = __shfl_sync(FULL, ab, 0);
+  // ---- Pbar: Pbar_t = (1-K)^2 Pbar_{t+1} + abar_{t+1} v s_e/F^2 + dF ----
+  R q[KS], dF[KS];
+  m = 1; c = 0;
+#pragma unroll
+  for (int k = KS - 1; k >= 0; --k) {
+    const R omk = (R)1 - B.K[k];
+    const R mult = omk * omk;
+    const R rF = B.rF[k], v = B.v[k];
+    dF[k] = (R)-0.5 * (rF - v * v * rF * rF);
+    q[k] = fma(abn[k] * v * s_e, rF * rF, dF[k]);
+    c = fma(mult, c, q[k]);
+    m = mult * m;
+  }
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const R mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
+    if (lane + off < 32) { c = fma(m, co, c); m = m * mo; }
+  }
+  me = __shfl_down_sync(FULL, m, 1); ce = __shfl_down_sync(FULL, c, 1);
+  if (lane == 31) { me = 1; ce = 0; }
+  R pb = fma(me, pb_c, ce);
+  R lge = 0, lgh = 0;
+#pragma unroll
+  for (int k = KS - 1; k >= 0; --k) {
+    const R K = B.K[k], rF = B.rF[k], v = B.v[k];
+    const R omk = (R)1 - K;
+    lgh += pb;
+    lge += fma(K * K, pb, dF[k]) - abn[k] * v * B.P[k] * rF * rF;
+    rbar[k] = fma(K, abn[k], -v * rF);
+    pb = fma(omk * omk, pb, q[k]);
+  }
+  pb_c = __shfl_sync(FULL, pb, 0);
+  ge += lge; gh += lgh;
+}
+
+// acc[s] (+)= sum_tl rb[tl] * x[tl][j],  j = jj + 32 s, over this lane's share
+// of the tile's rows (part, part+nparts, ...).  Transposed access: lanes <-> j.
+template <typename R, int JS>
+__device__ __forceinline__ void blk_xt_rbar(const R* __restrict__ tile, const R* __restrict__ rb,
+                                            int p, int ld, int jj, int part, int nparts,
+                                            R (&acc)[JS]) {
+  for (int tl = part; tl < TB; tl += nparts) {
+    const R rv = rb[tl + (tl >> 5)];
+    const R* row = tile + tile_off(tl, ld);
+#pragma unroll
+    for (int s = 0; s < JS; ++s) {
+      const int j = jj + 32 * s;
+      if (j < p) acc[s] = fma(rv, row[j], acc[s]);
+    }
+  }
+}
+
+}  // namespace ci
