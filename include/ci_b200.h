@@ -153,7 +153,7 @@ int ci_posterior_predict(ci_ctx* ctx, const void* theta_draws, int S,
                          void* traj, void* mean);
 int ci_posterior_predict_d(ci_ctx* ctx, const void* theta_draws_d, int S,
                            uint64_t seed, uint64_t draw_id0, void* level_d,
-                           void* traj_d, void* mean_sum_d, void* stream);
+                           void* traj_d, void* mean_d, void* stream);
 
 /* ---- K5: per-time quantiles across draws ---------------------------------
  * Replaces posterior_processing.calculate_trajectory_quantiles

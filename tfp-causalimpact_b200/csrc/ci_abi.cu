@@ -11,6 +11,8 @@
 
 #include "../../include/ci_b200.h"
 #include "ci_kernels.cuh"
+#include "ci_predict.cuh"
+#include "ci_hmc.cuh"
 
 namespace {
 
@@ -61,6 +63,7 @@ struct ci_ctx {
   size_t esz = 4;
   DevBuf tiles, omega;
   DevBuf w_theta, w_value, w_grad;   // workspaces of the host-pointer entry points
+  DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats;
   int64_t launches = 0;
   int force_G = 0;                   // CI_B200_G env override (tuning)
 };
@@ -95,7 +98,7 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out) {
   const uint32_t stage_bytes = cfg.stage_elems * esz;
   // per-warp scratch
   uint32_t e = 0;
-  cfg.w_off = e;     e += align_up((uint32_t)(p > 0 ? p : 1), 4);
+  cfg.w_off = e;     e += align_up((uint32_t)(p + 4), 4);   // holds the full theta in the HMC kernel
   cfg.rbuf_off = e;  e += TB + 8;
   cfg.ckpt_off = e;  e += align_up(2u * (uint32_t)NB, 4);
   cfg.extra_off = e; e += align_up(extra_elems, 4);
@@ -176,6 +179,108 @@ void build_tiles(const ci_problem* pb, const void* y_, const void* X_, int NB, i
   }
 }
 
+// Stan-style windowed adaptation schedule (oracle/hmc_np.py:adapt_schedule).
+void make_hmc_plan(const ci_hmc_opts* o, uint64_t seed, HmcPlan* pl) {
+  HmcPlan h{};
+  h.n_warmup = o->n_warmup; h.n_results = o->n_results; h.max_leapfrog = o->max_leapfrog;
+  h.adapt_mass = o->adapt_mass; h.init_step = (float)o->init_step;
+  h.target_accept = (float)o->target_accept;
+  const int W = o->n_warmup;
+  if (W < 20) { h.init_buf = W; h.slow_end = W; h.n_ends = 0; }
+  else {
+    int init = 75, term = 50, base = 25;
+    if (init + base + term > W) { init = (int)(0.15 * W); term = (int)(0.1 * W); base = W - init - term; }
+    const int last = W - term - 1;
+    int size = base, nxt = init + base - 1, n = 0;
+    while (n < 16) {
+      h.ends[n++] = nxt;
+      if (nxt == last) break;
+      size *= 2;
+      int n2 = nxt + size;
+      if (n2 != last && n2 + 2 * size >= W - term) n2 = last;
+      if (n2 > last) n2 = last;
+      nxt = n2;
+    }
+    h.init_buf = init; h.slow_end = W - term; h.n_ends = n;
+  }
+  long long ev = 1;
+  for (int it = 0; it < o->n_warmup + o->n_results; ++it)
+    ev += hmc_leapfrog_count(seed, it, o->max_leapfrog);
+  h.n_evals = ev;
+  *pl = h;
+}
+
+template <typename R>
+int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id0,
+               const void* theta0_d, int C, void* draws_d, ci_hmc_stats* stats_d,
+               cudaStream_t st) {
+  const int G = pick_G(c, C);
+  SmemCfg cfg;
+  int rc = plan_smem(c, G, 0, &cfg);
+  if (rc) return rc;
+  HmcPlan plan;
+  make_hmc_plan(o, seed, &plan);
+  auto kern = k_hmc<R>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)cfg.total_bytes));
+  const int grid = (C + G - 1) / G;
+  kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(
+      make_probdev<R>(c), cfg, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,
+      static_cast<R*>(draws_d), stats_d);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+template <typename R>
+int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_t draw_id0,
+                   void* level_d, void* traj_d, void* mean_d, cudaStream_t st) {
+  const int G = pick_G(c, S);
+  SmemCfg cfg;
+  int rc = plan_smem(c, G, 0, &cfg);
+  if (rc) return rc;
+  auto kern = k_predict<R>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)cfg.total_bytes));
+  const int grid = (S + G - 1) / G;
+  const ProbDev<R> pr = make_probdev<R>(c);
+  kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(pr, cfg, static_cast<const R*>(theta_d), S,
+                                                     seed, draw_id0, static_cast<R*>(level_d),
+                                                     static_cast<R*>(traj_d));
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  if (mean_d) {
+    k_predict_mean<R><<<(c->prob.T + 31) / 32, dim3(32, 32), 0, st>>>(
+        pr, static_cast<const R*>(theta_d), static_cast<const R*>(level_d), S,
+        static_cast<R*>(mean_d));
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  return CI_OK;
+}
+
+template <typename R>
+int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, int nq,
+                     void* out_d, cudaStream_t st) {
+  int n_pad = 2;
+  while (n_pad < S) n_pad <<= 1;
+  const size_t bytes = (size_t)n_pad * sizeof(R);
+  if (bytes > (size_t)c->smem_optin - 1024)
+    return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles: S=%d does not fit the shared-memory sort", S);
+  QuantArgs qa;
+  qa.nq = nq;
+  for (int i = 0; i < nq; ++i) qa.q[i] = q[i];
+  auto kern = k_row_quantiles<R>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  int nt = n_pad / 2;
+  if (nt > 1024) nt = 1024;
+  if (nt < 32) nt = 32;
+  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, n_pad, qa, static_cast<R*>(out_d));
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -223,6 +328,7 @@ int ci_ctx_destroy(ci_ctx* c) {
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   c->tiles.release(); c->omega.release();
   c->w_theta.release(); c->w_value.release(); c->w_grad.release();
+  c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release();
   delete c;
   return CI_OK;
 }
@@ -312,12 +418,113 @@ int ci_logprob(ci_ctx* c, const void* theta, int C, void* value, int variant, in
   return ci_logprob_grad(c, theta, C, value, nullptr, variant, flags);
 }
 
-// ---- not built yet (placeholders keep the ABI complete) -------------------
-int ci_hmc_run(ci_ctx*, const ci_hmc_opts*, uint64_t, uint64_t, const void*, int, void*, ci_hmc_stats*) { return fail(CI_ERR_UNSUPPORTED, "ci_hmc_run: not built yet"); }
-int ci_hmc_run_d(ci_ctx*, const ci_hmc_opts*, uint64_t, uint64_t, const void*, int, void*, ci_hmc_stats*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_hmc_run_d: not built yet"); }
-int ci_posterior_predict(ci_ctx*, const void*, int, uint64_t, uint64_t, void*, void*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_posterior_predict: not built yet"); }
-int ci_posterior_predict_d(ci_ctx*, const void*, int, uint64_t, uint64_t, void*, void*, void*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_posterior_predict_d: not built yet"); }
-int ci_row_quantiles(ci_ctx*, const void*, int, int, int, const double*, int, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles: not built yet"); }
-int ci_row_quantiles_d(ci_ctx*, const void*, int, int, int, const double*, int, void*, void*) { return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles_d: not built yet"); }
+
+int ci_posterior_predict_d(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_t draw_id0,
+                           void* level_d, void* traj_d, void* mean_d, void* stream) {
+  if (!c || !theta_d || !traj_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!level_d && mean_d) {   // the mean needs the level paths: use the workspace
+    CU_TRY(c->w_level.reserve((size_t)S * c->prob.T * c->esz));
+    level_d = c->w_level.p;
+  }
+  if (c->prob.dtype == CI_F64)
+    return launch_predict<double>(c, theta_d, S, seed, draw_id0, level_d, traj_d, mean_d, st);
+  return launch_predict<float>(c, theta_d, S, seed, draw_id0, level_d, traj_d, mean_d, st);
+}
+
+int ci_posterior_predict(ci_ctx* c, const void* theta, int S, uint64_t seed, uint64_t draw_id0,
+                         void* level, void* traj, void* mean) {
+  if (!c || !theta || !traj) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t tb = (size_t)S * c->dim * c->esz, st_b = (size_t)S * c->prob.T * c->esz;
+  const size_t mb = (size_t)c->prob.T * c->esz;
+  CU_TRY(c->w_theta.reserve(tb));
+  CU_TRY(c->w_level.reserve(st_b));
+  CU_TRY(c->w_traj.reserve(st_b));
+  CU_TRY(c->w_mean.reserve(mb));
+  CU_TRY(cudaMemcpyAsync(c->w_theta.p, theta, tb, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_posterior_predict_d(c, c->w_theta.p, S, seed, draw_id0, c->w_level.p, c->w_traj.p,
+                                  mean ? c->w_mean.p : nullptr, c->stream);
+  if (rc) return rc;
+  if (level) CU_TRY(cudaMemcpyAsync(level, c->w_level.p, st_b, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(traj, c->w_traj.p, st_b, cudaMemcpyDeviceToHost, c->stream));
+  if (mean) CU_TRY(cudaMemcpyAsync(mean, c->w_mean.p, mb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_row_quantiles_d(ci_ctx* c, const void* a_d, int S, int T, int dtype, const double* q,
+                       int nq, void* out_d, void* stream) {
+  if (!c || !a_d || !q || !out_d) return fail(CI_ERR_INVALID, "null argument");
+  if (S < 1 || T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (nq < 1 || nq > 8) return fail(CI_ERR_INVALID, "nq must be in [1,8]");
+  for (int i = 0; i < nq; ++i)
+    if (!(q[i] >= 0.0 && q[i] <= 1.0)) return fail(CI_ERR_INVALID, "quantile %d out of [0,1]", i);
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == CI_F64) return launch_quantiles<double>(c, a_d, S, T, q, nq, out_d, st);
+  if (dtype == CI_F32) return launch_quantiles<float>(c, a_d, S, T, q, nq, out_d, st);
+  return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+}
+
+int ci_row_quantiles(ci_ctx* c, const void* a, int S, int T, int dtype, const double* q, int nq,
+                     void* out) {
+  if (!c || !a || !q || !out) return fail(CI_ERR_INVALID, "null argument");
+  if (S < 1 || T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (dtype != CI_F32 && dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t es = dtype == CI_F64 ? 8 : 4;
+  const size_t ab = (size_t)S * T * es, ob = (size_t)T * nq * es;
+  CU_TRY(c->w_traj.reserve(ab));
+  CU_TRY(c->w_q.reserve(ob > 0 ? ob : 16));
+  CU_TRY(cudaMemcpyAsync(c->w_traj.p, a, ab, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_row_quantiles_d(c, c->w_traj.p, S, T, dtype, q, nq, c->w_q.p, c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(out, c->w_q.p, ob, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_hmc_run_d(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id0,
+                 const void* theta0_d, int C, void* draws_d, ci_hmc_stats* stats_d, void* stream) {
+  if (!c || !o || !theta0_d || !draws_d || !stats_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (C < 1) return fail(CI_ERR_INVALID, "n_chains must be >= 1");
+  if (o->n_warmup < 0 || o->n_results < 1) return fail(CI_ERR_INVALID, "n_warmup >= 0 and n_results >= 1 required");
+  if (o->max_leapfrog < 1 || o->max_leapfrog > 1024) return fail(CI_ERR_INVALID, "max_leapfrog must be in [1,1024]");
+  if (!(o->init_step > 0)) return fail(CI_ERR_INVALID, "init_step must be positive");
+  if (!(o->target_accept > 0 && o->target_accept < 1)) return fail(CI_ERR_INVALID, "target_accept must be in (0,1)");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prob.dtype == CI_F64)
+    return launch_hmc<double>(c, o, seed, chain_id0, theta0_d, C, draws_d, stats_d, st);
+  return launch_hmc<float>(c, o, seed, chain_id0, theta0_d, C, draws_d, stats_d, st);
+}
+
+int ci_hmc_run(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id0,
+               const void* theta0, int C, void* draws, ci_hmc_stats* stats) {
+  if (!c || !o || !theta0 || !draws || !stats) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (C < 1 || o->n_results < 1) return fail(CI_ERR_INVALID, "n_chains and n_results must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t tb = (size_t)C * c->dim * c->esz;
+  const size_t db = (size_t)o->n_results * tb, sb = (size_t)C * sizeof(ci_hmc_stats);
+  CU_TRY(c->w_theta.reserve(tb));
+  CU_TRY(c->w_draws.reserve(db));
+  CU_TRY(c->w_stats.reserve(sb));
+  CU_TRY(cudaMemcpyAsync(c->w_theta.p, theta0, tb, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_hmc_run_d(c, o, seed, chain_id0, c->w_theta.p, C, c->w_draws.p,
+                        static_cast<ci_hmc_stats*>(c->w_stats.p), c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(draws, c->w_draws.p, db, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(stats, c->w_stats.p, sb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
 
 }  // extern "C"

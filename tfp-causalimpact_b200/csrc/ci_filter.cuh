@@ -133,8 +133,36 @@ __device__ __forceinline__ void blk_residuals(Blk<R>& B, const R* __restrict__ t
   B.obs = obs;
 }
 
-// Forward over one tile.  (a_c, P_c) carry the predicted moments in and out.
+// Same, but also returns the regression term xw_k = x_k . w (needed where the
+// step is masked and y is NaN): r_k = y_k - xw_k.
 template <typename R>
+__device__ __forceinline__ void blk_residuals_xw(Blk<R>& B, R (&xw)[KS],
+                                                 const R* __restrict__ tile,
+                                                 const R* __restrict__ w_s, int p, int ld,
+                                                 int lane) {
+  const R* row0 = tile + tile_off(lane * KS, ld);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) xw[k] = 0;
+  for (int j = 0; j < p; ++j) {
+    const R wj = w_s[j];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) xw[k] = fma(row0[k * ld + j], wj, xw[k]);
+  }
+  uint32_t obs = 0;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const R y = row0[k * ld + p];
+    const bool o = (y == y);
+    obs |= (o ? 1u : 0u) << k;
+    B.r[k] = o ? (y - xw[k]) : (R)0;
+  }
+  B.obs = obs;
+}
+
+// Forward over one tile.  (a_c, P_c) carry the predicted moments in and out.
+// FILT = false: B.v[k] = innovation v_k (0 where masked).
+// FILT = true : B.v[k] = FILTERED mean m_k = a_k + K_k v_k (the smoother's input).
+template <typename R, bool FILT = false>
 __device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& P_c, int lane) {
   // ---- variance path: Moebius scan ----
   const R alpha = s_e + s_h, beta = s_e * s_h;
@@ -195,8 +223,8 @@ __device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& 
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
     const R v = ((B.obs >> k) & 1u) ? (B.r[k] - ac) : (R)0;
-    B.v[k] = v;
     ac = fma(B.K[k], v, ac);
+    B.v[k] = FILT ? ac : v;
   }
   a_c = __shfl_sync(FULL, ac, 31);
 }
