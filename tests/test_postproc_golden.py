@@ -1,0 +1,73 @@
+"""Host logic vs golden vectors produced by the REFERENCE's own code
+(oracle/make_golden_postproc.py ran causalimpact_lib._compute_impact and
+data.CausalImpactData unmodified).  CPU: the quantile kernel is replaced by the
+pandas oracle; the GPU variant of this test lives in test_gpu_fit.py."""
+import glob
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from causalimpact_b200 import frame as fr
+from causalimpact_b200 import impact
+from oracle import quantiles_np
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "postproc_*.npz")))
+
+
+def load_case(path):
+  g = np.load(path, allow_pickle=False)
+  idx = pd.DatetimeIndex(g["frame_index"]) if bool(g["index_is_datetime"]) \
+      else pd.Index(g["frame_index"])
+  data = pd.DataFrame(g["frame_values"], index=idx, columns=[str(c) for c in g["frame_columns"]])
+  pre = (idx[int(g["pre"][0])], idx[int(g["pre"][1])])
+  post = (idx[int(g["post"][0])], idx[int(g["post"][1])])
+  return g, data, pre, post
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[9:-4] for p in GOLDEN])
+def test_data_prep_matches_reference(path):
+  g, data, pre, post = load_case(path)
+  ci = fr.CausalImpactData(data, pre, post, standardize_data=bool(g["standardize"]))
+  np.testing.assert_allclose(ci.model_pre_data.values, g["model_pre"], rtol=1e-13, equal_nan=True)
+  np.testing.assert_allclose(ci.model_after_pre_data.values, g["model_after"], rtol=1e-13,
+                             equal_nan=True)
+  if g["feature_ts"].size:
+    np.testing.assert_allclose(ci.feature_ts.values, g["feature_ts"], rtol=1e-13)
+    assert list(ci.feature_ts.columns)[-1] == "intercept_"
+  else:
+    assert ci.feature_ts is None
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[9:-4] for p in GOLDEN])
+def test_compute_impact_matches_reference(path):
+  g, data, pre, post = load_case(path)
+  ci = fr.CausalImpactData(data, pre, post, standardize_data=bool(g["standardize"]))
+  series, summary = impact.compute_impact(g["posterior_means"], g["posterior_trajectories"], ci,
+                                          float(g["alpha"]), quantiles_np.row_quantiles)
+  cols = [str(c) for c in g["series_columns"]]
+  assert list(series.columns[:len(cols)]) == cols
+  # standardize_data=True: the reference un-scales into float64 first, so we agree
+  # to rounding.  standardize_data=False: the reference stays in float32 pandas
+  # arithmetic (posterior_processing.py:88-91 skips the float64 scaler); we
+  # compute in float64, so agreement is to float32 rounding of the values.
+  rtol, atol = (1e-11, 1e-11) if bool(g["standardize"]) else \
+      (1e-5, 4e-6 * float(np.nanmax(np.abs(g["series_values"]))))
+  np.testing.assert_allclose(series[cols].values.astype(float), g["series_values"], rtol=rtol,
+                             atol=atol, equal_nan=True)
+  assert [str(c) for c in g["summary_columns"]] == list(summary.columns)
+  assert list(summary.index) == ["average", "cumulative"]
+  np.testing.assert_allclose(summary.values.astype(float), g["summary_values"], rtol=rtol,
+                             atol=atol, equal_nan=True)
+  assert series.index.equals(data.index)
+  for c in ("pre_period_start", "pre_period_end", "post_period_start", "post_period_end"):
+    assert c in series.columns
+
+
+def test_alpha_is_validated():
+  g, data, pre, post = load_case(GOLDEN[0])
+  ci = fr.CausalImpactData(data, pre, post)
+  with pytest.raises(ValueError, match="alpha"):
+    impact.compute_impact(g["posterior_means"], g["posterior_trajectories"], ci, 1.5,
+                          quantiles_np.row_quantiles)
