@@ -1,0 +1,44 @@
+"""Oracle-backed stand-in for causalimpact_b200.Engine -- TESTS ONLY.
+
+Lets the host logic (chain sharding, the single all-gather, draw ordering,
+post-processing) run on CPU under gloo.  It answers the same methods as
+Engine with the float64 oracle, keyed by the same global chain / draw ids."""
+import numpy as np
+
+from oracle import c_port
+from oracle import hmc_np as H
+from oracle import kalman_np as K
+from oracle import quantiles_np
+from oracle import smoother_np as SM
+
+
+class FakeEngine:
+  def __init__(self, device=0):
+    self.device, self.spec, self.prob = device, None, None
+
+  def set_data(self, spec):
+    self.spec = spec
+    self.prob = K.Problem(
+        model=spec.model, y=np.asarray(spec.y, float),
+        X=None if spec.X is None else np.asarray(spec.X, float),
+        Omega=None if spec.Omega is None else np.asarray(spec.Omega, float),
+        m0=spec.m0, P0=spec.P0, obs_conc=spec.obs_conc, obs_scale=spec.obs_scale,
+        obs_ub=spec.obs_ub, lvl_conc=spec.lvl_conc, lvl_scale=spec.lvl_scale, lvl_ub=spec.lvl_ub)
+
+  def hmc_run(self, theta0, *, n_warmup, n_results, seed, chain_id0=0, max_leapfrog=8,
+              init_step=0.05, target_accept=0.8, adapt_mass=True):
+    f = lambda th: c_port.logpost_grad(self.prob, th)[:2]
+    draws, st = H.run(f, theta0, n_warmup=n_warmup, n_results=n_results, seed=seed,
+                      chain_id0=chain_id0, max_leapfrog=max_leapfrog, init_step=init_step,
+                      target_accept=target_accept, adapt_mass=adapt_mass)
+    stats = {k: np.asarray(st[k]) for k in ("accept_rate", "step_size", "n_divergent",
+                                            "n_leapfrog")}
+    return draws.astype(self.spec.np_dtype), stats
+
+  def posterior_predict(self, theta_draws, *, seed, draw_id0=0, want_level=True):
+    l, t, m = SM.posterior_predict(self.prob, theta_draws, seed, draw_id0)
+    dt = self.spec.np_dtype
+    return l.astype(dt), t.astype(dt), m.astype(dt)
+
+  def row_quantiles(self, a, q):
+    return quantiles_np.row_quantiles(a, q)

@@ -1,0 +1,81 @@
+"""N > 1 host path on CPU: world_size-2 gloo run of the sharded fit must equal
+the single-process result bit for bit (chains / draws are keyed by global ids;
+exactly one all-gather).  The engine is the oracle-backed FakeEngine."""
+import os
+import pickle
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from causalimpact_b200 import shard
+
+WORKER = r'''
+import os, pickle, sys
+import numpy as np, pandas as pd
+ROOT = sys.argv[1]
+for p in (ROOT, os.path.join(ROOT, "tfp-causalimpact_b200"), os.path.join(ROOT, "tests")):
+  sys.path.insert(0, p)
+import torch.distributed as dist
+from fake_engine import FakeEngine
+import causalimpact_b200 as cib
+from causalimpact_b200 import api
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+  dist.init_process_group("gloo")
+fake = FakeEngine()
+api._resolve_engine = lambda opts: fake
+rng = np.random.default_rng(3)
+n = 60
+x = 100 + np.cumsum(rng.normal(size=n)); y = 1.2 * x + rng.normal(size=n); y[40:] += 4
+df = pd.DataFrame({"y": y, "x": x}, index=pd.date_range("2021-01-01", periods=n))
+ci = cib.fit_causalimpact(df, (df.index[0], df.index[39]), (df.index[40], df.index[-1]), seed=(1, 2),
+    inference_options=cib.InferenceOptions(num_results=22),
+    engine_options=cib.EngineOptions(num_chains=5, min_warmup=25, max_leapfrog=3))
+if int(os.environ.get("RANK", "0")) == 0:
+  vals = [c for c in ci.series.columns if not c.endswith(("_start", "_end"))]
+  pickle.dump(dict(series=ci.series[vals].values, summary=ci.summary.values,
+                   level=np.asarray(ci.posterior_samples.level),
+                   weights=np.asarray(ci.posterior_samples.weights)), open(sys.argv[2], "wb"))
+if world > 1:
+  dist.destroy_process_group()
+'''
+
+
+def _run(world, out):
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+    f.write(WORKER)
+    script = f.name
+  env = dict(os.environ, OMP_NUM_THREADS="1")
+  if world == 1:
+    cmd = [sys.executable, script, root, out]
+  else:
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29731",
+           script, root, out]
+  res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+  os.unlink(script)
+  assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+  return pickle.load(open(out, "rb"))
+
+
+def test_split_range_is_a_partition():
+  for n in (1, 5, 64, 257):
+    for w in (1, 2, 3, 8):
+      parts = [shard.split_range(n, w, r) for r in range(w)]
+      assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+      for (s0, c0), (s1, _) in zip(parts, parts[1:]):
+        assert s0 + c0 == s1
+      assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_world2_gloo_equals_single_process(tmp_path):
+  one = _run(1, str(tmp_path / "w1.pkl"))
+  two = _run(2, str(tmp_path / "w2.pkl"))
+  for k in one:
+    assert np.array_equal(one[k], two[k], equal_nan=True), k
+  assert one["level"].shape == (22, 60)

@@ -1,3 +1,13 @@
-"""B200-native engine for the CausalImpact fit / posterior-predictive path."""
+"""B200-native engine for the CausalImpact fit / posterior-predictive path.
+
+Drop-in surface (reference causalimpact/__init__.py:29-37):
+    import causalimpact_b200 as causalimpact
+    ci = causalimpact.fit_causalimpact(data, pre_period, post_period)
+"""
+__version__ = "0.1.0"
+
 from ._engine import Engine, EngineError, ProblemSpec  # noqa: F401
+from .api import (CausalImpactAnalysis, CausalImpactPosteriorSamples, DataOptions,  # noqa: F401
+                  EngineOptions, InferenceOptions, ModelOptions, Seasons, fit_causalimpact)
+from .frame import CausalImpactData, InputDateType  # noqa: F401
 from .model import build_problem, initial_theta  # noqa: F401

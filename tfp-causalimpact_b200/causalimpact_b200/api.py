@@ -1,0 +1,309 @@
+"""``fit_causalimpact`` on the B200 engine -- same entry point, option structs and
+result object as the reference (causalimpact/causalimpact_lib.py:44-339).
+
+What changed underneath (BASELINE.json north_star): the TFP Gibbs call
+(causalimpact_lib.py:365-388) is replaced by batched-chain HMC over the CUDA
+Kalman log-prob kernel (ci_hmc_run), the per-draw predictive sampling
+(causalimpact_lib.py:609-632) by the CUDA simulation smoother
+(ci_posterior_predict), and the per-time quantiles
+(posterior_processing.py:25-60) by ci_row_quantiles.  No TensorFlow.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import os
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import pandas as pd
+
+from . import frame as _frame
+from . import impact as _impact
+from . import shard as _shard
+from ._engine import Engine, ProblemSpec
+from .model import build_problem, initial_theta
+
+
+class Samples(np.ndarray):
+  """ndarray that also answers ``.numpy()`` (the reference returns tf.Tensors and
+  its users call ``.numpy()``, e.g. causalimpact_lib_test.py:269, 335-338)."""
+
+  def __new__(cls, arr):
+    return np.asarray(arr).view(cls)
+
+  def numpy(self) -> np.ndarray:
+    return np.asarray(self)
+
+
+@dataclasses.dataclass
+class CausalImpactPosteriorSamples:
+  """Draws of the model's latents (reference causalimpact_lib.py:44-58)."""
+  observation_noise_scale: Samples            # [S]
+  level_scale: Optional[Samples]              # [S]
+  level: Optional[Samples]                    # [S, T]
+  weights: Optional[Samples]                  # [S, covariates + 1 intercept] or None
+  seasonal_drift_scales: Optional[Samples]    # None (no seasonal components)
+  seasonal_levels: Optional[Samples]          # [S, T, 0]
+
+
+@dataclasses.dataclass
+class CausalImpactAnalysis:
+  """``series`` / ``summary`` frames + latent draws (reference :61-144).
+
+  ``diagnostics`` is extra (not in the reference): per-chain HMC statistics.
+  """
+  series: pd.DataFrame
+  summary: pd.DataFrame
+  posterior_samples: CausalImpactPosteriorSamples
+  diagnostics: Optional[dict] = None
+
+
+@dataclasses.dataclass
+class DataOptions:
+  """reference :147-159.  ``dtype``: numpy float32 / float64 (or anything
+  np.dtype() understands, or an object with ``as_numpy_dtype`` such as a tf dtype)."""
+  outcome_column: Optional[str] = None
+  standardize_data: bool = True
+  dtype: object = np.float32
+
+
+@dataclasses.dataclass(frozen=True)
+class Seasons:
+  """reference :162-180.  Accepted for signature compatibility; seasonal
+  components are outside this engine's path and raise NotImplementedError."""
+  num_seasons: int
+  num_steps_per_season: Union[int, Tuple[int], Tuple[Tuple[int]]] = 1
+
+
+@dataclasses.dataclass
+class ModelOptions:
+  """reference :183-203."""
+  prior_level_sd: float = 0.01
+  seasons: List[Seasons] = dataclasses.field(default_factory=list)
+
+
+@dataclasses.dataclass
+class InferenceOptions:
+  """reference :206-220 (warm-up defaults to ceil(num_results / 9))."""
+  num_results: int = 900
+  num_warmup_steps: Optional[int] = None
+
+  def __post_init__(self):
+    if self.num_warmup_steps is None:
+      self.num_warmup_steps = math.ceil(self.num_results / 9)
+
+
+@dataclasses.dataclass
+class EngineOptions:
+  """Knobs of the B200 engine (new; passed as ``engine_options=`` kwarg).
+
+  num_chains: HMC chains (one warp each), sharded over the ranks of an
+    initialised torch.distributed process group.
+  min_warmup: HMC needs more adaptation than a Gibbs sweep count suggests; the
+    warm-up run is max(InferenceOptions.num_warmup_steps, min_warmup).
+  """
+  num_chains: int = 64
+  max_leapfrog: int = 8
+  min_warmup: int = 300
+  init_step: float = 0.05
+  target_accept: float = 0.8
+  device: Optional[int] = None
+  whiten: bool = True
+
+
+_ENGINES = {}
+
+
+def _engine_for(device: int) -> Engine:
+  if device not in _ENGINES:
+    _ENGINES[device] = Engine(device)
+  return _ENGINES[device]
+
+
+def _resolve_engine(opts: Optional["EngineOptions"]) -> Engine:
+  device = None if opts is None else opts.device
+  if device is None:
+    device = int(os.environ.get("LOCAL_RANK", "0")) if _shard.world()[1] > 1 else 0
+  return _engine_for(device)
+
+
+def _np_dtype(dtype) -> np.dtype:
+  if hasattr(dtype, "as_numpy_dtype"):
+    dtype = dtype.as_numpy_dtype
+  dt = np.dtype(dtype)
+  if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+    raise ValueError(f"dtype must be float32 or float64, got {dt}")
+  return dt
+
+
+def _seed_to_u64(seed) -> int:
+  """int -> (0, seed) like the reference (causalimpact_lib.py:535-539); a pair is
+  packed into 64 bits; None -> fresh entropy (non-deterministic, as upstream)."""
+  if seed is None:
+    return int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).astype(np.uint64)
+               @ np.array([1 << 32, 1], dtype=np.uint64))
+  if isinstance(seed, (int, np.integer)):
+    seed = (0, int(seed))
+  a, b = (int(v) for v in np.asarray(seed).reshape(-1)[:2])
+  return ((a & 0xFFFFFFFF) << 32) | (b & 0xFFFFFFFF)
+
+
+@dataclasses.dataclass
+class _Whitening:
+  """w = z @ Linv with L L' = X_obs' X_obs + Omega: the design matrix handed to
+  the engine has an identity Gram matrix, so HMC sees an almost isotropic
+  posterior in the regression block.  Purely a change of variables (constant
+  Jacobian); draws are mapped back before they are returned."""
+  Linv: np.ndarray
+
+  @staticmethod
+  def build(design, observed, omega) -> "_Whitening":
+    gram = design[observed].T @ design[observed] + omega
+    L = np.linalg.cholesky(gram)
+    return _Whitening(Linv=np.linalg.inv(L))
+
+  def design(self, design):
+    return design @ self.Linv.T
+
+  def omega(self, omega):
+    return self.Linv @ omega @ self.Linv.T
+
+  def to_weights(self, z):
+    return z @ self.Linv
+
+
+def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
+                            num_warmup_steps: int, model=None, dtype=np.float32, seasons=(),
+                            experimental_tf_function_cache_key_addition: int = 0,
+                            engine_options: Optional[EngineOptions] = None):
+  """The engine swap point: same contract as the reference's
+  ``_train_causalimpact_sts`` (causalimpact_lib.py:503-606) -- returns
+  ``(posterior_samples, posterior_means [T], posterior_trajectories [S, T])`` on
+  the standardized scale."""
+  del experimental_tf_function_cache_key_addition      # no tracing cache here
+  if model is not None:
+    raise NotImplementedError("experimental_model needs TFP objects; not supported by the "
+                              "B200 engine")
+  if seasons:
+    raise NotImplementedError("seasonal components are outside the B200 engine's path")
+  opts = engine_options or EngineOptions()
+  np_dt = _np_dtype(dtype)
+  seed64 = _seed_to_u64(seed)
+
+  rank, ws = _shard.world()
+  eng = _resolve_engine(opts)
+
+  y_ext, design, outcome_sd = ci_data.engine_inputs(np_dt)
+  spec = build_problem(y_ext, design, prior_level_sd=prior_level_sd, outcome_sd=outcome_sd,
+                       dtype=np_dt)
+  p, T = spec.p, spec.T
+  wh = None
+  if p and opts.whiten:
+    wh = _Whitening.build(design, ~np.isnan(y_ext), spec.Omega)
+    spec = dataclasses.replace(spec, X=wh.design(design), Omega=wh.omega(spec.Omega))
+  eng.set_data(spec)
+
+  # ---- chains: global ids 0..C-1, contiguous shard per rank ----
+  C = max(int(opts.num_chains), 1)
+  n_per = max(1, math.ceil(num_results / C))
+  c0, c_local = _shard.split_range(C, ws, rank)
+  rng = np.random.Generator(np.random.Philox(key=seed64))
+  theta0 = np.tile(initial_theta(spec, prior_level_sd), (C, 1))
+  if p:
+    seen = ~np.isnan(y_ext)
+    z_star = spec.X[seen].T @ y_ext[seen] if wh is not None else \
+        np.linalg.solve(spec.X[seen].T @ spec.X[seen] + spec.Omega, spec.X[seen].T @ y_ext[seen])
+    theta0[:, :p] = z_star + 0.05 * rng.normal(size=(C, p))
+  theta0[:, p:] += 0.1 * rng.normal(size=(C, spec.dim - p))
+  n_warm = max(int(num_warmup_steps), int(opts.min_warmup))
+
+  width = spec.dim + 2 * T
+  if c_local > 0:
+    draws, stats = eng.hmc_run(theta0[c0:c0 + c_local], n_warmup=n_warm, n_results=n_per,
+                               seed=seed64, chain_id0=c0, max_leapfrog=opts.max_leapfrog,
+                               init_step=opts.init_step, target_accept=opts.target_accept)
+    # chain-major draw ids: g = chain * n_per + iteration  (contiguous per rank)
+    local_theta = np.ascontiguousarray(draws.transpose(1, 0, 2)).reshape(c_local * n_per,
+                                                                           spec.dim)
+    level, traj, _ = eng.posterior_predict(local_theta, seed=seed64 ^ 0x9E3779B97F4A7C15,
+                                           draw_id0=c0 * n_per)
+    rows = np.concatenate([local_theta, level, traj], axis=1)
+  else:
+    stats = None
+    rows = np.zeros((0, width), dtype=spec.np_dtype)
+  # the ONE collective of the fit: every chain contributes n_per result rows
+  rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
+
+  theta = rows[:, :spec.dim].astype(np.float64)
+  level = rows[:, spec.dim:spec.dim + T]
+  traj = rows[:, spec.dim + T:]
+  z = theta[:, :p]
+  weights = wh.to_weights(z) if wh is not None else z
+  # mean of the predictive mixture = average of level + X.w over the draws
+  # (causalimpact_lib.py:627); float64, fixed order => same for any GPU count
+  loc_mean = level.astype(np.float64).mean(axis=0)
+  if p:
+    loc_mean = loc_mean + design @ weights.mean(axis=0)
+  S = rows.shape[0]
+  samples = CausalImpactPosteriorSamples(
+      observation_noise_scale=Samples(np.exp(0.5 * theta[:, p]).astype(np_dt)),
+      level_scale=Samples(np.exp(0.5 * theta[:, p + 1]).astype(np_dt)),
+      level=Samples(level.astype(np_dt)),
+      weights=Samples(weights.astype(np_dt)) if p else Samples(np.zeros((S, 0), np_dt)),
+      seasonal_drift_scales=Samples(np.zeros((S, 0), np_dt)),
+      seasonal_levels=Samples(np.zeros((S, T, 0), np_dt)))
+  samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
+  return samples, loc_mean.astype(np_dt), traj.astype(np_dt)
+
+
+def fit_causalimpact(data: pd.DataFrame,
+                     pre_period: Tuple[_frame.InputDateType, _frame.InputDateType],
+                     post_period: Tuple[_frame.InputDateType, _frame.InputDateType],
+                     alpha: float = 0.05,
+                     seed=None,
+                     data_options: Optional[DataOptions] = None,
+                     model_options: Optional[ModelOptions] = None,
+                     inference_options: Optional[InferenceOptions] = None,
+                     **kwargs) -> CausalImpactAnalysis:
+  """Fit a CausalImpact model (same signature as the reference,
+  causalimpact_lib.py:223-231).
+
+  Extra keyword (experimental, like the reference's): ``engine_options``.
+  Unknown keywords raise TypeError (causalimpact_lib.py:272-273).
+  """
+  data_options = data_options if data_options is not None else DataOptions()
+  model_options = model_options if model_options is not None else ModelOptions()
+  inference_options = inference_options if inference_options is not None else InferenceOptions()
+  experimental_model = kwargs.pop("experimental_model", None)
+  cache_key = kwargs.pop("experimental_tf_function_cache_key_addition", 0)
+  engine_options = kwargs.pop("engine_options", None)
+  if kwargs:
+    raise TypeError(f"Received unknown {kwargs=}")
+
+  np_dt = _np_dtype(data_options.dtype)
+  ci_data = _frame.CausalImpactData(
+      data=data, pre_period=pre_period, post_period=post_period,
+      outcome_column=data_options.outcome_column,
+      standardize_data=data_options.standardize_data, dtype=np_dt)
+  samples, means, trajectories = _train_causalimpact_sts(
+      ci_data=ci_data, prior_level_sd=model_options.prior_level_sd, seed=seed,
+      num_results=inference_options.num_results,
+      num_warmup_steps=inference_options.num_warmup_steps, model=experimental_model,
+      dtype=np_dt, seasons=model_options.seasons,
+      experimental_tf_function_cache_key_addition=cache_key, engine_options=engine_options)
+  eng = _resolve_engine(engine_options)
+  series, summary = _impact.compute_impact(means, trajectories, ci_data, alpha,
+                                           eng.row_quantiles)
+  stats = getattr(samples, "hmc_stats", None)
+  result_samples = CausalImpactPosteriorSamples(
+      observation_noise_scale=samples.observation_noise_scale,
+      level_scale=samples.level_scale, level=samples.level,
+      weights=samples.weights if samples.weights.shape[1] > 0 else None,    # :330-331
+      seasonal_drift_scales=None,                                            # :332-334
+      seasonal_levels=samples.seasonal_levels)
+  diag = None if stats is None else {
+      "accept_rate": np.asarray(stats["accept_rate"]), "step_size": np.asarray(stats["step_size"]),
+      "n_divergent": np.asarray(stats["n_divergent"]),
+      "n_leapfrog": np.asarray(stats["n_leapfrog"])}
+  return CausalImpactAnalysis(series, summary, result_samples, diag)
