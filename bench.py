@@ -239,10 +239,44 @@ def main():
   if not np.all(np.isfinite(val_pin.numpy())):
     raise SystemExit("non-finite log-prob in bench")
 
+  # ---- secondary metrics (BASELINE.json names both): HMC leapfrog evals/s inside the
+  # persistent kernel, and posterior draws/s (simulation smoother + predictive) ----
+  hmc_kw = dict(n_warmup=40, n_results=20, seed=20242, max_leapfrog=8, init_step=0.02)
+  th0 = th_np.astype(np.float64)
+  eng.hmc_run(th0, chain_id0=rank * C, **dict(hmc_kw, n_warmup=5, n_results=2))     # warm
+  sync_all()
+  t0 = time.perf_counter()
+  _, hstats = eng.hmc_run(th0, chain_id0=rank * C, **hmc_kw)
+  t_hmc = (time.perf_counter() - t0) * 1e3
+  hmc_evals = int(hstats["n_leapfrog"].sum())
+  S_pred = 4096
+  thp = torch.from_numpy(np.ascontiguousarray(np.tile(th_np, (S_pred // C + 1, 1))[:S_pred])).to(dev)
+  lvl = torch.empty(S_pred, cfg["T"], dtype=torch.float32, device=dev)
+  trj = torch.empty_like(lvl)
+  mean_d = torch.empty(cfg["T"], dtype=torch.float32, device=dev)
+  lib, ctx = eng._lib, eng._ctx                       # raw _d entry for device-resident timing
+  def predict():
+    rc = lib.ci_posterior_predict_d(ctx, thp.data_ptr(), S_pred, 7, rank * S_pred, lvl.data_ptr(),
+                                    trj.data_ptr(), mean_d.data_ptr(), stream.cuda_stream)
+    assert rc == 0, lib.ci_last_error()
+  for _ in range(3):
+    predict()
+  sync_all()
+  p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  p0.record(stream)
+  for _ in range(10):
+    predict()
+  p1.record(stream)
+  sync_all()
+  t_pred = float(p0.elapsed_time(p1)) / 10.0
+
   if world > 1:
-    t = torch.tensor([t_step, t_e2e, t_hot], dtype=torch.float64, device=dev)
+    t = torch.tensor([t_step, t_e2e, t_hot, t_hmc, t_pred], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_step, t_e2e, t_hot = (float(x) for x in t.tolist())
+    t_step, t_e2e, t_hot, t_hmc, t_pred = (float(x) for x in t.tolist())
+    he = torch.tensor([hmc_evals], dtype=torch.float64, device=dev)
+    dist.all_reduce(he, op=dist.ReduceOp.SUM)
+    hmc_evals = int(he.item())
 
   if rank == 0:
     total = C * world * args.steps
@@ -258,7 +292,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "local-level + 10 covariates, T=1000, 256 chains per GPU "
                                "(BASELINE.json configs[1]); value+gradient, prior included",
-                   "variant": "associative scan (warp shuffles), one warp per chain",
+                   "variant": "associative scan: warp-shuffle scan per 256-step tile, one warp per tile "
+                              "(team of 4 warps per chain), tile aggregates exchanged via smem",
                    "l2": "flushed (256 MB memset) between timed steps",
                    "timing": "CUDA events per step on the launching stream"},
         "e2e": {"value": total / (t_e2e * 1e-3), "unit": UNIT,
@@ -267,14 +302,21 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None,
-                     "kernel": "k_logpost_scan<float>", "peak_source": peak_src,
+                     "kernel": "k_logpost_team<float>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": C * B,
                      "kernel_ms": kern_ms},
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "clocks": clk.summary(),
         "extra": {"value_hot_l2": total / (t_hot * 1e-3),
-                  "ms_per_step_hot_l2": t_hot / args.steps},
+                  "ms_per_step_hot_l2": t_hot / args.steps,
+                  "hmc_leapfrog_evals_per_sec": hmc_evals / (t_hmc * 1e-3),
+                  "hmc_run": {"chains_per_gpu": C, "iterations": 60, "wall_ms": t_hmc,
+                              "note": "host-pointer ci_hmc_run incl. copies + sync"},
+                  "posterior_draws_per_sec": S_pred * world / (t_pred * 1e-3),
+                  "posterior_draws": {"draws_per_gpu": S_pred, "T": cfg["T"], "ms": t_pred,
+                                      "note": "ci_posterior_predict_d: level + trajectory + mean, "
+                                              "device resident, CUDA events"}},
     }
     print(json.dumps(out))
   if world > 1:

@@ -83,3 +83,25 @@ def test_linearity_property_full_size(engine):
   _, g = engine.logprob_grad(ths)
   np.testing.assert_allclose(g[1, :spec.p], 0.5 * (g[0, :spec.p] + g[2, :spec.p]),
                              rtol=1e-8, atol=1e-8)
+
+
+def test_team_and_single_warp_paths_agree(monkeypatch):
+  """T=1000 has 4 tiles: the default is TEAM mode (one warp per tile); with
+  CI_B200_TEAM=0 the same problem runs on the one-warp-per-chain path.  Both
+  must match the oracle, and each other to float32 rounding."""
+  y, X, _ = make_series(1000, 10, 2023, nan_frac=0.02)
+  spec = cib.build_problem(y, X)
+  prob = K.default_problem(y, X)
+  th = make_thetas(spec.dim, spec.p, 70, 11).astype(np.float32).astype(np.float64)
+  out = {}
+  for mode in ("1", "0"):
+    monkeypatch.setenv("CI_B200_TEAM", mode)
+    eng = cib.Engine(0)
+    eng.set_data(spec)
+    out[mode] = eng.logprob_grad(th, with_prior=True)
+    eng.close()
+  ov, og = K.log_post_grad(prob, th)
+  for mode in out:
+    np.testing.assert_allclose(out[mode][0], ov, rtol=2e-5, atol=2e-3)
+    np.testing.assert_allclose(out[mode][1], og, rtol=2e-3, atol=2e-2)
+  np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=1e-5, atol=1e-3)

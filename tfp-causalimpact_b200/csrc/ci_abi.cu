@@ -13,6 +13,7 @@
 #include "ci_kernels.cuh"
 #include "ci_predict.cuh"
 #include "ci_hmc.cuh"
+#include "ci_team_kernels.cuh"
 
 namespace {
 
@@ -66,6 +67,7 @@ struct ci_ctx {
   DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats;
   int64_t launches = 0;
   int force_G = 0;                   // CI_B200_G env override (tuning)
+  int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
 };
 
 namespace {
@@ -90,7 +92,8 @@ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 // Shared-memory plan for a kernel with G consumer warps and `extra_elems`
 // kernel-specific per-warp scratch elements.
-int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out) {
+int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
+              uint32_t tail_bytes = 0) {
   const uint32_t esz = (uint32_t)c->esz;
   const int p = c->prob.p, NB = c->NB;
   SmemCfg cfg{};
@@ -104,7 +107,7 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out) {
   cfg.extra_off = e; e += align_up(extra_elems, 4);
   cfg.warp_bytes = align_up(e * esz, 16);
   const uint32_t omega_bytes = align_up((uint32_t)(p * p) * esz, 16);
-  const uint32_t fixed = omega_bytes + (uint32_t)G * cfg.warp_bytes;
+  const uint32_t fixed = omega_bytes + (uint32_t)G * cfg.warp_bytes + tail_bytes + 16u;
   const uint32_t budget = (uint32_t)c->smem_optin;
   // stages: as many as fit (each stage also needs 16 bytes of barriers)
   if (fixed + 2u * (stage_bytes + 16u) + 128u > budget)
@@ -121,6 +124,7 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out) {
   off = align_up(off, 16);
   cfg.off_omega = off;  off += omega_bytes;
   cfg.off_warp = off;   off += (uint32_t)G * cfg.warp_bytes;
+  off = align_up(off, 16) + tail_bytes;
   cfg.total_bytes = off;
   *out = cfg;
   return CI_OK;
@@ -134,13 +138,41 @@ int pick_G(const ci_ctx* c, int C) {
   return G;
 }
 
+// Team mode (ci_team.cuh): one warp per tile, W = NB warps per chain.  Used when
+// the whole series is resident in shared memory and has 2..MAXW tiles.
+template <typename R>
+bool plan_team(const ci_ctx* c, int C, int* GT, SmemCfg* cfg) {
+  const int W = c->NB;
+  if (!c->team_mode || W < 2 || W > MAXW) return false;
+  int gt = (C >= 4 * c->sm_count) ? MAXW / W : 1;
+  if (gt < 1) gt = 1;
+  if (c->force_G > 0) gt = c->force_G * W <= MAXW ? c->force_G : 1;
+  const uint32_t tail = (uint32_t)gt * (uint32_t)sizeof(TeamShared<R>);
+  std::string keep = g_err;
+  if (plan_smem(c, gt * W, 0, cfg, tail) != CI_OK || !cfg->resident) { g_err = keep; return false; }
+  *GT = gt;
+  return true;
+}
+
 template <typename R>
 int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* grad_d, int variant,
                    int flags, cudaStream_t st) {
   if (variant != CI_VARIANT_SCAN)
     return fail(CI_ERR_UNSUPPORTED, "variant %d not available for this model", variant);
-  const int G = pick_G(c, C);
   SmemCfg cfg;
+  int GT = 0;
+  if (plan_team<R>(c, C, &GT, &cfg)) {
+    auto tk = k_logpost_team<R>;
+    CU_TRY(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.total_bytes));
+    tk<<<(C + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, c->NB, static_cast<const R*>(theta_d), C,
+        static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
+  const int G = pick_G(c, C);
   int rc = plan_smem(c, G, 0, &cfg);
   if (rc) return rc;
   auto kern = k_logpost_scan<R>;
@@ -183,8 +215,8 @@ void build_tiles(const ci_problem* pb, const void* y_, const void* X_, int NB, i
 void make_hmc_plan(const ci_hmc_opts* o, uint64_t seed, HmcPlan* pl) {
   HmcPlan h{};
   h.n_warmup = o->n_warmup; h.n_results = o->n_results; h.max_leapfrog = o->max_leapfrog;
-  h.adapt_mass = o->adapt_mass; h.init_step = (float)o->init_step;
-  h.target_accept = (float)o->target_accept;
+  h.adapt_mass = o->adapt_mass; h.init_step = o->init_step;
+  h.target_accept = o->target_accept;
   const int W = o->n_warmup;
   if (W < 20) { h.init_buf = W; h.slow_end = W; h.n_ends = 0; }
   else {
@@ -214,12 +246,24 @@ template <typename R>
 int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id0,
                const void* theta0_d, int C, void* draws_d, ci_hmc_stats* stats_d,
                cudaStream_t st) {
-  const int G = pick_G(c, C);
   SmemCfg cfg;
-  int rc = plan_smem(c, G, 0, &cfg);
-  if (rc) return rc;
   HmcPlan plan;
   make_hmc_plan(o, seed, &plan);
+  int GT = 0;
+  if (plan_team<R>(c, C, &GT, &cfg)) {
+    auto tk = k_hmc_team<R>;
+    CU_TRY(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.total_bytes));
+    tk<<<(C + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, c->NB, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,
+        static_cast<R*>(draws_d), stats_d);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
+  const int G = pick_G(c, C);
+  int rc = plan_smem(c, G, 0, &cfg);
+  if (rc) return rc;
   auto kern = k_hmc<R>;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)cfg.total_bytes));
@@ -318,6 +362,7 @@ int ci_ctx_create(int device, ci_ctx** out) {
   cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) { delete c; return fail(CI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
   if (const char* g = getenv("CI_B200_G")) c->force_G = atoi(g);
+  if (const char* g = getenv("CI_B200_TEAM")) c->team_mode = atoi(g);
   *out = c;
   return CI_OK;
 }

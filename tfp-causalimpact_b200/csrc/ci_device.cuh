@@ -5,7 +5,7 @@
 
 namespace ci {
 
-constexpr int MAXG = 8;     // chains (consumer warps) per CTA; +1 producer warp
+constexpr int MAXG = 7;     // chains (consumer warps) per CTA; +1 producer warp = 256 threads
 constexpr int JS = DSLOTS;  // covariate slots per lane in the X^T rbar product
 
 // Problem constants as the kernels see them (built by ci_set_data).
@@ -91,6 +91,11 @@ __device__ __forceinline__ void chain_eval(TilePipe<R>& pipe, const ProbDev<R>& 
   if (!want_grad) return;
   __syncwarp();
   const XtMap xm = xt_map(p, lane);
+  const bool small_p = p <= PSMALL;
+  R accw[PSMALL];
+#pragma unroll
+  for (int j = 0; j < PSMALL; ++j) accw[j] = 0;
+  R g1[1] = {0};
   R ab_c = 0, pb_c = 0;
   double ge = 0.0, gh = 0.0;
   for (int b = NB - 1; b >= 0; --b) {
@@ -103,21 +108,36 @@ __device__ __forceinline__ void chain_eval(TilePipe<R>& pipe, const ProbDev<R>& 
     R lge = 0, lgh = 0;
     blk_backward(B, s_e, ab_c, pb_c, lane, lge, lgh, rbar);
     ge += (double)lge; gh += (double)lgh;
-    if (p > 0) {
+    if (small_p) {
+      blk_xt_rbar_small(tile, rbar, p, ld, lane, accw);
+    } else {
 #pragma unroll
       for (int k = 0; k < KS; ++k) ws.rbuf[lane * KS + k + (lane >> 2)] = rbar[k];
       __syncwarp();
-      blk_xt_rbar<R, JS>(tile, ws.rbuf, p, ld, xm.jj, xm.part, xm.nparts, gw);
+      if (p <= 32) blk_xt_rbar<R, 1>(tile, ws.rbuf, p, ld, xm.jj, xm.part, xm.nparts, g1);
+      else blk_xt_rbar<R, JS>(tile, ws.rbuf, p, ld, xm.jj, xm.part, xm.nparts, gw);
       __syncwarp();
     }
     pipe.release(lane);
   }
   g_se = warp_sum(ge); g_sh = warp_sum(gh);
+  if (small_p) {
+    // lane j ends up owning d ll / d w_j
 #pragma unroll
-  for (int s = 0; s < JS; ++s) {
-    R a = gw[s];
-    for (int o = xm.PJ; o < 32; o <<= 1) a += __shfl_xor_sync(FULL, a, o);
-    gw[s] = -a;   // r = y - Xw  =>  d ll/d w = -X^T rbar
+    for (int j = 0; j < PSMALL; ++j) {
+      if (j < p) {
+        const R tot = warp_sum(accw[j]);
+        if (lane == j) gw[0] = -tot;
+      }
+    }
+  } else {
+    if (p <= 32) gw[0] = g1[0];
+#pragma unroll
+    for (int s = 0; s < JS; ++s) {
+      R a = gw[s];
+      for (int o = xm.PJ; o < 32; o <<= 1) a += __shfl_xor_sync(FULL, a, o);
+      gw[s] = -a;   // r = y - Xw  =>  d ll/d w = -X^T rbar
+    }
   }
 }
 

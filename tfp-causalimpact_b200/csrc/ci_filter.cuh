@@ -118,6 +118,7 @@ __device__ __forceinline__ void blk_residuals(Blk<R>& B, const R* __restrict__ t
   R acc[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) acc[k] = row0[k * ld + p];
+#pragma unroll 4
   for (int j = 0; j < p; ++j) {
     const R wj = w_s[j];
 #pragma unroll
@@ -143,6 +144,7 @@ __device__ __forceinline__ void blk_residuals_xw(Blk<R>& B, R (&xw)[KS],
   const R* row0 = tile + tile_off(lane * KS, ld);
 #pragma unroll
   for (int k = 0; k < KS; ++k) xw[k] = 0;
+#pragma unroll 4
   for (int j = 0; j < p; ++j) {
     const R wj = w_s[j];
 #pragma unroll
@@ -169,13 +171,13 @@ __device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& 
   Mob<R> M{(R)1, (R)0, (R)0, (R)1};
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
+    // observed: [[alpha, beta], [1, s_e]]   masked: [[1, s_h], [0, 1]]   (select, no branch)
+    const bool o = (B.obs >> k) & 1u;
+    const R e1 = o ? alpha : (R)1, e2 = o ? beta : s_h;
+    const R f1 = o ? (R)1 : (R)0, f2 = o ? s_e : (R)1;
     Mob<R> N;
-    if ((B.obs >> k) & 1u) {
-      N.a = alpha * M.a + beta * M.c; N.b = alpha * M.b + beta * M.d;
-      N.c = M.a + s_e * M.c;          N.d = M.b + s_e * M.d;
-    } else {
-      N.a = M.a + s_h * M.c; N.b = M.b + s_h * M.d; N.c = M.c; N.d = M.d;
-    }
+    N.a = fma(e1, M.a, e2 * M.c); N.b = fma(e1, M.b, e2 * M.d);
+    N.c = fma(f1, M.a, f2 * M.c); N.d = fma(f1, M.b, f2 * M.d);
     M = N;
   }
   {
@@ -189,19 +191,15 @@ __device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& 
   }
   Mob<R> E = mob_shfl_up(M, 1);
   if (lane == 0) { E.a = 1; E.b = 0; E.c = 0; E.d = 1; }
-  R Pc = (E.a * P_c + E.b) / (E.c * P_c + E.d);
+  R Pc = fma(E.a, P_c, E.b) * Num<R>::rcp(fma(E.c, P_c, E.d));
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
     B.P[k] = Pc;
-    if ((B.obs >> k) & 1u) {
-      const R rF = Num<R>::rcp(Pc + s_e);
-      const R K = Pc * rF;
-      B.rF[k] = rF; B.K[k] = K;
-      Pc = fma(-K, Pc, Pc);
-    } else {
-      B.rF[k] = 0; B.K[k] = 0;
-    }
-    Pc += s_h;
+    const bool o = (B.obs >> k) & 1u;
+    const R rF = o ? Num<R>::rcp(Pc + s_e) : (R)0;
+    const R K = Pc * rF;
+    B.rF[k] = rF; B.K[k] = K;
+    Pc = fma(-K, Pc, Pc) + s_h;
   }
   P_c = __shfl_sync(FULL, Pc, 31);
   // ---- mean path: affine scan ----
@@ -229,12 +227,21 @@ __device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& 
   a_c = __shfl_sync(FULL, ac, 31);
 }
 
-// sum over the lane's observed steps of  log F + v^2/F
+// sum over the lane's observed steps of  log F + v^2/F.  The logs are taken of
+// products of 4 innovation variances (2 logs per lane per tile instead of 8).
 template <typename R> __device__ __forceinline__ R blk_loglik_terms(const Blk<R>& B, R s_e) {
   R s = 0;
+  R prod[KS / 4];
 #pragma unroll
-  for (int k = 0; k < KS; ++k)
-    if ((B.obs >> k) & 1u) s += Num<R>::log(B.P[k] + s_e) + B.v[k] * B.v[k] * B.rF[k];
+  for (int h = 0; h < KS / 4; ++h) prod[h] = 1;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const bool o = (B.obs >> k) & 1u;
+    prod[k >> 2] *= o ? (B.P[k] + s_e) : (R)1;
+    s = fma(B.v[k] * B.v[k], B.rF[k], s);
+  }
+#pragma unroll
+  for (int h = 0; h < KS / 4; ++h) s += Num<R>::log(prod[h]);
   return s;
 }
 
@@ -308,13 +315,45 @@ template <typename R, int JS>
 __device__ __forceinline__ void blk_xt_rbar(const R* __restrict__ tile, const R* __restrict__ rb,
                                             int p, int ld, int jj, int part, int nparts,
                                             R (&acc)[JS]) {
-  for (int tl = part; tl < TB; tl += nparts) {
-    const R rv = rb[tl + (tl >> 5)];
-    const R* row = tile + tile_off(tl, ld);
+  // rows tl = part + nparts*i; 4 independent partial sums per slot hide the FMA latency
+  const int nrow = TB / nparts;          // nparts divides 32, TB is a multiple of 32
+  R a0[JS], a1[JS], a2[JS], a3[JS];
+#pragma unroll
+  for (int s = 0; s < JS; ++s) { a0[s] = 0; a1[s] = 0; a2[s] = 0; a3[s] = 0; }
+  for (int i = 0; i < nrow; i += 4) {
+    const int t0 = part + nparts * i, t1 = t0 + nparts, t2 = t1 + nparts, t3 = t2 + nparts;
+    const R r0 = rb[t0 + (t0 >> 5)], r1 = rb[t1 + (t1 >> 5)];
+    const R r2 = rb[t2 + (t2 >> 5)], r3 = rb[t3 + (t3 >> 5)];
+    const R* w0 = tile + tile_off(t0, ld);
+    const R* w1 = tile + tile_off(t1, ld);
+    const R* w2 = tile + tile_off(t2, ld);
+    const R* w3 = tile + tile_off(t3, ld);
 #pragma unroll
     for (int s = 0; s < JS; ++s) {
       const int j = jj + 32 * s;
-      if (j < p) acc[s] = fma(rv, row[j], acc[s]);
+      if (j < p) {
+        a0[s] = fma(r0, w0[j], a0[s]); a1[s] = fma(r1, w1[j], a1[s]);
+        a2[s] = fma(r2, w2[j], a2[s]); a3[s] = fma(r3, w3[j], a3[s]);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < JS; ++s) acc[s] += (a0[s] + a1[s]) + (a2[s] + a3[s]);
+}
+
+// Small-p variant (p <= PSMALL): keep the lane <-> time mapping of the residual
+// pass and accumulate one register per covariate; conflict-free, no rbar
+// round-trip through shared memory, 8 p FMAs per lane per tile.
+constexpr int PSMALL = 16;
+template <typename R>
+__device__ __forceinline__ void blk_xt_rbar_small(const R* __restrict__ tile, const R (&rbar)[KS],
+                                                  int p, int ld, int lane, R (&accw)[PSMALL]) {
+  const R* row0 = tile + tile_off(lane * KS, ld);
+#pragma unroll
+  for (int j = 0; j < PSMALL; ++j) {
+    if (j < p) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) accw[j] = fma(rbar[k], row0[k * ld + j], accw[j]);
     }
   }
 }

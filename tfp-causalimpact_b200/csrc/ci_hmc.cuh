@@ -18,7 +18,7 @@ namespace ci {
 
 struct HmcPlan {
   int n_warmup, n_results, max_leapfrog, adapt_mass;
-  float init_step, target_accept;
+  double init_step, target_accept;
   int init_buf, slow_end, n_ends;
   int ends[16];
   long long n_evals;       // 1 + sum_it L_it  (drives the tile producer)
@@ -29,68 +29,28 @@ __host__ __device__ inline int hmc_leapfrog_count(uint64_t seed, int it, int max
   return 1 + (int)(((uint64_t)x.x * (uint64_t)max_leapfrog) >> 32);
 }
 
-template <typename R>
-__global__ void __launch_bounds__(32 * (MAXG + 1))
-k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id0,
-      const R* __restrict__ theta0, int C, R* __restrict__ draws,
-      ci_hmc_stats* __restrict__ stats) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = (blockDim.x >> 5) - 1;
-  const int chain0 = blockIdx.x * G;
-  const int nactive = min(G, C - chain0);
-  const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
-  if (warp == G) {
-    if (lane == 0)
-      tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
-                    cfg.resident != 0, 2LL * plan.n_evals,
-                    [](long long s) { return (s & 1) == 0; });
-    return;
-  }
-  if (warp >= nactive) return;
-
-  const int c = chain0 + warp;
-  const int p = pr.p, dim = pr.dim;
-  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
-  TilePipe<R> pipe = make_pipe(cs, cfg);
-  const uint64_t gid = chain_id0 + (uint64_t)c;
+// The HMC loop of ONE chain.  `Ev` supplies the target:
+//   ev.publish(theta)   make theta visible to the evaluator (shared memory)
+//   ev.eval(lp, g)      log posterior + gradient slots at the published point
+//   ev.writer()         true for the warp that writes draws / stats
+// In team mode every warp of the team runs this loop redundantly on identical
+// values (same RNG keys, same totals), so no extra synchronisation is needed.
+template <typename R, typename Ev>
+__device__ __forceinline__ void hmc_chain(Ev& ev, const HmcPlan& plan, uint64_t seed, uint64_t gid,
+                                          const R* __restrict__ theta0_row, int dim, int lane,
+                                          int c, int C, R* __restrict__ draws,
+                                          ci_hmc_stats* __restrict__ stats) {
   const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
-
-  // evaluate log posterior + gradient at the point stored in ws.w[0..dim)
-  auto eval = [&](double& lp, R (&g)[DSLOTS]) {
-    const R u = ws.w[p], l = ws.w[p + 1];
-    const R s_e = Num<R>::exp(u), s_h = Num<R>::exp(l);
-    double ll, g_se, g_sh;
-    R gw[JS];
-    chain_eval(pipe, pr, ws, s_e, s_h, true, lane, ll, g_se, g_sh, gw);
-    double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
-    lp = ll + chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
-#pragma unroll
-    for (int s = 0; s < DSLOTS; ++s) {
-      const int i = lane + 32 * s;
-      g[s] = i < p ? gw[s] : (i == p ? (R)g_u : (i == p + 1 ? (R)g_l : (R)0));
-    }
-  };
-  auto publish = [&](const R (&t)[DSLOTS]) {
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < DSLOTS; ++s) {
-      const int i = lane + 32 * s;
-      if (i < dim) ws.w[i] = t[s];
-    }
-    __syncwarp();
-  };
-
   R th[DSLOTS], g[DSLOTS], minv[DSLOTS], wmean[DSLOTS], wm2[DSLOTS];
 #pragma unroll
   for (int s = 0; s < DSLOTS; ++s) {
     const int i = lane + 32 * s;
-    th[s] = i < dim ? theta0[(size_t)c * dim + i] : (R)0;
+    th[s] = i < dim ? theta0_row[i] : (R)0;
     minv[s] = 1; wmean[s] = 0; wm2[s] = 0;
   }
   double lp;
-  publish(th);
-  eval(lp, g);
+  ev.publish(th);
+  ev.eval(lp, g);
 
   double eps = plan.init_step;
   double mu = log(10.0 * eps), hbar = 0.0, leb = 0.0, dac = 0.0, wn = 0.0;
@@ -106,13 +66,16 @@ k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id
 #pragma unroll
     for (int s = 0; s < DSLOTS; ++s) {
       const int i = lane + 32 * s;
-      const uint4 x = Philox::gen(seed, id_lo, RNG_MOMENTUM | id_hi8, (uint32_t)it,
-                                  (uint32_t)(i >> 2));
-      R z0, z1, z2, z3;
-      box_muller<R>(x.x, x.y, z0, z1);
-      box_muller<R>(x.z, x.w, z2, z3);
-      const int sel = i & 3;
-      const R z = sel == 0 ? z0 : (sel == 1 ? z1 : (sel == 2 ? z2 : z3));
+      R z = 0;
+      if (i < dim) {
+        const uint4 x = Philox::gen(seed, id_lo, RNG_MOMENTUM | id_hi8, (uint32_t)it,
+                                    (uint32_t)(i >> 2));
+        R z0, z1, z2, z3;
+        box_muller<R>(x.x, x.y, z0, z1);
+        box_muller<R>(x.z, x.w, z2, z3);
+        const int sel = i & 3;
+        z = sel == 0 ? z0 : (sel == 1 ? z1 : (sel == 2 ? z2 : z3));
+      }
       rho[s] = i < dim ? z / Num<R>::sqrt(minv[s]) : (R)0;
       kin += (double)(minv[s] * rho[s] * rho[s]);
       thn[s] = th[s]; gn[s] = g[s];
@@ -126,8 +89,8 @@ k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id
     for (int i = 0; i < L; ++i) {
 #pragma unroll
       for (int s = 0; s < DSLOTS; ++s) thn[s] = fma(e * minv[s], rho[s], thn[s]);
-      publish(thn);
-      eval(lpn, gn);
+      ev.publish(thn);
+      ev.eval(lpn, gn);
       const R f = (i < L - 1) ? e : (R)0.5 * e;
 #pragma unroll
       for (int s = 0; s < DSLOTS; ++s) rho[s] = fma(f, gn[s], rho[s]);
@@ -152,7 +115,7 @@ k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id
       // ---- dual averaging ----
       dac += 1.0;
       const double eta = 1.0 / (dac + 10.0);
-      hbar = (1.0 - eta) * hbar + eta * ((double)plan.target_accept - alpha);
+      hbar = (1.0 - eta) * hbar + eta * (plan.target_accept - alpha);
       const double le = mu - hbar * sqrt(dac) / 0.05;
       const double ex = pow(dac, -0.75);
       leb = (1.0 - ex) * leb + ex * le;
@@ -182,17 +145,19 @@ k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id
       }
       if (it == plan.n_warmup - 1) eps = exp(leb);
     } else {
-      const size_t row = ((size_t)(it - plan.n_warmup) * C + c) * dim;
+      if (ev.writer()) {
+        const size_t row = ((size_t)(it - plan.n_warmup) * C + c) * dim;
 #pragma unroll
-      for (int s = 0; s < DSLOTS; ++s) {
-        const int i = lane + 32 * s;
-        if (i < dim) draws[row + i] = th[s];
+        for (int s = 0; s < DSLOTS; ++s) {
+          const int i = lane + 32 * s;
+          if (i < dim) draws[row + i] = th[s];
+        }
       }
       acc_sum += alpha;
       n_div += div ? 1 : 0;
     }
   }
-  if (lane == 0) {
+  if (ev.writer() && lane == 0) {
     ci_hmc_stats st;
     st.accept_rate = (float)(acc_sum / (plan.n_results > 0 ? plan.n_results : 1));
     st.step_size = (float)eps;
@@ -200,6 +165,63 @@ k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id
     st.n_leapfrog = n_leap;
     stats[c] = st;
   }
+}
+
+// ---- evaluator: one warp per chain, tiles walked sequentially (any T) ----
+template <typename R> struct WarpEval {
+  TilePipe<R>& pipe; const ProbDev<R>& pr; const WarpScratch<R>& ws; const R* omega; int lane;
+  __device__ __forceinline__ bool writer() const { return true; }
+  __device__ __forceinline__ void publish(const R (&t)[DSLOTS]) {
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < DSLOTS; ++s) {
+      const int i = lane + 32 * s;
+      if (i < pr.dim) ws.w[i] = t[s];
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void eval(double& lp, R (&g)[DSLOTS]) {
+    const int p = pr.p;
+    const R u = ws.w[p], l = ws.w[p + 1];
+    const R s_e = Num<R>::exp(u), s_h = Num<R>::exp(l);
+    double ll, g_se, g_sh;
+    R gw[JS];
+    chain_eval(pipe, pr, ws, s_e, s_h, true, lane, ll, g_se, g_sh, gw);
+    double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
+    lp = ll + chain_prior(pr, omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+#pragma unroll
+    for (int s = 0; s < DSLOTS; ++s) {
+      const int i = lane + 32 * s;
+      g[s] = i < p ? gw[s] : (i == p ? (R)g_u : (i == p + 1 ? (R)g_l : (R)0));
+    }
+  }
+};
+
+template <typename R>
+__global__ void __launch_bounds__(32 * (MAXG + 1), 1)
+k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id0,
+      const R* __restrict__ theta0, int C, R* __restrict__ draws,
+      ci_hmc_stats* __restrict__ stats) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (blockDim.x >> 5) - 1;
+  const int chain0 = blockIdx.x * G;
+  const int nactive = min(G, C - chain0);
+  const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
+  if (warp == G) {
+    if (lane == 0)
+      tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
+                    cfg.resident != 0, 2LL * plan.n_evals,
+                    [](long long s) { return (s & 1) == 0; });
+    return;
+  }
+  if (warp >= nactive) return;
+  const int c = chain0 + warp;
+  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
+  TilePipe<R> pipe = make_pipe(cs, cfg);
+  WarpEval<R> ev{pipe, pr, ws, cs.omega, lane};
+  hmc_chain<R>(ev, plan, seed, chain_id0 + (uint64_t)c, theta0 + (size_t)c * pr.dim, pr.dim, lane,
+               c, C, draws, stats);
 }
 
 }  // namespace ci

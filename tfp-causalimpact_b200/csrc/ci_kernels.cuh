@@ -44,7 +44,7 @@ __device__ __forceinline__ TilePipe<R> make_pipe(const CtaShared<R>& cs, const S
 // + 1 producer warp feeding [X|y] tiles through the mbarrier pipeline.
 // ---------------------------------------------------------------------------
 template <typename R>
-__global__ void __launch_bounds__(32 * (MAXG + 1))
+__global__ void __launch_bounds__(32 * (MAXG + 1), 1)
 k_logpost_scan(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int C,
                R* __restrict__ value, R* __restrict__ grad, int flags) {
   extern __shared__ __align__(128) unsigned char smem[];
