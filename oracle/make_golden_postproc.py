@@ -113,7 +113,8 @@ def main():
     np.savez_compressed(
         os.path.join(OUT, f"postproc_{name}.npz"),
         frame_values=frame.values.astype(np.float64), frame_columns=np.array(list(frame.columns)),
-        frame_index=(frame.index.asi8 if is_dt else np.asarray(frame.index, dtype=np.int64)),
+        frame_index=(frame.index.as_unit("ns").asi8 if is_dt
+                     else np.asarray(frame.index, dtype=np.int64)),
         index_is_datetime=is_dt,
         pre=np.array([frame.index.get_loc(ci_data.pre_period[0]),
                       frame.index.get_loc(ci_data.pre_period[1])]),

@@ -68,6 +68,8 @@ def make_thetas(spec_dim, p, C, seed, d=1):
 @pytest.fixture(scope="session")
 def engine():
   import causalimpact_b200 as cib
+  from causalimpact_b200 import _build
+  _build.build()          # no-op when lib/libci_b200.so is newer than csrc/ (nvcc is in the image)
   eng = cib.Engine(0)
   yield eng
   eng.close()
