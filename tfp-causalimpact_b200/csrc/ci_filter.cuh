@@ -69,6 +69,17 @@ template <typename R> struct TilePipe {
   }
 };
 
+// Source address of tile b.  Written as an explicit 64-bit mad.wide: with plain
+// pointer arithmetic ptxas 12.9 (sm_100a) lowered the unrolled resident loop to
+// `UMOV UR7, URZ ; ULEA UR6, UR6, UR10, 0x2` -- dropping the high 32 bits of the
+// pointer (caught by compute-sanitizer, round 1 GPU run 4).
+__device__ __forceinline__ const void* tile_src(const void* base, uint32_t b, uint32_t bytes) {
+  unsigned long long a;
+  asm volatile("mad.wide.u32 %0, %1, %2, %3;"
+               : "=l"(a) : "r"(b), "r"(bytes), "l"((unsigned long long)base));
+  return reinterpret_cast<const void*>(a);
+}
+
 // Producer (one elected thread): issues the bulk copies for `n_pass` sweeps.
 // Sweep s walks tiles 0..NB-1 when dir[s] > 0 and NB-1..0 otherwise; the
 // caller describes the schedule through the functor `sweep_dir(s)`.
@@ -80,7 +91,8 @@ __device__ void tile_producer(const R* gtiles, R* stage0, uint64_t* full, uint64
   if (resident) {
     for (int b = 0; b < NB; ++b) {
       mbar_expect_tx(&full[b], bytes);
-      bulk_g2s(stage0 + (size_t)b * stage_elems, gtiles + (size_t)b * stage_elems, bytes, &full[b]);
+      bulk_g2s(stage0 + (size_t)b * stage_elems, tile_src(gtiles, (uint32_t)b, bytes), bytes,
+               &full[b]);
     }
     return;
   }
@@ -92,7 +104,7 @@ __device__ void tile_producer(const R* gtiles, R* stage0, uint64_t* full, uint64
       const uint32_t st = it % nstage;
       if (it >= nstage) mbar_wait(&empty[st], ((it / nstage) - 1u) & 1u);
       mbar_expect_tx(&full[st], bytes);
-      bulk_g2s(stage0 + (size_t)st * stage_elems, gtiles + (size_t)b * stage_elems, bytes,
+      bulk_g2s(stage0 + (size_t)st * stage_elems, tile_src(gtiles, (uint32_t)b, bytes), bytes,
                &full[st]);
     }
   }
