@@ -14,6 +14,7 @@
 #include "ci_predict.cuh"
 #include "ci_hmc.cuh"
 #include "ci_team_kernels.cuh"
+#include "ci_seq.cuh"
 
 namespace {
 
@@ -157,9 +158,23 @@ bool plan_team(const ci_ctx* c, int C, int* GT, SmemCfg* cfg) {
 template <typename R>
 int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* grad_d, int variant,
                    int flags, cudaStream_t st) {
-  if (variant != CI_VARIANT_SCAN)
-    return fail(CI_ERR_UNSUPPORTED, "variant %d not available for this model", variant);
+  if (variant != CI_VARIANT_SCAN && variant != CI_VARIANT_SEQ)
+    return fail(CI_ERR_INVALID, "unknown variant %d", variant);
   SmemCfg cfg;
+  if (variant == CI_VARIANT_SEQ) {
+    const int G = pick_G(c, C);
+    int rc = plan_smem(c, G, 2u * (uint32_t)c->NB * (uint32_t)GROUPS_PER_TILE, &cfg);
+    if (rc) return rc;
+    auto sk = k_logpost_seq<R>;
+    CU_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.total_bytes));
+    sk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, static_cast<const R*>(theta_d), C, static_cast<R*>(value_d),
+        static_cast<R*>(grad_d), flags);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
   int GT = 0;
   if (plan_team<R>(c, C, &GT, &cfg)) {
     auto tk = k_logpost_team<R>;
