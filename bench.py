@@ -278,6 +278,7 @@ def main():
     dist.all_reduce(he, op=dist.ReduceOp.SUM)
     hmc_evals = int(he.item())
 
+  team = os.environ.get("CI_B200_TEAM", "1") != "0" and 2 <= -(-cfg["T"] // 256) <= 8
   if rank == 0:
     total = C * world * args.steps
     val = total / (t_step * 1e-3)
@@ -292,8 +293,9 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "local-level + 10 covariates, T=1000, 256 chains per GPU "
                                "(BASELINE.json configs[1]); value+gradient, prior included",
-                   "variant": "associative scan: warp-shuffle scan per 256-step tile, one warp per tile "
-                              "(team of 4 warps per chain), tile aggregates exchanged via smem",
+                   "variant": ("associative scan, TEAM mode: warp-shuffle scan per 256-step tile, one "
+                               "warp per tile (4 warps per chain), tile aggregates exchanged via smem")
+                              if team else "associative scan, one warp per chain (CI_B200_TEAM=0)",
                    "l2": "flushed (256 MB memset) between timed steps",
                    "timing": "CUDA events per step on the launching stream"},
         "e2e": {"value": total / (t_e2e * 1e-3), "unit": UNIT,
@@ -301,8 +303,11 @@ def main():
                 "d2h_bytes_per_step": int(C * 4 + C * dim * 4)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
-                     "kernel": "k_logpost_team<float>", "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     # dram__bytes_read+write per launch, ncu --set full (profiles/r01_k_logpost_*_ncu.md)
+                     "traffic": 137216 if team else 133888,
+                     "kernel": "k_logpost_team<float>" if team else "k_logpost_scan<float>",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": C * B,
                      "kernel_ms": kern_ms},
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
