@@ -1,0 +1,79 @@
+"""GPU parity for the local-linear-trend model (BASELINE config 3 family;
+capability extension -- the reference has no slope, causalimpact_lib.py:496).
+CUDA scan kernels (Sarkka/Garcia-Fernandez elements + congruence adjoints) vs
+the generic float64 oracle (oracle/kalman_np.py gen_filter_grad).
+Tolerances: float32 value 3e-5 rel + 5e-3, gradient 5e-3 rel + 5e-2;
+float64 1e-9 / 1e-6."""
+import numpy as np
+import pytest
+
+import causalimpact_b200 as cib
+from causalimpact_b200 import _engine
+from conftest import make_series, make_thetas
+from oracle import hmc_np as H
+from oracle import kalman_np as K
+
+pytestmark = pytest.mark.gpu
+LLT = _engine.MODEL_LOCAL_LINEAR_TREND
+
+
+@pytest.mark.parametrize("T,n_cov,C", [(100, 1, 8), (257, 0, 4), (700, 12, 20), (600, 40, 7)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_llt_logprob_and_grad_match_oracle(engine, T, n_cov, C, dtype):
+  y, X, _ = make_series(T, n_cov, 300 + T, nan_frac=0.02)
+  spec = cib.build_problem(y, X, prior_level_sd=0.05, model=LLT, dtype=dtype)
+  engine.set_data(spec)
+  prob = K.default_problem(y, X, prior_level_sd=0.05, model=K.MODEL_LOCAL_LINEAR_TREND)
+  assert spec.dim == prob.dim == (0 if X is None else X.shape[1]) + 3
+  th = make_thetas(spec.dim, spec.p, C, 5, d=2).astype(dtype).astype(np.float64)
+  for with_prior in (False, True):
+    val, grad = engine.logprob_grad(th, with_prior=with_prior)
+    v_only = engine.logprob(th, with_prior=with_prior)
+    ov, og = K.log_post_grad(prob, th) if with_prior else K.log_lik_grad(prob, th)
+    rv, av, rg, ag = (3e-5, 5e-3, 5e-3, 5e-2) if dtype == np.float32 else (1e-9, 1e-8, 1e-6, 1e-6)
+    np.testing.assert_allclose(val, ov, rtol=rv, atol=av)
+    np.testing.assert_allclose(v_only, val, rtol=1e-7, atol=1e-6)
+    np.testing.assert_allclose(grad, og, rtol=rg, atol=ag)
+
+
+def test_llt_config3_shape_streaming(engine):
+  """BASELINE config 3 shape (T=5000, 50 covariates): tiles stream through the
+  mbarrier ring (1 MB of [X|y] does not fit in shared memory)."""
+  y, X, _ = make_series(5000, 50, 2023)
+  spec = cib.build_problem(y, X, model=LLT, dtype=np.float64)
+  engine.set_data(spec)
+  prob = K.default_problem(y, X, model=K.MODEL_LOCAL_LINEAR_TREND)
+  th = make_thetas(spec.dim, spec.p, 6, 8, d=2)
+  val, grad = engine.logprob_grad(th, with_prior=True)
+  ov, og = K.log_post_grad(prob, th)
+  np.testing.assert_allclose(val, ov, rtol=1e-9, atol=1e-7)
+  np.testing.assert_allclose(grad, og, rtol=1e-6, atol=1e-5)
+  spec32 = cib.build_problem(y, X, model=LLT, dtype=np.float32)
+  engine.set_data(spec32)
+  th32 = th.astype(np.float32).astype(np.float64)
+  v32, g32 = engine.logprob_grad(th32, with_prior=True)
+  ov, og = K.log_post_grad(prob, th32)
+  np.testing.assert_allclose(v32, ov, rtol=5e-5, atol=5e-2)
+  np.testing.assert_allclose(g32, og, rtol=2e-2, atol=0.5)
+
+
+def test_llt_hmc_float64_pathwise(engine):
+  y, X, _ = make_series(100, 1, 31)
+  spec = cib.build_problem(y, X, prior_level_sd=0.05, model=LLT, dtype=np.float64)
+  engine.set_data(spec)
+  prob = K.default_problem(y, X, prior_level_sd=0.05, model=K.MODEL_LOCAL_LINEAR_TREND)
+  th0 = np.tile(cib.initial_theta(spec, 0.05), (4, 1))
+  th0[:, :spec.p] += 0.1 * np.random.default_rng(0).normal(size=(4, spec.p))
+  kw = dict(n_warmup=25, n_results=8, seed=3, max_leapfrog=4, init_step=0.01)
+  draws, stats = engine.hmc_run(th0, **kw)
+  od, ost = H.run(lambda t: K.log_post_grad(prob, t), th0, **kw)
+  np.testing.assert_allclose(draws, od, rtol=1e-6, atol=1e-6)
+  assert np.array_equal(stats["n_leapfrog"], ost["n_leapfrog"])
+
+
+def test_llt_predict_is_rejected(engine):
+  y, X, _ = make_series(100, 1, 31)
+  spec = cib.build_problem(y, X, model=LLT)
+  engine.set_data(spec)
+  with pytest.raises(cib.EngineError, match="local level only"):
+    engine.posterior_predict(np.zeros((2, spec.dim)), seed=1)

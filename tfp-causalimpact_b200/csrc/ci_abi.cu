@@ -15,6 +15,7 @@
 #include "ci_hmc.cuh"
 #include "ci_team_kernels.cuh"
 #include "ci_seq.cuh"
+#include "ci_llt_kernels.cuh"
 
 namespace {
 
@@ -89,6 +90,14 @@ template <typename R> ProbDev<R> make_probdev(const ci_ctx* c) {
   return pr;
 }
 
+template <typename R> LltDev<R> make_lltdev(const ci_ctx* c) {
+  LltDev<R> d;
+  d.q_conc = (R)c->prob.slope_conc; d.q_scale = (R)c->prob.slope_scale;
+  d.q_ub = (R)(c->prob.slope_ub > 1e30 ? 1e30 : c->prob.slope_ub);
+  d.m0s = (R)c->prob.m0_slope; d.P0s = (R)c->prob.P0_slope;
+  return d;
+}
+
 inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 // Shared-memory plan for a kernel with G consumer warps and `extra_elems`
@@ -104,7 +113,7 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
   uint32_t e = 0;
   cfg.w_off = e;     e += align_up((uint32_t)(p + 4), 4);   // holds the full theta in the HMC kernel
   cfg.rbuf_off = e;  e += TB + 8;
-  cfg.ckpt_off = e;  e += align_up(2u * (uint32_t)NB, 4);
+  cfg.ckpt_off = e;  e += align_up(6u * (uint32_t)NB, 4);    // (a,P) or the 5-value trend state
   cfg.extra_off = e; e += align_up(extra_elems, 4);
   cfg.warp_bytes = align_up(e * esz, 16);
   const uint32_t omega_bytes = align_up((uint32_t)(p * p) * esz, 16);
@@ -144,7 +153,7 @@ int pick_G(const ci_ctx* c, int C) {
 template <typename R>
 bool plan_team(const ci_ctx* c, int C, int* GT, SmemCfg* cfg) {
   const int W = c->NB;
-  if (!c->team_mode || W < 2 || W > MAXW) return false;
+  if (!c->team_mode || W < 2 || W > MAXW || c->prob.model != CI_MODEL_LOCAL_LEVEL) return false;
   int gt = (C >= 4 * c->sm_count) ? MAXW / W : 1;
   if (gt < 1) gt = 1;
   if (c->force_G > 0) gt = c->force_G * W <= MAXW ? c->force_G : 1;
@@ -161,6 +170,22 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
   if (variant != CI_VARIANT_SCAN && variant != CI_VARIANT_SEQ)
     return fail(CI_ERR_INVALID, "unknown variant %d", variant);
   SmemCfg cfg;
+  if (c->prob.model == CI_MODEL_LOCAL_LINEAR_TREND) {
+    if (variant != CI_VARIANT_SCAN)
+      return fail(CI_ERR_UNSUPPORTED, "the local linear trend model has only the scan variant");
+    const int G = pick_G(c, C);
+    int rc = plan_smem(c, G, 0, &cfg);
+    if (rc) return rc;
+    auto lk = k_logpost_llt<R>;
+    CU_TRY(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.total_bytes));
+    lk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), make_lltdev<R>(c), cfg, static_cast<const R*>(theta_d), C,
+        static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
   if (variant == CI_VARIANT_SEQ) {
     const int G = pick_G(c, C);
     int rc = plan_smem(c, G, 2u * (uint32_t)c->NB * (uint32_t)GROUPS_PER_TILE, &cfg);
@@ -264,6 +289,20 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
   SmemCfg cfg;
   HmcPlan plan;
   make_hmc_plan(o, seed, &plan);
+  if (c->prob.model == CI_MODEL_LOCAL_LINEAR_TREND) {
+    const int G = pick_G(c, C);
+    int rc = plan_smem(c, G, 0, &cfg);
+    if (rc) return rc;
+    auto lk = k_hmc_llt<R>;
+    CU_TRY(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.total_bytes));
+    lk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), make_lltdev<R>(c), cfg, plan, seed, chain_id0,
+        static_cast<const R*>(theta0_d), C, static_cast<R*>(draws_d), stats_d);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
   int GT = 0;
   if (plan_team<R>(c, C, &GT, &cfg)) {
     auto tk = k_hmc_team<R>;
@@ -403,8 +442,8 @@ int ci_set_data(ci_ctx* c, const ci_problem* pb, const void* y, const void* X, c
   if (pb->dtype != CI_F32 && pb->dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
   if (pb->model != CI_MODEL_LOCAL_LEVEL && pb->model != CI_MODEL_LOCAL_LINEAR_TREND)
     return fail(CI_ERR_INVALID, "unknown model %d", pb->model);
-  if (pb->model == CI_MODEL_LOCAL_LINEAR_TREND)
-    return fail(CI_ERR_UNSUPPORTED, "local linear trend kernels are not built yet");
+  if (pb->model == CI_MODEL_LOCAL_LINEAR_TREND && !(pb->P0_slope > 0))
+    return fail(CI_ERR_INVALID, "P0_slope must be positive");
   const int d = pb->model == CI_MODEL_LOCAL_LINEAR_TREND ? 2 : 1;
   if (pb->p + 1 + d > ci::MAX_DIM)
     return fail(CI_ERR_UNSUPPORTED, "p=%d exceeds the supported maximum %d", pb->p, ci::MAX_DIM - 1 - d);
@@ -484,6 +523,9 @@ int ci_posterior_predict_d(ci_ctx* c, const void* theta_d, int S, uint64_t seed,
   if (!c || !theta_d || !traj_d) return fail(CI_ERR_INVALID, "null argument");
   if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
   if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
+  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
+    return fail(CI_ERR_UNSUPPORTED, "ci_posterior_predict: local level only (the reference has "
+                "no slope component, causalimpact_lib.py:496)");
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!level_d && mean_d) {   // the mean needs the level paths: use the workspace
