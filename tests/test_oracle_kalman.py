@@ -96,3 +96,22 @@ def test_priors_match_reference_constants():
   np.testing.assert_allclose(prob.Omega, 0.01 * om / 200)
   prob0 = K.default_problem(y, None)
   assert prob0.obs_conc == 0.005 and np.isclose(prob0.obs_scale, 0.005 * sd ** 2)
+
+
+def test_llt_scan_formulation_equals_generic_filter():
+  """The d=2 formulation of csrc/ci_llt.cuh (filtering elements + congruence
+  adjoints) against the generic reverse-mode oracle."""
+  rng = np.random.default_rng(0)
+  T = 90
+  r = rng.normal(size=T) * 0.5 + np.cumsum(rng.normal(size=T)) * 0.05
+  mask = rng.random(T) < 0.1; mask[70:] = True; mask[0] = False
+  r[mask] = np.nan
+  s_e, q1, q2 = 0.2, 0.01, 0.001
+  m0 = np.array([0.3, 0.0]); P0 = np.diag([1.1, 0.9])
+  A = np.array([[1., 1.], [0., 1.]]); h = np.array([1., 0.])
+  ll, rbar, ge, gq = K.gen_filter_grad(r[None], mask, np.array([s_e]), np.array([[q1, q2]]), m0,
+                                       P0, A, h)
+  l2, rb2, ge2, g1, g2 = S.llt_scan_value_grad(r, mask, s_e, q1, q2, m0, P0)
+  assert abs(ll[0] - l2) < 1e-10
+  np.testing.assert_allclose(rbar[0], rb2, atol=1e-12)
+  assert abs(ge[0] - ge2) < 1e-10 and abs(gq[0, 0] - g1) < 1e-10 and abs(gq[0, 1] - g2) < 1e-9
