@@ -91,3 +91,27 @@ def test_row_quantiles_rejects_bad_input(engine):
     engine.row_quantiles(a, [1.5])
   with pytest.raises(cib.EngineError):
     engine.row_quantiles(np.zeros((70000, 2), np.float32), [0.5])
+
+
+def test_predict_team_and_single_warp_paths_agree(monkeypatch):
+  """T=1000: default TEAM mode (one warp per tile, no replay) vs CI_B200_TEAM=0
+  (one warp per draw with checkpoint replay): same Philox normals, so the paths
+  agree to float32 rounding and both match the oracle."""
+  y, X, _ = make_series(1000, 10, 77, nan_frac=0.02)
+  spec = cib.build_problem(y, X, prior_level_sd=0.05)
+  prob = K.default_problem(y, X, prior_level_sd=0.05)
+  th = make_thetas(spec.dim, spec.p, 37, 3).astype(np.float32).astype(np.float64)
+  th[:, spec.p + 1] += 2.0
+  out = {}
+  for mode in ("1", "0"):
+    monkeypatch.setenv("CI_B200_TEAM", mode)
+    eng = cib.Engine(0)
+    eng.set_data(spec)
+    out[mode] = eng.posterior_predict(th, seed=5, draw_id0=100)
+    eng.close()
+  ol, ot, om = SM.posterior_predict(prob, th, seed=5, draw_id0=100)
+  for mode in out:
+    np.testing.assert_allclose(out[mode][0], ol, rtol=1e-3, atol=3e-3)
+    np.testing.assert_allclose(out[mode][1], ot, rtol=1e-3, atol=3e-3)
+    np.testing.assert_allclose(out[mode][2], om, rtol=1e-3, atol=3e-3)
+  np.testing.assert_allclose(out["1"][1], out["0"][1], rtol=1e-4, atol=5e-4)

@@ -130,7 +130,7 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
   cfg.nstage = nst;
   uint32_t off = align_up(nst * stage_bytes, 128);
   cfg.off_full = off;   off += nst * 8;
-  cfg.off_empty = off;  off += nst * 8;
+  cfg.off_empty = off;  off += nst * 8 + 8;   // + the Omega barrier
   off = align_up(off, 16);
   cfg.off_omega = off;  off += omega_bytes;
   cfg.off_warp = off;   off += (uint32_t)G * cfg.warp_bytes;
@@ -333,8 +333,28 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
 template <typename R>
 int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_t draw_id0,
                    void* level_d, void* traj_d, void* mean_d, cudaStream_t st) {
-  const int G = pick_G(c, S);
   SmemCfg cfg;
+  const ProbDev<R> prt = make_probdev<R>(c);
+  int GT = 0;
+  if (plan_team<R>(c, S, &GT, &cfg)) {
+    auto tk = k_predict_team<R>;
+    CU_TRY(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.total_bytes));
+    tk<<<(S + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
+        prt, cfg, c->NB, static_cast<const R*>(theta_d), S, seed, draw_id0,
+        static_cast<R*>(level_d), static_cast<R*>(traj_d));
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    if (mean_d) {
+      k_predict_mean<R><<<(c->prob.T + 31) / 32, dim3(32, 32), 0, st>>>(
+          prt, static_cast<const R*>(theta_d), static_cast<const R*>(level_d), S,
+          static_cast<R*>(mean_d));
+      CU_TRY(cudaGetLastError());
+      c->launches++;
+    }
+    return CI_OK;
+  }
+  const int G = pick_G(c, S);
   int rc = plan_smem(c, G, 0, &cfg);
   if (rc) return rc;
   auto kern = k_predict<R>;
@@ -468,7 +488,7 @@ int ci_set_data(ci_ctx* c, const ci_problem* pb, const void* y, const void* X, c
     CU_TRY(cudaStreamSynchronize(c->stream));
   }
   const size_t ob = (size_t)pb->p * pb->p * c->esz;
-  CU_TRY(c->omega.reserve(ob > 0 ? ob : 16));
+  CU_TRY(c->omega.reserve(ob + 16));          // bulk copies move whole 16-byte units
   if (ob) {
     CU_TRY(cudaMemcpyAsync(c->omega.p, Omega, ob, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));

@@ -170,6 +170,7 @@ __device__ __forceinline__ void hmc_chain(Ev& ev, const HmcPlan& plan, uint64_t 
 // ---- evaluator: one warp per chain, tiles walked sequentially (any T) ----
 template <typename R> struct WarpEval {
   TilePipe<R>& pipe; const ProbDev<R>& pr; const WarpScratch<R>& ws; const R* omega; int lane;
+  // (the caller waits for Omega once before the HMC loop starts)
   __device__ __forceinline__ bool writer() const { return true; }
   __device__ __forceinline__ void publish(const R (&t)[DSLOTS]) {
     __syncwarp();
@@ -209,6 +210,7 @@ k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id
   const int nactive = min(G, C - chain0);
   const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
   if (warp == G) {
+    if (lane == 0) omega_fetch(cs, pr);
     if (lane == 0)
       tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
                     cfg.resident != 0, 2LL * plan.n_evals,
@@ -219,6 +221,7 @@ k_hmc(ProbDev<R> pr, SmemCfg cfg, HmcPlan plan, uint64_t seed, uint64_t chain_id
   const int c = chain0 + warp;
   const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
   TilePipe<R> pipe = make_pipe(cs, cfg);
+  omega_wait(cs);
   WarpEval<R> ev{pipe, pr, ws, cs.omega, lane};
   hmc_chain<R>(ev, plan, seed, chain_id0 + (uint64_t)c, theta0 + (size_t)c * pr.dim, pr.dim, lane,
                c, C, draws, stats);

@@ -7,7 +7,21 @@ namespace ci {
 // Common CTA prologue: barriers, Omega -> smem.  Returns pointers.
 template <typename R> struct CtaShared {
   R* stage0; uint64_t* full; uint64_t* empty; R* omega;
+  uint64_t* omega_bar;     // completes when the slab precision has landed in shared memory
 };
+
+// Issued by the producer thread: Omega travels as one bulk copy on its own
+// barrier, so no consumer thread ever waits for it at start-up.
+template <typename R>
+__device__ __forceinline__ void omega_fetch(const CtaShared<R>& cs, const ProbDev<R>& pr) {
+  const uint32_t bytes = ((uint32_t)(pr.p * pr.p) * (uint32_t)sizeof(R) + 15u) & ~15u;
+  if (bytes == 0) { mbar_arrive(cs.omega_bar); return; }
+  mbar_expect_tx(cs.omega_bar, bytes);
+  bulk_g2s(cs.omega, pr.omega, bytes, cs.omega_bar);
+}
+template <typename R> __device__ __forceinline__ void omega_wait(const CtaShared<R>& cs) {
+  mbar_wait(cs.omega_bar, 0u);
+}
 
 template <typename R>
 __device__ __forceinline__ CtaShared<R> cta_prologue(unsigned char* smem, const SmemCfg& cfg,
@@ -17,14 +31,15 @@ __device__ __forceinline__ CtaShared<R> cta_prologue(unsigned char* smem, const 
   cs.full = reinterpret_cast<uint64_t*>(smem + cfg.off_full);
   cs.empty = reinterpret_cast<uint64_t*>(smem + cfg.off_empty);
   cs.omega = reinterpret_cast<R*>(smem + cfg.off_omega);
+  cs.omega_bar = cs.empty + cfg.nstage;
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < cfg.nstage; ++s) {
       mbar_init(&cs.full[s], 1);
       mbar_init(&cs.empty[s], (uint32_t)n_consumers);
     }
+    mbar_init(cs.omega_bar, 1);
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < pr.p * pr.p; i += blockDim.x) cs.omega[i] = pr.omega[i];
   __syncthreads();
   return cs;
 }
@@ -56,10 +71,12 @@ k_logpost_scan(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int C,
   const bool want_grad = grad != nullptr;
 
   if (warp == G) {
-    if (lane == 0)
+    if (lane == 0) {
+      omega_fetch(cs, pr);
       tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
                     cfg.resident != 0, want_grad ? 2LL : 1LL,
                     [](long long s) { return (s & 1) == 0; });
+    }
     return;
   }
   if (warp >= nactive) return;
@@ -80,7 +97,10 @@ k_logpost_scan(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int C,
 
   double val = ll;
   double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
-  if (flags & 1) val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+  if (flags & 1) {
+    omega_wait(cs);
+    val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+  }
   if (lane == 0) value[c] = (R)val;
   if (want_grad) {
     R* g = grad + (size_t)c * dim;

@@ -18,6 +18,7 @@ k_logpost_llt(ProbDev<R> pr, LltDev<R> ld2, SmemCfg cfg, const R* __restrict__ t
   const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
   const bool want_grad = grad != nullptr;
   if (warp == G) {
+    if (lane == 0) omega_fetch(cs, pr);
     if (lane == 0)
       tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
                     cfg.resident != 0, want_grad ? 2LL : 1LL,
@@ -40,6 +41,7 @@ k_logpost_llt(ProbDev<R> pr, LltDev<R> ld2, SmemCfg cfg, const R* __restrict__ t
   double val = ll;
   double g_u = g_se * (double)s_e, g_l = g_q1 * (double)q1, g_s = g_q2 * (double)q2;
   if (flags & 1) {
+    omega_wait(cs);
     val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, q1, lane, gw, g_u, g_l);
     val += llt_slope_prior(ld2, s, q2, g_s);
   }
@@ -99,6 +101,7 @@ k_hmc_llt(ProbDev<R> pr, LltDev<R> ld2, SmemCfg cfg, HmcPlan plan, uint64_t seed
   const int nactive = min(G, C - chain0);
   const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
   if (warp == G) {
+    if (lane == 0) omega_fetch(cs, pr);
     if (lane == 0)
       tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
                     cfg.resident != 0, 2LL * plan.n_evals,
@@ -109,6 +112,7 @@ k_hmc_llt(ProbDev<R> pr, LltDev<R> ld2, SmemCfg cfg, HmcPlan plan, uint64_t seed
   const int c = chain0 + warp;
   const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
   TilePipe<R> pipe = make_pipe(cs, cfg);
+  omega_wait(cs);
   WarpEvalLlt<R> ev{pipe, pr, ld2, ws, cs.omega, lane};
   hmc_chain<R>(ev, plan, seed, chain_id0 + (uint64_t)c, theta0 + (size_t)c * pr.dim, pr.dim, lane,
                c, C, draws, stats);

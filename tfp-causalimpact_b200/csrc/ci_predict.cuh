@@ -32,6 +32,7 @@ k_predict(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int S, uint64
   const int nactive = min(G, S - s0);
   const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
   if (warp == G) {
+    if (lane == 0) omega_fetch(cs, pr);
     if (lane == 0)
       tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
                     cfg.resident != 0, 2LL, [](long long s) { return (s & 1) == 0; });

@@ -44,6 +44,7 @@ k_logpost_seq(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int C,
   const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
   const bool want_grad = grad != nullptr;
   if (warp == G) {
+    if (lane == 0) omega_fetch(cs, pr);
     if (lane == 0)
       tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
                     cfg.resident != 0, want_grad ? 2LL : 1LL,
@@ -157,7 +158,10 @@ k_logpost_seq(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int C,
 
   double val = ll;
   double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
-  if (flags & 1) val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+  if (flags & 1) {
+    omega_wait(cs);
+    val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+  }
   if (lane == 0) value[c] = (R)val;
   if (want_grad) {
     R* gout = grad + (size_t)c * dim;

@@ -57,6 +57,7 @@ __device__ __forceinline__ bool team_prologue(unsigned char* smem, const SmemCfg
   const int GT = n_warps / W;
   cs = cta_prologue(smem, cfg, pr, 1);
   if (warp == n_warps) {
+    if (lane == 0) omega_fetch(cs, pr);
     if (lane == 0)
       tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
                     true, 0LL, [](long long) { return true; });
@@ -93,7 +94,10 @@ k_logpost_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, i
   if (wt != 0) return;
   double val = ll;
   double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
-  if (flags & 1) val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+  if (flags & 1) {
+    omega_wait(cs);
+    val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+  }
   if (lane == 0) value[c] = (R)val;
   if (want_grad) {
     R* g = grad + (size_t)c * dim;
@@ -119,10 +123,34 @@ k_hmc_team(ProbDev<R> pr, SmemCfg cfg, int W, HmcPlan plan, uint64_t seed, uint6
   const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, threadIdx.x >> 5);
   mbar_wait(&cs.full[wt], 0u);
   const R* tile = cs.stage0 + (size_t)wt * cfg.stage_elems;
+  omega_wait(cs);
   TeamEval<R> ev{tile, pr, team_area<R>(smem, cfg, n_warps, team), ws, cs.omega, lane, wt, W,
                  team + 1};
   hmc_chain<R>(ev, plan, seed, chain_id0 + (uint64_t)c, theta0 + (size_t)c * pr.dim, pr.dim, lane,
                c, C, draws, stats);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(32 * (MAXW + 1), 1)
+k_predict_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, int S,
+               uint64_t seed, uint64_t draw_id0, R* __restrict__ level, R* __restrict__ traj) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (blockDim.x >> 5) - 1;
+  CtaShared<R> cs; int team, wt, s;
+  if (!team_prologue(smem, cfg, pr, W, S, cs, team, wt, s)) return;
+  const int p = pr.p, dim = pr.dim;
+  const R* th = theta + (size_t)s * dim;
+  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, threadIdx.x >> 5);
+  for (int j = lane; j < dim; j += 32) ws.w[j] = th[j];
+  __syncwarp();
+  const R s_e = Num<R>::exp(ws.w[p]), s_h = Num<R>::exp(ws.w[p + 1]);
+  mbar_wait(&cs.full[wt], 0u);
+  const R* tile = cs.stage0 + (size_t)wt * cfg.stage_elems;
+  const size_t row = (size_t)s * pr.T;
+  team_predict(tile, pr, team_area<R>(smem, cfg, n_warps, team), ws.w, s_e, s_h,
+               Num<R>::sqrt(s_e), seed, draw_id0 + (uint64_t)s, lane, wt, W, team + 1,
+               level ? level + row : nullptr, traj + row);
 }
 
 }  // namespace ci
