@@ -40,14 +40,9 @@ def test_llt_config3_shape_streaming(engine):
   """BASELINE config 3 shape (T=5000, 50 covariates): tiles stream through the
   mbarrier ring (1 MB of [X|y] does not fit in shared memory)."""
   y, X, _ = make_series(5000, 50, 2023)
-  spec = cib.build_problem(y, X, model=LLT, dtype=np.float64)
-  engine.set_data(spec)
   prob = K.default_problem(y, X, model=K.MODEL_LOCAL_LINEAR_TREND)
-  th = make_thetas(spec.dim, spec.p, 6, 8, d=2)
-  val, grad = engine.logprob_grad(th, with_prior=True)
-  ov, og = K.log_post_grad(prob, th)
-  np.testing.assert_allclose(val, ov, rtol=1e-9, atol=1e-7)
-  np.testing.assert_allclose(grad, og, rtol=1e-6, atol=1e-5)
+  th = make_thetas(prob.dim, prob.p, 6, 8, d=2)
+  # float32: the configuration itself (54 KB tiles, 3-stage ring)
   spec32 = cib.build_problem(y, X, model=LLT, dtype=np.float32)
   engine.set_data(spec32)
   th32 = th.astype(np.float32).astype(np.float64)
@@ -55,6 +50,13 @@ def test_llt_config3_shape_streaming(engine):
   ov, og = K.log_post_grad(prob, th32)
   np.testing.assert_allclose(v32, ov, rtol=5e-5, atol=5e-2)
   np.testing.assert_allclose(g32, og, rtol=2e-2, atol=0.5)
+  # float64: 109 KB tiles -> single-stage ring (correct, no copy/compute overlap)
+  spec = cib.build_problem(y, X, model=LLT, dtype=np.float64)
+  engine.set_data(spec)
+  val, grad = engine.logprob_grad(th, with_prior=True)
+  ov, og = K.log_post_grad(prob, th)
+  np.testing.assert_allclose(val, ov, rtol=1e-9, atol=1e-7)
+  np.testing.assert_allclose(grad, og, rtol=1e-6, atol=1e-5)
 
 
 def test_llt_hmc_float64_pathwise(engine):

@@ -120,7 +120,8 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
   const uint32_t fixed = omega_bytes + (uint32_t)G * cfg.warp_bytes + tail_bytes + 16u;
   const uint32_t budget = (uint32_t)c->smem_optin;
   // stages: as many as fit (each stage also needs 16 bytes of barriers)
-  if (fixed + 2u * (stage_bytes + 16u) + 128u > budget)
+  // one stage is enough to be correct (no copy/compute overlap); two or more overlap
+  if (fixed + 1u * (stage_bytes + 16u) + 128u > budget)
     return fail(CI_ERR_UNSUPPORTED,
                 "problem too wide for the tile pipeline: p=%d needs %u B per stage", p,
                 stage_bytes);
@@ -513,6 +514,15 @@ int ci_logprob_grad_d(ci_ctx* c, const void* theta_d, int C, void* value_d, void
   return launch_logpost<float>(c, theta_d, C, value_d, grad_d, variant, flags, st);
 }
 
+// Device-visible alias of a PINNED host buffer (cudaHostAlloc / cudaHostRegister),
+// or nullptr for pageable memory.
+static void* pinned_alias(const void* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return at.devicePointer;
+}
+
 int ci_logprob_grad(ci_ctx* c, const void* theta, int C, void* value, void* grad, int variant,
                     int flags) {
   if (!c || !theta || !value) return fail(CI_ERR_INVALID, "null argument");
@@ -520,6 +530,17 @@ int ci_logprob_grad(ci_ctx* c, const void* theta, int C, void* value, void* grad
   if (C < 1) return fail(CI_ERR_INVALID, "n_chains must be >= 1");
   CU_TRY(cudaSetDevice(c->device));
   const size_t tb = (size_t)C * c->dim * c->esz, vb = (size_t)C * c->esz;
+  // Pinned caller buffers: the kernel reads theta and writes value / grad straight
+  // over PCIe (zero-copy) -- one launch + one sync instead of three staged copies.
+  void* th_a = pinned_alias(theta);
+  void* va_a = th_a ? pinned_alias(value) : nullptr;
+  void* gr_a = (va_a && grad) ? pinned_alias(grad) : nullptr;
+  if (th_a && va_a && (!grad || gr_a) && tb <= (1u << 20)) {
+    int rc = ci_logprob_grad_d(c, th_a, C, va_a, gr_a, variant, flags, c->stream);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CI_OK;
+  }
   CU_TRY(c->w_theta.reserve(tb));
   CU_TRY(c->w_value.reserve(vb));
   if (grad) CU_TRY(c->w_grad.reserve(tb));
