@@ -107,3 +107,21 @@ def test_team_and_single_warp_paths_agree(monkeypatch):
     np.testing.assert_allclose(out[mode][0], ov, rtol=2e-5, atol=2e-3)
     np.testing.assert_allclose(out[mode][1], og, rtol=2e-3, atol=2e-2)
   np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=1e-5, atol=1e-3)
+
+
+def test_pinned_zero_copy_path_matches_staged_copies(engine):
+  """Host-pointer ABI: pinned caller buffers are read / written by the kernel
+  directly (zero-copy), pageable ones go through staged copies -- same bits."""
+  import torch
+  from causalimpact_b200 import _engine
+  y, X, _ = make_series(1000, 10, 2022)
+  spec = cib.build_problem(y, X)
+  engine.set_data(spec)
+  th = make_thetas(spec.dim, spec.p, 64, 3).astype(np.float32)
+  v_staged, g_staged = engine.logprob_grad(th.astype(np.float64), with_prior=True)
+  th_pin = torch.from_numpy(th).pin_memory()
+  v_pin = torch.empty(64, dtype=torch.float32).pin_memory()
+  g_pin = torch.empty(64, spec.dim, dtype=torch.float32).pin_memory()
+  engine.logprob_grad_ptr(th_pin.data_ptr(), 64, v_pin.data_ptr(), g_pin.data_ptr(),
+                          _engine.VARIANT_SCAN, _engine.WITH_PRIOR, host=True)
+  assert np.array_equal(v_pin.numpy(), v_staged) and np.array_equal(g_pin.numpy(), g_staged)
