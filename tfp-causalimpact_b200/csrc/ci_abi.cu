@@ -100,6 +100,16 @@ template <typename R> LltDev<R> make_lltdev(const ci_ctx* c) {
 
 inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+// Opt in to `bytes` of dynamic shared memory AND ask for the largest shared-memory
+// carveout: without the second attribute the driver may pick a carveout that fits a
+// single CTA per SM (ncu, round 1 run 7: occupancy_limit_shared_mem = 1 at 73 KB/CTA).
+template <typename Kern> cudaError_t set_smem(Kern kern, uint32_t bytes) {
+  cudaError_t e = set_smem(kern, (uint32_t)bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              (int)cudaSharedmemCarveoutMaxShared);
+}
+
 // Shared-memory plan for a kernel with G consumer warps and `extra_elems`
 // kernel-specific per-warp scratch elements.
 int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
@@ -178,8 +188,7 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
     int rc = plan_smem(c, G, 0, &cfg);
     if (rc) return rc;
     auto lk = k_logpost_llt<R>;
-    CU_TRY(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)cfg.total_bytes));
+    CU_TRY(set_smem(lk, (uint32_t)cfg.total_bytes));
     lk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
         make_probdev<R>(c), make_lltdev<R>(c), cfg, static_cast<const R*>(theta_d), C,
         static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
@@ -192,8 +201,7 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
     int rc = plan_smem(c, G, 2u * (uint32_t)c->NB * (uint32_t)GROUPS_PER_TILE, &cfg);
     if (rc) return rc;
     auto sk = k_logpost_seq<R>;
-    CU_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)cfg.total_bytes));
+    CU_TRY(set_smem(sk, (uint32_t)cfg.total_bytes));
     sk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
         make_probdev<R>(c), cfg, static_cast<const R*>(theta_d), C, static_cast<R*>(value_d),
         static_cast<R*>(grad_d), flags);
@@ -204,8 +212,7 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
   int GT = 0;
   if (plan_team<R>(c, C, &GT, &cfg)) {
     auto tk = k_logpost_team<R>;
-    CU_TRY(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)cfg.total_bytes));
+    CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
     tk<<<(C + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
         make_probdev<R>(c), cfg, c->NB, static_cast<const R*>(theta_d), C,
         static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
@@ -217,8 +224,7 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
   int rc = plan_smem(c, G, 0, &cfg);
   if (rc) return rc;
   auto kern = k_logpost_scan<R>;
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)cfg.total_bytes));
+  CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
   const int grid = (C + G - 1) / G;
   kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(
       make_probdev<R>(c), cfg, static_cast<const R*>(theta_d), C, static_cast<R*>(value_d),
@@ -295,8 +301,7 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
     int rc = plan_smem(c, G, 0, &cfg);
     if (rc) return rc;
     auto lk = k_hmc_llt<R>;
-    CU_TRY(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)cfg.total_bytes));
+    CU_TRY(set_smem(lk, (uint32_t)cfg.total_bytes));
     lk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
         make_probdev<R>(c), make_lltdev<R>(c), cfg, plan, seed, chain_id0,
         static_cast<const R*>(theta0_d), C, static_cast<R*>(draws_d), stats_d);
@@ -307,8 +312,7 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
   int GT = 0;
   if (plan_team<R>(c, C, &GT, &cfg)) {
     auto tk = k_hmc_team<R>;
-    CU_TRY(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)cfg.total_bytes));
+    CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
     tk<<<(C + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
         make_probdev<R>(c), cfg, c->NB, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,
         static_cast<R*>(draws_d), stats_d);
@@ -320,8 +324,7 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
   int rc = plan_smem(c, G, 0, &cfg);
   if (rc) return rc;
   auto kern = k_hmc<R>;
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)cfg.total_bytes));
+  CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
   const int grid = (C + G - 1) / G;
   kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(
       make_probdev<R>(c), cfg, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,
@@ -339,8 +342,7 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
   int GT = 0;
   if (plan_team<R>(c, S, &GT, &cfg)) {
     auto tk = k_predict_team<R>;
-    CU_TRY(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)cfg.total_bytes));
+    CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
     tk<<<(S + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
         prt, cfg, c->NB, static_cast<const R*>(theta_d), S, seed, draw_id0,
         static_cast<R*>(level_d), static_cast<R*>(traj_d));
@@ -359,8 +361,7 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
   int rc = plan_smem(c, G, 0, &cfg);
   if (rc) return rc;
   auto kern = k_predict<R>;
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)cfg.total_bytes));
+  CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
   const int grid = (S + G - 1) / G;
   const ProbDev<R> pr = make_probdev<R>(c);
   kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(pr, cfg, static_cast<const R*>(theta_d), S,
@@ -390,7 +391,7 @@ int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, 
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q[i];
   auto kern = k_row_quantiles<R>;
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CU_TRY(set_smem(kern, (uint32_t)bytes));
   int nt = n_pad / 2;
   if (nt > 1024) nt = 1024;
   if (nt < 32) nt = 32;

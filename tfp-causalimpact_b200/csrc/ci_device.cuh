@@ -175,4 +175,21 @@ __device__ __forceinline__ double chain_prior(const ProbDev<R>& pr, const R* om_
   return ok ? lp : -CUDART_INF;
 }
 
+// Store a lane's KS consecutive values dst[t0 .. t0+KS) (t < T guarded).  When the
+// address is 16-byte aligned and the whole run is in range, two 128-bit stores
+// replace eight scalar ones.
+template <typename R>
+__device__ __forceinline__ void store_run(R* __restrict__ dst, int t0, int T, const R (&v)[KS]) {
+  R* p = dst + t0;
+  if (sizeof(R) == 4 && t0 + KS <= T && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    q[1] = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      if (t0 + k < T) p[k] = v[k];
+  }
+}
+
 }  // namespace ci

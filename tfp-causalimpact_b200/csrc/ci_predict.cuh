@@ -106,14 +106,11 @@ k_predict(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int S, uint64
     for (int k = KS - 1; k >= 0; --k) { x = fma(J[k], x, off[k]); lv[k] = x; }
     x_c = __shfl_sync(FULL, x, 0);
     const size_t row = (size_t)s * T;
+    R tr[KS];
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const int t = t0 + k;
-      if (t < T) {
-        if (level) level[row + t] = lv[k];
-        traj[row + t] = lv[k] + xw[k] + sig_e * zp[k];
-      }
-    }
+    for (int k = 0; k < KS; ++k) tr[k] = lv[k] + xw[k] + sig_e * zp[k];
+    if (level) store_run(level + row, t0, T, lv);
+    store_run(traj + row, t0, T, tr);
     pipe.release(lane);
   }
 }

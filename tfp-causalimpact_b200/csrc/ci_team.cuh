@@ -369,15 +369,15 @@ __device__ __forceinline__ void team_predict(const R* __restrict__ tile, const P
   R x_in = 0;
   for (int t = W - 1; t > wt; --t) x_in = fma(ts->aggAB[t][0], x_in, ts->aggAB[t][1]);
   R x = fma(me, x_in, ce);
+  R lv[KS], tr[KS];
 #pragma unroll
   for (int k = KS - 1; k >= 0; --k) {
     x = fma(J[k], x, off_[k]);
-    const int t = t0 + k;
-    if (t < T) {
-      if (level_row) level_row[t] = x;
-      traj_row[t] = x + xw[k] + sig_e * zp[k];
-    }
+    lv[k] = x;
+    tr[k] = x + xw[k] + sig_e * zp[k];
   }
+  if (level_row) store_run(level_row, t0, T, lv);
+  store_run(traj_row, t0, T, tr);
 }
 
 }  // namespace ci
