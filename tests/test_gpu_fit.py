@@ -209,3 +209,15 @@ def test_statistical_parity_with_restated_reference_sampler():
   post_rows = res.series.index >= post[0]
   d = (res.series.loc[post_rows, "posterior_mean"] - ser_o.loc[post_rows, "posterior_mean"]).abs()
   assert d.max() < 0.1 * sd_y
+
+
+def test_large_prior_level_sd_starts_inside_support():
+  """prior_level_sd > 1 puts the reference's initial level scale above its own
+  upper bound (lib.py:432, 572); chains must still start inside the support."""
+  df = synthetic(n=80, treat=50, seed=4)
+  res = ci.fit_causalimpact(df, (df.index[0], df.index[49]), (df.index[50], df.index[-1]), seed=2,
+                            model_options=ci.ModelOptions(prior_level_sd=1.5),
+                            inference_options=ci.InferenceOptions(num_results=40))
+  assert np.all(np.isfinite(res.summary.values.astype(float)))
+  assert res.diagnostics["accept_rate"].mean() > 0.3
+  assert np.all(res.posterior_samples.level_scale.numpy() <= 1.0 + 1e-6)

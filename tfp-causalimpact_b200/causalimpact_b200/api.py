@@ -216,6 +216,10 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
         np.linalg.solve(spec.X[seen].T @ spec.X[seen] + spec.Omega, spec.X[seen].T @ y_ext[seen])
     theta0[:, :p] = z_star + 0.05 * rng.normal(size=(C, p))
   theta0[:, p:] += 0.1 * rng.normal(size=(C, spec.dim - p))
+  # keep every start strictly inside the truncated support (lib.py:432, 442-443):
+  # a chain that starts at log-density -inf could never move
+  theta0[:, p] = np.minimum(theta0[:, p], 2.0 * np.log(0.9 * spec.obs_ub))
+  theta0[:, p + 1] = np.minimum(theta0[:, p + 1], 2.0 * np.log(0.9 * spec.lvl_ub))
   n_warm = max(int(num_warmup_steps), int(opts.min_warmup))
 
   width = spec.dim + 2 * T
