@@ -104,7 +104,7 @@ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 // carveout: without the second attribute the driver may pick a carveout that fits a
 // single CTA per SM (ncu, round 1 run 7: occupancy_limit_shared_mem = 1 at 73 KB/CTA).
 template <typename Kern> cudaError_t set_smem(Kern kern, uint32_t bytes) {
-  cudaError_t e = set_smem(kern, (uint32_t)bytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                               (int)cudaSharedmemCarveoutMaxShared);
