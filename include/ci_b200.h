@@ -139,6 +139,33 @@ int ci_hmc_run_d(ci_ctx* ctx, const ci_hmc_opts* opts, uint64_t seed,
                  uint64_t chain_id0, const void* theta0_d, int n_chains,
                  void* draws_d, ci_hmc_stats* stats_d, void* stream);
 
+/* ---- Gibbs sampler with spike-and-slab regression (the reference's sampler) -
+ * Replaces gibbs_sampler.fit_with_gibbs_sampling exactly as the reference calls
+ * it (lib.py:365-388): one sweep = spike-and-slab (sigma_obs^2, weights) draw,
+ * FFBS level draw, sigma_level^2 draw; local level model only.  The initial
+ * state is the reference's (lib.py:566-581).
+ *   draws [n_results, C, dim]  (w, log sigma_obs^2, log sigma_level^2) per sweep
+ *   level [n_results, C, T]    level path of each kept sweep        (may be NULL)
+ *   traj  [n_results, C, T]    level + X.w + sigma_obs N(0,1)       (may be NULL)
+ *   incl  [C, p] float         inclusion frequency per feature      (may be NULL)
+ * sparse = 1: inclusion probability nonzero_prob (lib.py:449-450: min(1, 3/p));
+ * sparse = 0: every feature always included.
+ */
+typedef struct {
+  int32_t n_warmup;
+  int32_t n_results;
+  int32_t sparse;
+  int32_t reserved;
+  double nonzero_prob;
+} ci_gibbs_opts;
+
+int ci_gibbs_run(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
+                 uint64_t chain_id0, int n_chains, void* draws, void* level,
+                 void* traj, float* incl);
+int ci_gibbs_run_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
+                   uint64_t chain_id0, int n_chains, void* draws_d,
+                   void* level_d, void* traj_d, float* incl_d, void* stream);
+
 /* ---- K4: simulation smoother + one-step predictive draw ------------------
  * Replaces _resample_latents' LGSSM posterior_sample (inside the sampler,
  * lib.py:365-388) and _get_posterior_means_and_trajectories (lib.py:609-632).

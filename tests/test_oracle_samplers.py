@@ -43,3 +43,21 @@ def test_hmc_oracle_agrees_with_restated_reference_gibbs():
     se = np.sqrt(a.var() / (a.size / 20) + b.var() / (b.size / 20))
     assert abs(a.mean() - b.mean()) < max(5 * se, 2e-3)
     assert abs(a.std() / b.std() - 1) < 0.2
+
+
+def test_spike_and_slab_oracle_selects_true_features():
+  """The restated spike-and-slab sweep (Scott & Varian marginal, inclusion prior
+  3/p as in causalimpact_lib.py:449-450) keeps the 3 true covariates and drops
+  the 7 noise ones; with inclusion probability 1 it reduces to the dense sweep."""
+  y, X, _ = make_series(300, 10, 2022)
+  prob = K.default_problem(y, X)
+  sp = G.run(prob, n_results=600, n_warmup=200, seed=1, sparse=True)
+  inc = (sp["w"] != 0).mean(0)
+  assert np.all(inc[:3] > 0.9) and np.all(inc[3:10] < 0.2)
+  y2, X2, _ = make_series(100, 1, 7)                      # p = 2 -> inclusion prob 1
+  prob2 = K.default_problem(y2, X2)
+  a = G.run(prob2, n_results=1500, n_warmup=200, seed=2, sparse=True)
+  b = G.run(prob2, n_results=1500, n_warmup=200, seed=3, sparse=False)
+  assert np.all(a["w"] != 0)
+  assert abs(a["w"][:, 0].mean() - b["w"][:, 0].mean()) < 0.02
+  assert abs(np.sqrt(a["s_e"]).mean() - np.sqrt(b["s_e"]).mean()) < 0.01

@@ -39,6 +39,11 @@ class CiHmcOpts(C.Structure):
               ("adapt_mass", C.c_int32), ("init_step", C.c_double), ("target_accept", C.c_double)]
 
 
+class CiGibbsOpts(C.Structure):
+  _fields_ = [("n_warmup", C.c_int32), ("n_results", C.c_int32), ("sparse", C.c_int32),
+              ("reserved", C.c_int32), ("nonzero_prob", C.c_double)]
+
+
 class CiHmcStats(C.Structure):
   _fields_ = [("accept_rate", C.c_float), ("step_size", C.c_float),
               ("n_divergent", C.c_int32), ("n_leapfrog", C.c_int32)]
@@ -51,7 +56,7 @@ HMC_STATS_DTYPE = np.dtype([("accept_rate", np.float32), ("step_size", np.float3
 EXPORTS = (
     "ci_version", "ci_last_error", "ci_device_count", "ci_ctx_create", "ci_ctx_destroy",
     "ci_launch_count", "ci_set_data", "ci_logprob", "ci_logprob_grad", "ci_logprob_grad_d",
-    "ci_hmc_run", "ci_hmc_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
+    "ci_hmc_run", "ci_hmc_run_d", "ci_gibbs_run", "ci_gibbs_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
     "ci_row_quantiles", "ci_row_quantiles_d",
 )
 
@@ -84,6 +89,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
   lib.ci_logprob_grad_d.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp]
   lib.ci_hmc_run.argtypes = [vp, C.POINTER(CiHmcOpts), u64, u64, vp, i32, vp, vp]
   lib.ci_hmc_run_d.argtypes = [vp, C.POINTER(CiHmcOpts), u64, u64, vp, i32, vp, vp, vp]
+  lib.ci_gibbs_run.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp]
+  lib.ci_gibbs_run_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp, vp]
   lib.ci_posterior_predict.argtypes = [vp, vp, i32, u64, u64, vp, vp, vp]
   lib.ci_posterior_predict_d.argtypes = [vp, vp, i32, u64, u64, vp, vp, vp, vp]
   lib.ci_row_quantiles.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_double), i32, vp]
@@ -239,6 +246,26 @@ class Engine:
     self._check(self._lib.ci_hmc_run(self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0,
                                      _ptr(theta0), n, _ptr(draws), _ptr(stats)))
     return draws, stats
+
+  # -- the reference's Gibbs sampler (spike-and-slab) --------------------------
+  def gibbs_run(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
+                chain_id0: int = 0, sparse: bool = True, nonzero_prob: Optional[float] = None,
+                want_level: bool = True, want_traj: bool = True):
+    """Returns draws [n_results, C, dim], level, traj [n_results, C, T], incl [C, p]."""
+    sp = self.spec
+    if nonzero_prob is None:
+      nonzero_prob = min(1.0, 3.0 / sp.p) if sp.p else 1.0     # lib.py:449-450
+    dt = sp.np_dtype
+    draws = np.empty((n_results, n_chains, sp.dim), dtype=dt)
+    level = np.empty((n_results, n_chains, sp.T), dtype=dt) if want_level else None
+    traj = np.empty((n_results, n_chains, sp.T), dtype=dt) if want_traj else None
+    incl = np.zeros((n_chains, max(sp.p, 1)), dtype=np.float32)
+    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), reserved=0,
+                       nonzero_prob=float(nonzero_prob))
+    self._check(self._lib.ci_gibbs_run(self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0,
+                                       n_chains, _ptr(draws), _ptr(level), _ptr(traj),
+                                       _ptr(incl)))
+    return draws, level, traj, incl[:, :sp.p]
 
   # -- K4 --------------------------------------------------------------------
   def posterior_predict(self, theta_draws, *, seed: int, draw_id0: int = 0,

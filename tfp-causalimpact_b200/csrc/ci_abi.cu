@@ -16,6 +16,7 @@
 #include "ci_team_kernels.cuh"
 #include "ci_seq.cuh"
 #include "ci_llt_kernels.cuh"
+#include "ci_gibbs.cuh"
 
 namespace {
 
@@ -66,7 +67,10 @@ struct ci_ctx {
   size_t esz = 4;
   DevBuf tiles, omega;
   DevBuf w_theta, w_value, w_grad;   // workspaces of the host-pointer entry points
-  DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats;
+  DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats, w_incl;
+  DevBuf gram, xty0;                 // X'X, X'y over observed rows (Gibbs regression step)
+  double yty0 = 0.0;
+  int n_obs = 0;
   int64_t launches = 0;
   int force_G = 0;                   // CI_B200_G env override (tuning)
   int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
@@ -335,6 +339,38 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
 }
 
 template <typename R>
+int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0, int C,
+                 void* draws_d, void* level_d, void* traj_d, float* incl_d, cudaStream_t st) {
+  const int p = c->prob.p;
+  const uint32_t extra = (uint32_t)(2 * p * p + 5 * p + 8);
+  const uint32_t tail = (uint32_t)(p * p) * (uint32_t)c->esz + 16u;
+  SmemCfg cfg;
+  int G = pick_G(c, C), rc = CI_OK;
+  for (; G >= 1; --G) {            // wide problems: fewer chains per CTA
+    rc = plan_smem(c, G, extra, &cfg, tail);
+    if (rc == CI_OK) break;
+  }
+  if (rc) return rc;
+  GibbsPlan plan;
+  plan.n_warmup = o->n_warmup; plan.n_results = o->n_results; plan.sparse = o->sparse ? 1 : 0;
+  plan.n_obs = c->n_obs;
+  const double pi = o->nonzero_prob;
+  plan.logit_pi = (plan.sparse && pi < 1.0) ? std::log(pi) - std::log1p(-pi) : 1e30;
+  if (!(pi < 1.0)) plan.sparse = 0;
+  GibbsDev<R> gd;
+  gd.gram = static_cast<const R*>(c->gram.p); gd.xty0 = static_cast<const R*>(c->xty0.p);
+  gd.yty0 = (R)c->yty0;
+  auto kern = k_gibbs<R>;
+  CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
+  kern<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+      make_probdev<R>(c), gd, cfg, plan, seed, chain_id0, C, static_cast<R*>(draws_d),
+      static_cast<R*>(level_d), static_cast<R*>(traj_d), incl_d);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+template <typename R>
 int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_t draw_id0,
                    void* level_d, void* traj_d, void* mean_d, cudaStream_t st) {
   SmemCfg cfg;
@@ -449,7 +485,8 @@ int ci_ctx_destroy(ci_ctx* c) {
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   c->tiles.release(); c->omega.release();
   c->w_theta.release(); c->w_value.release(); c->w_grad.release();
-  c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release();
+  c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release(); c->w_incl.release();
+  c->gram.release(); c->xty0.release();
   delete c;
   return CI_OK;
 }
@@ -494,6 +531,44 @@ int ci_set_data(ci_ctx* c, const ci_problem* pb, const void* y, const void* X, c
   if (ob) {
     CU_TRY(cudaMemcpyAsync(c->omega.p, Omega, ob, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  {  // sufficient statistics of the regression step over OBSERVED rows (float64 on the host)
+    const int T = pb->T, p = pb->p;
+    std::vector<double> gram((size_t)p * p, 0.0), xty((size_t)(p > 0 ? p : 1), 0.0);
+    double yty = 0.0; int nobs = 0;
+    for (int t = 0; t < T; ++t) {
+      const double yt = pb->dtype == CI_F64 ? static_cast<const double*>(y)[t]
+                                            : (double)static_cast<const float*>(y)[t];
+      if (!(yt == yt)) continue;
+      ++nobs; yty += yt * yt;
+      for (int i = 0; i < p; ++i) {
+        const double xi = pb->dtype == CI_F64 ? static_cast<const double*>(X)[(size_t)t * p + i]
+                                              : (double)static_cast<const float*>(X)[(size_t)t * p + i];
+        xty[i] += xi * yt;
+        for (int j = 0; j <= i; ++j) {
+          const double xj = pb->dtype == CI_F64 ? static_cast<const double*>(X)[(size_t)t * p + j]
+                                                : (double)static_cast<const float*>(X)[(size_t)t * p + j];
+          gram[(size_t)i * p + j] += xi * xj;
+        }
+      }
+    }
+    for (int i = 0; i < p; ++i)
+      for (int j = i + 1; j < p; ++j) gram[(size_t)i * p + j] = gram[(size_t)j * p + i];
+    c->yty0 = yty; c->n_obs = nobs;
+    CU_TRY(c->gram.reserve((size_t)p * p * c->esz + 16));
+    CU_TRY(c->xty0.reserve((size_t)p * c->esz + 16));
+    if (p > 0) {
+      if (pb->dtype == CI_F64) {
+        CU_TRY(cudaMemcpyAsync(c->gram.p, gram.data(), (size_t)p * p * 8, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->xty0.p, xty.data(), (size_t)p * 8, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+      } else {
+        std::vector<float> gf(gram.begin(), gram.end()), xf(xty.begin(), xty.end());
+        CU_TRY(cudaMemcpyAsync(c->gram.p, gf.data(), (size_t)p * p * 4, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->xty0.p, xf.data(), (size_t)p * 4, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+      }
+    }
   }
   // validate that the pipeline fits before accepting the problem
   ci::SmemCfg cfg;
@@ -667,6 +742,51 @@ int ci_hmc_run(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
   if (rc) return rc;
   CU_TRY(cudaMemcpyAsync(draws, c->w_draws.p, db, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaMemcpyAsync(stats, c->w_stats.p, sb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_gibbs_run_d(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0, int C,
+                   void* draws_d, void* level_d, void* traj_d, float* incl_d, void* stream) {
+  if (!c || !o || !draws_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
+    return fail(CI_ERR_UNSUPPORTED, "ci_gibbs_run: local level model only (as the reference)");
+  if (C < 1 || o->n_results < 1 || o->n_warmup < 0)
+    return fail(CI_ERR_INVALID, "n_chains >= 1, n_results >= 1, n_warmup >= 0 required");
+  if (o->sparse && !(o->nonzero_prob > 0.0 && o->nonzero_prob <= 1.0))
+    return fail(CI_ERR_INVALID, "nonzero_prob must be in (0, 1]");
+  if (c->n_obs < 2) return fail(CI_ERR_INVALID, "need at least 2 observed points");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prob.dtype == CI_F64)
+    return launch_gibbs<double>(c, o, seed, chain_id0, C, draws_d, level_d, traj_d, incl_d, st);
+  return launch_gibbs<float>(c, o, seed, chain_id0, C, draws_d, level_d, traj_d, incl_d, st);
+}
+
+int ci_gibbs_run(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0, int C,
+                 void* draws, void* level, void* traj, float* incl) {
+  if (!c || !o || !draws) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (C < 1 || o->n_results < 1) return fail(CI_ERR_INVALID, "n_chains and n_results must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t rows = (size_t)o->n_results * C;
+  const size_t db = rows * c->dim * c->esz, tb = rows * c->prob.T * c->esz;
+  const size_t ib = (size_t)C * (c->prob.p > 0 ? c->prob.p : 1) * sizeof(float);
+  CU_TRY(c->w_draws.reserve(db));
+  if (level) CU_TRY(c->w_level.reserve(tb));
+  if (traj) CU_TRY(c->w_traj.reserve(tb));
+  if (incl) CU_TRY(c->w_incl.reserve(ib));
+  int rc = ci_gibbs_run_d(c, o, seed, chain_id0, C, c->w_draws.p, level ? c->w_level.p : nullptr,
+                          traj ? c->w_traj.p : nullptr,
+                          incl ? static_cast<float*>(c->w_incl.p) : nullptr, c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(draws, c->w_draws.p, db, cudaMemcpyDeviceToHost, c->stream));
+  if (level) CU_TRY(cudaMemcpyAsync(level, c->w_level.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  if (traj) CU_TRY(cudaMemcpyAsync(traj, c->w_traj.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  if (incl && c->prob.p > 0)
+    CU_TRY(cudaMemcpyAsync(incl, c->w_incl.p, (size_t)C * c->prob.p * sizeof(float),
+                           cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   return CI_OK;
 }
