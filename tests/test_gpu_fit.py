@@ -237,7 +237,9 @@ def test_ten_covariates_match_slab_only_gibbs():
   df = pd.DataFrame(np.column_stack([y, xs]), columns=["y"] + [f"x{i}" for i in range(k)])
   res = ci.fit_causalimpact(df, (0, 209), (210, 299), seed=3,
                             inference_options=ci.InferenceOptions(num_results=1500),
-                            engine_options=ci.EngineOptions(num_chains=128, min_warmup=500))
+                            engine_options=ci.EngineOptions(num_chains=128, min_warmup=500,
+                                                            sampler="hmc"))
+  assert res.diagnostics["sampler"] == "hmc"
   cid = fr.CausalImpactData(df, (0, 209), (210, 299))
   y_ext, design, sd = cid.engine_inputs(np.float32)
   prob = K.default_problem(y_ext, design, outcome_sd=sd)
@@ -255,3 +257,38 @@ def test_ten_covariates_match_slab_only_gibbs():
   sd_y = float(np.std(y[:210], ddof=1))
   assert d.max() < 0.05 * sd_y, d.max()
   assert res.diagnostics["n_divergent"].sum() <= 15
+
+
+def test_auto_sampler_reproduces_reference_spike_and_slab_posterior():
+  """With > 2 covariates the reference's prior is spike-and-slab (inclusion prob
+  3/p, lib.py:449-450).  sampler="auto" then runs the GPU Gibbs kernel; the
+  whole fit is compared with the restated reference sampler (sparse=True):
+  sparse weights, inclusion pattern, counterfactual and its uncertainty."""
+  rng = np.random.default_rng(12)
+  n, k = 300, 10
+  xs = 100 + np.cumsum(rng.normal(size=(n, k)), axis=0) * 0.3
+  beta = np.zeros(k); beta[:3] = (1.2, 0.6, -0.4)
+  y = xs @ beta + rng.normal(size=n)
+  y[210:] += 8.0
+  df = pd.DataFrame(np.column_stack([y, xs]), columns=["y"] + [f"x{i}" for i in range(k)])
+  res = ci.fit_causalimpact(df, (0, 209), (210, 299), seed=3,
+                            inference_options=ci.InferenceOptions(num_results=1920))
+  assert res.diagnostics["sampler"] == "gibbs"
+  cid = fr.CausalImpactData(df, (0, 209), (210, 299))
+  y_ext, design, sd = cid.engine_inputs(np.float32)
+  prob = K.default_problem(y_ext, design, outcome_sd=sd)
+  gb = G.run(prob, n_results=5000, n_warmup=800, seed=8, sparse=True)
+  w = res.posterior_samples.weights.numpy()
+  inc_gpu, inc_ref = (w != 0).mean(0), (gb["w"] != 0).mean(0)
+  np.testing.assert_allclose(inc_gpu, inc_ref, atol=0.12)
+  assert (w == 0).any()                                    # exact zeros, like the reference
+  loc = gb["level"] + gb["w"] @ design.T
+  rng2 = np.random.default_rng(0)
+  traj = loc + np.sqrt(gb["s_e"])[:, None] * rng2.normal(size=loc.shape)
+  ser_o, sum_o = impact.compute_impact(loc.mean(0), traj, cid, 0.05, quantiles_np.row_quantiles)
+  sd_y = float(np.std(y[:210], ddof=1))
+  for col in ("abs_effect", "abs_effect_lower", "abs_effect_upper", "predicted"):
+    a, b = res.summary.loc["average", col], sum_o.loc["average", col]
+    assert abs(a - b) < 0.05 * sd_y, (col, a, b)
+  ratio = res.summary.loc["average", "abs_effect_sd"] / sum_o.loc["average", "abs_effect_sd"]
+  assert 0.75 < ratio < 1.33, ratio

@@ -102,8 +102,15 @@ class EngineOptions:
     initialised torch.distributed process group.
   min_warmup: HMC needs more adaptation than a Gibbs sweep count suggests; the
     warm-up run is max(InferenceOptions.num_warmup_steps, min_warmup).
+  sampler: "auto" (default) = the reference's posterior: batched-chain HMC when the
+    spike-and-slab inclusion probability min(1, 3/p) is 1 (<= 2 covariates -- the prior
+    is then the continuous slab and HMC targets exactly the reference's posterior),
+    the GPU Gibbs kernel with spike-and-slab otherwise; "hmc" forces HMC on the
+    slab-only model, "gibbs" forces the Gibbs kernel.
   """
   num_chains: int = 64
+  sampler: str = "auto"
+  gibbs_min_warmup: int = 100
   max_leapfrog: int = 8
   min_warmup: int = 300
   init_step: float = 0.05
@@ -198,8 +205,11 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   spec = build_problem(y_ext, design, prior_level_sd=prior_level_sd, outcome_sd=outcome_sd,
                        dtype=np_dt)
   p, T = spec.p, spec.T
+  if opts.sampler not in ("auto", "hmc", "gibbs"):
+    raise ValueError(f"EngineOptions.sampler must be auto|hmc|gibbs, got {opts.sampler!r}")
+  use_gibbs = opts.sampler == "gibbs" or (opts.sampler == "auto" and p > 3)
   wh = None
-  if p and opts.whiten:
+  if p and opts.whiten and not use_gibbs:
     wh = _Whitening.build(design, ~np.isnan(y_ext), spec.Omega)
     spec = dataclasses.replace(spec, X=wh.design(design), Omega=wh.omega(spec.Omega))
   eng.set_data(spec)
@@ -208,34 +218,47 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   C = max(int(opts.num_chains), 1)
   n_per = max(1, math.ceil(num_results / C))
   c0, c_local = _shard.split_range(C, ws, rank)
-  rng = np.random.Generator(np.random.Philox(key=seed64))
-  theta0 = np.tile(initial_theta(spec, prior_level_sd), (C, 1))
-  if p:
-    seen = ~np.isnan(y_ext)
-    z_star = spec.X[seen].T @ y_ext[seen] if wh is not None else \
-        np.linalg.solve(spec.X[seen].T @ spec.X[seen] + spec.Omega, spec.X[seen].T @ y_ext[seen])
-    theta0[:, :p] = z_star + 0.05 * rng.normal(size=(C, p))
-  theta0[:, p:] += 0.1 * rng.normal(size=(C, spec.dim - p))
-  # keep every start strictly inside the truncated support (lib.py:432, 442-443):
-  # a chain that starts at log-density -inf could never move
-  theta0[:, p] = np.minimum(theta0[:, p], 2.0 * np.log(0.9 * spec.obs_ub))
-  theta0[:, p + 1] = np.minimum(theta0[:, p + 1], 2.0 * np.log(0.9 * spec.lvl_ub))
-  n_warm = max(int(num_warmup_steps), int(opts.min_warmup))
-
   width = spec.dim + 2 * T
-  if c_local > 0:
-    draws, stats = eng.hmc_run(theta0[c0:c0 + c_local], n_warmup=n_warm, n_results=n_per,
-                               seed=seed64, chain_id0=c0, max_leapfrog=opts.max_leapfrog,
-                               init_step=opts.init_step, target_accept=opts.target_accept)
+  stats = None
+  if c_local == 0:
+    rows = np.zeros((0, width), dtype=spec.np_dtype)
+  elif use_gibbs:
+    # the reference's sampler (lib.py:365-388): spike-and-slab Gibbs sweeps, started
+    # from its initial state (lib.py:566-581); chain-major rows like the HMC path
+    n_warm = max(int(num_warmup_steps), int(opts.gibbs_min_warmup))
+    draws, level, traj, incl = eng.gibbs_run(c_local, n_warmup=n_warm, n_results=n_per,
+                                             seed=seed64, chain_id0=c0, sparse=True)
+    rows = np.concatenate([draws.transpose(1, 0, 2).reshape(c_local * n_per, spec.dim),
+                           level.transpose(1, 0, 2).reshape(c_local * n_per, T),
+                           traj.transpose(1, 0, 2).reshape(c_local * n_per, T)], axis=1)
+    stats = {"sampler": "gibbs", "inclusion": incl}
+  else:
+    rng = np.random.Generator(np.random.Philox(key=seed64))
+    theta0 = np.tile(initial_theta(spec, prior_level_sd), (C, 1))
+    if p:
+      seen = ~np.isnan(y_ext)
+      z_star = spec.X[seen].T @ y_ext[seen] if wh is not None else \
+          np.linalg.solve(spec.X[seen].T @ spec.X[seen] + spec.Omega, spec.X[seen].T @ y_ext[seen])
+      theta0[:, :p] = z_star + 0.05 * rng.normal(size=(C, p))
+    theta0[:, p:] += 0.1 * rng.normal(size=(C, spec.dim - p))
+    # keep every start strictly inside the truncated support (lib.py:432, 442-443):
+    # a chain that starts at log-density -inf could never move
+    theta0[:, p] = np.minimum(theta0[:, p], 2.0 * np.log(0.9 * spec.obs_ub))
+    theta0[:, p + 1] = np.minimum(theta0[:, p + 1], 2.0 * np.log(0.9 * spec.lvl_ub))
+    n_warm = max(int(num_warmup_steps), int(opts.min_warmup))
+    draws, hstats = eng.hmc_run(theta0[c0:c0 + c_local], n_warmup=n_warm, n_results=n_per,
+                                seed=seed64, chain_id0=c0, max_leapfrog=opts.max_leapfrog,
+                                init_step=opts.init_step, target_accept=opts.target_accept)
     # chain-major draw ids: g = chain * n_per + iteration  (contiguous per rank)
     local_theta = np.ascontiguousarray(draws.transpose(1, 0, 2)).reshape(c_local * n_per,
                                                                            spec.dim)
     level, traj, _ = eng.posterior_predict(local_theta, seed=seed64 ^ 0x9E3779B97F4A7C15,
                                            draw_id0=c0 * n_per)
     rows = np.concatenate([local_theta, level, traj], axis=1)
-  else:
-    stats = None
-    rows = np.zeros((0, width), dtype=spec.np_dtype)
+    stats = {"sampler": "hmc", "accept_rate": np.asarray(hstats["accept_rate"]),
+             "step_size": np.asarray(hstats["step_size"]),
+             "n_divergent": np.asarray(hstats["n_divergent"]),
+             "n_leapfrog": np.asarray(hstats["n_leapfrog"])}
   # the ONE collective of the fit: every chain contributes n_per result rows
   rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
 
@@ -306,8 +329,4 @@ def fit_causalimpact(data: pd.DataFrame,
       weights=samples.weights if samples.weights.shape[1] > 0 else None,    # :330-331
       seasonal_drift_scales=None,                                            # :332-334
       seasonal_levels=samples.seasonal_levels)
-  diag = None if stats is None else {
-      "accept_rate": np.asarray(stats["accept_rate"]), "step_size": np.asarray(stats["step_size"]),
-      "n_divergent": np.asarray(stats["n_divergent"]),
-      "n_leapfrog": np.asarray(stats["n_leapfrog"])}
-  return CausalImpactAnalysis(series, summary, result_samples, diag)
+  return CausalImpactAnalysis(series, summary, result_samples, stats)
