@@ -41,6 +41,39 @@ template <typename R> __device__ __forceinline__ Mob<R> mob_mul(const Mob<R>& L,
 }
 
 // ---------------------------------------------------------------------------
+// Branch-free Kogge-Stone scan steps: a lane without a partner combines with the
+// identity instead of skipping the step, so there is no divergence region
+// (BSSY/BSYNC) per level.
+// ---------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ void affine_scan_up(R& m, R& c, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    R mo = __shfl_up_sync(FULL, m, off), co = __shfl_up_sync(FULL, c, off);
+    const bool ok = lane >= off;
+    mo = ok ? mo : (R)1; co = ok ? co : (R)0;
+    c = fma(m, co, c); m = m * mo;
+  }
+}
+template <typename R> __device__ __forceinline__ void affine_scan_down(R& m, R& c, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    R mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
+    const bool ok = lane + off < 32;
+    mo = ok ? mo : (R)1; co = ok ? co : (R)0;
+    c = fma(m, co, c); m = m * mo;
+  }
+}
+template <typename R> __device__ __forceinline__ void mob_scan_up(Mob<R>& M, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    Mob<R> O = mob_shfl_up(M, off);
+    const bool ok = lane >= off;
+    O.a = ok ? O.a : (R)1; O.b = ok ? O.b : (R)0; O.c = ok ? O.c : (R)0; O.d = ok ? O.d : (R)1;
+    M = mob_mul(M, O);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // consumer side of the tile pipeline
 // ---------------------------------------------------------------------------
 template <typename R> struct TilePipe {
@@ -196,11 +229,7 @@ __device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& 
     const R s = Num<R>::rcp_fast(M.a + M.b + M.c + M.d);
     M.a *= s; M.b *= s; M.c *= s; M.d *= s;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const Mob<R> O = mob_shfl_up(M, off);
-    if (lane >= off) M = mob_mul(M, O);
-  }
+mob_scan_up(M, lane);
   Mob<R> E = mob_shfl_up(M, 1);
   if (lane == 0) { E.a = 1; E.b = 0; E.c = 0; E.d = 1; }
   R Pc = fma(E.a, P_c, E.b) * Num<R>::rcp(fma(E.c, P_c, E.d));
@@ -222,11 +251,7 @@ __device__ __forceinline__ void blk_forward(Blk<R>& B, R s_e, R s_h, R& a_c, R& 
     c = fma(omk, c, B.K[k] * B.r[k]);
     m = omk * m;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const R mo = __shfl_up_sync(FULL, m, off), co = __shfl_up_sync(FULL, c, off);
-    if (lane >= off) { c = fma(m, co, c); m = m * mo; }
-  }
+affine_scan_up(m, c, lane);
   R me = __shfl_up_sync(FULL, m, 1), ce = __shfl_up_sync(FULL, c, 1);
   if (lane == 0) { me = 1; ce = 0; }
   R ac = fma(me, a_c, ce);
@@ -271,11 +296,7 @@ __device__ __forceinline__ void blk_backward(const Blk<R>& B, R s_e, R& ab_c, R&
     c = fma(omk, c, B.v[k] * B.rF[k]);
     m = omk * m;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const R mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
-    if (lane + off < 32) { c = fma(m, co, c); m = m * mo; }
-  }
+affine_scan_down(m, c, lane);
   R me = __shfl_down_sync(FULL, m, 1), ce = __shfl_down_sync(FULL, c, 1);
   if (lane == 31) { me = 1; ce = 0; }
   R ab = fma(me, ab_c, ce);
@@ -299,11 +320,7 @@ __device__ __forceinline__ void blk_backward(const Blk<R>& B, R s_e, R& ab_c, R&
     c = fma(mult, c, q[k]);
     m = mult * m;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const R mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
-    if (lane + off < 32) { c = fma(m, co, c); m = m * mo; }
-  }
+affine_scan_down(m, c, lane);
   me = __shfl_down_sync(FULL, m, 1); ce = __shfl_down_sync(FULL, c, 1);
   if (lane == 31) { me = 1; ce = 0; }
   R pb = fma(me, pb_c, ce);

@@ -280,11 +280,7 @@ k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t see
         cc = fma(Jk, cc, off[kk]);
         m = Jk * m;
       }
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const R mo = __shfl_down_sync(FULL, m, o), co = __shfl_down_sync(FULL, cc, o);
-        if (lane + o < 32) { cc = fma(m, co, cc); m = m * mo; }
-      }
+affine_scan_down(m, cc, lane);
       R me = __shfl_down_sync(FULL, m, 1), ce = __shfl_down_sync(FULL, cc, 1);
       if (lane == 31) { me = 1; ce = 0; }
       R x = fma(me, x_c, ce);

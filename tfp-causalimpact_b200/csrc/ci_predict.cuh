@@ -93,11 +93,7 @@ k_predict(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int S, uint64
       c = fma(Jk, c, off[k]);
       m = Jk * m;
     }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const R mo = __shfl_down_sync(FULL, m, o), co = __shfl_down_sync(FULL, c, o);
-      if (lane + o < 32) { c = fma(m, co, c); m = m * mo; }
-    }
+affine_scan_down(m, c, lane);
     R me = __shfl_down_sync(FULL, m, 1), ce = __shfl_down_sync(FULL, c, 1);
     if (lane == 31) { me = 1; ce = 0; }
     R x = fma(me, x_c, ce);

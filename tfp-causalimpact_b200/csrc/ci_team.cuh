@@ -65,11 +65,7 @@ __device__ __forceinline__ void team_eval(const R* __restrict__ tile, const Prob
     const R s = Num<R>::rcp_fast(M.a + M.b + M.c + M.d);
     M.a *= s; M.b *= s; M.c *= s; M.d *= s;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const Mob<R> O = mob_shfl_up(M, off);
-    if (lane >= off) M = mob_mul(M, O);
-  }
+mob_scan_up(M, lane);
   if (lane == 31) { ts->aggM[wt][0] = M.a; ts->aggM[wt][1] = M.b; ts->aggM[wt][2] = M.c; ts->aggM[wt][3] = M.d; }
   Mob<R> E = mob_shfl_up(M, 1);
   if (lane == 0) { E.a = 1; E.b = 0; E.c = 0; E.d = 1; }
@@ -101,11 +97,7 @@ __device__ __forceinline__ void team_eval(const R* __restrict__ tile, const Prob
     c = fma(omk, c, B.K[k] * B.r[k]);
     m = omk * m;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const R mo = __shfl_up_sync(FULL, m, off), co = __shfl_up_sync(FULL, c, off);
-    if (lane >= off) { c = fma(m, co, c); m = m * mo; }
-  }
+affine_scan_up(m, c, lane);
   if (lane == 31) { ts->aggA[wt][0] = m; ts->aggA[wt][1] = c; }
   R me = __shfl_up_sync(FULL, m, 1), ce = __shfl_up_sync(FULL, c, 1);
   if (lane == 0) { me = 1; ce = 0; }
@@ -135,11 +127,7 @@ __device__ __forceinline__ void team_eval(const R* __restrict__ tile, const Prob
       c = fma(omk, c, B.v[k] * B.rF[k]);
       m = omk * m;
     }
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const R mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
-      if (lane + off < 32) { c = fma(m, co, c); m = m * mo; }
-    }
+affine_scan_down(m, c, lane);
     if (lane == 0) { ts->aggAB[wt][0] = m; ts->aggAB[wt][1] = c; }
     me = __shfl_down_sync(FULL, m, 1); ce = __shfl_down_sync(FULL, c, 1);
     if (lane == 31) { me = 1; ce = 0; }
@@ -164,11 +152,7 @@ __device__ __forceinline__ void team_eval(const R* __restrict__ tile, const Prob
       c = fma(mult, c, q[k]);
       m = mult * m;
     }
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const R mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
-      if (lane + off < 32) { c = fma(m, co, c); m = m * mo; }
-    }
+affine_scan_down(m, c, lane);
     if (lane == 0) { ts->aggPB[wt][0] = m; ts->aggPB[wt][1] = c; }
     me = __shfl_down_sync(FULL, m, 1); ce = __shfl_down_sync(FULL, c, 1);
     if (lane == 31) { me = 1; ce = 0; }
@@ -286,11 +270,7 @@ __device__ __forceinline__ void team_predict(const R* __restrict__ tile, const P
     const R s = Num<R>::rcp_fast(M.a + M.b + M.c + M.d);
     M.a *= s; M.b *= s; M.c *= s; M.d *= s;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const Mob<R> O = mob_shfl_up(M, off);
-    if (lane >= off) M = mob_mul(M, O);
-  }
+mob_scan_up(M, lane);
   if (lane == 31) { ts->aggM[wt][0] = M.a; ts->aggM[wt][1] = M.b; ts->aggM[wt][2] = M.c; ts->aggM[wt][3] = M.d; }
   Mob<R> E = mob_shfl_up(M, 1);
   if (lane == 0) { E.a = 1; E.b = 0; E.c = 0; E.d = 1; }
@@ -321,11 +301,7 @@ __device__ __forceinline__ void team_predict(const R* __restrict__ tile, const P
     c = fma(omk, c, B.K[k] * B.r[k]);
     m = omk * m;
   }
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const R mo = __shfl_up_sync(FULL, m, off), co = __shfl_up_sync(FULL, c, off);
-    if (lane >= off) { c = fma(m, co, c); m = m * mo; }
-  }
+affine_scan_up(m, c, lane);
   if (lane == 31) { ts->aggA[wt][0] = m; ts->aggA[wt][1] = c; }
   R me = __shfl_up_sync(FULL, m, 1), ce = __shfl_up_sync(FULL, c, 1);
   if (lane == 0) { me = 1; ce = 0; }
@@ -357,11 +333,7 @@ __device__ __forceinline__ void team_predict(const R* __restrict__ tile, const P
   m = 1; c = 0;
 #pragma unroll
   for (int k = KS - 1; k >= 0; --k) { c = fma(J[k], c, off_[k]); m = J[k] * m; }
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const R mo = __shfl_down_sync(FULL, m, o), co = __shfl_down_sync(FULL, c, o);
-    if (lane + o < 32) { c = fma(m, co, c); m = m * mo; }
-  }
+affine_scan_down(m, c, lane);
   if (lane == 0) { ts->aggAB[wt][0] = m; ts->aggAB[wt][1] = c; }
   me = __shfl_down_sync(FULL, m, 1); ce = __shfl_down_sync(FULL, c, 1);
   if (lane == 31) { me = 1; ce = 0; }
