@@ -35,6 +35,27 @@ class FakeEngine:
                                             "n_leapfrog")}
     return draws.astype(self.spec.np_dtype), stats
 
+  def gibbs_run(self, n_chains, *, n_warmup, n_results, seed, chain_id0=0, sparse=True,
+                nonzero_prob=None, want_level=True, want_traj=True):
+    from oracle import gibbs_np as G
+    sp, dt = self.spec, self.spec.np_dtype
+    draws = np.empty((n_results, n_chains, sp.dim), dt)
+    level = np.empty((n_results, n_chains, sp.T), dt)
+    traj = np.empty((n_results, n_chains, sp.T), dt)
+    incl = np.zeros((n_chains, max(sp.p, 1)), np.float32)
+    for c in range(n_chains):
+      g = G.run(self.prob, n_results=n_results, n_warmup=n_warmup,
+                seed=(int(seed) % (2 ** 31)) * 1000003 + chain_id0 + c, sparse=sparse)
+      draws[:, c, :sp.p] = g["w"]
+      draws[:, c, sp.p] = np.log(g["s_e"]); draws[:, c, sp.p + 1] = np.log(g["s_h"])
+      level[:, c] = g["level"]
+      rng = np.random.default_rng(chain_id0 + c)
+      loc = g["level"] + (g["w"] @ self.prob.X.T if sp.p else 0.0)
+      traj[:, c] = loc + np.sqrt(g["s_e"])[:, None] * rng.normal(size=loc.shape)
+      if sp.p:
+        incl[c, :sp.p] = (g["w"] != 0).mean(0)
+    return draws, level, traj, incl[:, :sp.p]
+
   def posterior_predict(self, theta_draws, *, seed, draw_id0=0, want_level=True):
     l, t, m = SM.posterior_predict(self.prob, theta_draws, seed, draw_id0)
     dt = self.spec.np_dtype

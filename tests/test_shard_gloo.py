@@ -30,11 +30,14 @@ fake = FakeEngine()
 api._resolve_engine = lambda opts: fake
 rng = np.random.default_rng(3)
 n = 60
-x = 100 + np.cumsum(rng.normal(size=n)); y = 1.2 * x + rng.normal(size=n); y[40:] += 4
-df = pd.DataFrame({"y": y, "x": x}, index=pd.date_range("2021-01-01", periods=n))
+n_cov = int(sys.argv[3])
+xs = 100 + np.cumsum(rng.normal(size=(n, n_cov)), axis=0); y = 1.2 * xs[:, 0] + rng.normal(size=n); y[40:] += 4
+df = pd.DataFrame(np.column_stack([y, xs]), columns=["y"] + [f"x{i}" for i in range(n_cov)],
+                  index=pd.date_range("2021-01-01", periods=n))
 ci = cib.fit_causalimpact(df, (df.index[0], df.index[39]), (df.index[40], df.index[-1]), seed=(1, 2),
     inference_options=cib.InferenceOptions(num_results=22),
-    engine_options=cib.EngineOptions(num_chains=5, min_warmup=25, max_leapfrog=3))
+    engine_options=cib.EngineOptions(num_chains=5, min_warmup=25, max_leapfrog=3,
+                                     gibbs_min_warmup=10))
 if int(os.environ.get("RANK", "0")) == 0:
   vals = [c for c in ci.series.columns if not c.endswith(("_start", "_end"))]
   pickle.dump(dict(series=ci.series[vals].values, summary=ci.summary.values,
@@ -45,18 +48,18 @@ if world > 1:
 '''
 
 
-def _run(world, out):
+def _run(world, out, n_cov=1):
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
     f.write(WORKER)
     script = f.name
   env = dict(os.environ, OMP_NUM_THREADS="1")
   if world == 1:
-    cmd = [sys.executable, script, root, out]
+    cmd = [sys.executable, script, root, out, str(n_cov)]
   else:
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29731",
-           script, root, out]
+           script, root, out, str(n_cov)]
   res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
   os.unlink(script)
   assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
@@ -73,9 +76,11 @@ def test_split_range_is_a_partition():
       assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
 
 
-def test_world2_gloo_equals_single_process(tmp_path):
-  one = _run(1, str(tmp_path / "w1.pkl"))
-  two = _run(2, str(tmp_path / "w2.pkl"))
+@pytest.mark.parametrize("n_cov", [1, 4], ids=["hmc_path", "gibbs_path"])
+def test_world2_gloo_equals_single_process(tmp_path, n_cov):
+  """n_cov = 1 -> sampler auto = HMC; n_cov = 4 (p = 5 > 3) -> the Gibbs kernel path."""
+  one = _run(1, str(tmp_path / "w1.pkl"), n_cov)
+  two = _run(2, str(tmp_path / "w2.pkl"), n_cov)
   for k in one:
     assert np.array_equal(one[k], two[k], equal_nan=True), k
   assert one["level"].shape == (22, 60)

@@ -376,7 +376,9 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
   SmemCfg cfg;
   const ProbDev<R> prt = make_probdev<R>(c);
   int GT = 0;
-  if (plan_team<R>(c, S, &GT, &cfg)) {
+  // team mode wins when few draws leave the GPU latency-bound; with thousands of draws
+  // the one-warp kernel has the better occupancy (run 8: 21.5 vs 20.0 M draws/s at 4096)
+  if (S <= 2048 && plan_team<R>(c, S, &GT, &cfg)) {
     auto tk = k_predict_team<R>;
     CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
     tk<<<(S + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
