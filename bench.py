@@ -270,6 +270,15 @@ def main():
   sync_all()
   t_pred = float(p0.elapsed_time(p1)) / 10.0
 
+  # ---- the reference's own sampler on the GPU: Gibbs sweeps/s (spike-and-slab, 256 chains)
+  eng.gibbs_run(C, n_warmup=2, n_results=2, seed=1, chain_id0=rank * C, want_level=False,
+                want_traj=False)
+  sync_all()
+  t0 = time.perf_counter()
+  eng.gibbs_run(C, n_warmup=30, n_results=30, seed=1, chain_id0=rank * C, want_level=False,
+                want_traj=False)
+  t_gibbs = (time.perf_counter() - t0) * 1e3
+
   # ---- the product call itself: fit_causalimpact on the quickstart shape (configs[0]:
   # T=100, 1 covariate, defaults = 900 draws).  The reference's only published number is
   # 5.17 s wall for this call on an unspecified notebook CPU (docs/quickstart.ipynb:361-362).
@@ -288,9 +297,10 @@ def main():
       t_fit = (time.perf_counter() - tq) * 1e3
 
   if world > 1:
-    t = torch.tensor([t_step, t_e2e, t_hot, t_hmc, t_pred], dtype=torch.float64, device=dev)
+    t = torch.tensor([t_step, t_e2e, t_hot, t_hmc, t_pred, t_gibbs], dtype=torch.float64,
+                     device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_step, t_e2e, t_hot, t_hmc, t_pred = (float(x) for x in t.tolist())
+    t_step, t_e2e, t_hot, t_hmc, t_pred, t_gibbs = (float(x) for x in t.tolist())
     he = torch.tensor([hmc_evals], dtype=torch.float64, device=dev)
     dist.all_reduce(he, op=dist.ReduceOp.SUM)
     hmc_evals = int(he.item())
@@ -335,6 +345,11 @@ def main():
                   "hmc_leapfrog_evals_per_sec": hmc_evals / (t_hmc * 1e-3),
                   "hmc_run": {"chains_per_gpu": C, "iterations": 60, "wall_ms": t_hmc,
                               "note": "host-pointer ci_hmc_run incl. copies + sync"},
+                  "gibbs_sweeps_per_sec": C * world * 60 / (t_gibbs * 1e-3),
+                  "gibbs_run": {"chains_per_gpu": C, "sweeps": 60, "wall_ms": t_gibbs,
+                                "note": "ci_gibbs_run, spike-and-slab (inclusion prob 3/11), "
+                                        "one sweep = SSVS + FFBS + 2 InvGamma draws; the reference "
+                                        "publishes <= 5.2 ms per sweep (1 chain, T=100)"},
                   "fit_causalimpact_quickstart_ms": t_fit,
                   "fit_note": "T=100, 1 covariate, 900 draws, 64 chains, 2nd call; reference "
                               "publishes 5170 ms for this call (other hardware, incl. tracing)",
