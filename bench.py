@@ -51,25 +51,51 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  """SM clock / throttle reasons sampled DURING the timed region (NVML every 5 ms;
+  nvidia-smi as a fallback)."""
   Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
        "clocks_event_reasons.sw_power_cap")
 
   def __init__(self, index):
     self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+    self._nvml = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self._nvml = pynvml
+    except Exception:   # pylint: disable=broad-except
+      self._nvml = None
+
+  def _sample_nvml(self):
+    n = self._nvml
+    sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+    mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+    try:
+      r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+    except Exception:   # pylint: disable=broad-except
+      r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+    act = lambda bit: "Active" if (r & bit) else "Not Active"
+    self.rows.append([str(sm), str(mx), act(n.nvmlClocksThrottleReasonHwSlowdown),
+                      act(n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                      act(n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                      act(n.nvmlClocksThrottleReasonSwPowerCap)])
 
   def _run(self):
     while not self._stop.is_set():
       try:
-        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                             timeout=5).stdout.strip()
-        if out:
-          self.rows.append([c.strip() for c in out.split(",")])
+        if self._nvml is not None:
+          self._sample_nvml()
+        else:
+          out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                               timeout=5).stdout.strip()
+          if out:
+            self.rows.append([c.strip() for c in out.split(",")])
       except Exception:   # pylint: disable=broad-except
         pass
-      self._stop.wait(0.1)
+      self._stop.wait(0.005 if self._nvml is not None else 0.1)
 
   def __enter__(self):
     self._th = threading.Thread(target=self._run, daemon=True)
@@ -88,7 +114,7 @@ class ClockSampler:
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-            "samples": len(self.rows)}
+            "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def cpu_port_rate(cfg, seconds=10.0, nthreads=0):
