@@ -117,11 +117,13 @@ class ClockSampler:
             "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
-def cpu_port_rate(cfg, seconds=10.0, nthreads=0):
+def cpu_port_rate(cfg, seconds=10.0, nthreads=None):
   """Times oracle/_ref (C port of the oracle, float64, OpenMP over chains) on a
   bounded sample of the SAME workload; returns evals/s and a description."""
   from oracle import c_port
   from oracle import kalman_np as K
+  if nthreads is None:
+    nthreads = os.cpu_count() or 1      # explicit: torchrun exports OMP_NUM_THREADS=1
   y, X, th = make_inputs(cfg)
   prob = K.default_problem(y, X)
   c_port.logpost_grad(prob, th[:8])                     # load + warm
@@ -308,19 +310,21 @@ def main():
   # ---- the product call itself: fit_causalimpact on the quickstart shape (configs[0]:
   # T=100, 1 covariate, defaults = 900 draws).  The reference's only published number is
   # 5.17 s wall for this call on an unspecified notebook CPU (docs/quickstart.ipynb:361-362).
+  # (every rank calls it: with a process group the fit shards its chains over the ranks
+  # and ends with one all-gather, so a rank-0-only call would wait forever)
+  import pandas as pd
+  rs = np.random.Generator(np.random.PCG64(20241))
+  xq = 100 + np.cumsum(rs.normal(size=100)) * 0.3
+  yq = 1.2 * xq + rs.normal(size=100)
+  yq[71:] += 10
+  dfq = pd.DataFrame({"y": yq, "x": xq})
   t_fit = None
-  if rank == 0:
-    import pandas as pd
-    rs = np.random.Generator(np.random.PCG64(20241))
-    xq = 100 + np.cumsum(rs.normal(size=100)) * 0.3
-    yq = 1.2 * xq + rs.normal(size=100)
-    yq[71:] += 10
-    dfq = pd.DataFrame({"y": yq, "x": xq})
-    for _ in range(2):
-      tq = time.perf_counter()
-      cib.fit_causalimpact(dfq, (0, 70), (71, 99), seed=1,
-                           engine_options=cib.EngineOptions(device=local))
-      t_fit = (time.perf_counter() - tq) * 1e3
+  for _ in range(2):
+    sync_all()
+    tq = time.perf_counter()
+    cib.fit_causalimpact(dfq, (0, 70), (71, 99), seed=1,
+                         engine_options=cib.EngineOptions(device=local))
+    t_fit = (time.perf_counter() - tq) * 1e3
 
   if world > 1:
     t = torch.tensor([t_step, t_e2e, t_hot, t_hmc, t_pred, t_gibbs], dtype=torch.float64,
