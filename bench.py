@@ -146,7 +146,7 @@ def run_reference(args):
   if rank != 0:
     return
   cfg = dict(WORKLOAD)
-  per_step = max(1.0, min(8.0, 60.0 / max(1, args.steps + args.warmup)))
+  per_step = max(0.2, min(8.0, 90.0 / max(1, args.steps + args.warmup)))   # whole arm <= ~1.5 min
   rates = []
   for i in range(args.warmup + args.steps):
     r, used, sample = cpu_port_rate(cfg, seconds=per_step)
