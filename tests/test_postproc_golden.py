@@ -71,3 +71,29 @@ def test_alpha_is_validated():
   with pytest.raises(ValueError, match="alpha"):
     impact.compute_impact(g["posterior_means"], g["posterior_trajectories"], ci, 1.5,
                           quantiles_np.row_quantiles)
+
+
+def test_text_summary_layout():
+  """causalimpact.summary(impact) (reference summary.py:133-178): same layout as
+  the reference's golden text (testdata/test_summary_output.txt), own formatter."""
+  import types
+  from causalimpact_b200 import report
+  cols = ["actual", "predicted", "predicted_lower", "predicted_upper", "predicted_sd",
+          "abs_effect", "abs_effect_lower", "abs_effect_upper", "abs_effect_sd", "rel_effect",
+          "rel_effect_lower", "rel_effect_upper", "rel_effect_sd", "p_value", "alpha"]
+  tab = pd.DataFrame([[5.3, 4.3, 3.3, 6.3, 0.0, 3.3, 2.3, 6.3, 0.0, .123, .143, .343, .001, .4593, .1],
+                      [10.3, 9.3, 8.3, 9.3, 0.1, 10.3, 4.3, 9.3, 0.1, .233, .133, .333, .1, .4593, .1]],
+                     index=["average", "cumulative"], columns=cols)
+  text = report.summary(types.SimpleNamespace(summary=tab))
+  lines = text.splitlines()
+  assert lines[0] == "Posterior Inference {CausalImpact}"
+  assert lines[2] == "Actual                    5.3                10.3"
+  assert lines[3] == "Prediction (s.d.)         4.3 (0.0)          9.3 (0.1)"
+  assert lines[4] == "90% CI                    [3.3, 6.3]         [8.3, 9.3]"
+  assert lines[9] == "Relative effect (s.d.)    12.3% (0.1%)       23.3% (10.0%)"
+  assert "Posterior tail-area probability p: 0.459" in text
+  assert "Posterior probability of an effect: 54.07%" in text
+  assert "not statistically significant" not in report.summary(
+      types.SimpleNamespace(summary=tab), output_format="report")
+  with pytest.raises(ValueError):
+    report.summary(types.SimpleNamespace(summary=tab), output_format="x")

@@ -11,3 +11,4 @@ from .api import (CausalImpactAnalysis, CausalImpactPosteriorSamples, DataOption
                   EngineOptions, InferenceOptions, ModelOptions, Seasons, fit_causalimpact)
 from .frame import CausalImpactData, InputDateType  # noqa: F401
 from .model import build_problem, initial_theta  # noqa: F401
+from .report import plot, summary  # noqa: F401
