@@ -123,7 +123,9 @@ def cpu_port_rate(cfg, seconds=10.0, nthreads=None):
   from oracle import c_port
   from oracle import kalman_np as K
   if nthreads is None:
-    nthreads = os.cpu_count() or 1      # explicit: torchrun exports OMP_NUM_THREADS=1
+    # explicit (torchrun exports OMP_NUM_THREADS=1); the CPUs this process may use, not
+    # os.cpu_count(): 128 threads on a 64-CPU affinity mask ran 6x slower (run 11)
+    nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
   y, X, th = make_inputs(cfg)
   prob = K.default_problem(y, X)
   c_port.logpost_grad(prob, th[:8])                     # load + warm

@@ -94,9 +94,10 @@ def test_row_quantiles_rejects_bad_input(engine):
 
 
 def test_predict_team_and_single_warp_paths_agree(monkeypatch):
-  """T=1000: default TEAM mode (one warp per tile, no replay) vs CI_B200_TEAM=0
-  (one warp per draw with checkpoint replay): same Philox normals, so the paths
-  agree to float32 rounding and both match the oracle."""
+  """T=1000: the opt-in TEAM kernel (CI_B200_PREDICT_TEAM=1: one warp per tile, no
+  replay) vs the default one-warp-per-draw kernel: same Philox normals, so the
+  paths agree to float32 rounding and both match the oracle.  (The default never
+  depends on the batch size, so draws are bit-identical under any split.)"""
   y, X, _ = make_series(1000, 10, 77, nan_frac=0.02)
   spec = cib.build_problem(y, X, prior_level_sd=0.05)
   prob = K.default_problem(y, X, prior_level_sd=0.05)
@@ -104,7 +105,7 @@ def test_predict_team_and_single_warp_paths_agree(monkeypatch):
   th[:, spec.p + 1] += 2.0
   out = {}
   for mode in ("1", "0"):
-    monkeypatch.setenv("CI_B200_TEAM", mode)
+    monkeypatch.setenv("CI_B200_PREDICT_TEAM", mode)
     eng = cib.Engine(0)
     eng.set_data(spec)
     out[mode] = eng.posterior_predict(th, seed=5, draw_id0=100)

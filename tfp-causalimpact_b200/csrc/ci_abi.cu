@@ -74,6 +74,7 @@ struct ci_ctx {
   int64_t launches = 0;
   int force_G = 0;                   // CI_B200_G env override (tuning)
   int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
+  int predict_team = 0;              // CI_B200_PREDICT_TEAM=1: team kernel for ci_posterior_predict
 };
 
 namespace {
@@ -376,9 +377,11 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
   SmemCfg cfg;
   const ProbDev<R> prt = make_probdev<R>(c);
   int GT = 0;
-  // team mode wins when few draws leave the GPU latency-bound; with thousands of draws
-  // the one-warp kernel has the better occupancy (run 8: 21.5 vs 20.0 M draws/s at 4096)
-  if (S <= 2048 && plan_team<R>(c, S, &GT, &cfg)) {
+  // The kernel choice must NOT depend on S: a draw has to come out bit-identical however
+  // the batch is split over calls / GPUs.  The one-warp kernel is the default (better
+  // occupancy at thousands of draws: 21.5 vs 20.0 M draws/s at S=4096, run 8); the team
+  // kernel (lower latency for a handful of draws) is opt-in via CI_B200_PREDICT_TEAM=1.
+  if (c->predict_team && plan_team<R>(c, S, &GT, &cfg)) {
     auto tk = k_predict_team<R>;
     CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
     tk<<<(S + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
@@ -477,6 +480,7 @@ int ci_ctx_create(int device, ci_ctx** out) {
   if (se != cudaSuccess) { delete c; return fail(CI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
   if (const char* g = getenv("CI_B200_G")) c->force_G = atoi(g);
   if (const char* g = getenv("CI_B200_TEAM")) c->team_mode = atoi(g);
+  if (const char* g = getenv("CI_B200_PREDICT_TEAM")) c->predict_team = atoi(g);
   *out = c;
   return CI_OK;
 }

@@ -39,8 +39,8 @@ def time_logprob(name, T, n_cov, C, model, reps=20):
     prob = K.default_problem(y, X)
     t0 = time.perf_counter(); n = 0
     while time.perf_counter() - t0 < 3.0:
-      c_port.logpost_grad(prob, th, nthreads=os.cpu_count()); n += C
-    line += f"; CPU port {n/(time.perf_counter()-t0)/1e6:.4f} M evals/s on {os.cpu_count()} threads"
+      c_port.logpost_grad(prob, th, nthreads=len(os.sched_getaffinity(0))); n += C
+    line += f"; CPU port {n/(time.perf_counter()-t0)/1e6:.4f} M evals/s on {len(os.sched_getaffinity(0))} threads"
   print(line, flush=True)
 
 
