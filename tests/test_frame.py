@@ -1,0 +1,128 @@
+"""Host-side data preparation (frame.py) against the behaviours the reference's
+own unit tests pin: indices_test.py:47-153 (period parsing, alignment, error
+strings), standardize_test.py:24-118 (nan-aware ddof=1 scaler) and
+data_test.py:40-154 (column defaults, splits, validation).  CPU only."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from causalimpact_b200 import frame as fr
+from test_postproc_golden import GOLDEN, load_case
+
+
+@pytest.fixture(scope="module")
+def csv():
+  """The reference's 91-row, 10-second fixture, rebuilt from the golden file."""
+  g, data, _, _ = load_case([p for p in GOLDEN if p.endswith("postproc_csv.npz")][0])
+  data = data.copy()
+  data.iloc[[1, 3, 7], 0] = np.array([125.0, 128.0, 124.0])   # the golden has NaNs there
+  return data
+
+
+@pytest.mark.parametrize("period,msg", [
+    ((pd.Timestamp("2016-01-20 22:41:20"), pd.Timestamp("2016-01-21 22:41:20")),
+     "Aligned period end not found in the index."),
+    ((pd.Timestamp("2022-01-20 22:41:20"), pd.Timestamp("2022-01-21 22:41:20")),
+     "Aligned period start not found in the index."),
+    ((pd.Timestamp("2016-02-20 22:41:50"), pd.Timestamp("2016-02-20 22:41:20")),
+     "Period end must be after period start. "),
+])
+def test_align_period_errors(csv, period, msg):                    # indices_test.py:47-71
+  with pytest.raises(ValueError, match=msg):
+    fr.align_period(period, csv)
+
+
+@pytest.mark.parametrize("pre,post,msg", [
+    ((pd.Timestamp("2016-02-20 22:41:20"), pd.Timestamp("2016-02-20 22:41:50")),
+     (pd.Timestamp("2016-02-20 22:41:40"), pd.Timestamp("2016-02-20 22:41:50")),
+     "pre_period and post_period cannot overlap."),
+    ((pd.Timestamp("2016-02-20 22:41:20"), pd.Timestamp("2016-02-20 22:41:30")),
+     (pd.Timestamp("2016-02-20 22:41:40"), pd.Timestamp("2016-02-20 22:41:50")),
+     "pre_period must span at least 3 time points."),
+])
+def test_validate_periods_errors(csv, pre, post, msg):             # indices_test.py:73-95
+  with pytest.raises(ValueError, match=msg):
+    fr.validate_periods(pre, post, csv)
+
+
+@pytest.mark.parametrize("pre,post", [
+    ((0, 10), (11, 90)),
+    (("2016-02-20 22:41:20", "2016-02-20 22:43:00"), ("2016-02-20 22:43:10", "2016-02-20 22:56:20")),
+    (("2016-02-20 22:41:15", "2016-02-20 22:43:05"), ("2016-02-20 22:43:06", "2016-02-20 22:56:28")),
+    ((pd.Timestamp("2016-02-20 22:41:11"), pd.Timestamp("2016-02-20 22:43:07")),
+     (pd.Timestamp("2016-02-20 22:43:09"), pd.Timestamp("2016-02-20 22:56:23"))),
+])
+def test_period_formats_round_inwards(csv, pre, post):             # indices_test.py:97-139
+  got_pre, got_post = fr.parse_and_validate_date_data(csv, pre, post)
+  assert got_pre == (pd.Timestamp("2016-02-20 22:41:20"), pd.Timestamp("2016-02-20 22:43:00"))
+  assert got_post == (pd.Timestamp("2016-02-20 22:43:10"), pd.Timestamp("2016-02-20 22:56:20"))
+
+
+def test_integer_index(csv):                                       # indices_test.py:141-153
+  data = csv.copy()
+  data.index = np.arange(len(data))
+  assert fr.parse_and_validate_date_data(data, (0, 10), (11, 90)) == ((0, 10), (11, 90))
+  with pytest.raises(ValueError, match="Expected argument to be str, int, or datetime"):
+    fr.parse_and_validate_date_data(data, (0.5, 10), (11, 90))
+
+
+def test_scaler_matches_reference_semantics():                     # standardize_test.py:24-118
+  idx = pd.date_range("2022-01-01", periods=3, freq="h")
+  df = pd.DataFrame({"x1": [4., 5., 6.], "x2": [100., 101., 102.]}, index=idx)
+  sc = fr.Scaler()
+  z = sc.fit_transform(df)
+  pd.testing.assert_frame_equal(z, pd.DataFrame({"x1": [-1., 0., 1.], "x2": [-1., 0., 1.]},
+                                                index=idx))
+  pd.testing.assert_frame_equal(sc.inverse_transform(z), df)
+  ints = pd.DataFrame({"x": np.int32([4, 5, 6, 12])})
+  pd.testing.assert_frame_equal(
+      fr.Scaler().fit_transform(ints),
+      pd.DataFrame({"x": np.float64([-0.7651691780042776, -0.48692584054817667,
+                                     -0.20868250309207573, 1.46077752164453])}))
+  idx4 = pd.date_range("2022-01-01", periods=4, freq="h")
+  nan_df = pd.DataFrame({"x1": [4., 5., np.nan, 6.], "x2": [98., np.nan, 102., 106.]}, index=idx4)
+  pd.testing.assert_frame_equal(
+      fr.Scaler().fit_transform(nan_df),
+      pd.DataFrame({"x1": [-1., 0., np.nan, 1.], "x2": [-1., np.nan, 0., 1.]}, index=idx4))
+  with pytest.raises(fr.NotFittedError):
+    fr.Scaler().transform(df)
+  const = pd.DataFrame({"c": [3., 3., 3.]})
+  pd.testing.assert_frame_equal(fr.Scaler().fit_transform(const), const)   # zero variance: untouched
+
+
+def test_causalimpact_data_defaults_and_splits(csv):               # data_test.py:40-135
+  pre = (csv.index[0], csv.index[59]); post = (csv.index[60], csv.index[-1])
+  d = fr.CausalImpactData(csv, pre, post)
+  assert d.outcome_column == "y" and d.feature_columns == ["x1", "x2"]
+  assert len(d.pre_data) == 60 and len(d.after_pre_data) == 31 and d.num_steps_forecast == 31
+  assert list(d.feature_ts.columns) == ["x1", "x2", "intercept_"] and len(d.feature_ts) == 91
+  assert d.outcome_ts.time_series.dtype == np.float32 and d.outcome_ts.time_series.shape == (60,)
+  np.testing.assert_allclose(d.model_pre_data["y"].mean(), 0.0, atol=1e-12)
+  np.testing.assert_allclose(d.model_pre_data["y"].std(ddof=1), 1.0, rtol=1e-12)
+  y_ext, design, sd = d.engine_inputs(np.float32)
+  assert y_ext.shape == (91,) and np.isnan(y_ext[60:]).all() and not np.isnan(y_ext[:60]).any()
+  assert design.shape == (91, 3) and np.all(design[:, -1] == 1.0)
+  assert abs(sd - 1.0) < 1e-6
+  d2 = fr.CausalImpactData(csv, pre, post, outcome_column="x1")
+  assert d2.outcome_column == "x1" and d2.feature_columns == ["y", "x2"]
+  d3 = fr.CausalImpactData(csv["y"], pre, post)                    # a Series is accepted
+  assert d3.feature_ts is None and d3.feature_columns is None
+  d4 = fr.CausalImpactData(csv, pre, post, standardize_data=False)
+  assert d4.outcome_scaler is None and d4.model_pre_data is d4.pre_data
+
+
+def test_causalimpact_data_validation(csv):                        # data_test.py:90-154
+  pre = (csv.index[0], csv.index[59]); post = (csv.index[60], csv.index[-1])
+  with pytest.raises(KeyError):
+    fr.CausalImpactData(csv, pre, post, outcome_column="nope")
+  bad = csv.copy(); bad.iloc[5, 1] = np.nan
+  with pytest.raises(ValueError, match="cannot have any missing values"):
+    fr.CausalImpactData(bad, pre, post)
+  const = csv.copy(); const["y"] = 1.0
+  with pytest.raises(ValueError, match="cannot be constant"):
+    fr.CausalImpactData(const, pre, post)
+  text = csv.copy(); text["x1"] = "a"
+  with pytest.raises(ValueError, match="only numeric"):
+    fr.CausalImpactData(text, pre, post)
