@@ -116,3 +116,16 @@ def test_predict_team_and_single_warp_paths_agree(monkeypatch):
     np.testing.assert_allclose(out[mode][1], ot, rtol=1e-3, atol=3e-3)
     np.testing.assert_allclose(out[mode][2], om, rtol=1e-3, atol=3e-3)
   np.testing.assert_allclose(out["1"][1], out["0"][1], rtol=1e-4, atol=5e-4)
+
+
+def test_row_quantiles_large_draw_counts(engine):
+  """S between the float64 (16 384) and float32 (32 768) shared-memory limits is
+  sorted in float32; larger S is rejected with a clear error."""
+  rng = np.random.default_rng(0)
+  a = rng.normal(size=(20000, 3))
+  out = engine.row_quantiles(a, [0.025, 0.975])
+  want = np.quantile(a, [0.025, 0.975], axis=0).T
+  assert out.dtype == np.float64
+  np.testing.assert_allclose(out, want, rtol=2e-6, atol=2e-6)
+  with pytest.raises(cib.EngineError, match="does not fit"):
+    engine.row_quantiles(rng.normal(size=(40000, 2)), [0.5])
