@@ -109,10 +109,18 @@ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 // carveout: without the second attribute the driver may pick a carveout that fits a
 // single CTA per SM (ncu, round 1 run 7: occupancy_limit_shared_mem = 1 at 73 KB/CTA).
 template <typename Kern> cudaError_t set_smem(Kern kern, uint32_t bytes) {
+  // two driver calls per launch cost ~2 us of host time on the e2e path: remember what
+  // was last set for this kernel on this device and skip when nothing changes
+  static thread_local uint32_t last[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && last[dev] == bytes + 1u) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              (int)cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) last[dev] = bytes + 1u;
+  return e;
 }
 
 // Shared-memory plan for a kernel with G consumer warps and `extra_elems`
