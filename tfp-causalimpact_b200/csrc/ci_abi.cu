@@ -109,17 +109,25 @@ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 // carveout: without the second attribute the driver may pick a carveout that fits a
 // single CTA per SM (ncu, round 1 run 7: occupancy_limit_shared_mem = 1 at 73 KB/CTA).
 template <typename Kern> cudaError_t set_smem(Kern kern, uint32_t bytes) {
-  // two driver calls per launch cost ~2 us of host time on the e2e path: remember what
-  // was last set for this kernel on this device and skip when nothing changes
-  static thread_local uint32_t last[64] = {0};
+  // Two driver calls per launch cost ~2 us of host time on the e2e path: remember what
+  // was last set per (kernel ADDRESS, device) -- kernels with equal signatures share this
+  // template instantiation, so the key must be the pointer -- and skip when unchanged.
+  struct Slot { const void* fn; int dev; uint32_t bytes; };
+  static thread_local Slot cache[64] = {};
+  const void* fn = reinterpret_cast<const void*>(kern);
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && last[dev] == bytes + 1u) return cudaSuccess;
+  Slot* slot = nullptr;
+  for (auto& sl : cache) {
+    if (sl.fn == fn && sl.dev == dev) { slot = &sl; break; }
+    if (sl.fn == nullptr) { slot = &sl; break; }
+  }
+  if (slot && slot->fn == fn && slot->bytes == bytes) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess && dev >= 0 && dev < 64) last[dev] = bytes + 1u;
+  if (e == cudaSuccess && slot) { slot->fn = fn; slot->dev = dev; slot->bytes = bytes; }
   return e;
 }
 
