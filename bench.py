@@ -117,18 +117,51 @@ class ClockSampler:
             "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
+_BEST_THREADS = None
+
+
+def usable_cpus():
+  """CPUs this process may actually use: affinity mask, capped by a cgroup quota."""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+  try:
+    quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+    if quota != "max":
+      n = max(1, min(n, int(np.ceil(int(quota) / int(period)))))
+  except Exception:   # pylint: disable=broad-except
+    pass
+  return n
+
+
 def cpu_port_rate(cfg, seconds=10.0, nthreads=None):
   """Times oracle/_ref (C port of the oracle, float64, OpenMP over chains) on a
-  bounded sample of the SAME workload; returns evals/s and a description."""
+  bounded sample of the SAME workload; returns evals/s and a description.
+
+  The thread count is CALIBRATED once (0.3 s each for n, n/2, n/4, ... of the
+  usable CPUs, best kept): torchrun exports OMP_NUM_THREADS=1, and on a shared
+  box 128 spinning threads ran 180x slower than 64 (run 12) -- the baseline must
+  be the fastest the host can do, not an accident of the environment."""
+  global _BEST_THREADS
+  os.environ.setdefault("OMP_WAIT_POLICY", "passive")
   from oracle import c_port
   from oracle import kalman_np as K
-  if nthreads is None:
-    # explicit (torchrun exports OMP_NUM_THREADS=1); the CPUs this process may use, not
-    # os.cpu_count(): 128 threads on a 64-CPU affinity mask ran 6x slower (run 11)
-    nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
   y, X, th = make_inputs(cfg)
   prob = K.default_problem(y, X)
   c_port.logpost_grad(prob, th[:8])                     # load + warm
+  if nthreads is None:
+    if _BEST_THREADS is None:
+      best, n = (0.0, 1), usable_cpus()
+      cand = []
+      while n >= 1:
+        cand.append(n); n //= 2
+      for nt in cand:
+        t0 = time.perf_counter(); k = 0
+        while time.perf_counter() - t0 < 0.3:
+          c_port.logpost_grad(prob, th, nthreads=nt); k += th.shape[0]
+        rate = k / (time.perf_counter() - t0)
+        if rate > best[0]:
+          best = (rate, nt)
+      _BEST_THREADS = best[1]
+    nthreads = _BEST_THREADS
   t0 = time.perf_counter(); n = 0; used = 1
   while True:
     _, _, used = c_port.logpost_grad(prob, th, nthreads=nthreads)
@@ -136,7 +169,9 @@ def cpu_port_rate(cfg, seconds=10.0, nthreads=None):
     dt = time.perf_counter() - t0
     if dt >= seconds:
       break
-  return n / dt, used, f"{n} value+grad evals of the workload ({n // th.shape[0]} passes, {dt:.1f} s)"
+  return n / dt, used, (f"{n} value+grad evals of the workload ({n // th.shape[0]} passes, "
+                        f"{dt:.1f} s; {used} threads chosen by calibration out of "
+                        f"{usable_cpus()} usable CPUs)")
 
 
 def run_reference(args):

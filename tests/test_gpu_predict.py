@@ -119,13 +119,16 @@ def test_predict_team_and_single_warp_paths_agree(monkeypatch):
 
 
 def test_row_quantiles_large_draw_counts(engine):
-  """S between the float64 (16 384) and float32 (32 768) shared-memory limits is
-  sorted in float32; larger S is rejected with a clear error."""
+  """The radix select keeps a whole column in shared memory: float64 up to ~27k
+  draws, beyond that (up to ~55k) a float64 input is selected in float32; larger S
+  is rejected with a clear error."""
   rng = np.random.default_rng(0)
   a = rng.normal(size=(20000, 3))
   out = engine.row_quantiles(a, [0.025, 0.975])
-  want = np.quantile(a, [0.025, 0.975], axis=0).T
+  np.testing.assert_allclose(out, np.quantile(a, [0.025, 0.975], axis=0).T, rtol=1e-13)
+  b = rng.normal(size=(40000, 2))
+  out = engine.row_quantiles(b, [0.025, 0.5])
   assert out.dtype == np.float64
-  np.testing.assert_allclose(out, want, rtol=2e-6, atol=2e-6)
+  np.testing.assert_allclose(out, np.quantile(b, [0.025, 0.5], axis=0).T, rtol=2e-6, atol=2e-6)
   with pytest.raises(cib.EngineError, match="does not fit"):
-    engine.row_quantiles(rng.normal(size=(40000, 2)), [0.5])
+    engine.row_quantiles(rng.normal(size=(60000, 2)), [0.5])

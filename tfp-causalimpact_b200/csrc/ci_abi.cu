@@ -439,20 +439,19 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
 template <typename R>
 int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, int nq,
                      void* out_d, cudaStream_t st) {
-  int n_pad = 2;
-  while (n_pad < S) n_pad <<= 1;
-  const size_t bytes = (size_t)n_pad * sizeof(R);
-  if (bytes > (size_t)c->smem_optin - 1024)
-    return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles: S=%d does not fit the shared-memory sort", S);
+  // the whole column lives in shared memory as integer keys
+  const size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
+  if (bytes + 12 * 1024 > (size_t)c->smem_optin)
+    return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles: S=%d does not fit the shared-memory select "
+                "(max %d draws for this dtype)", S, (int)((c->smem_optin - 12 * 1024) / sizeof(R)));
   QuantArgs qa;
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q[i];
   auto kern = k_row_quantiles<R>;
   CU_TRY(set_smem(kern, (uint32_t)bytes));
-  int nt = n_pad / 2;
-  if (nt > 1024) nt = 1024;
-  if (nt < 32) nt = 32;
-  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, n_pad, qa, static_cast<R*>(out_d));
+  int nt = 1024;
+  while (nt > 64 && nt / 2 >= S) nt >>= 1;
+  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, 0, qa, static_cast<R*>(out_d));
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;

@@ -145,63 +145,138 @@ __global__ void k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta,
 }
 
 // ---------------------------------------------------------------------------
-// K5: one CTA per time column; bitonic sort of the column in shared memory.
+// K5: one CTA per time column.  The column's S values are gathered into shared
+// memory as order-preserving integer keys; every needed order statistic
+// (floor / ceil rank of each quantile) is found by an exact MSB-first RADIX
+// SELECT: per 11-bit digit one histogram sweep over the keys that still match
+// the prefix (shared-memory atomics, integer => deterministic), a warp-level
+// search for the bin that contains the rank, repeat.  3 sweeps per rank for
+// float32, 6 for float64 -- O(S) work per rank instead of the O(S log^2 S)
+// of a bitonic sort (round-1 run 12: the sort took 1.8 ms of a 2.8 ms
+// 10000-draw forecast).  Interpolation is numpy's _lerp, bit for bit.
 // ---------------------------------------------------------------------------
 struct QuantArgs { double q[8]; int nq; };
+
+template <typename R> struct KeyOf;
+template <> struct KeyOf<float> {
+  using type = uint32_t;
+  static constexpr int NPASS = 3;
+  static __device__ __forceinline__ uint32_t enc(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  }
+  static __device__ __forceinline__ float dec(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+  }
+  static __device__ __forceinline__ int shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+  static __device__ __forceinline__ int bits(int pass) { return pass == 2 ? 10 : 11; }
+  static __device__ __forceinline__ uint32_t nan_key() { return 0xffffffffu; }
+};
+template <> struct KeyOf<double> {
+  using type = unsigned long long;
+  static constexpr int NPASS = 6;
+  static __device__ __forceinline__ unsigned long long enc(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  }
+  static __device__ __forceinline__ double dec(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+  }
+  static __device__ __forceinline__ int shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
+  static __device__ __forceinline__ int bits(int pass) { return pass < 5 ? 11 : 9; }
+  static __device__ __forceinline__ unsigned long long nan_key() { return ~0ull; }
+};
+
+constexpr int QBINS = 2048;
+
+// k-th smallest key (0-based) among keys[0..n); executed by the whole CTA.
+template <typename R>
+__device__ typename KeyOf<R>::type radix_select(const typename KeyOf<R>::type* keys, int n, int k,
+                                                int* hist, int* res) {
+  using Key = typename KeyOf<R>::type;
+  Key prefix = 0, mask = 0;
+  int remaining = k;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int pass = 0; pass < KeyOf<R>::NPASS; ++pass) {
+    const int sh = KeyOf<R>::shift(pass), nb = 1 << KeyOf<R>::bits(pass);
+    for (int b = tid; b < nb; b += nt) hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      const Key key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> sh) & (Key)(nb - 1))], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {                       // warp 0 locates the bin holding the rank
+      const int per = nb / 32;
+      int loc = 0;
+      for (int b = 0; b < per; ++b) loc += hist[tid * per + b];
+      int inc = loc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (tid >= o) inc += t;
+      }
+      const int before = inc - loc;
+      if (remaining >= before && remaining < inc) {
+        int acc = before, b = tid * per;
+        while (acc + hist[b] <= remaining) { acc += hist[b]; ++b; }
+        res[0] = b; res[1] = acc;
+      }
+    }
+    __syncthreads();
+    prefix |= (Key)res[0] << sh;
+    mask |= (Key)(nb - 1) << sh;
+    remaining -= res[1];
+    __syncthreads();
+  }
+  return prefix;
+}
 
 template <typename R>
 __global__ void k_row_quantiles(const R* __restrict__ a, int S, int T, int n_pad, QuantArgs qa,
                                 R* __restrict__ out) {
+  using Key = typename KeyOf<R>::type;
   extern __shared__ __align__(16) unsigned char qsmem[];
-  R* buf = reinterpret_cast<R*>(qsmem);
+  Key* keys = reinterpret_cast<Key*>(qsmem);
+  __shared__ int hist[QBINS];
+  __shared__ int res[2];
   __shared__ int n_valid;
+  (void)n_pad;
   const int t = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) n_valid = 0;
   __syncthreads();
-  const R inf = sizeof(R) == 4 ? (R)CUDART_INF_F : (R)CUDART_INF;
   int cnt = 0;
-  for (int i = tid; i < n_pad; i += nt) {
-    R v = inf;
-    if (i < S) {
-      v = a[(size_t)i * T + t];
-      if (v == v) ++cnt; else v = inf;      // pandas skips NaN
-    }
-    buf[i] = v;
+  for (int i = tid; i < S; i += nt) {
+    const R v = a[(size_t)i * T + t];
+    const bool ok = (v == v);                      // pandas skips NaN
+    keys[i] = ok ? KeyOf<R>::enc(v) : KeyOf<R>::nan_key();
+    cnt += ok ? 1 : 0;
   }
-  if (cnt) atomicAdd(&n_valid, cnt);
+  cnt = __reduce_add_sync(FULL, cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(&n_valid, cnt);
   __syncthreads();
-  for (int k = 2; k <= n_pad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int pid = tid; pid < (n_pad >> 1); pid += nt) {
-        const int i = 2 * j * (pid / j) + (pid % j);
-        const int ixj = i + j;
-        const bool up = (i & k) == 0;
-        const R x = buf[i], y = buf[ixj];
-        if ((x > y) == up) { buf[i] = y; buf[ixj] = x; }
-      }
-      __syncthreads();
-    }
-  }
-  if (tid < qa.nq) {
-    const int n = n_valid;
-    R res;
+  const int n = n_valid;
+  for (int iq = 0; iq < qa.nq; ++iq) {
+    R res_v;
     if (n == 0) {
-      res = Num<R>::nan();
+      res_v = Num<R>::nan();
     } else {
-      const double pos = qa.q[tid] * (double)(n - 1);
+      const double pos = qa.q[iq] * (double)(n - 1);
       int lo = (int)floor(pos);
       if (lo < 0) lo = 0;
       if (lo > n - 1) lo = n - 1;
       const int hi = lo + 1 < n ? lo + 1 : n - 1;
       const R g = (R)(pos - (double)lo);
-      const R va = buf[lo], vb = buf[hi];
+      const R va = KeyOf<R>::dec(radix_select<R>(keys, S, lo, hist, res));
+      const R vb = (hi == lo || g == (R)0) ? va
+                                           : KeyOf<R>::dec(radix_select<R>(keys, S, hi, hist, res));
       const R diff = vb - va;
       // numpy.lib._function_base_impl._lerp
-      res = va + diff * g;
-      if (g >= (R)0.5) res = vb - diff * ((R)1 - g);
-      if (g == (R)0) res = va;   // guards inf - inf when hi is a +inf pad
+      res_v = va + diff * g;
+      if (g >= (R)0.5) res_v = vb - diff * ((R)1 - g);
+      if (g == (R)0) res_v = va;
     }
-    out[(size_t)t * qa.nq + tid] = res;
+    if (tid == 0) out[(size_t)t * qa.nq + iq] = res_v;
   }
 }
 
