@@ -144,6 +144,17 @@ template <typename R> __device__ __forceinline__ R u01(uint32_t x) {
 template <typename R> __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, R& z0,
                                                                  R& z1) {
   const R u = u01<R>(x0), w = u01<R>(x1);
+#ifdef CI_FAST_RNG
+  if (sizeof(R) == 4) {
+    // MUFU-based log / sin / cos: |error| ~ 1e-6 on a standard normal, far below the Monte-Carlo
+    // error of anything built from the draws; ~15 instructions instead of ~70.
+    const float rad_f = __fsqrt_rn(-2.0f * __logf((float)u));
+    float fs, fc;
+    __sincosf(6.283185307179586f * (float)w, &fs, &fc);
+    z0 = (R)(rad_f * fc); z1 = (R)(rad_f * fs);
+    return;
+  }
+#endif
   const R rad = Num<R>::sqrt((R)-2 * Num<R>::log(u));
   R s, c;
   if (sizeof(R) == 4) { float fs, fc; sincospif(2.0f * (float)w, &fs, &fc); s = fs; c = fc; }

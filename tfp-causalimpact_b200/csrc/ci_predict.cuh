@@ -21,8 +21,11 @@
 
 namespace ci {
 
+#ifndef CI_PREDICT_MINB
+#define CI_PREDICT_MINB 1
+#endif
 template <typename R>
-__global__ void __launch_bounds__(32 * (MAXG + 1), 1)
+__global__ void __launch_bounds__(32 * (MAXG + 1), CI_PREDICT_MINB)
 k_predict(ProbDev<R> pr, SmemCfg cfg, const R* __restrict__ theta, int S, uint64_t seed,
           uint64_t draw_id0, R* __restrict__ level, R* __restrict__ traj) {
   extern __shared__ __align__(128) unsigned char smem[];
