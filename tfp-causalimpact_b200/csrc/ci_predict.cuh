@@ -121,20 +121,47 @@ template <typename R>
 __global__ void k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta,
                                const R* __restrict__ level, int S, R* __restrict__ mean) {
   __shared__ double part[32][33];
+  __shared__ double wpart[32][8];
   __shared__ double wbar[MAX_DIM];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int p = pr.p, dim = pr.dim, T = pr.T;
   const int tid = ty * 32 + tx;
-  for (int j = tid; j < p; j += 1024) {
-    double a = 0.0;
-    for (int s = 0; s < S; ++s) a += (double)theta[(size_t)s * dim + j];
-    wbar[j] = a / S;
+  // wbar_j = mean_s w[s][j]: all 1024 threads stride over the draws, 8 covariates at a
+  // time; warp sums, then a fixed-order sum over the 32 warps (deterministic).
+  for (int j0 = 0; j0 < p; j0 += 8) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = tid; s < S; s += 1024) {
+      const R* row = theta + (size_t)s * dim + j0;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (j0 + jj < p) acc[jj] += (double)row[jj];
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const double v = warp_sum(acc[jj]);
+      if (tx == 0) wpart[ty][jj] = v;
+    }
+    __syncthreads();
+    if (tid < 8 && j0 + tid < p) {
+      double tot = 0.0;
+      for (int w = 0; w < 32; ++w) tot += wpart[w][tid];
+      wbar[j0 + tid] = tot / S;
+    }
+    __syncthreads();
   }
   const int t = blockIdx.x * 32 + tx;
-  double acc = 0.0;
-  if (t < T)
-    for (int s = ty; s < S; s += 32) acc += (double)level[(size_t)s * T + t];
-  part[ty][tx] = acc;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     // 4 loads in flight per thread
+  if (t < T) {
+    int s = ty;
+    for (; s + 96 < S; s += 128) {
+      a0 += (double)level[(size_t)s * T + t];
+      a1 += (double)level[(size_t)(s + 32) * T + t];
+      a2 += (double)level[(size_t)(s + 64) * T + t];
+      a3 += (double)level[(size_t)(s + 96) * T + t];
+    }
+    for (; s < S; s += 32) a0 += (double)level[(size_t)s * T + t];
+  }
+  part[ty][tx] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (ty == 0 && t < T) {
     double tot = 0.0;
