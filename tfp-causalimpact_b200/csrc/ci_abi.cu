@@ -406,7 +406,7 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
     CU_TRY(cudaGetLastError());
     c->launches++;
     if (mean_d) {
-      k_predict_mean<R><<<(c->prob.T + 31) / 32, dim3(32, 32), 0, st>>>(
+      k_predict_mean<R><<<(c->prob.T + MEAN_COLS - 1) / MEAN_COLS, dim3(MEAN_COLS, MEAN_ROWS), 0, st>>>(
           prt, static_cast<const R*>(theta_d), static_cast<const R*>(level_d), S,
           static_cast<R*>(mean_d));
       CU_TRY(cudaGetLastError());
@@ -427,7 +427,7 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
   CU_TRY(cudaGetLastError());
   c->launches++;
   if (mean_d) {
-    k_predict_mean<R><<<(c->prob.T + 31) / 32, dim3(32, 32), 0, st>>>(
+    k_predict_mean<R><<<(c->prob.T + MEAN_COLS - 1) / MEAN_COLS, dim3(MEAN_COLS, MEAN_ROWS), 0, st>>>(
         pr, static_cast<const R*>(theta_d), static_cast<const R*>(level_d), S,
         static_cast<R*>(mean_d));
     CU_TRY(cudaGetLastError());

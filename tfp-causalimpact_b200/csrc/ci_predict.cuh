@@ -117,15 +117,20 @@ affine_scan_down(m, c, lane);
 // mean_t = (1/S) sum_s level[s,t] + x_t . wbar,  wbar = (1/S) sum_s w_s
 // (lib.py:627: mixture mean == average of loc over draws).  Deterministic:
 // fixed summation order, no atomics.  block = (32 columns, 32 row-groups).
+// block = (MEAN_COLS columns, MEAN_ROWS row-groups): 8 consecutive floats of a row are one
+// 32-byte sector, so T/8 CTAs spread over the whole GPU while every load stays sector-exact.
+constexpr int MEAN_COLS = 8, MEAN_ROWS = 128;
+
 template <typename R>
-__global__ void k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta,
-                               const R* __restrict__ level, int S, R* __restrict__ mean) {
-  __shared__ double part[32][33];
+__global__ void __launch_bounds__(MEAN_COLS * MEAN_ROWS)
+k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta, const R* __restrict__ level, int S,
+               R* __restrict__ mean) {
+  __shared__ double part[MEAN_ROWS][MEAN_COLS + 1];
   __shared__ double wpart[32][8];
   __shared__ double wbar[MAX_DIM];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int p = pr.p, dim = pr.dim, T = pr.T;
-  const int tid = ty * 32 + tx;
+  const int tid = ty * MEAN_COLS + tx, lane = tid & 31, warp = tid >> 5;
   // wbar_j = mean_s w[s][j]: all 1024 threads stride over the draws, 8 covariates at a
   // time; warp sums, then a fixed-order sum over the 32 warps (deterministic).
   for (int j0 = 0; j0 < p; j0 += 8) {
@@ -139,7 +144,7 @@ __global__ void k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta,
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       const double v = warp_sum(acc[jj]);
-      if (tx == 0) wpart[ty][jj] = v;
+      if (lane == 0) wpart[warp][jj] = v;
     }
     __syncthreads();
     if (tid < 8 && j0 + tid < p) {
@@ -149,23 +154,23 @@ __global__ void k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta,
     }
     __syncthreads();
   }
-  const int t = blockIdx.x * 32 + tx;
+  const int t = blockIdx.x * MEAN_COLS + tx;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     // 4 loads in flight per thread
   if (t < T) {
     int s = ty;
-    for (; s + 96 < S; s += 128) {
+    for (; s + 3 * MEAN_ROWS < S; s += 4 * MEAN_ROWS) {
       a0 += (double)level[(size_t)s * T + t];
-      a1 += (double)level[(size_t)(s + 32) * T + t];
-      a2 += (double)level[(size_t)(s + 64) * T + t];
-      a3 += (double)level[(size_t)(s + 96) * T + t];
+      a1 += (double)level[(size_t)(s + MEAN_ROWS) * T + t];
+      a2 += (double)level[(size_t)(s + 2 * MEAN_ROWS) * T + t];
+      a3 += (double)level[(size_t)(s + 3 * MEAN_ROWS) * T + t];
     }
-    for (; s < S; s += 32) a0 += (double)level[(size_t)s * T + t];
+    for (; s < S; s += MEAN_ROWS) a0 += (double)level[(size_t)s * T + t];
   }
   part[ty][tx] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (ty == 0 && t < T) {
     double tot = 0.0;
-    for (int g = 0; g < 32; ++g) tot += part[g][tx];
+    for (int g = 0; g < MEAN_ROWS; ++g) tot += part[g][tx];
     tot /= S;
     const int b = t / TB, tl = t - b * TB;
     const R* row = pr.tiles + (size_t)b * tile_elems(p) + tile_off(tl, pr.ld);
