@@ -70,9 +70,16 @@ template <typename R, typename Elem>
 __device__ __forceinline__ double warp_cholesky(R* L, int n, int n_log, int lane, Elem elem) {
   double logdiag = 0.0;
   for (int c = 0; c < n; ++c) {
-    R part = 0;
-    for (int m = lane; m < c; m += 32) part = fma(L[c * n + m], L[c * n + m], part);
-    const R s = elem(c, c) - warp_sum(part);
+    R s = elem(c, c);
+    if (c <= 32) {
+      // small systems (the usual case: a handful of active features): every lane forms the
+      // pivot redundantly from broadcast shared-memory reads -- no shuffle reduction
+      for (int m = 0; m < c; ++m) s = fma(-L[c * n + m], L[c * n + m], s);
+    } else {
+      R part = 0;
+      for (int m = lane; m < c; m += 32) part = fma(L[c * n + m], L[c * n + m], part);
+      s -= warp_sum(part);
+    }
     const R dd = Num<R>::sqrt(s > (R)1e-30 ? s : (R)1e-30);
     const R rd = (R)1 / dd;
     if (c < n_log) logdiag += (double)Num<R>::log(dd);
@@ -216,9 +223,15 @@ k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t see
       }
       __syncwarp();
       for (int a = k - 1; a >= 0; --a) {
-        R part = 0;
-        for (int m = a + 1 + lane; m < k; m += 32) part = fma(gs.La[m * n + a], gs.vec[m], part);
-        const R xa = (gs.vec[a] - warp_sum(part)) / gs.La[a * n + a];
+        R acc = gs.vec[a];
+        if (k <= 32) {
+          for (int m = a + 1; m < k; ++m) acc = fma(-gs.La[m * n + a], gs.vec[m], acc);
+        } else {
+          R part = 0;
+          for (int m = a + 1 + lane; m < k; m += 32) part = fma(gs.La[m * n + a], gs.vec[m], part);
+          acc -= warp_sum(part);
+        }
+        const R xa = acc / gs.La[a * n + a];
         __syncwarp();
         if (lane == 0) gs.vec[a] = xa;
         __syncwarp();
