@@ -10,6 +10,7 @@ import causalimpact_b200 as cib
 from causalimpact_b200 import _engine
 from conftest import make_series, make_thetas
 from oracle import c_port, kalman_np as K
+import bench as _bench
 
 dev = torch.device("cuda", 0)
 s = torch.cuda.current_stream()
@@ -39,8 +40,8 @@ def time_logprob(name, T, n_cov, C, model, reps=20):
     prob = K.default_problem(y, X)
     t0 = time.perf_counter(); n = 0
     while time.perf_counter() - t0 < 3.0:
-      c_port.logpost_grad(prob, th, nthreads=len(os.sched_getaffinity(0))); n += C
-    line += f"; CPU port {n/(time.perf_counter()-t0)/1e6:.4f} M evals/s on {len(os.sched_getaffinity(0))} threads"
+      c_port.logpost_grad(prob, th, nthreads=_bench.usable_cpus()); n += C
+    line += f"; CPU port {n/(time.perf_counter()-t0)/1e6:.4f} M evals/s on {_bench.usable_cpus()} threads (cgroup-aware)"
   print(line, flush=True)
 
 
