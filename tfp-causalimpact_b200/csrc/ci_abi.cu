@@ -451,7 +451,7 @@ int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, 
   CU_TRY(set_smem(kern, (uint32_t)bytes));
   int nt = 1024;
   while (nt > 64 && nt / 2 >= S) nt >>= 1;
-  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, 0, qa, static_cast<R*>(out_d));
+  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, qa, static_cast<R*>(out_d));
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;

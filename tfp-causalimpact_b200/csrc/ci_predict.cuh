@@ -268,7 +268,7 @@ __device__ typename KeyOf<R>::type radix_select(const typename KeyOf<R>::type* k
 }
 
 template <typename R>
-__global__ void k_row_quantiles(const R* __restrict__ a, int S, int T, int n_pad, QuantArgs qa,
+__global__ void k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs qa,
                                 R* __restrict__ out) {
   using Key = typename KeyOf<R>::type;
   extern __shared__ __align__(16) unsigned char qsmem[];
@@ -276,7 +276,6 @@ __global__ void k_row_quantiles(const R* __restrict__ a, int S, int T, int n_pad
   __shared__ int hist[QBINS];
   __shared__ int res[2];
   __shared__ int n_valid;
-  (void)n_pad;
   const int t = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) n_valid = 0;
   __syncthreads();
