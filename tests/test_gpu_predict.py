@@ -132,3 +132,15 @@ def test_row_quantiles_large_draw_counts(engine):
   np.testing.assert_allclose(out, np.quantile(b, [0.025, 0.5], axis=0).T, rtol=2e-6, atol=2e-6)
   with pytest.raises(cib.EngineError, match="does not fit"):
     engine.row_quantiles(rng.normal(size=(60000, 2)), [0.5])
+
+
+def test_quantiles_of_standard_normal_draws(engine):
+  """posterior_processing_test.py:26-45 (the reference draws 1e7 N(0,1) per time
+  point and expects +-1.96 within 0.01); scaled to the 50 000 draws per column the
+  shared-memory select holds -- tolerance widened to the MC error of that size."""
+  rng = np.random.default_rng(1)
+  a = rng.standard_normal((50000, 10)).astype(np.float32)
+  q = engine.row_quantiles(a, [0.025, 0.975])
+  assert q.shape == (10, 2)
+  np.testing.assert_allclose(q[:, 0], -1.96, atol=0.04)
+  np.testing.assert_allclose(q[:, 1], 1.96, atol=0.04)
