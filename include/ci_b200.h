@@ -155,7 +155,9 @@ typedef struct {
   int32_t n_warmup;
   int32_t n_results;
   int32_t sparse;
-  int32_t reserved;
+  int32_t chain_major;    /* 0: outputs [n_results, C, .] (sweep-major, as documented above)
+                             1: outputs [C, n_results, .] -- every chain's draws contiguous,
+                                the layout the multi-GPU all-gather wants             */
   double nonzero_prob;
 } ci_gibbs_opts;
 
@@ -193,6 +195,56 @@ int ci_row_quantiles(ci_ctx* ctx, const void* a, int S, int T, int dtype,
                      const double* q, int nq, void* out);
 int ci_row_quantiles_d(ci_ctx* ctx, const void* a_d, int S, int T, int dtype,
                        const double* q, int nq, void* out_d, void* stream);
+
+/* Mean of the predictive mixture alone (lib.py:627): mean_t = avg_s level[s,t] + x_t . avg_s w_s,
+ * for draws whose level paths are already on the device (the Gibbs kernel's output).
+ * Deterministic: fixed summation order, float64 accumulation. */
+int ci_predictive_mean_d(ci_ctx* ctx, const void* theta_draws_d, const void* level_d,
+                         int S, void* mean_d, void* stream);
+
+/* ---- impact series + summary ----------------------------
+ * Replaces the O(S*T) part of _compute_impact (causalimpact_lib.py:635-705):
+ * un-standardising (posterior_processing.py:88-89 -> standardize.py:60-64),
+ * point / cumulative effect paths (lib.py:793-837), the three per-time quantile
+ * passes (posterior_processing.py:25-60 at lib.py:760, 886, 888) and the
+ * post-period summary statistics (lib.py:934-1093).  Float64 arithmetic.
+ *   traj     [S,T]  predictive draws on the standardized scale (args.dtype)
+ *   mean     [T]    predictive mean on the standardized scale  (args.dtype)
+ *   observed [T]    float64 HOST array: the outcome on the ORIGINAL scale over the
+ *                   modelled span; NaN where it does not count (gap between the
+ *                   periods, after the post-period, missing)
+ *   period   [T]    uint8 HOST array: 0 = before the post-period starts,
+ *                   1 = inside the post-period, 2 = after it; must be non-decreasing
+ *   series   [T,9]  float64 out: posterior_mean, posterior_lower, posterior_upper,
+ *                   point_effects_{mean,lower,upper}, cumulative_effects_{mean,lower,upper}
+ *                   (rows not yet NaN-ed by the gap / after-post rules of lib.py:899-915,
+ *                   which are O(T) host work)
+ *   summary  [CI_IMPACT_SUMMARY_LEN] float64 out:
+ *     [0..9]   (lower, upper) quantiles over draws of: post-period mean prediction, summed
+ *              prediction, mean effect, summed effect, relative effect
+ *     [10..14] their sample standard deviations (ddof = 1)
+ *     [15]     mean relative effect          [16],[17]  #draws with obs_sum <= / >= summed prediction
+ *     [18],[19] post-period mean / sum of the predictive mean
+ * S is limited to what one column of float64 keys fits in shared memory (~27 000).
+ */
+#define CI_IMPACT_SERIES_COLS 9
+#define CI_IMPACT_SUMMARY_LEN 20
+typedef struct {
+  int32_t S, T;
+  int32_t dtype;          /* CI_F32 / CI_F64: element type of traj and mean          */
+  int32_t reserved;
+  double scale, offset;   /* original = standardized * scale + offset (1, 0 = none)  */
+  double q_lo, q_hi;      /* alpha/2 and 1 - alpha/2                                 */
+  double obs_sum;         /* sum of the observed outcome over the post-period        */
+} ci_impact_args;
+
+int ci_impact(ci_ctx* ctx, const ci_impact_args* args, const void* traj, const void* mean,
+              const double* observed, const uint8_t* period, double* series,
+              double* summary);
+/* traj_d / mean_d / series_d / summary_d are device pointers; observed / period stay HOST. */
+int ci_impact_d(ci_ctx* ctx, const ci_impact_args* args, const void* traj_d,
+                const void* mean_d, const double* observed, const uint8_t* period,
+                double* series_d, double* summary_d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ import numpy as np
 
 from oracle import c_port
 from oracle import hmc_np as H
+from oracle import impact_np
 from oracle import kalman_np as K
 from oracle import quantiles_np
 from oracle import smoother_np as SM
@@ -63,3 +64,40 @@ class FakeEngine:
 
   def row_quantiles(self, a, q):
     return quantiles_np.row_quantiles(a, q)
+
+  # ---- the tensor-in / tensor-out surface api._train_causalimpact_sts drives (CPU tensors) ----
+  def hmc_run_t(self, theta0, **kw):
+    import torch
+    draws, stats = self.hmc_run(np.asarray(theta0), **kw)
+    rec = np.zeros(draws.shape[1], dtype=[("accept_rate", "f4"), ("step_size", "f4"),
+                                          ("n_divergent", "i4"), ("n_leapfrog", "i4")])
+    for k in rec.dtype.names:
+      rec[k] = stats[k]
+    return torch.from_numpy(np.ascontiguousarray(draws)), rec
+
+  def gibbs_run_t(self, n_chains, **kw):
+    import torch
+    draws, level, traj, incl = self.gibbs_run(n_chains, **kw)
+    cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.transpose(1, 0, 2)).reshape(
+        a.shape[0] * a.shape[1], a.shape[2]))
+    return cm(draws), cm(level), cm(traj), incl
+
+  def posterior_predict_t(self, theta_draws, *, seed, draw_id0=0):
+    import torch
+    l, t, _ = self.posterior_predict(np.asarray(theta_draws), seed=seed, draw_id0=draw_id0)
+    return torch.from_numpy(l), torch.from_numpy(t)
+
+  def predictive_mean_t(self, theta_draws, level):
+    import torch
+    th, lv = np.asarray(theta_draws, np.float64), np.asarray(level, np.float64)
+    m = lv.mean(axis=0)
+    if self.spec.p:
+      m = m + self.prob.X @ th[:, :self.spec.p].mean(axis=0)
+    return torch.from_numpy(m.astype(self.spec.np_dtype))
+
+  def to_host(self, t):
+    return t.detach().cpu().numpy()
+
+  def impact(self, traj, mean, meta):
+    return impact_np.impact_arrays(np.asarray(traj), np.asarray(mean), meta.observed, meta.period,
+                                   meta.scale, meta.offset, meta.q_lo, meta.q_hi, meta.obs_sum)

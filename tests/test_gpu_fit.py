@@ -14,9 +14,8 @@ from causalimpact_b200 import frame as fr
 from causalimpact_b200 import impact
 from oracle import gibbs_np as G
 from oracle import kalman_np as K
-from oracle import quantiles_np
 from oracle import smoother_np as SM
-from test_postproc_golden import GOLDEN, load_case
+from test_postproc_golden import GOLDEN, load_case, oracle_impact
 
 pytestmark = pytest.mark.gpu
 
@@ -169,12 +168,12 @@ def test_missing_pre_period_observations():            # lib_test.py:814-844
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[9:-4] for p in GOLDEN])
 def test_postprocessing_on_gpu_matches_reference_golden(engine, path):
-  """_compute_impact with the CUDA quantile kernel (float64) vs the reference's
-  own outputs (golden files)."""
+  """_compute_impact through ci_impact (host buffers, float64) vs the reference's own
+  outputs (golden files)."""
   g, data, pre, post = load_case(path)
   cid = fr.CausalImpactData(data, pre, post, standardize_data=bool(g["standardize"]))
   series, summary = impact.compute_impact(g["posterior_means"], g["posterior_trajectories"], cid,
-                                          float(g["alpha"]), engine.row_quantiles)
+                                          float(g["alpha"]), engine.impact)
   cols = [str(c) for c in g["series_columns"]]
   rtol, atol = (1e-11, 1e-11) if bool(g["standardize"]) else \
       (1e-5, 4e-6 * float(np.nanmax(np.abs(g["series_values"]))))
@@ -200,7 +199,7 @@ def test_statistical_parity_with_restated_reference_sampler():
   rng = np.random.default_rng(0)
   loc = gb["level"] + gb["w"] @ design.T
   traj = loc + np.sqrt(gb["s_e"])[:, None] * rng.normal(size=loc.shape)
-  ser_o, sum_o = impact.compute_impact(loc.mean(0), traj, cid, 0.05, quantiles_np.row_quantiles)
+  ser_o, sum_o = impact.compute_impact(loc.mean(0), traj, cid, 0.05, oracle_impact)
   sd_y = float(np.nanstd(df["y"].values[:70], ddof=1))
   for col in ("abs_effect", "abs_effect_lower", "abs_effect_upper", "predicted"):
     a, b = res.summary.loc["average", col], sum_o.loc["average", col]
@@ -285,7 +284,7 @@ def test_auto_sampler_reproduces_reference_spike_and_slab_posterior():
   loc = gb["level"] + gb["w"] @ design.T
   rng2 = np.random.default_rng(0)
   traj = loc + np.sqrt(gb["s_e"])[:, None] * rng2.normal(size=loc.shape)
-  ser_o, sum_o = impact.compute_impact(loc.mean(0), traj, cid, 0.05, quantiles_np.row_quantiles)
+  ser_o, sum_o = impact.compute_impact(loc.mean(0), traj, cid, 0.05, oracle_impact)
   sd_y = float(np.std(y[:210], ddof=1))
   for col in ("abs_effect", "abs_effect_lower", "abs_effect_upper", "predicted"):
     a, b = res.summary.loc["average", col], sum_o.loc["average", col]

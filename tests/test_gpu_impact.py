@@ -1,0 +1,177 @@
+"""ci_impact (impact series + summary on the device) vs
+  (a) the REFERENCE's own outputs -- tests/golden/postproc_*.npz, produced by running
+      causalimpact_lib._compute_impact unmodified (oracle/make_golden_postproc.py);
+  (b) the numpy oracle oracle/impact_np.py (itself pinned to (a) in
+      tests/test_postproc_golden.py) on seeded random inputs: NaNs in the observed
+      series, a gap between the periods, rows after the post-period, float32 and
+      float64 draws, 1 draw, sizes up to BASELINE config 5 (10 000 draws, T = 2000).
+Tolerance: float64 rounding of differently-ordered sums -- rtol 1e-11 (stated per test).
+All calls go through the C ABI (host-pointer ci_impact and device-pointer ci_impact_d)."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from causalimpact_b200 import EngineError
+from causalimpact_b200 import frame as fr
+from causalimpact_b200 import impact
+from oracle import impact_np
+from test_postproc_golden import GOLDEN, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def make_meta(T, t_pre, t_post0, t_post1, rng, scale=3.7, offset=101.5, nan_obs=3, alpha=0.05):
+  """Period layout: [0, t_pre) pre, [t_pre, t_post0) gap, [t_post0, t_post1) post, rest after."""
+  observed = offset + scale * rng.normal(size=T)
+  observed[t_pre:t_post0] = np.nan
+  observed[t_post1:] = np.nan
+  if nan_obs:
+    observed[rng.choice(np.arange(1, t_pre), size=nan_obs, replace=False)] = np.nan
+    observed[t_post0 + 1] = np.nan                      # a missing point inside the post-period
+  period = np.zeros(T, np.uint8)
+  period[t_post0:t_post1] = 1
+  period[t_post1:] = 2
+  y_post = observed[t_post0:t_post1]
+  return types.SimpleNamespace(observed=observed, period=period, scale=scale, offset=offset,
+                               q_lo=impact._percentile_q(alpha / 2),
+                               q_hi=impact._percentile_q(1 - alpha / 2),
+                               obs_sum=float(np.nansum(y_post)))
+
+
+def oracle(traj, mean, m):
+  return impact_np.impact_arrays(traj, mean, m.observed, m.period, m.scale, m.offset, m.q_lo,
+                                 m.q_hi, m.obs_sum)
+
+
+def check(got, want, rtol=1e-11, atol=1e-11):
+  np.testing.assert_allclose(got[0], want[0], rtol=rtol, atol=atol, equal_nan=True)
+  np.testing.assert_allclose(got[1], want[1], rtol=rtol, atol=atol, equal_nan=True)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[9:-4] for p in GOLDEN])
+def test_reference_golden_through_host_abi(engine, path):
+  """The reference's own series / summary frames, reproduced by ci_impact + O(T) packaging."""
+  g, data, pre, post = load_case(path)
+  cid = fr.CausalImpactData(data, pre, post, standardize_data=bool(g["standardize"]))
+  series, summary = impact.compute_impact(g["posterior_means"], g["posterior_trajectories"], cid,
+                                          float(g["alpha"]), engine.impact)
+  cols = [str(c) for c in g["series_columns"]]
+  # standardize=False: the reference itself stays in float32 pandas arithmetic there
+  rtol, atol = (1e-11, 1e-11) if bool(g["standardize"]) else \
+      (1e-5, 4e-6 * float(np.nanmax(np.abs(g["series_values"]))))
+  np.testing.assert_allclose(series[cols].values.astype(float), g["series_values"], rtol=rtol,
+                             atol=atol, equal_nan=True)
+  np.testing.assert_allclose(summary.values.astype(float), g["summary_values"], rtol=rtol,
+                             atol=atol, equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("S,T,t_pre,t_post0,t_post1", [
+    (1, 40, 20, 25, 35), (2, 33, 20, 20, 33), (7, 100, 70, 70, 100), (900, 100, 71, 71, 100),
+    (1000, 517, 300, 310, 500), (4096, 257, 129, 129, 257)])
+def test_device_path_matches_oracle(engine, dtype, S, T, t_pre, t_post0, t_post1):
+  import torch
+  rng = np.random.default_rng(S * 1000 + T)
+  m = make_meta(T, t_pre, t_post0, t_post1, rng)
+  traj = rng.normal(size=(S, T)).astype(dtype)
+  traj[:, t_post0:] += 0.5
+  mean = traj.mean(axis=0).astype(dtype)
+  want = oracle(traj, mean, m)
+  # device pointers (ci_impact_d) and host pointers (ci_impact) must agree with the oracle
+  got_d = engine.impact(torch.from_numpy(traj).cuda(), torch.from_numpy(mean).cuda(), m)
+  got_h = engine.impact(traj, mean, m)
+  check(got_d, want)
+  check(got_h, want)
+  np.testing.assert_array_equal(got_d[0], got_h[0])
+  np.testing.assert_array_equal(got_d[1], got_h[1])
+
+
+def test_ties_and_constant_columns(engine):
+  """Heavily tied draws (the Gibbs sampler repeats values): order statistics with ties."""
+  rng = np.random.default_rng(5)
+  S, T = 500, 64
+  m = make_meta(T, 40, 40, 64, rng, nan_obs=0)
+  traj = rng.integers(-3, 4, size=(S, T)).astype(np.float32)
+  traj[:, 7] = 1.25
+  mean = traj.mean(axis=0).astype(np.float32)
+  check(engine.impact(traj, mean, m), oracle(traj, mean, m))
+
+
+def test_no_standardisation_and_other_alpha(engine):
+  rng = np.random.default_rng(6)
+  S, T = 333, 90
+  m = make_meta(T, 50, 55, 80, rng, scale=1.0, offset=0.0, alpha=0.2)
+  traj = (100 + rng.normal(size=(S, T))).astype(np.float64)
+  mean = traj.mean(axis=0)
+  check(engine.impact(traj, mean, m), oracle(traj, mean, m))
+
+
+def test_config5_scale(engine):
+  """BASELINE config 5 shape: 10 000 draws, T = 2000 (float32 draws, device resident)."""
+  import torch
+  rng = np.random.default_rng(7)
+  S, T = 10000, 2000
+  m = make_meta(T, 1400, 1400, 2000, rng, nan_obs=14)
+  traj = rng.normal(size=(S, T)).astype(np.float32)
+  traj += np.linspace(0, 1, T, dtype=np.float32)[None, :]
+  mean = traj.mean(axis=0).astype(np.float32)
+  got = engine.impact(torch.from_numpy(traj).cuda(), torch.from_numpy(mean).cuda(), m)
+  check(got, oracle(traj, mean, m), rtol=1e-10, atol=1e-9)
+  # size-independent properties: interval ordering, cumulative = running sum of point means
+  s9 = got[0]
+  assert np.all(s9[:, 1] <= s9[:, 0] + 1e-9) and np.all(s9[:, 0] <= s9[:, 2] + 1e-9)
+  ok = ~np.isnan(s9[:, 3]) & (m.period > 0)
+  np.testing.assert_allclose(np.nancumsum(np.where(ok, s9[:, 3], 0.0))[ok], s9[ok, 6], rtol=1e-10)
+
+
+def test_rejects_bad_input(engine):
+  rng = np.random.default_rng(8)
+  m = make_meta(30, 20, 20, 30, rng)
+  traj = rng.normal(size=(5, 30)).astype(np.float32)
+  bad = types.SimpleNamespace(**vars(m)); bad.period = m.period[::-1].copy()
+  with pytest.raises(EngineError, match="non-decreasing"):
+    engine.impact(traj, traj[0], bad)
+  bad = types.SimpleNamespace(**vars(m)); bad.period = np.zeros(30, np.uint8)
+  with pytest.raises(EngineError, match="post-period is empty"):
+    engine.impact(traj, traj[0], bad)
+  bad = types.SimpleNamespace(**vars(m)); bad.q_hi = 1.5
+  with pytest.raises(EngineError, match="quantiles"):
+    engine.impact(traj, traj[0], bad)
+  with pytest.raises(EngineError, match="exceeds"):
+    engine.impact(np.zeros((40000, 30), np.float32), traj[0], m)
+
+
+def test_fit_keeps_trajectories_on_device():
+  """fit_causalimpact: the trajectories go sampler -> ci_impact without a host copy; the
+  waist function hands them out as DeviceArray (np.asarray copies on demand)."""
+  import pandas as pd
+  import causalimpact_b200 as ci
+  from causalimpact_b200 import api
+  rng = np.random.default_rng(9)
+  n = 120
+  x = 100 + np.cumsum(rng.normal(size=n))
+  y = 1.2 * x + rng.normal(size=n); y[80:] += 6
+  df = pd.DataFrame({"y": y, "x": x})
+  cid = fr.CausalImpactData(df, (0, 79), (80, 119))
+  samples, means, traj = api._train_causalimpact_sts(
+      ci_data=cid, prior_level_sd=0.01, seed=3, num_results=200, num_warmup_steps=50)
+  assert isinstance(traj, ci.DeviceArray) and traj.tensor.is_cuda
+  assert traj.shape == (200, n) and means.shape == (n,)
+  host = np.asarray(traj)
+  ser_d, sum_d = impact.compute_impact(means, traj, cid, 0.05, api._resolve_engine(None).impact)
+  ser_o, sum_o = impact.compute_impact(
+      np.asarray(means), host, cid, 0.05,
+      lambda t, mu, m: impact_np.impact_arrays(t, mu, m.observed, m.period, m.scale, m.offset,
+                                               m.q_lo, m.q_hi, m.obs_sum))
+  vals = impact.SERIES_VALUE_COLUMNS
+  np.testing.assert_allclose(ser_d[vals].values.astype(float), ser_o[vals].values.astype(float),
+                             rtol=1e-11, atol=1e-11, equal_nan=True)
+  np.testing.assert_allclose(sum_d.values.astype(float), sum_o.values.astype(float), rtol=1e-11)
+  # predictive mean kernel == float64 average of level + X.w over the same draws
+  lvl = samples.level.numpy().astype(np.float64)
+  w = samples.weights.numpy().astype(np.float64)
+  _, design, _ = cid.engine_inputs(np.float32)
+  np.testing.assert_allclose(np.asarray(means), lvl.mean(0) + design @ w.mean(0), rtol=2e-5,
+                             atol=2e-5)

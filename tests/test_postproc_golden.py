@@ -1,7 +1,8 @@
-"""Host logic vs golden vectors produced by the REFERENCE's own code
-(oracle/make_golden_postproc.py ran causalimpact_lib._compute_impact and
-data.CausalImpactData unmodified).  CPU: the quantile kernel is replaced by the
-pandas oracle; the GPU variant of this test lives in test_gpu_fit.py."""
+"""Host logic + the impact oracle vs golden vectors produced by the REFERENCE's own
+code (oracle/make_golden_postproc.py ran causalimpact_lib._compute_impact and
+data.CausalImpactData unmodified).  CPU: the device call ci_impact is replaced by its
+numpy oracle (oracle/impact_np.py) -- this pins the oracle; the GPU variant of this
+test (the real kernels against the same goldens) lives in test_gpu_impact.py."""
 import glob
 import os
 
@@ -11,9 +12,14 @@ import pytest
 
 from causalimpact_b200 import frame as fr
 from causalimpact_b200 import impact
-from oracle import quantiles_np
+from oracle import impact_np
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "postproc_*.npz")))
+
+
+def oracle_impact(traj, mean, meta):
+  return impact_np.impact_arrays(traj, mean, meta.observed, meta.period, meta.scale, meta.offset,
+                                 meta.q_lo, meta.q_hi, meta.obs_sum)
 
 
 def load_case(path):
@@ -45,7 +51,7 @@ def test_compute_impact_matches_reference(path):
   g, data, pre, post = load_case(path)
   ci = fr.CausalImpactData(data, pre, post, standardize_data=bool(g["standardize"]))
   series, summary = impact.compute_impact(g["posterior_means"], g["posterior_trajectories"], ci,
-                                          float(g["alpha"]), quantiles_np.row_quantiles)
+                                          float(g["alpha"]), oracle_impact)
   cols = [str(c) for c in g["series_columns"]]
   assert list(series.columns[:len(cols)]) == cols
   # standardize_data=True: the reference un-scales into float64 first, so we agree
@@ -70,7 +76,7 @@ def test_alpha_is_validated():
   ci = fr.CausalImpactData(data, pre, post)
   with pytest.raises(ValueError, match="alpha"):
     impact.compute_impact(g["posterior_means"], g["posterior_trajectories"], ci, 1.5,
-                          quantiles_np.row_quantiles)
+                          oracle_impact)
 
 
 def test_text_summary_layout():

@@ -41,7 +41,16 @@ class CiHmcOpts(C.Structure):
 
 class CiGibbsOpts(C.Structure):
   _fields_ = [("n_warmup", C.c_int32), ("n_results", C.c_int32), ("sparse", C.c_int32),
-              ("reserved", C.c_int32), ("nonzero_prob", C.c_double)]
+              ("chain_major", C.c_int32), ("nonzero_prob", C.c_double)]
+
+
+class CiImpactArgs(C.Structure):
+  _fields_ = [("S", C.c_int32), ("T", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
+              ("scale", C.c_double), ("offset", C.c_double), ("q_lo", C.c_double),
+              ("q_hi", C.c_double), ("obs_sum", C.c_double)]
+
+
+IMPACT_SERIES_COLS, IMPACT_SUMMARY_LEN = 9, 20
 
 
 class CiHmcStats(C.Structure):
@@ -57,7 +66,7 @@ EXPORTS = (
     "ci_version", "ci_last_error", "ci_device_count", "ci_ctx_create", "ci_ctx_destroy",
     "ci_launch_count", "ci_set_data", "ci_logprob", "ci_logprob_grad", "ci_logprob_grad_d",
     "ci_hmc_run", "ci_hmc_run_d", "ci_gibbs_run", "ci_gibbs_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
-    "ci_row_quantiles", "ci_row_quantiles_d",
+    "ci_row_quantiles", "ci_row_quantiles_d", "ci_predictive_mean_d", "ci_impact", "ci_impact_d",
 )
 
 _lib = None
@@ -95,6 +104,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
   lib.ci_posterior_predict_d.argtypes = [vp, vp, i32, u64, u64, vp, vp, vp, vp]
   lib.ci_row_quantiles.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_double), i32, vp]
   lib.ci_row_quantiles_d.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_double), i32, vp, vp]
+  lib.ci_predictive_mean_d.argtypes = [vp, vp, vp, i32, vp, vp]
+  lib.ci_impact.argtypes = [vp, C.POINTER(CiImpactArgs), vp, vp, vp, vp, vp, vp]
+  lib.ci_impact_d.argtypes = [vp, C.POINTER(CiImpactArgs), vp, vp, vp, vp, vp, vp, vp]
   _lib = lib
   return lib
 
@@ -144,6 +156,36 @@ class ProblemSpec:
 
 def _ptr(a: Optional[np.ndarray]):
   return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceArray:
+  """An array that lives in the engine's HBM (a torch CUDA tensor inside -- torch is
+  only the allocator).  Quacks enough like the ndarray / tf.Tensor the reference
+  returns (``.shape``, ``.numpy()``, ``np.asarray``) that callers which do want the
+  values on the host get them, copied on demand; ``fit_causalimpact`` itself never
+  asks: the trajectories go from the sampler kernels to ``ci_impact`` without leaving
+  the device."""
+
+  def __init__(self, tensor):
+    self.tensor = tensor
+
+  @property
+  def shape(self):
+    return tuple(self.tensor.shape)
+
+  @property
+  def dtype(self):
+    return np.dtype(str(self.tensor.dtype).replace("torch.", ""))
+
+  def __len__(self):
+    return int(self.tensor.shape[0])
+
+  def numpy(self) -> np.ndarray:
+    return self.tensor.detach().cpu().numpy()
+
+  def __array__(self, dtype=None, copy=None):
+    a = self.numpy()
+    return a if dtype is None else a.astype(dtype, copy=False)
 
 
 class Engine:
@@ -278,6 +320,134 @@ class Engine:
     self._check(self._lib.ci_posterior_predict(self._ctx, _ptr(th), S, seed & (2**64 - 1),
                                                draw_id0, _ptr(level), _ptr(traj), _ptr(mean)))
     return level, traj, mean
+
+  # -- device-resident variants (torch CUDA tensors as buffers, *_d entry points) ---
+  def _torch_dev(self):
+    import torch
+    return torch, torch.device("cuda", self.device)
+
+  def _tdtype(self, torch):
+    return torch.float64 if self.spec.dtype == F64 else torch.float32
+
+  def _stream(self, torch) -> int:
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def _as_dev(self, a):
+    """numpy / tensor -> contiguous tensor of the problem dtype on this device."""
+    torch, dev = self._torch_dev()
+    if not hasattr(a, "data_ptr"):
+      a = torch.from_numpy(np.ascontiguousarray(a, dtype=self.spec.np_dtype))
+    return a.to(device=dev, dtype=self._tdtype(torch)).contiguous()
+
+  def hmc_run_t(self, theta0, *, n_warmup: int, n_results: int, seed: int, chain_id0: int = 0,
+                max_leapfrog: int = 8, init_step: float = 0.05, target_accept: float = 0.8,
+                adapt_mass: bool = True):
+    """ci_hmc_run_d: returns (draws tensor [n_results, C, dim] on the device, stats ndarray)."""
+    torch, dev = self._torch_dev()
+    th = self._as_dev(np.atleast_2d(theta0) if not hasattr(theta0, "data_ptr") else theta0)
+    n = th.shape[0]
+    draws = torch.empty((n_results, n, self.spec.dim), dtype=th.dtype, device=dev)
+    stats = torch.zeros(n * HMC_STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    opts = CiHmcOpts(n_warmup=n_warmup, n_results=n_results, max_leapfrog=max_leapfrog,
+                     adapt_mass=int(adapt_mass), init_step=init_step,
+                     target_accept=target_accept)
+    self._check(self._lib.ci_hmc_run_d(self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0,
+                                       th.data_ptr(), n, draws.data_ptr(), stats.data_ptr(),
+                                       self._stream(torch)))
+    return draws, stats.cpu().numpy().view(HMC_STATS_DTYPE)
+
+  def gibbs_run_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
+                  chain_id0: int = 0, sparse: bool = True, nonzero_prob: Optional[float] = None):
+    """ci_gibbs_run_d, chain-major: returns (theta [C*n_results, dim], level [C*n_results, T],
+    traj [C*n_results, T]) device tensors -- row c*n_results + i is kept sweep i of chain c --
+    and incl [C, p] ndarray."""
+    torch, dev = self._torch_dev()
+    sp, dt = self.spec, self._tdtype(torch)
+    if nonzero_prob is None:
+      nonzero_prob = min(1.0, 3.0 / sp.p) if sp.p else 1.0     # lib.py:449-450
+    rows = n_chains * n_results
+    draws = torch.empty((rows, sp.dim), dtype=dt, device=dev)
+    level = torch.empty((rows, sp.T), dtype=dt, device=dev)
+    traj = torch.empty((rows, sp.T), dtype=dt, device=dev)
+    incl = torch.zeros((n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
+    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
+                       nonzero_prob=float(nonzero_prob))
+    self._check(self._lib.ci_gibbs_run_d(self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0,
+                                         n_chains, draws.data_ptr(), level.data_ptr(),
+                                         traj.data_ptr(), incl.data_ptr(), self._stream(torch)))
+    return draws, level, traj, incl.cpu().numpy()[:, :sp.p]
+
+  def posterior_predict_t(self, theta_draws, *, seed: int, draw_id0: int = 0):
+    """ci_posterior_predict_d: (level [S,T], traj [S,T]) device tensors."""
+    torch, dev = self._torch_dev()
+    th = self._as_dev(theta_draws)
+    S, T = th.shape[0], self.spec.T
+    level = torch.empty((S, T), dtype=th.dtype, device=dev)
+    traj = torch.empty((S, T), dtype=th.dtype, device=dev)
+    self._check(self._lib.ci_posterior_predict_d(self._ctx, th.data_ptr(), S, seed & (2**64 - 1),
+                                                 draw_id0, level.data_ptr(), traj.data_ptr(),
+                                                 None, self._stream(torch)))
+    return level, traj
+
+  def predictive_mean_t(self, theta_draws, level):
+    """ci_predictive_mean_d (lib.py:627): [T] device tensor."""
+    torch, dev = self._torch_dev()
+    th, lv = self._as_dev(theta_draws), self._as_dev(level)
+    mean = torch.empty((self.spec.T,), dtype=th.dtype, device=dev)
+    self._check(self._lib.ci_predictive_mean_d(self._ctx, th.data_ptr(), lv.data_ptr(),
+                                               th.shape[0], mean.data_ptr(), self._stream(torch)))
+    return mean
+
+  def to_host(self, t) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+  # -- impact series + summary (SURVEY 8 f1) -----------------------------------
+  def impact(self, traj, mean, meta) -> Tuple[np.ndarray, np.ndarray]:
+    """ci_impact: (series [T,9], summary [20]) float64 from predictive draws [S,T] and mean [T]
+    on the standardized scale.  ``traj`` / ``mean`` may be DeviceArray / torch CUDA tensors
+    (no copy: ci_impact_d) or host arrays (ci_impact uploads them once).  ``meta``:
+    impact.ImpactMeta."""
+    if isinstance(traj, DeviceArray):
+      traj = traj.tensor
+    if isinstance(mean, DeviceArray):
+      mean = mean.tensor
+    on_dev = hasattr(traj, "data_ptr")
+    obs = np.ascontiguousarray(meta.observed, dtype=np.float64)
+    per = np.ascontiguousarray(meta.period, dtype=np.uint8)
+    if on_dev:
+      torch, dev = self._torch_dev()
+      if traj.dtype not in (torch.float32, torch.float64):
+        traj = traj.to(torch.float32)
+      traj = traj.to(dev).contiguous()
+      mean_t = mean if hasattr(mean, "data_ptr") else torch.from_numpy(np.ascontiguousarray(mean))
+      mean_t = mean_t.to(device=dev, dtype=traj.dtype).contiguous().reshape(-1)
+      S, T = traj.shape
+      dt = F64 if traj.dtype == torch.float64 else F32
+    else:
+      traj = np.ascontiguousarray(traj)
+      if traj.dtype not in (np.float32, np.float64):
+        traj = traj.astype(np.float64)
+      mean_h = np.ascontiguousarray(np.asarray(mean).reshape(-1), dtype=traj.dtype)
+      S, T = traj.shape
+      dt = F64 if traj.dtype == np.float64 else F32
+    if obs.shape != (T,) or per.shape != (T,):
+      raise ValueError(f"observed / period must be [{T}]")
+    args = CiImpactArgs(S=S, T=T, dtype=dt, reserved=0, scale=meta.scale, offset=meta.offset,
+                        q_lo=meta.q_lo, q_hi=meta.q_hi, obs_sum=meta.obs_sum)
+    if on_dev:
+      out = torch.empty(T * IMPACT_SERIES_COLS + IMPACT_SUMMARY_LEN, dtype=torch.float64,
+                        device=dev)
+      self._check(self._lib.ci_impact_d(
+          self._ctx, C.byref(args), traj.data_ptr(), mean_t.data_ptr(), _ptr(obs), _ptr(per),
+          out.data_ptr(), out.data_ptr() + 8 * T * IMPACT_SERIES_COLS, self._stream(torch)))
+      out = out.cpu().numpy()
+      return out[:T * IMPACT_SERIES_COLS].reshape(T, IMPACT_SERIES_COLS), \
+          out[T * IMPACT_SERIES_COLS:]
+    series = np.empty((T, IMPACT_SERIES_COLS), dtype=np.float64)
+    summ = np.empty(IMPACT_SUMMARY_LEN, dtype=np.float64)
+    self._check(self._lib.ci_impact(self._ctx, C.byref(args), _ptr(traj), _ptr(mean_h), _ptr(obs),
+                                    _ptr(per), _ptr(series), _ptr(summ)))
+    return series, summ
 
   # -- K5 --------------------------------------------------------------------
   def row_quantiles(self, a, q) -> np.ndarray:

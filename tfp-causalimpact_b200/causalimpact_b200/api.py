@@ -21,7 +21,7 @@ import pandas as pd
 from . import frame as _frame
 from . import impact as _impact
 from . import shard as _shard
-from ._engine import Engine, ProblemSpec
+from ._engine import DeviceArray, Engine, ProblemSpec
 from .model import build_problem, initial_theta
 
 
@@ -187,7 +187,8 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   """The engine swap point: same contract as the reference's
   ``_train_causalimpact_sts`` (causalimpact_lib.py:503-606) -- returns
   ``(posterior_samples, posterior_means [T], posterior_trajectories [S, T])`` on
-  the standardized scale."""
+  the standardized scale.  The last two are ``DeviceArray``s: they stay in HBM for
+  ``ci_impact`` and are copied to the host only if the caller asks (``np.asarray``)."""
   del experimental_tf_function_cache_key_addition      # no tracing cache here
   if model is not None:
     raise NotImplementedError("experimental_model needs TFP objects; not supported by the "
@@ -215,23 +216,22 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   eng.set_data(spec)
 
   # ---- chains: global ids 0..C-1, contiguous shard per rank ----
+  # Everything below stays in the engine's HBM (tensors on eng's device; torch is the
+  # allocator and the collective plumbing, every kernel is the engine's own): sampler ->
+  # smoother -> predictive mean, and later ci_impact, with no host round trip of the
+  # [S,T] arrays.  Only theta and the level paths (part of the result object) come back.
   C = max(int(opts.num_chains), 1)
   n_per = max(1, math.ceil(num_results / C))
   c0, c_local = _shard.split_range(C, ws, rank)
-  width = spec.dim + 2 * T
   stats = None
-  if c_local == 0:
-    rows = np.zeros((0, width), dtype=spec.np_dtype)
-  elif use_gibbs:
+  if use_gibbs:
     # the reference's sampler (lib.py:365-388): spike-and-slab Gibbs sweeps, started
     # from its initial state (lib.py:566-581); chain-major rows like the HMC path
     n_warm = max(int(num_warmup_steps), int(opts.gibbs_min_warmup))
-    draws, level, traj, incl = eng.gibbs_run(c_local, n_warmup=n_warm, n_results=n_per,
-                                             seed=seed64, chain_id0=c0, sparse=True)
-    rows = np.concatenate([draws.transpose(1, 0, 2).reshape(c_local * n_per, spec.dim),
-                           level.transpose(1, 0, 2).reshape(c_local * n_per, T),
-                           traj.transpose(1, 0, 2).reshape(c_local * n_per, T)], axis=1)
-    stats = {"sampler": "gibbs", "inclusion": incl}
+    theta_l, level_l, traj_l, incl = eng.gibbs_run_t(max(c_local, 1), n_warmup=n_warm,
+                                                     n_results=n_per, seed=seed64,
+                                                     chain_id0=c0, sparse=True)
+    stats = {"sampler": "gibbs", "inclusion": incl[:c_local]}
   else:
     rng = np.random.Generator(np.random.Philox(key=seed64))
     theta0 = np.tile(initial_theta(spec, prior_level_sd), (C, 1))
@@ -246,42 +246,52 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
     theta0[:, p] = np.minimum(theta0[:, p], 2.0 * np.log(0.9 * spec.obs_ub))
     theta0[:, p + 1] = np.minimum(theta0[:, p + 1], 2.0 * np.log(0.9 * spec.lvl_ub))
     n_warm = max(int(num_warmup_steps), int(opts.min_warmup))
-    draws, hstats = eng.hmc_run(theta0[c0:c0 + c_local], n_warmup=n_warm, n_results=n_per,
-                                seed=seed64, chain_id0=c0, max_leapfrog=opts.max_leapfrog,
-                                init_step=opts.init_step, target_accept=opts.target_accept)
+    # a rank without chains (more ranks than chains) still runs one throw-away chain so
+    # that every rank holds tensors of the right width for the all-gather
+    lo = min(c0, C - 1)
+    draws, hstats = eng.hmc_run_t(theta0[lo:lo + max(c_local, 1)], n_warmup=n_warm,
+                                  n_results=n_per, seed=seed64, chain_id0=lo,
+                                  max_leapfrog=opts.max_leapfrog, init_step=opts.init_step,
+                                  target_accept=opts.target_accept)
     # chain-major draw ids: g = chain * n_per + iteration  (contiguous per rank)
-    local_theta = np.ascontiguousarray(draws.transpose(1, 0, 2)).reshape(c_local * n_per,
-                                                                           spec.dim)
-    level, traj, _ = eng.posterior_predict(local_theta, seed=seed64 ^ 0x9E3779B97F4A7C15,
-                                           draw_id0=c0 * n_per)
-    rows = np.concatenate([local_theta, level, traj], axis=1)
+    theta_l = draws.permute(1, 0, 2).reshape(-1, spec.dim).contiguous()
+    level_l, traj_l = eng.posterior_predict_t(theta_l, seed=seed64 ^ 0x9E3779B97F4A7C15,
+                                              draw_id0=lo * n_per)
+    hstats = hstats[:c_local]
     stats = {"sampler": "hmc", "accept_rate": np.asarray(hstats["accept_rate"]),
              "step_size": np.asarray(hstats["step_size"]),
              "n_divergent": np.asarray(hstats["n_divergent"]),
              "n_leapfrog": np.asarray(hstats["n_leapfrog"])}
-  # the ONE collective of the fit: every chain contributes n_per result rows
-  rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
+  n_local = c_local * n_per
+  if ws == 1:
+    theta_t, level_t, traj_t = (t[:num_results] for t in (theta_l, level_l, traj_l))
+  else:
+    # the ONE collective of the fit: every chain contributes n_per result rows
+    import torch
+    rows = torch.cat([theta_l[:n_local], level_l[:n_local], traj_l[:n_local]], dim=1)
+    rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
+    theta_t = rows[:, :spec.dim].contiguous()
+    level_t = rows[:, spec.dim:spec.dim + T].contiguous()
+    traj_t = rows[:, spec.dim + T:].contiguous()
+  # mean of the predictive mixture = average of level + X.w over the draws
+  # (causalimpact_lib.py:627); fixed summation order over the gathered draws => the same
+  # for any GPU count
+  mean_t = eng.predictive_mean_t(theta_t, level_t)
 
-  theta = rows[:, :spec.dim].astype(np.float64)
-  level = rows[:, spec.dim:spec.dim + T]
-  traj = rows[:, spec.dim + T:]
+  theta = eng.to_host(theta_t).astype(np.float64)
+  level = eng.to_host(level_t)
   z = theta[:, :p]
   weights = wh.to_weights(z) if wh is not None else z
-  # mean of the predictive mixture = average of level + X.w over the draws
-  # (causalimpact_lib.py:627); float64, fixed order => same for any GPU count
-  loc_mean = level.astype(np.float64).mean(axis=0)
-  if p:
-    loc_mean = loc_mean + design @ weights.mean(axis=0)
-  S = rows.shape[0]
+  S = theta.shape[0]
   samples = CausalImpactPosteriorSamples(
       observation_noise_scale=Samples(np.exp(0.5 * theta[:, p]).astype(np_dt)),
       level_scale=Samples(np.exp(0.5 * theta[:, p + 1]).astype(np_dt)),
-      level=Samples(level.astype(np_dt)),
+      level=Samples(level.astype(np_dt, copy=False)),
       weights=Samples(weights.astype(np_dt)) if p else Samples(np.zeros((S, 0), np_dt)),
       seasonal_drift_scales=Samples(np.zeros((S, 0), np_dt)),
       seasonal_levels=Samples(np.zeros((S, T, 0), np_dt)))
   samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
-  return samples, loc_mean.astype(np_dt), traj.astype(np_dt)
+  return samples, DeviceArray(mean_t), DeviceArray(traj_t)
 
 
 def fit_causalimpact(data: pd.DataFrame,
@@ -320,8 +330,7 @@ def fit_causalimpact(data: pd.DataFrame,
       dtype=np_dt, seasons=model_options.seasons,
       experimental_tf_function_cache_key_addition=cache_key, engine_options=engine_options)
   eng = _resolve_engine(engine_options)
-  series, summary = _impact.compute_impact(means, trajectories, ci_data, alpha,
-                                           eng.row_quantiles)
+  series, summary = _impact.compute_impact(means, trajectories, ci_data, alpha, eng.impact)
   stats = getattr(samples, "hmc_stats", None)
   result_samples = CausalImpactPosteriorSamples(
       observation_noise_scale=samples.observation_noise_scale,

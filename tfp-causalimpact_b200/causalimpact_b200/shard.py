@@ -31,13 +31,14 @@ def split_range(n: int, world_size: int, rank: int) -> Tuple[int, int]:
   return start, base + (1 if rank < extra else 0)
 
 
-def all_gather_rows(local: np.ndarray, n_items: int, rows_per_item: int = 1) -> np.ndarray:
+def all_gather_rows(local, n_items: int, rows_per_item: int = 1):
   """Concatenate every rank's rows (axis 0) in rank order with ONE all-gather.
 
-  ``local`` is this rank's [n_local_items * rows_per_item, width] block, where the
-  items (chains) are split by ``split_range(n_items, world, rank)``.  Uses NCCL on
-  the rank's current CUDA device when the backend is nccl, gloo (CPU tensors)
-  otherwise.
+  ``local`` is this rank's [n_local_items * rows_per_item, width] tensor (torch; on the
+  rank's GPU in production, on the CPU under the gloo tests), where the items (chains)
+  are split by ``split_range(n_items, world, rank)``.  NCCL over NVLink when the backend
+  is nccl -- the rows never leave the devices -- gloo (CPU tensors) otherwise.  Returns a
+  tensor on ``local``'s device.
   """
   rank, ws = world()
   if ws == 1:
@@ -48,10 +49,11 @@ def all_gather_rows(local: np.ndarray, n_items: int, rows_per_item: int = 1) -> 
   counts = [split_range(n_items, ws, r)[1] * rows_per_item for r in range(ws)]
   cap = max(counts)
   on_gpu = dist.get_backend() == "nccl"
+  home = local.device
   dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
-  send = torch.zeros((cap, width), dtype=torch.from_numpy(local).dtype, device=dev)
-  send[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+  send = torch.zeros((cap, width), dtype=local.dtype, device=dev)
+  send[:local.shape[0]] = local.to(dev)
   recv = torch.empty((ws * cap, width), dtype=send.dtype, device=dev)
   dist.all_gather_into_tensor(recv, send)
-  recv = recv.cpu().numpy().reshape(ws, cap, width)
-  return np.concatenate([recv[r, :counts[r]] for r in range(ws)], axis=0)
+  recv = recv.reshape(ws, cap, width)
+  return torch.cat([recv[r, :counts[r]] for r in range(ws)], dim=0).to(home)

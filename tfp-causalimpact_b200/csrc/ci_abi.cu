@@ -17,6 +17,7 @@
 #include "ci_seq.cuh"
 #include "ci_llt_kernels.cuh"
 #include "ci_gibbs.cuh"
+#include "ci_impact.cuh"
 
 namespace {
 
@@ -69,6 +70,7 @@ struct ci_ctx {
   DevBuf w_theta, w_value, w_grad;   // workspaces of the host-pointer entry points
   DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats, w_incl;
   DevBuf gram, xty0;                 // X'X, X'y over observed rows (Gibbs regression step)
+  DevBuf i_cum, i_stats, i_meta, i_series, i_summ;   // ci_impact workspaces
   double yty0 = 0.0;
   int n_obs = 0;
   int64_t launches = 0;
@@ -370,7 +372,7 @@ int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
   if (rc) return rc;
   GibbsPlan plan;
   plan.n_warmup = o->n_warmup; plan.n_results = o->n_results; plan.sparse = o->sparse ? 1 : 0;
-  plan.n_obs = c->n_obs;
+  plan.n_obs = c->n_obs; plan.chain_major = o->chain_major ? 1 : 0;
   const double pi = o->nonzero_prob;
   plan.logit_pi = (plan.sparse && pi < 1.0) ? std::log(pi) - std::log1p(-pi) : 1e30;
   if (!(pi < 1.0)) plan.sparse = 0;
@@ -438,7 +440,7 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
 
 template <typename R>
 int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, int nq,
-                     void* out_d, cudaStream_t st) {
+                     void* out_d, cudaStream_t st, int out_ld = 0) {
   // the whole column lives in shared memory as integer keys
   const size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
   if (bytes + 12 * 1024 > (size_t)c->smem_optin)
@@ -451,7 +453,45 @@ int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, 
   CU_TRY(set_smem(kern, (uint32_t)bytes));
   int nt = 1024;
   while (nt > 64 && nt / 2 >= S) nt >>= 1;
-  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, qa, static_cast<R*>(out_d));
+  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, qa, static_cast<R*>(out_d),
+                             out_ld > 0 ? out_ld : nq);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+template <typename R>
+int launch_impact(ci_ctx* c, const ImpactDev& a, const void* traj_d, const void* mean_d,
+                  const double* obs_d, const uint8_t* period_d, double* series_d, double* summ_d,
+                  cudaStream_t st) {
+  const int S = a.S, T = a.T, Tc = T - a.t_c0;
+  double* cum = static_cast<double*>(c->i_cum.p);
+  double* stats = static_cast<double*>(c->i_stats.p);
+  k_impact_rows<R><<<(S + 1 + IMP_ROWS_PER_CTA - 1) / IMP_ROWS_PER_CTA, 32 * IMP_ROWS_PER_CTA, 0, st>>>(
+      static_cast<const R*>(traj_d), static_cast<const R*>(mean_d), obs_d, period_d, a, cum, stats,
+      series_d, summ_d);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  {
+    const size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
+    auto kern = k_impact_cols<R>;
+    CU_TRY(set_smem(kern, (uint32_t)bytes));
+    int nt = 1024;
+    while (nt > 64 && nt / 2 >= S) nt >>= 1;
+    kern<<<T, nt, bytes, st>>>(static_cast<const R*>(traj_d), obs_d, a, series_d);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  const double q[2] = {a.q_lo, a.q_hi};
+  if (Tc > 0) {   // cumulative-effect quantiles (lib.py:888) straight into series columns 7, 8
+    int rc = launch_quantiles<double>(c, cum, S, Tc, q, 2,
+                                      series_d + (size_t)a.t_c0 * IMP_SERIES_COLS + 7, st,
+                                      IMP_SERIES_COLS);
+    if (rc) return rc;
+  }
+  int rc = launch_quantiles<double>(c, stats, S, IMP_STATS, q, 2, summ_d, st);
+  if (rc) return rc;
+  k_impact_summary<<<1, 1024, 0, st>>>(stats, a, summ_d);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;
@@ -508,6 +548,7 @@ int ci_ctx_destroy(ci_ctx* c) {
   c->w_theta.release(); c->w_value.release(); c->w_grad.release();
   c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release(); c->w_incl.release();
   c->gram.release(); c->xty0.release();
+  c->i_cum.release(); c->i_stats.release(); c->i_meta.release(); c->i_series.release(); c->i_summ.release();
   delete c;
   return CI_OK;
 }
@@ -808,6 +849,100 @@ int ci_gibbs_run(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
   if (incl && c->prob.p > 0)
     CU_TRY(cudaMemcpyAsync(incl, c->w_incl.p, (size_t)C * c->prob.p * sizeof(float),
                            cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_predictive_mean_d(ci_ctx* c, const void* theta_d, const void* level_d, int S, void* mean_d,
+                         void* stream) {
+  if (!c || !theta_d || !level_d || !mean_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
+  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
+    return fail(CI_ERR_UNSUPPORTED, "ci_predictive_mean: local level only");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 blk(ci::MEAN_COLS, ci::MEAN_ROWS);
+  const int grid = (c->prob.T + ci::MEAN_COLS - 1) / ci::MEAN_COLS;
+  if (c->prob.dtype == CI_F64)
+    ci::k_predict_mean<double><<<grid, blk, 0, st>>>(
+        make_probdev<double>(c), static_cast<const double*>(theta_d),
+        static_cast<const double*>(level_d), S, static_cast<double*>(mean_d));
+  else
+    ci::k_predict_mean<float><<<grid, blk, 0, st>>>(
+        make_probdev<float>(c), static_cast<const float*>(theta_d),
+        static_cast<const float*>(level_d), S, static_cast<float*>(mean_d));
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+int ci_impact_d(ci_ctx* c, const ci_impact_args* a, const void* traj_d, const void* mean_d,
+                const double* observed, const uint8_t* period, double* series_d, double* summ_d,
+                void* stream) {
+  if (!c || !a || !traj_d || !mean_d || !observed || !period || !series_d || !summ_d)
+    return fail(CI_ERR_INVALID, "null argument");
+  if (a->S < 1 || a->T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (a->dtype != CI_F32 && a->dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  if (!(a->q_lo >= 0.0 && a->q_lo <= 1.0 && a->q_hi >= 0.0 && a->q_hi <= 1.0))
+    return fail(CI_ERR_INVALID, "quantiles must be in [0,1]");
+  if (!(a->scale > 0.0)) return fail(CI_ERR_INVALID, "scale must be positive");
+  const int S = a->S, T = a->T;
+  ci::ImpactDev d{};
+  d.S = S; d.T = T; d.scale = a->scale; d.offset = a->offset; d.q_lo = a->q_lo; d.q_hi = a->q_hi;
+  d.obs_sum = a->obs_sum;
+  d.t_c0 = T; d.n_post = 0;
+  for (int t = 0; t < T; ++t) {
+    if (period[t] > 2 || (t > 0 && period[t] < period[t - 1]))
+      return fail(CI_ERR_INVALID, "period[] must be non-decreasing values in {0,1,2}");
+    if (period[t] != 0 && d.t_c0 == T) d.t_c0 = t;
+    d.n_post += period[t] == 1;
+  }
+  if (d.n_post < 1) return fail(CI_ERR_INVALID, "the post-period is empty");
+  const size_t keyb = (size_t)S * sizeof(double);
+  if (keyb + 12 * 1024 > (size_t)c->smem_optin)
+    return fail(CI_ERR_UNSUPPORTED, "ci_impact: S=%d exceeds the shared-memory select (max %d draws)",
+                S, (int)((c->smem_optin - 12 * 1024) / sizeof(double)));
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Tc = T - d.t_c0;
+  CU_TRY(c->i_cum.reserve((size_t)S * (Tc > 0 ? Tc : 1) * sizeof(double)));
+  CU_TRY(c->i_stats.reserve((size_t)S * ci::IMP_STATS * sizeof(double)));
+  const size_t ob = (size_t)T * sizeof(double);
+  CU_TRY(c->i_meta.reserve(ob + (size_t)T));
+  CU_TRY(cudaMemcpyAsync(c->i_meta.p, observed, ob, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(static_cast<char*>(c->i_meta.p) + ob, period, (size_t)T,
+                         cudaMemcpyHostToDevice, st));
+  const double* obs_d = static_cast<const double*>(c->i_meta.p);
+  const uint8_t* per_d = reinterpret_cast<const uint8_t*>(static_cast<char*>(c->i_meta.p) + ob);
+  if (a->dtype == CI_F64)
+    return launch_impact<double>(c, d, traj_d, mean_d, obs_d, per_d, series_d, summ_d, st);
+  return launch_impact<float>(c, d, traj_d, mean_d, obs_d, per_d, series_d, summ_d, st);
+}
+
+int ci_impact(ci_ctx* c, const ci_impact_args* a, const void* traj, const void* mean,
+              const double* observed, const uint8_t* period, double* series, double* summary) {
+  if (!c || !a || !traj || !mean || !observed || !period || !series || !summary)
+    return fail(CI_ERR_INVALID, "null argument");
+  if (a->S < 1 || a->T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (a->dtype != CI_F32 && a->dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t es = a->dtype == CI_F64 ? 8 : 4;
+  const size_t tb = (size_t)a->S * a->T * es, mb = (size_t)a->T * es;
+  const size_t sb = (size_t)a->T * CI_IMPACT_SERIES_COLS * sizeof(double);
+  const size_t ub = CI_IMPACT_SUMMARY_LEN * sizeof(double);
+  CU_TRY(c->w_traj.reserve(tb));
+  CU_TRY(c->w_mean.reserve(mb));
+  CU_TRY(c->i_series.reserve(sb));
+  CU_TRY(c->i_summ.reserve(ub));
+  CU_TRY(cudaMemcpyAsync(c->w_traj.p, traj, tb, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(c->w_mean.p, mean, mb, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_impact_d(c, a, c->w_traj.p, c->w_mean.p, observed, period,
+                       static_cast<double*>(c->i_series.p), static_cast<double*>(c->i_summ.p),
+                       c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(series, c->i_series.p, sb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(summary, c->i_summ.p, ub, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   return CI_OK;
 }

@@ -28,7 +28,7 @@ namespace ci {
 enum : uint32_t { RNG_G_INCL = 6, RNG_G_GAMMA = 7, RNG_G_W = 8 };
 
 struct GibbsPlan {
-  int n_warmup, n_results, sparse, n_obs;
+  int n_warmup, n_results, sparse, n_obs, chain_major;
   double logit_pi;
 };
 
@@ -254,7 +254,9 @@ k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t see
     }
     __syncwarp();
     const bool keep = it >= plan.n_warmup;
-    const size_t out_row = keep ? ((size_t)(it - plan.n_warmup) * C + c) : 0;
+    const size_t out_row = !keep ? 0
+        : plan.chain_major ? ((size_t)c * plan.n_results + (size_t)(it - plan.n_warmup))
+                           : ((size_t)(it - plan.n_warmup) * C + c);
     const XtMap xm = xt_map(p, lane);
     const bool small_p = p <= PSMALL;
     R accw[PSMALL];

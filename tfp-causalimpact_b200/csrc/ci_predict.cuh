@@ -269,7 +269,7 @@ __device__ typename KeyOf<R>::type radix_select(const typename KeyOf<R>::type* k
 
 template <typename R>
 __global__ void k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs qa,
-                                R* __restrict__ out) {
+                                R* __restrict__ out, int out_ld) {
   using Key = typename KeyOf<R>::type;
   extern __shared__ __align__(16) unsigned char qsmem[];
   Key* keys = reinterpret_cast<Key*>(qsmem);
@@ -310,7 +310,7 @@ __global__ void k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs
       if (g >= (R)0.5) res_v = vb - diff * ((R)1 - g);
       if (g == (R)0) res_v = va;
     }
-    if (tid == 0) out[(size_t)t * qa.nq + iq] = res_v;
+    if (tid == 0) out[(size_t)t * out_ld + iq] = res_v;
   }
 }
 
