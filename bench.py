@@ -335,6 +335,33 @@ def main():
   sync_all()
   t_pred = float(p0.elapsed_time(p1)) / 10.0
 
+  # ---- impact series + summary on the device (ci_impact_d) on those draws ----
+  import types
+  Tn = cfg["T"]
+  t_pre = int(0.7 * Tn)
+  per = np.zeros(Tn, np.uint8); per[t_pre:] = 1
+  obs = np.random.Generator(np.random.PCG64(5)).normal(size=Tn)
+  meta = types.SimpleNamespace(observed=obs, period=per, scale=2.0, offset=100.0, q_lo=0.025,
+                               q_hi=0.975, obs_sum=float(obs[t_pre:].sum()))
+  out_d = torch.empty(Tn * 9 + 20, dtype=torch.float64, device=dev)
+  iargs = _engine.CiImpactArgs(S=S_pred, T=Tn, dtype=0, reserved=0, scale=2.0, offset=100.0,
+                               q_lo=0.025, q_hi=0.975, obs_sum=meta.obs_sum)
+  import ctypes
+  def impact_step():
+    rc = lib.ci_impact_d(ctx, ctypes.byref(iargs), trj.data_ptr(), mean_d.data_ptr(),
+                         obs.ctypes.data_as(ctypes.c_void_p), per.ctypes.data_as(ctypes.c_void_p),
+                         out_d.data_ptr(), out_d.data_ptr() + 8 * Tn * 9, stream.cuda_stream)
+    assert rc == 0, lib.ci_last_error()
+  for _ in range(3):
+    impact_step()
+  sync_all()
+  p0.record(stream)
+  for _ in range(10):
+    impact_step()
+  p1.record(stream)
+  sync_all()
+  t_impact = float(p0.elapsed_time(p1)) / 10.0
+
   # ---- the reference's own sampler on the GPU: Gibbs sweeps/s (spike-and-slab, 256 chains)
   eng.gibbs_run(C, n_warmup=2, n_results=2, seed=1, chain_id0=rank * C, want_level=False,
                 want_traj=False)
@@ -420,6 +447,10 @@ def main():
                   "fit_causalimpact_quickstart_ms": t_fit,
                   "fit_note": "T=100, 1 covariate, 900 draws, 64 chains, 2nd call; reference "
                               "publishes 5170 ms for this call (other hardware, incl. tracing)",
+                  "impact_ms": t_impact,
+                  "impact_note": f"ci_impact_d on {S_pred} draws x T={cfg['T']}: effect paths, 3 per-time "
+                                 "quantile families, post-period summary; device resident "
+                                 "(rank 0's time)",
                   "posterior_draws_per_sec": S_pred * world / (t_pred * 1e-3),
                   "posterior_draws": {"draws_per_gpu": S_pred, "T": cfg["T"], "ms": t_pred,
                                       "note": "ci_posterior_predict_d: level + trajectory + mean, "
