@@ -196,6 +196,44 @@ int ci_row_quantiles(ci_ctx* ctx, const void* a, int S, int T, int dtype,
 int ci_row_quantiles_d(ci_ctx* ctx, const void* a_d, int S, int T, int dtype,
                        const double* q, int nq, void* out_d, void* stream);
 
+/* ---- seasonal components --------------------------------
+ * Replaces the tfp.sts.Seasonal components the reference adds to its Gibbs model for
+ * every ModelOptions.seasons entry (lib.py:471-489: allow_drift, mean effect constrained
+ * to zero, drift variance ~ InverseGamma(drift_conc, drift_scale) bounded by drift_ub,
+ * initial effects ~ N(0, init_sd)) and the sampler's joint (level, seasonal) latent draw
+ * + drift-scale draws (lib.py:365-388; initial drift scale 0.01 sd, :573-574).
+ *   active [K][T] uint8 HOST: season index (0 .. num_seasons-1) active at step t
+ *   ends   [K][T] uint8 HOST: 1 when that season is over after step t
+ * (the host derives both from Seasons.num_steps_per_season, lib.py:162-180).
+ * Limits: K <= CI_MAX_SEASONAL, 1 + sum(num_seasons) <= 32 (one warp lane per state
+ * element); beyond that CI_ERR_UNSUPPORTED.  Call after ci_set_data; n_components = 0
+ * (or seas == NULL) removes the components; ci_set_data also removes them.
+ */
+#define CI_MAX_SEASONAL 7
+typedef struct {
+  int32_t n_components;
+  int32_t num_seasons[CI_MAX_SEASONAL];
+  const uint8_t* active;
+  const uint8_t* ends;
+  double init_sd;
+  double drift_conc, drift_scale, drift_ub;
+} ci_seasonal;
+
+int ci_set_seasonal(ci_ctx* ctx, const ci_seasonal* seas);
+
+/* Gibbs run with the seasonal components of ci_set_seasonal.  Outputs as ci_gibbs_run plus
+ *   latent   [rows, T]     level + sum of the seasonal contributions       (may be NULL)
+ *   seasonal [rows, T, K]  contribution of each component at every step    (may be NULL)
+ *   drift    [rows, K]     log drift VARIANCE of each component            (may be NULL)
+ * (rows ordered like draws: opts->chain_major).  traj = latent + X.w + sigma_obs N(0,1). */
+int ci_gibbs_seasonal_run(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
+                          uint64_t chain_id0, int n_chains, void* draws, void* level,
+                          void* traj, float* incl, void* latent, void* seasonal, void* drift);
+int ci_gibbs_seasonal_run_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
+                            uint64_t chain_id0, int n_chains, void* draws_d, void* level_d,
+                            void* traj_d, float* incl_d, void* latent_d, void* seasonal_d,
+                            void* drift_d, void* stream);
+
 /* Mean of the predictive mixture alone (lib.py:627): mean_t = avg_s level[s,t] + x_t . avg_s w_s,
  * for draws whose level paths are already on the device (the Gibbs kernel's output).
  * Deterministic: fixed summation order, float64 accumulation. */

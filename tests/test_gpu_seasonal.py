@@ -1,0 +1,182 @@
+"""Seasonal components on the GPU (reference
+causalimpact_lib.py:162-180, 471-489 and its test causalimpact_lib_test.py:704-773).
+
+  * the joint (level, seasonal) simulation smoother of k_gibbs_seasonal against the EXACT
+    Gaussian conditional (dense T x T algebra in oracle/seasonal_np.py): variances pinned
+    through near-degenerate priors, so every sweep's latent draw is an independent draw from
+    p(x | y) -- mean and variance of level / contributions / their sum per time step;
+  * the whole sweep against the restated sampler (oracle/seasonal_np.run), statistically;
+  * the reference's own seasonal test through fit_causalimpact (abs_effect_sd 9.5 +- 1
+    without seasons, 0.5 +- 0.1 with; seasonal_levels [1000, 300, 3]).
+Tolerances are Monte-Carlo: stated per assertion."""
+import dataclasses
+import types
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import causalimpact_b200 as ci
+from causalimpact_b200 import EngineError, model
+from oracle import kalman_np as K
+from oracle import seasonal_np as S
+
+pytestmark = pytest.mark.gpu
+
+
+def seasons(*args):
+  return [types.SimpleNamespace(num_seasons=n, num_steps_per_season=s) for n, s in args]
+
+
+def pinned_spec(y_ext, s_e, s_h, dtype, m0=0.3, P0=1.4):
+  """ProblemSpec whose variance priors are (numerically) point masses at s_e, s_h."""
+  spec = ci.build_problem(y_ext, None, outcome_sd=1.0, dtype=dtype)
+  big = 1e9
+  return dataclasses.replace(spec, m0=m0, P0=P0, obs_conc=big, obs_scale=big * s_e, obs_ub=1e3,
+                             lvl_conc=big, lvl_scale=big * s_h, lvl_ub=1e3)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_joint_smoother_matches_dense_gaussian_conditional(engine, dtype):
+  rng = np.random.default_rng(0)
+  T = 60
+  ss = seasons((4, (2, 1, 1, 1)), (7, 1))
+  y = 0.5 + rng.normal(size=T)
+  y[[3, 11]] = np.nan; y[45:] = np.nan
+  mask = np.isnan(y)
+  s_e, s_h, s_d = 0.2, 0.01, [0.03, 0.004]
+  spec = pinned_spec(y, s_e, s_h, dtype)
+  engine.set_data(spec)
+  sched = model.build_seasonal(ss, T, 1.1)
+  # pin the drift variances too
+  sched = dataclasses.replace(sched, drift_conc=1e9, drift_scale=1e9 * s_d[0], drift_ub=1e3)
+  # (one drift prior for all components in the ABI: use equal drift for the exact test)
+  s_d = [s_d[0], s_d[0]]
+  engine.set_seasonal(sched)
+  out = engine.gibbs_seasonal_run(64, n_warmup=2, n_results=60, seed=7, sparse=False)
+  lvl = out["level"].reshape(-1, T).astype(np.float64)
+  sea = out["seasonal"].reshape(-1, T, 2).astype(np.float64)
+  lat = out["latent"].reshape(-1, T).astype(np.float64)
+  n = lvl.shape[0]
+  np.testing.assert_allclose(lat, lvl + sea.sum(-1), atol=2e-5)
+  np.testing.assert_allclose(np.sqrt(np.exp(out["draws"][..., 0].astype(np.float64))), np.sqrt(s_e),
+                             rtol=1e-3)
+  np.testing.assert_allclose(out["drift"], np.sqrt(s_d[0]), rtol=1e-3)
+
+  sp = S.make_spec(ss, T, 1.1)
+  mu, Syy, Sxy, covs = S.dense_moments(sp, T, s_e, s_h, s_d, spec.m0, spec.P0)
+  o = ~mask
+  Sinv_r = np.linalg.solve(Syy[np.ix_(o, o)], (y - mu)[o])
+  for t in range(T):
+    G = Sxy[t][:, o]
+    cmean = np.r_[spec.m0, np.zeros(sp.d - 1)] + G @ Sinv_r
+    ccov = covs[t] - G @ np.linalg.solve(Syy[np.ix_(o, o)], G.T)
+    cols = S.obs_cols(sp, t)
+    # level, each contribution, and their sum: mean within 5 MC standard errors (+ float32 slack)
+    for got, idx in ((lvl[:, t], [0]), (sea[:, t, 0], [cols[1]]), (sea[:, t, 1], [cols[2]]),
+                     (lat[:, t], cols)):
+      m_ref = cmean[idx].sum()
+      v_ref = ccov[np.ix_(idx, idx)].sum()
+      assert abs(got.mean() - m_ref) < 5 * np.sqrt(v_ref / n) + 2e-4, (t, idx)
+      assert abs(got.var() - v_ref) < 6 * v_ref * np.sqrt(2.0 / n) + 1e-5, (t, idx, got.var(), v_ref)
+  # predictive draw: traj = latent + sigma_obs * N(0,1)
+  e = (out["traj"] - out["latent"]).reshape(-1).astype(np.float64)
+  assert abs(e.std() - np.sqrt(s_e)) < 0.01 and abs(e.mean()) < 0.01
+
+
+def test_full_sweep_matches_restated_sampler(engine):
+  """Weekly pattern + 2 covariates + random-walk level: posterior means of the scales, the
+  weights and the seasonal contributions agree with oracle/seasonal_np.run."""
+  rng = np.random.default_rng(3)
+  T, t_pre = 160, 120
+  pat = np.array([1.0, 4.0, 5.0, 2.0, -1.0, -2.0, -3.0]); pat -= pat.mean()
+  x = np.cumsum(rng.normal(size=(T, 2)), axis=0) * 0.3
+  yraw = 1.0 * x[:, 0] - 0.5 * x[:, 1] + 0.6 * pat[np.arange(T) % 7] + 0.3 * rng.normal(size=T)
+  mu, sd = yraw[:t_pre].mean(), yraw[:t_pre].std(ddof=1)
+  y = (yraw - mu) / sd
+  y[t_pre:] = np.nan; y[[5, 50]] = np.nan
+  X = np.column_stack([(x - x[:t_pre].mean(0)) / x[:t_pre].std(0, ddof=1), np.ones(T)])
+  ss = seasons((7, 1))
+  spec = ci.build_problem(y, X, outcome_sd=1.0, dtype=np.float32)
+  engine.set_data(spec)
+  engine.set_seasonal(model.build_seasonal(ss, T, 1.0))
+  out = engine.gibbs_seasonal_run(128, n_warmup=150, n_results=20, seed=11, sparse=True)
+  prob = K.default_problem(y, X, outcome_sd=1.0)
+  ref = S.run(prob, S.make_spec(ss, T, 1.0), n_results=600, n_warmup=200, seed=5, sparse=False)
+  dr = out["draws"].reshape(-1, spec.dim).astype(np.float64)
+  p = spec.p
+  # scales (posterior means on the sd scale): 10 % or 0.01 absolute
+  for got, want, name in ((np.exp(0.5 * dr[:, p]), np.sqrt(ref["s_e"]), "sigma_obs"),
+                          (np.exp(0.5 * dr[:, p + 1]), np.sqrt(ref["s_h"]), "sigma_level")):
+    assert abs(got.mean() - want.mean()) < max(0.1 * want.mean(), 0.01), (name, got.mean(), want.mean())
+  for j in range(2):                                  # slopes; p = 3 <= 3: every feature included
+    assert abs(dr[:, j].mean() - ref["w"][:, j].mean()) < 0.05, j
+  sea = out["seasonal"].reshape(-1, T).astype(np.float64)
+  np.testing.assert_allclose(sea.mean(0), ref["seasonal"][:, :, 0].mean(0), atol=0.06)
+  truth = 0.6 * pat[np.arange(T) % 7] / sd
+  assert np.abs(sea.mean(0) - truth).max() < 0.2
+  # counterfactual (latent + X.w) in the masked tail
+  loc_gpu = (out["latent"].reshape(-1, T) + dr[:, :p] @ X.T).mean(0)
+  loc_ref = (ref["level"] + ref["seasonal"].sum(-1) + ref["w"] @ X.T).mean(0)
+  assert np.abs(loc_gpu - loc_ref)[t_pre:].max() < 0.12
+
+
+def _reference_seasonal_data(seed=0):
+  """causalimpact_lib_test.py:704-733 with a seeded generator."""
+  rng = np.random.default_rng(seed)
+  n, treat = 300, 290
+  five = [[8., 8., 4., 3., -4.][i % 5] for i in range(n)]
+  seven = [10 * [1., 4., 5., 2., -1., -2., -3.][i % 7] for i in range(n)]
+  eight = [[1., 1., 3., 3., 4.5, 2.0, -7., 0.][i % 8] for i in range(n)]
+  y = rng.normal(size=n, scale=0.4) + seven + five + eight
+  y[treat:] += 2.5
+  idx = pd.date_range("2018-01-01", periods=n, freq="D")
+  return pd.DataFrame({"y": y}, index=idx), treat
+
+
+def test_reference_seasonality_test():
+  """testNumericImpactValuesWithSeasonality (causalimpact_lib_test.py:704-773)."""
+  df, treat = _reference_seasonal_data()
+  kw = dict(pre_period=(df.index[0], df.index[treat - 1]),
+            post_period=(df.index[treat], df.index[-1]), seed=3,
+            inference_options=ci.InferenceOptions(num_results=1000))
+  without = ci.fit_causalimpact(df, **kw)
+  with_s = ci.fit_causalimpact(df, model_options=ci.ModelOptions(seasons=[
+      ci.Seasons(num_seasons=4, num_steps_per_season=(2, 1, 1, 1)),
+      ci.Seasons(num_seasons=7),
+      ci.Seasons(num_seasons=6, num_steps_per_season=((2, 2, 1, 1, 1, 1), (2, 2, 1, 1, 1, 1)))]),
+                               **kw)
+  assert abs(without.summary["abs_effect_sd"]["average"] - 9.5) < 1.0
+  assert abs(with_s.summary["abs_effect_sd"]["average"] - 0.5) < 0.1
+  assert without.posterior_samples.seasonal_levels.shape == (1000, 300, 0)
+  assert with_s.posterior_samples.seasonal_levels.shape == (1000, 300, 3)
+  assert without.posterior_samples.seasonal_drift_scales is None
+  assert with_s.posterior_samples.seasonal_drift_scales.shape == (1000, 3)
+  assert np.all(np.isfinite(with_s.series["posterior_mean"].values))
+  # same seed -> identical frames (causalimpact_lib_test.py:493-502)
+  again = ci.fit_causalimpact(df, model_options=ci.ModelOptions(seasons=[
+      ci.Seasons(num_seasons=4, num_steps_per_season=(2, 1, 1, 1)),
+      ci.Seasons(num_seasons=7),
+      ci.Seasons(num_seasons=6, num_steps_per_season=((2, 2, 1, 1, 1, 1), (2, 2, 1, 1, 1, 1)))]),
+                              **kw)
+  pd.testing.assert_frame_equal(with_s.series, again.series)
+  pd.testing.assert_frame_equal(with_s.summary, again.summary)
+
+
+def test_limits_and_errors(engine):
+  rng = np.random.default_rng(1)
+  y = rng.normal(size=80); y[60:] = np.nan
+  engine.set_data(ci.build_problem(y, None, outcome_sd=1.0))
+  with pytest.raises(EngineError, match="state dimension"):
+    engine.set_seasonal(model.build_seasonal(seasons((24, 1), (12, 2)), 80, 1.0))
+  engine.set_seasonal(None)
+  with pytest.raises(EngineError, match="ci_set_seasonal"):
+    engine.seasonal = model.build_seasonal(seasons((7, 1)), 80, 1.0)
+    engine.gibbs_seasonal_run(2, n_warmup=1, n_results=1, seed=1)
+  df = pd.DataFrame({"y": rng.normal(size=60)})
+  with pytest.raises(NotImplementedError, match="Gibbs"):
+    ci.fit_causalimpact(df, (0, 39), (40, 59), seed=1,
+                        model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=7)]),
+                        engine_options=ci.EngineOptions(sampler="hmc"))
+  with pytest.raises(ValueError, match="num_steps_per_season"):
+    model.build_seasonal(seasons((4, (1, 2, 3))), 60, 1.0)

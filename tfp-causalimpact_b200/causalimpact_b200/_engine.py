@@ -51,6 +51,13 @@ class CiImpactArgs(C.Structure):
 
 
 IMPACT_SERIES_COLS, IMPACT_SUMMARY_LEN = 9, 20
+MAX_SEASONAL = 7
+
+
+class CiSeasonal(C.Structure):
+  _fields_ = [("n_components", C.c_int32), ("num_seasons", C.c_int32 * MAX_SEASONAL),
+              ("active", C.c_void_p), ("ends", C.c_void_p), ("init_sd", C.c_double),
+              ("drift_conc", C.c_double), ("drift_scale", C.c_double), ("drift_ub", C.c_double)]
 
 
 class CiHmcStats(C.Structure):
@@ -67,6 +74,7 @@ EXPORTS = (
     "ci_launch_count", "ci_set_data", "ci_logprob", "ci_logprob_grad", "ci_logprob_grad_d",
     "ci_hmc_run", "ci_hmc_run_d", "ci_gibbs_run", "ci_gibbs_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
     "ci_row_quantiles", "ci_row_quantiles_d", "ci_predictive_mean_d", "ci_impact", "ci_impact_d",
+    "ci_set_seasonal", "ci_gibbs_seasonal_run", "ci_gibbs_seasonal_run_d",
 )
 
 _lib = None
@@ -107,6 +115,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
   lib.ci_predictive_mean_d.argtypes = [vp, vp, vp, i32, vp, vp]
   lib.ci_impact.argtypes = [vp, C.POINTER(CiImpactArgs), vp, vp, vp, vp, vp, vp]
   lib.ci_impact_d.argtypes = [vp, C.POINTER(CiImpactArgs), vp, vp, vp, vp, vp, vp, vp]
+  lib.ci_set_seasonal.argtypes = [vp, C.POINTER(CiSeasonal)]
+  lib.ci_gibbs_seasonal_run.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp,
+                                        vp, vp, vp]
+  lib.ci_gibbs_seasonal_run_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp,
+                                          vp, vp, vp, vp, vp]
   _lib = lib
   return lib
 
@@ -196,6 +209,7 @@ class Engine:
     self._ctx = C.c_void_p()
     self.device = device
     self.spec: Optional[ProblemSpec] = None
+    self.seasonal = None
     self._check(self._lib.ci_ctx_create(device, C.byref(self._ctx)))
 
   # -- plumbing ------------------------------------------------------------
@@ -228,6 +242,7 @@ class Engine:
   # -- problem -------------------------------------------------------------
   def set_data(self, spec: ProblemSpec):
     self.spec = spec
+    self.seasonal = None
     dt = spec.np_dtype
     y = np.ascontiguousarray(spec.y, dtype=dt)
     X = None if spec.X is None else np.ascontiguousarray(spec.X, dtype=dt)
@@ -239,6 +254,74 @@ class Engine:
                    slope_ub=min(spec.slope_ub, 1e300), m0=spec.m0, P0=spec.P0,
                    m0_slope=spec.m0_slope, P0_slope=spec.P0_slope)
     self._check(self._lib.ci_set_data(self._ctx, C.byref(pb), _ptr(y), _ptr(X), _ptr(Om)))
+
+  def set_seasonal(self, sched):
+    """ci_set_seasonal: ``sched`` is a model.SeasonalSchedule (or None to remove)."""
+    self.seasonal = sched
+    if sched is None or sched.K == 0:
+      self.seasonal = None
+      self._check(self._lib.ci_set_seasonal(self._ctx, None))
+      return
+    if sched.K > MAX_SEASONAL:
+      raise EngineError(f"at most {MAX_SEASONAL} seasonal components are supported")
+    act = np.ascontiguousarray(sched.active, dtype=np.uint8)
+    ends = np.ascontiguousarray(sched.ends, dtype=np.uint8)
+    if act.shape != (sched.K, self.spec.T) or ends.shape != act.shape:
+      raise ValueError(f"seasonal schedule must be [{sched.K},{self.spec.T}]")
+    cs = CiSeasonal(n_components=sched.K, active=act.ctypes.data, ends=ends.ctypes.data,
+                    init_sd=sched.init_sd, drift_conc=sched.drift_conc,
+                    drift_scale=sched.drift_scale, drift_ub=sched.drift_ub)
+    for k, n in enumerate(sched.num_seasons):
+      cs.num_seasons[k] = int(n)
+    self._check(self._lib.ci_set_seasonal(self._ctx, C.byref(cs)))
+
+  def gibbs_seasonal_run(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
+                         chain_id0: int = 0, sparse: bool = True,
+                         nonzero_prob: Optional[float] = None):
+    """Host-buffer ci_gibbs_seasonal_run.  Returns dict: draws [n_results, C, dim], level,
+    latent, traj [n_results, C, T], seasonal [n_results, C, T, K], drift [n_results, C, K]
+    (drift SCALES), incl [C, p]."""
+    sp, K = self.spec, self.seasonal.K
+    if nonzero_prob is None:
+      nonzero_prob = min(1.0, 3.0 / sp.p) if sp.p else 1.0
+    dt = sp.np_dtype
+    shp = (n_results, n_chains)
+    out = dict(draws=np.empty(shp + (sp.dim,), dt), level=np.empty(shp + (sp.T,), dt),
+               traj=np.empty(shp + (sp.T,), dt), latent=np.empty(shp + (sp.T,), dt),
+               seasonal=np.empty(shp + (sp.T, K), dt), drift=np.empty(shp + (K,), dt))
+    incl = np.zeros((n_chains, max(sp.p, 1)), dtype=np.float32)
+    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=0,
+                       nonzero_prob=float(nonzero_prob))
+    self._check(self._lib.ci_gibbs_seasonal_run(
+        self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, _ptr(out["draws"]),
+        _ptr(out["level"]), _ptr(out["traj"]), _ptr(incl), _ptr(out["latent"]),
+        _ptr(out["seasonal"]), _ptr(out["drift"])))
+    out["drift"] = np.exp(0.5 * out["drift"].astype(np.float64)).astype(dt)
+    out["incl"] = incl[:, :sp.p]
+    return out
+
+  def gibbs_seasonal_run_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
+                           chain_id0: int = 0, sparse: bool = True,
+                           nonzero_prob: Optional[float] = None):
+    """ci_gibbs_seasonal_run_d, chain-major device tensors: (theta [R, dim], level [R, T],
+    latent [R, T], traj [R, T], seasonal [R, T, K], log drift variance [R, K], incl ndarray),
+    R = C * n_results."""
+    torch, dev = self._torch_dev()
+    sp, dt, K = self.spec, self._tdtype(torch), self.seasonal.K
+    if nonzero_prob is None:
+      nonzero_prob = min(1.0, 3.0 / sp.p) if sp.p else 1.0
+    rows = n_chains * n_results
+    mk = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+    draws, level, latent, traj = mk(rows, sp.dim), mk(rows, sp.T), mk(rows, sp.T), mk(rows, sp.T)
+    seas, drift = mk(rows, sp.T, K), mk(rows, K)
+    incl = torch.zeros((n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
+    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
+                       nonzero_prob=float(nonzero_prob))
+    self._check(self._lib.ci_gibbs_seasonal_run_d(
+        self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, draws.data_ptr(),
+        level.data_ptr(), traj.data_ptr(), incl.data_ptr(), latent.data_ptr(), seas.data_ptr(),
+        drift.data_ptr(), self._stream(torch)))
+    return draws, level, latent, traj, seas, drift, incl.cpu().numpy()[:, :sp.p]
 
   # -- K1/K2/K3 --------------------------------------------------------------
   def logprob(self, theta, variant: int = VARIANT_SCAN, with_prior: bool = False) -> np.ndarray:

@@ -22,7 +22,7 @@ from . import frame as _frame
 from . import impact as _impact
 from . import shard as _shard
 from ._engine import DeviceArray, Engine, ProblemSpec
-from .model import build_problem, initial_theta
+from .model import build_problem, build_seasonal, initial_theta
 
 
 class Samples(np.ndarray):
@@ -70,8 +70,10 @@ class DataOptions:
 
 @dataclasses.dataclass(frozen=True)
 class Seasons:
-  """reference :162-180.  Accepted for signature compatibility; seasonal
-  components are outside this engine's path and raise NotImplementedError."""
+  """reference :162-180.  One seasonal effect (e.g. day of week): ``num_seasons`` effects,
+  each lasting ``num_steps_per_season`` steps (int, per-season tuple, or per-cycle tuple of
+  tuples).  Sampled by the seasonal Gibbs kernel (csrc/ci_seasonal.cuh); the sum of
+  num_seasons over all components is limited to 31."""
   num_seasons: int
   num_steps_per_season: Union[int, Tuple[int], Tuple[Tuple[int]]] = 1
 
@@ -193,9 +195,11 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   if model is not None:
     raise NotImplementedError("experimental_model needs TFP objects; not supported by the "
                               "B200 engine")
-  if seasons:
-    raise NotImplementedError("seasonal components are outside the B200 engine's path")
   opts = engine_options or EngineOptions()
+  seasons = list(seasons or ())
+  if seasons and opts.sampler == "hmc":
+    raise NotImplementedError("seasonal components are sampled by the Gibbs kernel "
+                              "(EngineOptions.sampler 'auto' or 'gibbs'), not by HMC")
   np_dt = _np_dtype(dtype)
   seed64 = _seed_to_u64(seed)
 
@@ -208,12 +212,16 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   p, T = spec.p, spec.T
   if opts.sampler not in ("auto", "hmc", "gibbs"):
     raise ValueError(f"EngineOptions.sampler must be auto|hmc|gibbs, got {opts.sampler!r}")
-  use_gibbs = opts.sampler == "gibbs" or (opts.sampler == "auto" and p > 3)
+  use_gibbs = opts.sampler == "gibbs" or (opts.sampler == "auto" and p > 3) or bool(seasons)
   wh = None
   if p and opts.whiten and not use_gibbs:
     wh = _Whitening.build(design, ~np.isnan(y_ext), spec.Omega)
     spec = dataclasses.replace(spec, X=wh.design(design), Omega=wh.omega(spec.Omega))
   eng.set_data(spec)
+  sched = build_seasonal(seasons, T, outcome_sd)                 # lib.py:471-489
+  if sched is not None:
+    eng.set_seasonal(sched)
+  K = 0 if sched is None else sched.K
 
   # ---- chains: global ids 0..C-1, contiguous shard per rank ----
   # Everything below stays in the engine's HBM (tensors on eng's device; torch is the
@@ -224,7 +232,17 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   n_per = max(1, math.ceil(num_results / C))
   c0, c_local = _shard.split_range(C, ws, rank)
   stats = None
-  if use_gibbs:
+  extra_l = []            # seasonal only: [latent, contributions (flattened), log drift variances]
+  if sched is not None:
+    # the reference's sampler with seasonal components (lib.py:365-388, 471-489): the joint
+    # (level, seasonal) draw replaces the level draw; one drift variance per component
+    n_warm = max(int(num_warmup_steps), int(opts.gibbs_min_warmup))
+    theta_l, level_l, latent_l, traj_l, seas_l, drift_l, incl = eng.gibbs_seasonal_run_t(
+        max(c_local, 1), n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=c0,
+        sparse=True)
+    extra_l = [latent_l, seas_l.reshape(seas_l.shape[0], T * K), drift_l]
+    stats = {"sampler": "gibbs", "inclusion": incl[:c_local]}
+  elif use_gibbs:
     # the reference's sampler (lib.py:365-388): spike-and-slab Gibbs sweeps, started
     # from its initial state (lib.py:566-581); chain-major rows like the HMC path
     n_warm = max(int(num_warmup_steps), int(opts.gibbs_min_warmup))
@@ -263,33 +281,41 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
              "n_divergent": np.asarray(hstats["n_divergent"]),
              "n_leapfrog": np.asarray(hstats["n_leapfrog"])}
   n_local = c_local * n_per
+  parts = [theta_l, level_l, traj_l] + extra_l
   if ws == 1:
-    theta_t, level_t, traj_t = (t[:num_results] for t in (theta_l, level_l, traj_l))
+    parts = [t[:num_results] for t in parts]
   else:
     # the ONE collective of the fit: every chain contributes n_per result rows
     import torch
-    rows = torch.cat([theta_l[:n_local], level_l[:n_local], traj_l[:n_local]], dim=1)
+    widths = [t.shape[1] for t in parts]
+    rows = torch.cat([t[:n_local] for t in parts], dim=1)
     rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
-    theta_t = rows[:, :spec.dim].contiguous()
-    level_t = rows[:, spec.dim:spec.dim + T].contiguous()
-    traj_t = rows[:, spec.dim + T:].contiguous()
-  # mean of the predictive mixture = average of level + X.w over the draws
+    parts = [t.contiguous() for t in torch.split(rows, widths, dim=1)]
+  theta_t, level_t, traj_t = parts[:3]
+  # mean of the predictive mixture = average of level (+ seasonal) + X.w over the draws
   # (causalimpact_lib.py:627); fixed summation order over the gathered draws => the same
   # for any GPU count
-  mean_t = eng.predictive_mean_t(theta_t, level_t)
+  mean_t = eng.predictive_mean_t(theta_t, parts[3] if sched is not None else level_t)
 
   theta = eng.to_host(theta_t).astype(np.float64)
   level = eng.to_host(level_t)
   z = theta[:, :p]
   weights = wh.to_weights(z) if wh is not None else z
   S = theta.shape[0]
+  if sched is not None:
+    # each component's contribution at every step: what the reference extracts as the
+    # 0-th element of the component's latent (lib.py:299-317), [S, T, K]
+    seas_levels = eng.to_host(parts[4]).reshape(S, T, K).astype(np_dt, copy=False)
+    drift_scales = np.exp(0.5 * eng.to_host(parts[5]).astype(np.float64)).astype(np_dt)
+  else:
+    seas_levels, drift_scales = np.zeros((S, T, 0), np_dt), np.zeros((S, 0), np_dt)
   samples = CausalImpactPosteriorSamples(
       observation_noise_scale=Samples(np.exp(0.5 * theta[:, p]).astype(np_dt)),
       level_scale=Samples(np.exp(0.5 * theta[:, p + 1]).astype(np_dt)),
       level=Samples(level.astype(np_dt, copy=False)),
       weights=Samples(weights.astype(np_dt)) if p else Samples(np.zeros((S, 0), np_dt)),
-      seasonal_drift_scales=Samples(np.zeros((S, 0), np_dt)),
-      seasonal_levels=Samples(np.zeros((S, T, 0), np_dt)))
+      seasonal_drift_scales=Samples(drift_scales),
+      seasonal_levels=Samples(seas_levels))
   samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
   return samples, DeviceArray(mean_t), DeviceArray(traj_t)
 
@@ -336,6 +362,7 @@ def fit_causalimpact(data: pd.DataFrame,
       observation_noise_scale=samples.observation_noise_scale,
       level_scale=samples.level_scale, level=samples.level,
       weights=samples.weights if samples.weights.shape[1] > 0 else None,    # :330-331
-      seasonal_drift_scales=None,                                            # :332-334
+      seasonal_drift_scales=(samples.seasonal_drift_scales
+                             if samples.seasonal_drift_scales.shape[-1] > 0 else None),   # :332-334
       seasonal_levels=samples.seasonal_levels)
   return CausalImpactAnalysis(series, summary, result_samples, stats)

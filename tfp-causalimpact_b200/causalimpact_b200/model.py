@@ -6,7 +6,8 @@ causalimpact/causalimpact_lib.py:398-500 and :563-581).
 """
 from __future__ import annotations
 
-from typing import Optional
+import dataclasses
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -78,3 +79,67 @@ def initial_theta(spec: ProblemSpec, prior_level_sd: float = 0.01) -> np.ndarray
   if spec.model == MODEL_LOCAL_LINEAR_TREND:
     th[spec.p + 2] = np.log((prior_level_sd * sd) ** 2)
   return th
+
+
+# ---------------------------------------------------------------------------
+# seasonal components (ModelOptions.seasons; causalimpact_lib.py:162-180, 471-489)
+# ---------------------------------------------------------------------------
+@dataclasses.dataclass
+class SeasonalSchedule:
+  """What ``ci_set_seasonal`` needs: per component the active season of every step and
+  whether that season is over after the step, plus the priors of lib.py:471-489."""
+  num_seasons: List[int]
+  active: np.ndarray          # [K, T] uint8
+  ends: np.ndarray            # [K, T] uint8
+  init_sd: float              # initial_effect_prior = Normal(0, outcome_sd)        (:489)
+  drift_conc: float = 0.005   # drift variance ~ InverseGamma(0.005, 5e-7 sd^2)     (:472-473)
+  drift_scale: float = 5e-7
+  drift_ub: float = 1.0       # .upper_bound = outcome_sd                           (:474)
+
+  @property
+  def K(self) -> int:
+    return len(self.num_seasons)
+
+
+def _season_steps(num_seasons: int, num_steps_per_season) -> np.ndarray:
+  """int | [num_seasons] | [num_cycles, num_seasons]  ->  flat run lengths, cycle-major."""
+  steps = np.asarray(num_steps_per_season)
+  if steps.dtype.kind not in "iu":
+    raise ValueError("num_steps_per_season must be integer valued")
+  if steps.ndim == 0:
+    steps = np.full((1, num_seasons), int(steps))
+  elif steps.ndim == 1:
+    steps = steps.reshape(1, -1)
+  if steps.ndim != 2 or steps.shape[1] != num_seasons or np.any(steps < 1):
+    raise ValueError("num_steps_per_season must be a positive int, a [num_seasons] tuple or a "
+                     f"[num_cycles, num_seasons] tuple of tuples; got shape {steps.shape} for "
+                     f"num_seasons={num_seasons}")
+  return steps.reshape(-1).astype(np.int64)
+
+
+def build_seasonal(seasons: Sequence, T: int, outcome_sd: float) -> Optional[SeasonalSchedule]:
+  """Season calendar of every ``Seasons`` option over the T modelled steps: step 0 is the
+  first step of season 0 (of cycle 0); run lengths repeat cyclically (tfp.sts.Seasonal
+  semantics, which the reference instantiates at lib.py:475-489)."""
+  if not seasons:
+    return None
+  K = len(seasons)
+  active = np.zeros((K, T), np.uint8)
+  ends = np.zeros((K, T), np.uint8)
+  ns = []
+  for k, s in enumerate(seasons):
+    n = int(s.num_seasons)
+    if n < 2:
+      raise ValueError("Seasons.num_seasons must be at least 2")
+    runs = _season_steps(n, s.num_steps_per_season)
+    # expand the run lengths until they cover T steps
+    reps = int(np.ceil(T / runs.sum())) + 1
+    lengths = np.tile(runs, reps)
+    season_of_run = np.tile(np.arange(runs.size) % n, reps)
+    active[k] = np.repeat(season_of_run, lengths)[:T]
+    last = np.cumsum(lengths) - 1
+    ends[k, last[last < T]] = 1
+    ns.append(n)
+  return SeasonalSchedule(num_seasons=ns, active=active, ends=ends, init_sd=float(outcome_sd),
+                          drift_conc=0.005, drift_scale=5e-7 * outcome_sd ** 2,
+                          drift_ub=float(outcome_sd))

@@ -18,6 +18,7 @@
 #include "ci_llt_kernels.cuh"
 #include "ci_gibbs.cuh"
 #include "ci_impact.cuh"
+#include "ci_seasonal.cuh"
 
 namespace {
 
@@ -71,6 +72,8 @@ struct ci_ctx {
   DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats, w_incl;
   DevBuf gram, xty0;                 // X'X, X'y over observed rows (Gibbs regression step)
   DevBuf i_cum, i_stats, i_meta, i_series, i_summ;   // ci_impact workspaces
+  DevBuf s_sched, s_scratch, w_latent, w_seas, w_drift;   // seasonal components
+  ci::SeasDev seas{};                // seas.K == 0: no seasonal components
   double yty0 = 0.0;
   int n_obs = 0;
   int64_t launches = 0;
@@ -390,6 +393,43 @@ int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
 }
 
 template <typename R>
+int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0, int C,
+                          void* draws_d, void* level_d, void* traj_d, float* incl_d, void* latent_d,
+                          void* seas_d, void* drift_d, cudaStream_t st) {
+  const int p = c->prob.p, d = c->seas.d;
+  const uint32_t extra = (uint32_t)(2 * p * p + 5 * p + 8) + (uint32_t)(d * (d | 1) + d);
+  const uint32_t tail = (uint32_t)(p * p) * (uint32_t)c->esz + 16u;
+  SmemCfg cfg;
+  int G = pick_G(c, C), rc = CI_OK;
+  for (; G >= 1; --G) {
+    rc = plan_smem(c, G, extra, &cfg, tail);
+    if (rc == CI_OK) break;
+  }
+  if (rc) return rc;
+  GibbsPlan plan;
+  plan.n_warmup = o->n_warmup; plan.n_results = o->n_results; plan.sparse = o->sparse ? 1 : 0;
+  plan.n_obs = c->n_obs; plan.chain_major = o->chain_major ? 1 : 0;
+  const double pi = o->nonzero_prob;
+  plan.logit_pi = (plan.sparse && pi < 1.0) ? std::log(pi) - std::log1p(-pi) : 1e30;
+  if (!(pi < 1.0)) plan.sparse = 0;
+  GibbsDev<R> gd;
+  gd.gram = static_cast<const R*>(c->gram.p); gd.xty0 = static_cast<const R*>(c->xty0.p);
+  gd.yty0 = (R)c->yty0;
+  CU_TRY(c->s_scratch.reserve((size_t)C * c->prob.T * (d + 1) * sizeof(R)));
+  SeasDev sz = c->seas;
+  sz.scratch = c->s_scratch.p;
+  auto kern = k_gibbs_seasonal<R>;
+  CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
+  kern<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+      make_probdev<R>(c), gd, sz, cfg, plan, seed, chain_id0, C, static_cast<R*>(draws_d),
+      static_cast<R*>(level_d), static_cast<R*>(traj_d), static_cast<R*>(latent_d),
+      static_cast<R*>(seas_d), static_cast<R*>(drift_d), incl_d);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+template <typename R>
 int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_t draw_id0,
                    void* level_d, void* traj_d, void* mean_d, cudaStream_t st) {
   SmemCfg cfg;
@@ -548,6 +588,7 @@ int ci_ctx_destroy(ci_ctx* c) {
   c->w_theta.release(); c->w_value.release(); c->w_grad.release();
   c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release(); c->w_incl.release();
   c->gram.release(); c->xty0.release();
+  c->s_sched.release(); c->s_scratch.release(); c->w_latent.release(); c->w_seas.release(); c->w_drift.release();
   c->i_cum.release(); c->i_stats.release(); c->i_meta.release(); c->i_series.release(); c->i_summ.release();
   delete c;
   return CI_OK;
@@ -571,6 +612,7 @@ int ci_set_data(ci_ctx* c, const ci_problem* pb, const void* y, const void* X, c
   if (!(pb->P0 > 0)) return fail(CI_ERR_INVALID, "P0 must be positive");
   CU_TRY(cudaSetDevice(c->device));
   c->has_data = false;
+  c->seas = ci::SeasDev{};
   c->prob = *pb;
   c->esz = pb->dtype == CI_F64 ? 8 : 4;
   c->NB = (pb->T + ci::TB - 1) / ci::TB;
@@ -846,6 +888,111 @@ int ci_gibbs_run(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
   CU_TRY(cudaMemcpyAsync(draws, c->w_draws.p, db, cudaMemcpyDeviceToHost, c->stream));
   if (level) CU_TRY(cudaMemcpyAsync(level, c->w_level.p, tb, cudaMemcpyDeviceToHost, c->stream));
   if (traj) CU_TRY(cudaMemcpyAsync(traj, c->w_traj.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  if (incl && c->prob.p > 0)
+    CU_TRY(cudaMemcpyAsync(incl, c->w_incl.p, (size_t)C * c->prob.p * sizeof(float),
+                           cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_set_seasonal(ci_ctx* c, const ci_seasonal* sp) {
+  if (!c) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  c->seas = ci::SeasDev{};
+  if (!sp || sp->n_components == 0) return CI_OK;
+  const int K = sp->n_components, T = c->prob.T;
+  if (K < 0 || K > CI_MAX_SEASONAL)
+    return fail(CI_ERR_UNSUPPORTED, "at most %d seasonal components (got %d)", CI_MAX_SEASONAL, K);
+  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
+    return fail(CI_ERR_UNSUPPORTED, "seasonal components need the local level model");
+  if (!sp->active || !sp->ends) return fail(CI_ERR_INVALID, "null schedule");
+  if (!(sp->init_sd > 0) || !(sp->drift_conc > 0) || !(sp->drift_scale > 0) || !(sp->drift_ub > 0))
+    return fail(CI_ERR_INVALID, "init_sd, drift_conc, drift_scale, drift_ub must be positive");
+  ci::SeasDev sz{};
+  sz.K = K;
+  int d = 1;
+  for (int k = 0; k < K; ++k) {
+    if (sp->num_seasons[k] < 2) return fail(CI_ERR_INVALID, "num_seasons must be >= 2");
+    sz.n[k] = sp->num_seasons[k]; sz.off[k] = d; d += sz.n[k];
+  }
+  if (d > ci::SEAS_MAXD)
+    return fail(CI_ERR_UNSUPPORTED, "1 + sum(num_seasons) = %d exceeds the supported state "
+                "dimension %d", d, ci::SEAS_MAXD);
+  sz.d = d;
+  std::vector<uint8_t> sched((size_t)T * (K + 1));
+  for (int t = 0; t < T; ++t) {
+    uint8_t em = 0;
+    for (int k = 0; k < K; ++k) {
+      const uint8_t a = sp->active[(size_t)k * T + t];
+      if (a >= sz.n[k]) return fail(CI_ERR_INVALID, "active[%d][%d] = %d out of range", k, t, (int)a);
+      sched[(size_t)t * (K + 1) + k] = a;
+      if (sp->ends[(size_t)k * T + t]) { em |= (uint8_t)(1u << k); if (t < T - 1) sz.n_ends[k]++; }
+    }
+    sched[(size_t)t * (K + 1) + K] = em;
+  }
+  sz.init_var = sp->init_sd * sp->init_sd;
+  sz.drift_conc = sp->drift_conc; sz.drift_scale = sp->drift_scale; sz.drift_ub = sp->drift_ub;
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(c->s_sched.reserve(sched.size()));
+  CU_TRY(cudaMemcpyAsync(c->s_sched.p, sched.data(), sched.size(), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  sz.sched = static_cast<const uint8_t*>(c->s_sched.p);
+  c->seas = sz;
+  return CI_OK;
+}
+
+int ci_gibbs_seasonal_run_d(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0,
+                            int C, void* draws_d, void* level_d, void* traj_d, float* incl_d,
+                            void* latent_d, void* seas_d, void* drift_d, void* stream) {
+  if (!c || !o || !draws_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (c->seas.K < 1) return fail(CI_ERR_STATE, "ci_set_seasonal has not been called");
+  if (C < 1 || o->n_results < 1 || o->n_warmup < 0)
+    return fail(CI_ERR_INVALID, "n_chains >= 1, n_results >= 1, n_warmup >= 0 required");
+  if (o->sparse && !(o->nonzero_prob > 0.0 && o->nonzero_prob <= 1.0))
+    return fail(CI_ERR_INVALID, "nonzero_prob must be in (0, 1]");
+  if (c->n_obs < 2) return fail(CI_ERR_INVALID, "need at least 2 observed points");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prob.dtype == CI_F64)
+    return launch_gibbs_seasonal<double>(c, o, seed, chain_id0, C, draws_d, level_d, traj_d, incl_d,
+                                         latent_d, seas_d, drift_d, st);
+  return launch_gibbs_seasonal<float>(c, o, seed, chain_id0, C, draws_d, level_d, traj_d, incl_d,
+                                      latent_d, seas_d, drift_d, st);
+}
+
+int ci_gibbs_seasonal_run(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0,
+                          int C, void* draws, void* level, void* traj, float* incl, void* latent,
+                          void* seasonal, void* drift) {
+  if (!c || !o || !draws) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (c->seas.K < 1) return fail(CI_ERR_STATE, "ci_set_seasonal has not been called");
+  if (C < 1 || o->n_results < 1) return fail(CI_ERR_INVALID, "n_chains and n_results must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const int K = c->seas.K;
+  const size_t rows = (size_t)o->n_results * C;
+  const size_t db = rows * c->dim * c->esz, tb = rows * c->prob.T * c->esz;
+  const size_t ib = (size_t)C * (c->prob.p > 0 ? c->prob.p : 1) * sizeof(float);
+  CU_TRY(c->w_draws.reserve(db));
+  if (level) CU_TRY(c->w_level.reserve(tb));
+  if (traj) CU_TRY(c->w_traj.reserve(tb));
+  if (incl) CU_TRY(c->w_incl.reserve(ib));
+  if (latent) CU_TRY(c->w_latent.reserve(tb));
+  if (seasonal) CU_TRY(c->w_seas.reserve(tb * K));
+  if (drift) CU_TRY(c->w_drift.reserve(rows * K * c->esz));
+  int rc = ci_gibbs_seasonal_run_d(c, o, seed, chain_id0, C, c->w_draws.p,
+                                   level ? c->w_level.p : nullptr, traj ? c->w_traj.p : nullptr,
+                                   incl ? static_cast<float*>(c->w_incl.p) : nullptr,
+                                   latent ? c->w_latent.p : nullptr,
+                                   seasonal ? c->w_seas.p : nullptr, drift ? c->w_drift.p : nullptr,
+                                   c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(draws, c->w_draws.p, db, cudaMemcpyDeviceToHost, c->stream));
+  if (level) CU_TRY(cudaMemcpyAsync(level, c->w_level.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  if (traj) CU_TRY(cudaMemcpyAsync(traj, c->w_traj.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  if (latent) CU_TRY(cudaMemcpyAsync(latent, c->w_latent.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  if (seasonal) CU_TRY(cudaMemcpyAsync(seasonal, c->w_seas.p, tb * K, cudaMemcpyDeviceToHost, c->stream));
+  if (drift) CU_TRY(cudaMemcpyAsync(drift, c->w_drift.p, rows * K * c->esz, cudaMemcpyDeviceToHost, c->stream));
   if (incl && c->prob.p > 0)
     CU_TRY(cudaMemcpyAsync(incl, c->w_incl.p, (size_t)C * c->prob.p * sizeof(float),
                            cudaMemcpyDeviceToHost, c->stream));

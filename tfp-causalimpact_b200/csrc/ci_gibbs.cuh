@@ -95,6 +95,123 @@ __device__ __forceinline__ double warp_cholesky(R* L, int n, int n_log, int lane
   return logdiag;
 }
 
+// ---------------------------------------------------------------------------
+// Step A of the sweep (spike-and-slab regression + sigma_obs^2), shared by k_gibbs and the
+// seasonal kernel (ci_seasonal.cuh).  Warp-cooperative; every lane holds the same scalars.
+// ---------------------------------------------------------------------------
+template <typename R> struct GibbsReg {
+  const ProbDev<R>& pr;
+  GibbsScratch<R> gs;
+  const R* gram_s;
+  const R* om_s;
+  int p, lane;
+  double conc_e;
+  uint64_t seed;
+  uint32_t id_lo, id_hi8;
+
+  // number of active features and their list -> gs.idx; returns k
+  __device__ __forceinline__ int build_idx(const uint32_t (&g)[4]) const {
+    int k = 0;
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+      const int j = lane + 32 * wd;
+      const bool on = j < p && ((g[wd] >> lane) & 1u);
+      const int pos = k + __popc(g[wd] & ((1u << lane) - 1u));
+      if (on) gs.idx[pos] = (R)j;
+      k += __popc(g[wd]);
+    }
+    __syncwarp();
+    return k;
+  }
+  // log marginal of configuration g (Scott & Varian 2014, b = 0); leaves the
+  // augmented factor in gs.La (stride k+1) and returns SS through `ss`
+  __device__ __forceinline__ double log_marginal(const uint32_t (&g)[4], double yty, int& k_out,
+                                                 double& ss) const {
+    const int k = build_idx(g);
+    k_out = k;
+    const int n = k + 1;
+    const R ytyR = (R)yty;
+    const GibbsScratch<R>& s_ = gs;
+    const R* gram = gram_s; const R* om = om_s; const int pp = p;
+    const double ld_lam = warp_cholesky<R>(gs.La, n, k, lane, [&](int i, int j) -> R {
+      if (i == k) return j == k ? ytyR : s_.bvec[(int)s_.idx[j]];
+      const int a = (int)s_.idx[i], b = (int)s_.idx[j];
+      return gram[a * pp + b] + om[a * pp + b];
+    });
+    const double ld_om = warp_cholesky<R>(gs.Lo, k, k, lane, [&](int i, int j) -> R {
+      return om[(int)s_.idx[i] * pp + (int)s_.idx[j]];
+    });
+    const double piv = (double)gs.La[k * n + k];
+    ss = piv * piv;
+    return ld_om - ld_lam - conc_e * log((double)pr.obs_scale + 0.5 * ss);
+  }
+
+  // One regression step: inclusion indicators (gam), sigma_obs^2 (s_e), weights -> w_s.
+  // Inputs: gs.bvec = X'(targets), yty = |targets|^2 over observed steps.
+  __device__ __forceinline__ void step(int it, const GibbsPlan& plan, uint32_t (&gam)[4], double yty,
+                                       double& s_e, R* w_s) const {
+    double ss = yty;
+    int k = 0;
+    if (p > 0) {
+      double lm_cur = log_marginal(gam, yty, k, ss);
+      if (plan.sparse) {
+        for (int j = 0; j < p; ++j) {
+          uint32_t gf[4] = {gam[0], gam[1], gam[2], gam[3]};
+          gf[j >> 5] ^= 1u << (j & 31);
+          int kf; double ssf;
+          const double lm_new = log_marginal(gf, yty, kf, ssf);
+          const bool cur = (gam[j >> 5] >> (j & 31)) & 1u;
+          const double d = (cur ? lm_cur - lm_new : lm_new - lm_cur) + plan.logit_pi;
+          const uint4 x = Philox::gen(seed, id_lo, RNG_G_INCL | id_hi8, (uint32_t)it, (uint32_t)j);
+          const bool take = u01<double>(x.x) < 1.0 / (1.0 + exp(-d));
+          if (take != cur) { gam[j >> 5] ^= 1u << (j & 31); lm_cur = lm_new; }
+        }
+        lm_cur = log_marginal(gam, yty, k, ss);      // factor of the final configuration
+      }
+      (void)lm_cur;
+    }
+    {
+      const double g = gamma_draw(conc_e, seed, id_lo, RNG_G_GAMMA | id_hi8, (uint32_t)it, 0u);
+      s_e = ((double)pr.obs_scale + 0.5 * ss) / g;
+      const double ub2 = (double)pr.obs_ub * (double)pr.obs_ub;
+      if (s_e > ub2) s_e = ub2;                                        // lib.py:442-443
+    }
+    if (p > 0) {
+      // w_active = L^-T (z + sqrt(s_e) eps),  z = last row of the augmented factor
+      const int n = k + 1;
+      const R sig = (R)sqrt(s_e);
+      for (int a = lane; a < k; a += 32) {
+        const uint4 x = Philox::gen(seed, id_lo, RNG_G_W | id_hi8, (uint32_t)it, (uint32_t)(a >> 2));
+        R z0, z1, z2, z3;
+        box_muller<R>(x.x, x.y, z0, z1);
+        box_muller<R>(x.z, x.w, z2, z3);
+        const int sel = a & 3;
+        const R e = sel == 0 ? z0 : (sel == 1 ? z1 : (sel == 2 ? z2 : z3));
+        gs.vec[a] = fma(sig, e, gs.La[k * n + a]);
+      }
+      __syncwarp();
+      for (int a = k - 1; a >= 0; --a) {
+        R acc = gs.vec[a];
+        if (k <= 32) {
+          for (int m = a + 1; m < k; ++m) acc = fma(-gs.La[m * n + a], gs.vec[m], acc);
+        } else {
+          R part = 0;
+          for (int m = a + 1 + lane; m < k; m += 32) part = fma(gs.La[m * n + a], gs.vec[m], part);
+          acc -= warp_sum(part);
+        }
+        const R xa = acc / gs.La[a * n + a];
+        __syncwarp();
+        if (lane == 0) gs.vec[a] = xa;
+        __syncwarp();
+      }
+      for (int j = lane; j < p; j += 32) w_s[j] = 0;
+      __syncwarp();
+      for (int a = lane; a < k; a += 32) w_s[(int)gs.idx[a]] = gs.vec[a];
+      __syncwarp();
+    }
+  }
+};
+
 template <typename R>
 __global__ void __launch_bounds__(32 * (MAXG + 1), 1)
 k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t seed,
@@ -146,101 +263,11 @@ k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t see
   const double conc_e = (double)pr.obs_conc + 0.5 * plan.n_obs;
   __syncwarp();
 
-  // number of active features and their list -> gs.idx; returns k
-  auto build_idx = [&](const uint32_t (&g)[4]) -> int {
-    int k = 0;
-#pragma unroll
-    for (int wd = 0; wd < 4; ++wd) {
-      const int j = lane + 32 * wd;
-      const bool on = j < p && ((g[wd] >> lane) & 1u);
-      const int pos = k + __popc(g[wd] & ((1u << lane) - 1u));
-      if (on) gs.idx[pos] = (R)j;
-      k += __popc(g[wd]);
-    }
-    __syncwarp();
-    return k;
-  };
-  // log marginal of configuration g (Scott & Varian 2014, b = 0); leaves the
-  // augmented factor in gs.La (stride k+1) and returns SS through `ss`
-  auto log_marginal = [&](const uint32_t (&g)[4], int& k_out, double& ss) -> double {
-    const int k = build_idx(g);
-    k_out = k;
-    const int n = k + 1;
-    const R ytyR = (R)yty;
-    const double ld_lam = warp_cholesky<R>(gs.La, n, k, lane, [&](int i, int j) -> R {
-      if (i == k) return j == k ? ytyR : gs.bvec[(int)gs.idx[j]];
-      const int a = (int)gs.idx[i], b = (int)gs.idx[j];
-      return gram_s[a * p + b] + om_s[a * p + b];
-    });
-    const double ld_om = warp_cholesky<R>(gs.Lo, k, k, lane, [&](int i, int j) -> R {
-      return om_s[(int)gs.idx[i] * p + (int)gs.idx[j]];
-    });
-    const double piv = (double)gs.La[k * n + k];
-    ss = piv * piv;
-    return ld_om - ld_lam - conc_e * log((double)pr.obs_scale + 0.5 * ss);
-  };
+  const GibbsReg<R> reg{pr, gs, gram_s, om_s, p, lane, conc_e, seed, id_lo, id_hi8};
 
   for (int it = 0; it < n_iter; ++it) {
     // =================== A. regression block ===================
-    double ss = yty;
-    int k = 0;
-    if (p > 0) {
-      double lm_cur = log_marginal(gam, k, ss);
-      if (plan.sparse) {
-        for (int j = 0; j < p; ++j) {
-          uint32_t gf[4] = {gam[0], gam[1], gam[2], gam[3]};
-          gf[j >> 5] ^= 1u << (j & 31);
-          int kf; double ssf;
-          const double lm_new = log_marginal(gf, kf, ssf);
-          const bool cur = (gam[j >> 5] >> (j & 31)) & 1u;
-          const double d = (cur ? lm_cur - lm_new : lm_new - lm_cur) + plan.logit_pi;
-          const uint4 x = Philox::gen(seed, id_lo, RNG_G_INCL | id_hi8, (uint32_t)it, (uint32_t)j);
-          const bool take = u01<double>(x.x) < 1.0 / (1.0 + exp(-d));
-          if (take != cur) { gam[j >> 5] ^= 1u << (j & 31); lm_cur = lm_new; }
-        }
-        lm_cur = log_marginal(gam, k, ss);      // factor of the final configuration
-      }
-      (void)lm_cur;
-    }
-    {
-      const double g = gamma_draw(conc_e, seed, id_lo, RNG_G_GAMMA | id_hi8, (uint32_t)it, 0u);
-      s_e = ((double)pr.obs_scale + 0.5 * ss) / g;
-      const double ub2 = (double)pr.obs_ub * (double)pr.obs_ub;
-      if (s_e > ub2) s_e = ub2;                                        // lib.py:442-443
-    }
-    if (p > 0) {
-      // w_active = L^-T (z + sqrt(s_e) eps),  z = last row of the augmented factor
-      const int n = k + 1;
-      const R sig = (R)sqrt(s_e);
-      for (int a = lane; a < k; a += 32) {
-        const uint4 x = Philox::gen(seed, id_lo, RNG_G_W | id_hi8, (uint32_t)it, (uint32_t)(a >> 2));
-        R z0, z1, z2, z3;
-        box_muller<R>(x.x, x.y, z0, z1);
-        box_muller<R>(x.z, x.w, z2, z3);
-        const int sel = a & 3;
-        const R e = sel == 0 ? z0 : (sel == 1 ? z1 : (sel == 2 ? z2 : z3));
-        gs.vec[a] = fma(sig, e, gs.La[k * n + a]);
-      }
-      __syncwarp();
-      for (int a = k - 1; a >= 0; --a) {
-        R acc = gs.vec[a];
-        if (k <= 32) {
-          for (int m = a + 1; m < k; ++m) acc = fma(-gs.La[m * n + a], gs.vec[m], acc);
-        } else {
-          R part = 0;
-          for (int m = a + 1 + lane; m < k; m += 32) part = fma(gs.La[m * n + a], gs.vec[m], part);
-          acc -= warp_sum(part);
-        }
-        const R xa = acc / gs.La[a * n + a];
-        __syncwarp();
-        if (lane == 0) gs.vec[a] = xa;
-        __syncwarp();
-      }
-      for (int j = lane; j < p; j += 32) ws.w[j] = 0;
-      __syncwarp();
-      for (int a = lane; a < k; a += 32) ws.w[(int)gs.idx[a]] = gs.vec[a];
-      __syncwarp();
-    }
+    reg.step(it, plan, gam, yty, s_e, ws.w);
     // =================== B. level | rest : FFBS ===================
     const R se = (R)s_e, sh = (R)s_h, sig_e = (R)sqrt(s_e);
     R a_c = pr.m0, P_c = pr.P0;

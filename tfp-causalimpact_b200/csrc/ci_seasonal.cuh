@@ -1,0 +1,419 @@
+// ci_seasonal.cuh -- SURVEY section 8 row f3: the reference's Gibbs sweep for models WITH
+// seasonal components (ModelOptions.seasons), one warp per chain.
+//
+// Replaces gibbs_sampler.fit_with_gibbs_sampling as the reference calls it when
+// `seasons` is non-empty (causalimpact/causalimpact_lib.py:365-388; the components are
+// tfp.sts.Seasonal(allow_drift, constrain_mean_effect_to_zero) built at :471-489, initial
+// drift scale 0.01 sd at :573-574).  Per sweep:
+//   A. spike-and-slab regression + sigma_obs^2      (GibbsReg, ci_gibbs.cuh)
+//   B. (level, seasonal effects) | rest, drawn JOINTLY with Durbin & Koopman's
+//      mean-correction simulation smoother + Koopman's fast state smoother
+//   C. sigma_level^2 and one drift variance per component ~ InverseGamma.
+//
+// State ("effects space", oracle/seasonal_np.py proves it equal in law to TFP's rotating
+// constrained construction): x = (level, effects of component 0, effects of component 1, ..),
+// dimension d <= 32, LANE i OWNS ELEMENT i.  Transition = identity; the observation sums the
+// level and each component's ACTIVE season; when a season ends its effect receives
+// drift * N(0,1) * (e_j - 1/n) (zero-sum direction); prior of a block: sd^2 (I - 11'/n).
+//   pass A (forward):  simulate x+, y+ from the prior; Kalman filter on y* = r - y+ with
+//                      the d x d covariance in shared memory (row i in lane i): rank-1
+//                      downdates; gains K_t and e_t = v_t / F_t go to an L2-resident scratch
+//   pass B (backward): r_{t-1} = r_t + h_t (e_t - K_t' r_t); r_t overwrites K_t
+//   pass C (forward):  xhat_0 = P_0 r_{-1}, xhat_{t+1} = xhat_t + Q_t r_t; x = x+ + xhat with
+//                      x+ REGENERATED from the same Philox counters (nothing stored);
+//                      emits level, per-component contributions, the trajectory, and the
+//                      sufficient statistics of the next sweep's steps A and C.
+// [X|y] is streamed twice per sweep through the same tile pipeline as every other kernel.
+#pragma once
+#include "ci_gibbs.cuh"
+
+namespace ci {
+
+enum : uint32_t { RNG_S_PATH = 9, RNG_S_INIT = 10, RNG_S_DRIFT = 11, RNG_S_GAMMA_U = 12 };
+constexpr int MAX_SEAS = 7;     // components (the "season ends" flags of a step are one byte)
+constexpr int SEAS_MAXD = 32;   // 1 + sum of num_seasons
+
+struct SeasDev {
+  int K, d;
+  int n[MAX_SEAS], off[MAX_SEAS], n_ends[MAX_SEAS];
+  const uint8_t* sched;         // [T][K+1]: active season of each component, then the ends mask
+  double init_var;              // initial_effect_prior variance (lib.py:489: sd^2)
+  double drift_conc, drift_scale, drift_ub;   // InverseGamma on the drift variance (lib.py:472-474)
+  void* scratch;                // [C][T][d+1] elements of R
+};
+
+// Gamma(shape, 1) for any shape > 0 (boost for shape < 1: G(a) = G(a+1) U^(1/a)).
+__device__ __forceinline__ double gamma_draw_any(double shape, uint64_t seed, uint32_t c0,
+                                                 uint32_t c1, uint32_t it, uint32_t site) {
+  if (shape >= 1.0) return gamma_draw(shape, seed, c0, c1, it, site);
+  const double g = gamma_draw(shape + 1.0, seed, c0, c1, it, site);
+  const uint4 x = Philox::gen(seed, c0, (c1 & ~0xffu) | RNG_S_GAMMA_U, it, site);
+  return g * pow(u01<double>(x.x), 1.0 / shape);
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+template <typename R>
+__global__ void __launch_bounds__(32 * (MAXG + 1), 1)
+k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPlan plan,
+                 uint64_t seed, uint64_t chain_id0, int C, R* __restrict__ draws,
+                 R* __restrict__ level_out, R* __restrict__ traj_out, R* __restrict__ latent_out,
+                 R* __restrict__ seas_out, R* __restrict__ drift_out,
+                 float* __restrict__ incl_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (blockDim.x >> 5) - 1;
+  const int chain0 = blockIdx.x * G;
+  const int nactive = min(G, C - chain0);
+  const CtaShared<R> cs = cta_prologue(smem, cfg, pr, nactive);
+  const int p = pr.p, dim = pr.dim, ld = pr.ld, NB = pr.NB, T = pr.T;
+  R* gram_s = reinterpret_cast<R*>(smem + (((size_t)cfg.off_warp + (size_t)G * cfg.warp_bytes + 15) & ~(size_t)15));
+  for (int i = threadIdx.x; i < p * p; i += blockDim.x) gram_s[i] = gd.gram[i];
+  __syncthreads();
+  const int n_iter = plan.n_warmup + plan.n_results;
+  if (warp == G) {
+    if (lane == 0) {
+      omega_fetch(cs, pr);
+      tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, NB,
+                    cfg.resident != 0, 2LL * n_iter, [](long long) { return true; });
+    }
+    return;
+  }
+  if (warp >= nactive) return;
+  omega_wait(cs);
+  const R* om_s = cs.omega;
+  const int c = chain0 + warp;
+  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
+  GibbsScratch<R> gs;
+  gs.bvec = ws.extra; gs.La = gs.bvec + p; gs.Lo = gs.La + (p + 1) * (p + 1);
+  gs.idx = gs.Lo + p * p; gs.vec = gs.idx + p;
+  const int d = sz.d, K = sz.K, LDP = d | 1;
+  R* Ps = gs.vec + (p + 1);             // [d][LDP] state covariance, row i <-> lane i
+  R* phs = Ps + d * LDP;                // [d]      P h of the current step
+  R* Prow = Ps + (lane < d ? lane : 0) * LDP;
+  R* scr = static_cast<R*>(sz.scratch) + (size_t)c * T * (d + 1);
+  TilePipe<R> pipe = make_pipe(cs, cfg);
+  const uint64_t gid = chain_id0 + (uint64_t)c;
+  const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
+
+  // which block element `lane` belongs to: -1 level, k component, -2 unused lane
+  int comp = lane == 0 ? -1 : -2, my_n = 1, my_off = 0;
+  for (int k = 0; k < K; ++k)
+    if (lane >= sz.off[k] && lane < sz.off[k] + sz.n[k]) { comp = k; my_n = sz.n[k]; my_off = sz.off[k]; }
+  const R inv_n = (R)1 / (R)my_n;
+  const int src_off = lane < K ? sz.off[lane] : 0;   // lane l < K describes component l; lane K the level
+
+  // ---- initial state: the reference's (lib.py:566-581) ----
+  double s_e = p > 0 ? 0.2 * (double)pr.P0 : (double)pr.P0;
+  double s_h = (double)pr.lvl_scale / (double)pr.lvl_conc;
+  double sd_l = 1e-4 * sz.init_var;                  // drift VARIANCE of component `lane` (0.01 sd)^2
+  uint32_t gam[4] = {0u, 0u, 0u, 0u};
+  if (!plan.sparse)
+    for (int j = 0; j < p; ++j) gam[j >> 5] |= 1u << (j & 31);
+  for (int j = lane; j < p; j += 32) { gs.bvec[j] = gd.xty0[j]; ws.w[j] = 0; }
+  double yty = (double)gd.yty0;
+  double incl_cnt[DSLOTS] = {0.0, 0.0, 0.0, 0.0};
+  const double conc_e = (double)pr.obs_conc + 0.5 * plan.n_obs;
+  __syncwarp();
+  const GibbsReg<R> reg{pr, gs, gram_s, om_s, p, lane, conc_e, seed, id_lo, id_hi8};
+  const R sd0 = Num<R>::sqrt(pr.P0), sdi = (R)sqrt(sz.init_var);
+
+  // mean over component k's block of the lane-distributed vector v (0 outside blocks)
+  auto block_centered = [&](R v) -> R {
+    R out = 0;
+    for (int k = 0; k < K; ++k) {
+      const R s = warp_sum(comp == k ? v : (R)0);
+      if (comp == k) out = v - s * inv_n;
+    }
+    return out;
+  };
+  // the step's schedule: per-lane source index (lane <= K), mask of observed columns, ends
+  auto step_sched = [&](int t, int& src, unsigned& cmask, int& em) {
+    const uint8_t* sc = sz.sched + (size_t)t * (K + 1);
+    em = sc[K];
+    src = lane < K ? src_off + (int)sc[lane] : 0;
+    cmask = __reduce_or_sync(FULL, lane <= K ? (1u << src) : 0u);
+  };
+  auto gather = [&](R v, int src) -> R {              // h' v
+    const R g = __shfl_sync(FULL, v, src);
+    return warp_sum(lane <= K ? g : (R)0);
+  };
+  auto drift_normal = [&](int t, int it, int k) -> R {
+    const uint4 x = Philox::gen(seed, id_lo, RNG_S_DRIFT | id_hi8, (uint32_t)t,
+                                (uint32_t)it * 8u + (uint32_t)k);
+    R z0, z1;
+    box_muller<R>(x.x, x.y, z0, z1);
+    return z0;
+  };
+  auto init_xplus = [&](int it) -> R {
+    const uint4 x = Philox::gen(seed, id_lo, RNG_S_INIT | id_hi8, (uint32_t)lane, (uint32_t)it);
+    R z0, z1;
+    box_muller<R>(x.x, x.y, z0, z1);
+    const R zc = block_centered(z0);
+    return lane == 0 ? fma(sd0, z0, pr.m0) : (comp >= 0 ? sdi * zc : (R)0);
+  };
+
+  for (int it = 0; it < n_iter; ++it) {
+    // =================== A. regression block ===================
+    reg.step(it, plan, gam, yty, s_e, ws.w);
+
+    // =================== B. (level, seasonal) | rest ===================
+    const R se = (R)s_e, sh = (R)s_h, sig_e = (R)sqrt(s_e), sig_h = (R)sqrt(s_h);
+    const R sdv = (R)sd_l;
+    // ---- pass A ----
+    if (lane < d) {
+      for (int j = 0; j < d; ++j) Prow[j] = 0;
+      if (lane == 0) Prow[0] = pr.P0;
+      if (comp >= 0)
+        for (int j = 0; j < my_n; ++j)
+          Prow[my_off + j] = (R)sz.init_var * ((my_off + j == lane ? (R)1 : (R)0) - inv_n);
+    }
+    __syncwarp();
+    R xp = init_xplus(it), a = 0;
+    for (int b = 0; b < NB; ++b) {
+      const R* tile = pipe.acquire(b);
+      Blk<R> B;
+      R xw[KS];
+      blk_residuals_xw(B, xw, tile, ws.w, p, ld, lane);
+      const int t0 = b * TB + lane * KS;
+      R zeta[KS], zeps[KS];
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const uint4 x = Philox::gen(seed, id_lo, RNG_S_PATH | id_hi8, (uint32_t)(t0 + kk), (uint32_t)it);
+        box_muller<R>(x.x, x.y, zeta[kk], zeps[kk]);
+      }
+      for (int L = 0; L < 32; ++L) {
+        if (b * TB + L * KS >= T) break;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+          const int t = b * TB + L * KS + kk;
+          const R r_t = __shfl_sync(FULL, B.r[kk], L);
+          const bool o = (__shfl_sync(FULL, B.obs, L) >> kk) & 1u;
+          const R eta = __shfl_sync(FULL, zeta[kk], L), eps = __shfl_sync(FULL, zeps[kk], L);
+          if (t < T) {
+            int src, em; unsigned cmask;
+            step_sched(t, src, cmask, em);
+            R Kg = 0, e = 0;
+            if (o) {
+              const R hxa = gather(xp + a, src);
+              R Ph = 0;
+              if (lane < d)
+                for (unsigned m = cmask; m; m &= m - 1) Ph += Prow[__ffs(m) - 1];
+              const R rF = Num<R>::rcp(gather(Ph, src) + se);
+              const R v = (r_t - sig_e * eps) - hxa;
+              e = v * rF; Kg = Ph * rF;
+              a = fma(Kg, v, a);
+              if (lane < d) phs[lane] = Ph;
+              __syncwarp();
+              if (lane < d)
+                for (int j = 0; j < d; ++j) Prow[j] = fma(-(Ph * phs[j]), rF, Prow[j]);
+              __syncwarp();
+            }
+            R* srow = scr + (size_t)t * (d + 1);
+            if (lane < d) srow[lane] = Kg;
+            if (lane == 0) srow[d] = e;
+            // x_{t+1} = x_t + noise_t
+            if (lane == 0) { Prow[0] += sh; xp = fma(sig_h, eta, xp); }
+            if (em) {
+              for (int k = 0; k < K; ++k) {
+                if (!((em >> k) & 1)) continue;
+                const int jk = __shfl_sync(FULL, src, k);
+                const R sdk = __shfl_sync(FULL, sdv, k);
+                const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
+                if (comp == k)
+                  for (int j = 0; j < my_n; ++j)
+                    Prow[my_off + j] = fma(sdk * ci, (my_off + j == jk ? (R)1 : (R)0) - inv_n,
+                                           Prow[my_off + j]);
+                xp = fma(Num<R>::sqrt(sdk) * drift_normal(t, it, k), ci, xp);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      pipe.release(lane);
+    }
+    __syncwarp();
+    // ---- pass B ----
+    R rr = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      int src, em; unsigned cmask;
+      step_sched(t, src, cmask, em);
+      R* srow = scr + (size_t)t * (d + 1);
+      if (t >= 4 && lane == 0) prefetch_l1(srow - 4 * (d + 1));
+      const R Kg = lane < d ? srow[lane] : (R)0;
+      const R e = srow[d];
+      if (lane < d) srow[lane] = rr;                       // r_t, read back by pass C
+      const R dot = warp_sum(Kg * rr);
+      if ((cmask >> lane) & 1u) rr += e - dot;
+    }
+    __syncwarp();
+    // ---- pass C ----
+    const bool keep = it >= plan.n_warmup;
+    const size_t out_row = !keep ? 0
+        : plan.chain_major ? ((size_t)c * plan.n_results + (size_t)(it - plan.n_warmup))
+                           : ((size_t)(it - plan.n_warmup) * C + c);
+    R xt = init_xplus(it);                                 // x = x+ + xhat, element `lane`
+    {
+      const R rc = block_centered(rr);
+      xt += lane == 0 ? pr.P0 * rr : (comp >= 0 ? (R)sz.init_var * rc : (R)0);
+    }
+    const XtMap xm = xt_map(p, lane);
+    const bool small_p = p <= PSMALL;
+    R accw[PSMALL];
+#pragma unroll
+    for (int j = 0; j < PSMALL; ++j) accw[j] = 0;
+    R accg[JS];
+#pragma unroll
+    for (int s = 0; s < JS; ++s) accg[s] = 0;
+    double n_yty = 0.0, d2 = 0.0, su2 = 0.0;
+    R prev_level = 0;
+    for (int b = 0; b < NB; ++b) {
+      const R* tile = pipe.acquire(b);
+      Blk<R> B;
+      R xw[KS];
+      blk_residuals_xw(B, xw, tile, ws.w, p, ld, lane);
+      const int t0 = b * TB + lane * KS;
+      R zeta[KS], zp[KS];
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const uint4 x = Philox::gen(seed, id_lo, RNG_S_PATH | id_hi8, (uint32_t)(t0 + kk), (uint32_t)it);
+        R zeps;
+        box_muller<R>(x.x, x.y, zeta[kk], zeps);
+        box_muller<R>(x.z, x.w, zp[kk], zeps);
+      }
+      R lv[KS], sc[KS];
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) { lv[kk] = 0; sc[kk] = 0; }
+      for (int L = 0; L < 32; ++L) {
+        if (b * TB + L * KS >= T) break;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+          const int t = b * TB + L * KS + kk;
+          const R eta = __shfl_sync(FULL, zeta[kk], L);
+          if (t < T) {
+            int src, em; unsigned cmask;
+            step_sched(t, src, cmask, em);
+            const R* srow = scr + (size_t)t * (d + 1);
+            if (t + 4 < T && lane == 0) prefetch_l1(srow + 4 * (d + 1));
+            const R g = __shfl_sync(FULL, xt, src);        // lane k < K: contribution of component k
+            const R tot = warp_sum(lane <= K ? g : (R)0);  // level + all contributions
+            const R level_t = __shfl_sync(FULL, xt, 0);
+            if (lane == L) { lv[kk] = level_t; sc[kk] = tot - level_t; }
+            if (keep && seas_out && lane < K) seas_out[(out_row * T + t) * K + lane] = g;
+            if (t > 0) { const double dl = (double)(level_t - prev_level); d2 += dl * dl; }
+            prev_level = level_t;
+            if (t < T - 1) {
+              const R rt = lane < d ? srow[lane] : (R)0;
+              if (lane == 0) xt += fma(sh, rt, sig_h * eta);
+              if (em) {
+                for (int k = 0; k < K; ++k) {
+                  if (!((em >> k) & 1)) continue;
+                  const int jk = __shfl_sync(FULL, src, k);
+                  const R sdk = __shfl_sync(FULL, sdv, k);
+                  const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
+                  const R cr = __shfl_sync(FULL, rt, jk) -
+                               warp_sum(comp == k ? rt : (R)0) / (R)sz.n[k];
+                  const R u = fma(sdk, cr, Num<R>::sqrt(sdk) * drift_normal(t, it, k));
+                  xt = fma(u, ci, xt);
+                  if (lane == k) su2 += (double)u * (double)u;
+                }
+              }
+            }
+          }
+        }
+      }
+      // ---- per-lane epilogue for the tile's 8 owned steps (as k_gibbs) ----
+      R tgt[KS];
+      R ly = 0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const bool o = (B.obs >> kk) & 1u;
+        tgt[kk] = o ? (B.r[kk] - lv[kk] - sc[kk]) : (R)0;   // y - x.w - level - seasonal ... + x.w below
+        tgt[kk] = o ? tgt[kk] + xw[kk] : (R)0;              // targets of step A: y - level - seasonal
+        ly = fma(tgt[kk], tgt[kk], ly);
+      }
+      n_yty += (double)ly;
+      if (p > 0) {
+        if (small_p) {
+          blk_xt_rbar_small(tile, tgt, p, ld, lane, accw);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < KS; ++kk) ws.rbuf[lane * KS + kk + (lane >> 2)] = tgt[kk];
+          __syncwarp();
+          blk_xt_rbar<R, JS>(tile, ws.rbuf, p, ld, xm.jj, xm.part, xm.nparts, accg);
+          __syncwarp();
+        }
+      }
+      if (keep) {
+        R la[KS], tr[KS];
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+          la[kk] = lv[kk] + sc[kk];
+          tr[kk] = la[kk] + xw[kk] + sig_e * zp[kk];
+        }
+        if (level_out) store_run(level_out + out_row * T, t0, T, lv);
+        if (latent_out) store_run(latent_out + out_row * T, t0, T, la);
+        if (traj_out) store_run(traj_out + out_row * T, t0, T, tr);
+      }
+      pipe.release(lane);
+    }
+    // publish the statistics of the next sweep
+    yty = warp_sum(n_yty);
+    __syncwarp();
+    if (small_p) {
+#pragma unroll
+      for (int j = 0; j < PSMALL; ++j) {
+        if (j < p) {
+          const R tot = warp_sum(accw[j]);
+          if (lane == 0) gs.bvec[j] = tot;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < JS; ++s) {
+        R av = accg[s];
+        for (int o = xm.PJ; o < 32; o <<= 1) av += __shfl_xor_sync(FULL, av, o);
+        const int j = lane + 32 * s;
+        if (j < p && lane < xm.PJ) gs.bvec[j] = av;
+      }
+    }
+    __syncwarp();
+    // =================== C. variances ===================
+    {
+      const double g = gamma_draw((double)pr.lvl_conc + 0.5 * (T - 1), seed, id_lo,
+                                  RNG_G_GAMMA | id_hi8, (uint32_t)it, 1u);
+      s_h = ((double)pr.lvl_scale + 0.5 * d2) / g;
+      const double ub2 = (double)pr.lvl_ub * (double)pr.lvl_ub;
+      if (s_h > ub2) s_h = ub2;                                        // lib.py:432
+    }
+    for (int k = 0; k < K; ++k) {
+      const double u2 = __shfl_sync(FULL, su2, k);
+      const double g = gamma_draw_any(sz.drift_conc + 0.5 * sz.n_ends[k], seed, id_lo,
+                                      RNG_G_GAMMA | id_hi8, (uint32_t)it, 2u + (uint32_t)k);
+      double v = (sz.drift_scale + 0.5 * u2) / g;
+      const double ub2 = sz.drift_ub * sz.drift_ub;
+      if (v > ub2) v = ub2;                                            // lib.py:474
+      if (lane == k) sd_l = v;
+    }
+    if (keep) {
+      R* row = draws + out_row * dim;
+      for (int j = lane; j < p; j += 32) row[j] = ws.w[j];
+      if (lane == 0) { row[p] = (R)log(s_e); row[p + 1] = (R)log(s_h); }
+      if (drift_out && lane < K) drift_out[out_row * K + lane] = (R)log(sd_l);
+#pragma unroll
+      for (int wd = 0; wd < DSLOTS; ++wd) incl_cnt[wd] += (double)((gam[wd] >> lane) & 1u);
+    }
+  }
+  if (incl_out) {
+#pragma unroll
+    for (int wd = 0; wd < DSLOTS; ++wd) {
+      const int j = lane + 32 * wd;
+      if (j < p) incl_out[(size_t)c * p + j] = (float)(incl_cnt[wd] / (plan.n_results > 0 ? plan.n_results : 1));
+    }
+  }
+}
+
+}  // namespace ci
