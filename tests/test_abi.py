@@ -30,6 +30,12 @@ def test_struct_layouts_match_header():
   assert ctypes.sizeof(_engine.CiProblem) == 4 * 4 + 13 * 8
   assert ctypes.sizeof(_engine.CiHmcOpts) == 4 * 4 + 2 * 8
   assert ctypes.sizeof(_engine.CiHmcStats) == 16 == _engine.HMC_STATS_DTYPE.itemsize
+  assert ctypes.sizeof(_engine.CiGibbsOpts) == 4 * 4 + 8
+  assert ctypes.sizeof(_engine.CiImpactArgs) == 4 * 4 + 5 * 8
+  assert ctypes.sizeof(_engine.CiSeasonal) == 8 * 4 + 2 * 8 + 4 * 8
+  assert _engine.MAX_SEASONAL == 7 and _engine.IMPACT_SERIES_COLS == 9
+  header = open(os.path.join(ROOT, "include", "ci_b200.h")).read()
+  assert "#define CI_MAX_SEASONAL 7" in header and "#define CI_IMPACT_SUMMARY_LEN 20" in header
 
 
 def test_no_cpu_fallback_without_gpu():

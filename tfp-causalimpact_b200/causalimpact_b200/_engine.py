@@ -482,7 +482,16 @@ class Engine:
     return mean
 
   def to_host(self, t) -> np.ndarray:
-    return t.detach().cpu().numpy()
+    """Device tensor -> ndarray.  Large arrays (the [S,T] level paths) go through pinned
+    memory: 1.4 ms instead of 38 ms for 80 MB on the B200 box (run 21); the returned
+    array aliases the pinned block, which torch's host allocator recycles once freed."""
+    t = t.detach()
+    if t.is_cuda and t.numel() * t.element_size() >= (1 << 20):
+      import torch
+      host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+      host.copy_(t)                      # synchronous for device -> pinned host
+      return host.numpy()
+    return t.cpu().numpy()
 
   # -- impact series + summary (SURVEY 8 f1) -----------------------------------
   def impact(self, traj, mean, meta) -> Tuple[np.ndarray, np.ndarray]:
