@@ -26,19 +26,21 @@ torch.cuda.set_device(local)
 if world > 1:
   dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 out = {}
-for name, n_cov in (("hmc_path", 1), ("gibbs_path", 6)):
+for name, n_cov in (("hmc_path", 1), ("gibbs_path", 6), ("seasonal_path", 1)):
   rng = np.random.default_rng(5)
   n = 400
   xs = 100 + np.cumsum(rng.normal(size=(n, n_cov)), axis=0) * 0.3
   y = 1.2 * xs[:, 0] + rng.normal(size=n); y[280:] += 6
   df = pd.DataFrame(np.column_stack([y, xs]), columns=["y"] + [f"x{i}" for i in range(n_cov)])
-  res = cib.fit_causalimpact(df, (0, 279), (280, 399), seed=(3, 4),
+  mo = cib.ModelOptions(seasons=[cib.Seasons(num_seasons=7)]) if name == "seasonal_path" else None
+  res = cib.fit_causalimpact(df, (0, 279), (280, 399), seed=(3, 4), model_options=mo,
                              inference_options=cib.InferenceOptions(num_results=500),
                              engine_options=cib.EngineOptions(num_chains=50))
   vals = [c for c in res.series.columns if not c.endswith(("_start", "_end"))]
   out[name] = dict(series=res.series[vals].values, summary=res.summary.values,
                    level=np.asarray(res.posterior_samples.level),
-                   weights=np.asarray(res.posterior_samples.weights))
+                   weights=np.asarray(res.posterior_samples.weights),
+                   seasonal=np.asarray(res.posterior_samples.seasonal_levels))
   if int(os.environ.get("RANK", "0")) == 0:
     print(name, res.diagnostics["sampler"], "abs_effect", float(res.summary.loc["average", "abs_effect"]))
 if int(os.environ.get("RANK", "0")) == 0:
