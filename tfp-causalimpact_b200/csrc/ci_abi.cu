@@ -108,6 +108,9 @@ template <typename R> LltDev<R> make_lltdev(const ci_ctx* c) {
   return d;
 }
 
+// static shared memory of the select kernels (16 x 256 histograms + bookkeeping), rounded up
+constexpr size_t QSTATIC = 20 * 1024;
+
 inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 // Opt in to `bytes` of dynamic shared memory AND ask for the largest shared-memory
@@ -483,9 +486,9 @@ int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, 
                      void* out_d, cudaStream_t st, int out_ld = 0) {
   // the whole column lives in shared memory as integer keys
   const size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
-  if (bytes + 12 * 1024 > (size_t)c->smem_optin)
+  if (bytes + QSTATIC > (size_t)c->smem_optin)
     return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles: S=%d does not fit the shared-memory select "
-                "(max %d draws for this dtype)", S, (int)((c->smem_optin - 12 * 1024) / sizeof(R)));
+                "(max %d draws for this dtype)", S, (int)((c->smem_optin - QSTATIC) / sizeof(R)));
   QuantArgs qa;
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q[i];
@@ -1047,9 +1050,9 @@ int ci_impact_d(ci_ctx* c, const ci_impact_args* a, const void* traj_d, const vo
   }
   if (d.n_post < 1) return fail(CI_ERR_INVALID, "the post-period is empty");
   const size_t keyb = (size_t)S * sizeof(double);
-  if (keyb + 12 * 1024 > (size_t)c->smem_optin)
+  if (keyb + QSTATIC > (size_t)c->smem_optin)
     return fail(CI_ERR_UNSUPPORTED, "ci_impact: S=%d exceeds the shared-memory select (max %d draws)",
-                S, (int)((c->smem_optin - 12 * 1024) / sizeof(double)));
+                S, (int)((c->smem_optin - QSTATIC) / sizeof(double)));
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Tc = T - d.t_c0;

@@ -125,62 +125,45 @@ __global__ void k_impact_cols(const R* __restrict__ traj, const double* __restri
   using Key = typename KeyOf<R>::type;
   extern __shared__ __align__(16) unsigned char qsmem[];
   Key* keys = reinterpret_cast<Key*>(qsmem);
-  __shared__ int hist[QBINS];
-  __shared__ int res[2];
-  __shared__ int n_valid;
-  const int t = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  __shared__ SelectShared<R> sh;
+  __shared__ int n_valid, s_nr;
+  __shared__ int slot[2][4];     // per quantile: lo, hi, mirrored lo, mirrored hi
+  const int t = blockIdx.x, tid = threadIdx.x;
   const int S = a.S, T = a.T;
-  if (tid == 0) n_valid = 0;
-  __syncthreads();
-  int cnt = 0;
-  for (int i = tid; i < S; i += nt) {
-    const R v = traj[(size_t)i * T + t];
-    const bool ok = (v == v);
-    keys[i] = ok ? KeyOf<R>::enc(v) : KeyOf<R>::nan_key();
-    cnt += ok ? 1 : 0;
-  }
-  cnt = __reduce_add_sync(FULL, cnt);
-  if ((tid & 31) == 0 && cnt) atomicAdd(&n_valid, cnt);
-  __syncthreads();
-  const int n = n_valid;
+  const int n = load_column_keys<R>(traj, S, T, t, keys, &n_valid);
   double* row = series + (size_t)t * IMP_SERIES_COLS;
   if (t < a.t_c0 && tid == 0) { row[7] = 0.0; row[8] = 0.0; }   // cumulative effect is 0 before post
   if (n == 0) {
     if (tid == 0) { row[1] = row[2] = row[4] = row[5] = CUDART_NAN; }
     return;
   }
-  // order statistics already selected for this column (uniform across the CTA)
-  int c_rank[8];
-  double c_val[8];
-  int nc = 0;
-  auto order_stat = [&](int k) -> double {
-    for (int i = 0; i < nc; ++i)
-      if (c_rank[i] == k) return c_val[i];
-    const double v = imp_unscale((double)KeyOf<R>::dec(radix_select<R>(keys, S, k, hist, res)),
-                                 a.scale, a.offset);
-    c_rank[nc] = k; c_val[nc] = v; ++nc;
-    return v;
-  };
-  const double o = obs[t];
-  const bool o_nan = !(o == o);
-#pragma unroll 1
-  for (int iq = 0; iq < 2; ++iq) {
+  if (tid == 0) {
+    int nr = 0;
+    for (int iq = 0; iq < 2; ++iq) {
+      const double pos = (iq == 0 ? a.q_lo : a.q_hi) * (double)(n - 1);
+      int lo = (int)floor(pos);
+      lo = lo < 0 ? 0 : (lo > n - 1 ? n - 1 : lo);
+      const int hi = lo + 1 < n ? lo + 1 : n - 1;
+      slot[iq][0] = add_rank(sh, nr, lo);
+      slot[iq][1] = add_rank(sh, nr, hi);
+      // k-th smallest of (o - x) = o - (k-th largest x)
+      slot[iq][2] = add_rank(sh, nr, n - 1 - lo);
+      slot[iq][3] = add_rank(sh, nr, n - 1 - hi);
+    }
+    s_nr = nr;
+  }
+  __syncthreads();
+  radix_select_multi<R>(keys, S, s_nr, sh);
+  if (tid < 2) {
+    const int iq = tid;
     const double pos = (iq == 0 ? a.q_lo : a.q_hi) * (double)(n - 1);
     int lo = (int)floor(pos);
     lo = lo < 0 ? 0 : (lo > n - 1 ? n - 1 : lo);
-    const int hi = lo + 1 < n ? lo + 1 : n - 1;
     const double g = pos - (double)lo;
-    const bool one = (hi == lo || g == 0.0);
-    const double va = order_stat(lo);
-    const double vb = one ? va : order_stat(hi);
-    const double pred_q = imp_lerp(va, vb, g);
-    double point_q = CUDART_NAN;
-    if (!o_nan) {                                      // k-th smallest of (o - x) = o - (k-th largest x)
-      const double pa = o - order_stat(n - 1 - lo);
-      const double pb = one ? pa : o - order_stat(n - 1 - hi);
-      point_q = imp_lerp(pa, pb, g);
-    }
-    if (tid == 0) { row[1 + iq] = pred_q; row[4 + iq] = point_q; }
+    auto val = [&](int s_) { return imp_unscale((double)KeyOf<R>::dec(sh.out[slot[iq][s_]]), a.scale, a.offset); };
+    row[1 + iq] = imp_lerp(val(0), val(1), g);
+    const double o = obs[t];
+    row[4 + iq] = (o == o) ? imp_lerp(o - val(2), o - val(3), g) : CUDART_NAN;
   }
 }
 
