@@ -71,7 +71,7 @@ struct ci_ctx {
   DevBuf w_theta, w_value, w_grad;   // workspaces of the host-pointer entry points
   DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats, w_incl;
   DevBuf gram, xty0;                 // X'X, X'y over observed rows (Gibbs regression step)
-  DevBuf i_cum, i_stats, i_meta, i_series, i_summ;   // ci_impact workspaces
+  DevBuf i_cum, i_stats, i_meta, i_series, i_summ, i_trT;   // ci_impact workspaces
   DevBuf s_sched, s_scratch, w_latent, w_seas, w_drift;   // seasonal components
   ci::SeasDev seas{};                // seas.K == 0: no seasonal components
   double yty0 = 0.0;
@@ -508,33 +508,21 @@ int launch_impact(ci_ctx* c, const ImpactDev& a, const void* traj_d, const void*
                   const double* obs_d, const uint8_t* period_d, double* series_d, double* summ_d,
                   cudaStream_t st) {
   const int S = a.S, T = a.T, Tc = T - a.t_c0;
-  double* cum = static_cast<double*>(c->i_cum.p);
-  double* stats = static_cast<double*>(c->i_stats.p);
-  k_impact_rows<R><<<(S + 1 + IMP_ROWS_PER_CTA - 1) / IMP_ROWS_PER_CTA, 32 * IMP_ROWS_PER_CTA, 0, st>>>(
-      static_cast<const R*>(traj_d), static_cast<const R*>(mean_d), obs_d, period_d, a, cum, stats,
-      series_d, summ_d);
+  R* trT = static_cast<R*>(c->i_trT.p);
+  double* cumT = static_cast<double*>(c->i_cum.p);
+  double* statsT = static_cast<double*>(c->i_stats.p);
+  const int row_ctas = (S + IMP_TILE - 1) / IMP_TILE + 1;            // + the predictive mean
+  k_impact_rows<R><<<row_ctas, 32 * IMP_TILE, 0, st>>>(
+      static_cast<const R*>(traj_d), static_cast<const R*>(mean_d), obs_d, period_d, a, trT, cumT,
+      statsT, series_d, summ_d);
   CU_TRY(cudaGetLastError());
   c->launches++;
-  {
-    const size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
-    auto kern = k_impact_cols<R>;
-    CU_TRY(set_smem(kern, (uint32_t)bytes));
-    int nt = 1024;
-    while (nt > 64 && nt / 2 >= S) nt >>= 1;
-    kern<<<T, nt, bytes, st>>>(static_cast<const R*>(traj_d), obs_d, a, series_d);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
-  }
-  const double q[2] = {a.q_lo, a.q_hi};
-  if (Tc > 0) {   // cumulative-effect quantiles (lib.py:888) straight into series columns 7, 8
-    int rc = launch_quantiles<double>(c, cum, S, Tc, q, 2,
-                                      series_d + (size_t)a.t_c0 * IMP_SERIES_COLS + 7, st,
-                                      IMP_SERIES_COLS);
-    if (rc) return rc;
-  }
-  int rc = launch_quantiles<double>(c, stats, S, IMP_STATS, q, 2, summ_d, st);
-  if (rc) return rc;
-  k_impact_summary<<<1, 1024, 0, st>>>(stats, a, summ_d);
+  const size_t bytes = (((size_t)S * sizeof(double)) + 15) & ~(size_t)15;   // float64 jobs
+  auto kern = k_impact_jobs<R>;
+  CU_TRY(set_smem(kern, (uint32_t)bytes));
+  int nt = 1024;
+  while (nt > 64 && nt / 2 >= S) nt >>= 1;
+  kern<<<Tc + IMP_STATS + T + 1, nt, bytes, st>>>(trT, cumT, statsT, obs_d, a, series_d, summ_d);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;
@@ -592,7 +580,7 @@ int ci_ctx_destroy(ci_ctx* c) {
   c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release(); c->w_incl.release();
   c->gram.release(); c->xty0.release();
   c->s_sched.release(); c->s_scratch.release(); c->w_latent.release(); c->w_seas.release(); c->w_drift.release();
-  c->i_cum.release(); c->i_stats.release(); c->i_meta.release(); c->i_series.release(); c->i_summ.release();
+  c->i_trT.release(); c->i_cum.release(); c->i_stats.release(); c->i_meta.release(); c->i_series.release(); c->i_summ.release();
   delete c;
   return CI_OK;
 }
@@ -1058,6 +1046,7 @@ int ci_impact_d(ci_ctx* c, const ci_impact_args* a, const void* traj_d, const vo
   const int Tc = T - d.t_c0;
   CU_TRY(c->i_cum.reserve((size_t)S * (Tc > 0 ? Tc : 1) * sizeof(double)));
   CU_TRY(c->i_stats.reserve((size_t)S * ci::IMP_STATS * sizeof(double)));
+  CU_TRY(c->i_trT.reserve((size_t)S * T * (a->dtype == CI_F64 ? 8 : 4)));
   const size_t ob = (size_t)T * sizeof(double);
   CU_TRY(c->i_meta.reserve(ob + (size_t)T));
   CU_TRY(cudaMemcpyAsync(c->i_meta.p, observed, ob, cudaMemcpyHostToDevice, st));

@@ -14,12 +14,18 @@
 // selected values are un-scaled; the point-effect quantiles reuse the same
 // column: the k-th smallest of (y_t - x) is y_t minus the k-th LARGEST x.
 //
-// Three kernels + two launches of K5 (ci_predict.cuh):
-//   k_impact_rows   one warp per draw (+1 warp for the predictive mean): cumulative
-//                   effect paths (warp scan over time), post-period per-draw statistics
-//   k_impact_cols   one CTA per time step: prediction and point-effect quantiles
-//   k_row_quantiles<double> on the cumulative paths and on the per-draw statistics
-//   k_impact_summary  one CTA: sd (ddof=1), mean relative effect, tail counts
+// Two launches:
+//   k_impact_rows  one warp per draw, 32 draws per CTA (+1 CTA for the predictive mean):
+//                  cumulative effect paths (warp scan over time), post-period per-draw
+//                  statistics; the raw draws and the cumulative paths leave the CTA
+//                  TRANSPOSED ([T,S], through a 32x32 shared-memory tile, coalesced on both
+//                  sides) so that every column job below reads one contiguous run.  (Run 22:
+//                  gathering a column from the [S,T] layout cost a 32-byte sector per 4-byte
+//                  value and 0.6 ms of the 1.25 ms call.)
+//   k_impact_jobs  one CTA per column job, all independent: T_c cumulative-effect columns
+//                  (float64 keys), the 5 per-draw statistics, T prediction / point-effect
+//                  columns (raw keys), and one CTA for sd / mean / tail counts.  Each job =
+//                  contiguous key load + the multi-rank radix select of ci_predict.cuh.
 #pragma once
 #include "ci_predict.cuh"
 
@@ -39,31 +45,38 @@ __device__ __forceinline__ double imp_unscale(double x, double scale, double off
   return __dadd_rn(__dmul_rn(x, scale), offset);
 }
 
-constexpr int IMP_ROWS_PER_CTA = 8;
+constexpr int IMP_TILE = 32;         // draws per CTA == time steps per chunk
 
-// Row r < S: draw r of traj; row S: the predictive mean (its cumulative path and
-// post-period mean / sum are the *_mean series columns and `predicted`).
+// Row r < S: draw r of traj (CTA b holds draws 32b .. 32b+31, warp w <-> draw, lane <-> t);
+// the LAST CTA's warp 0 handles the predictive mean (its cumulative path and post-period
+// mean / sum are the *_mean series columns and `predicted`).
 template <typename R>
-__global__ void __launch_bounds__(32 * IMP_ROWS_PER_CTA)
+__global__ void __launch_bounds__(32 * IMP_TILE)
 k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
               const double* __restrict__ obs, const uint8_t* __restrict__ period, ImpactDev a,
-              double* __restrict__ cum, double* __restrict__ stats, double* __restrict__ series,
-              double* __restrict__ summ) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * IMP_ROWS_PER_CTA + (threadIdx.x >> 5);
-  if (r > a.S) return;
-  const bool is_mean = (r == a.S);
-  const R* src = is_mean ? mean : traj + (size_t)r * a.T;
-  const int Tc = a.T - a.t_c0;
+              R* __restrict__ trT, double* __restrict__ cumT, double* __restrict__ statsT,
+              double* __restrict__ series, double* __restrict__ summ) {
+  __shared__ R tile_raw[IMP_TILE][IMP_TILE + 1];
+  __shared__ double tile_cum[IMP_TILE][IMP_TILE + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool mean_cta = blockIdx.x == gridDim.x - 1;
+  const int r0 = blockIdx.x * IMP_TILE;
+  const int r = mean_cta ? a.S : r0 + warp;
+  const bool is_mean = mean_cta;
+  if (mean_cta && warp != 0) return;                 // (no CTA-wide barrier on this path)
+  const bool row_ok = is_mean || r < a.S;
+  const R* src = is_mean ? mean : traj + (size_t)(row_ok ? r : 0) * a.T;
   double carry = 0.0, pred_sum = 0.0, eff_sum = 0.0;
   int eff_cnt = 0;
-  for (int base = is_mean ? 0 : a.t_c0; base < a.T; base += 32) {
+  for (int base = 0; base < a.T; base += IMP_TILE) {
     const int t = base + lane;
-    const bool valid = t < a.T;
+    const bool valid = row_ok && t < a.T;
     double x = 0.0, pt = CUDART_NAN;
+    R raw = 0;
     int per = 0;
     if (valid) {
-      x = imp_unscale((double)src[t], a.scale, a.offset);
+      raw = src[t];
+      x = imp_unscale((double)raw, a.scale, a.offset);
       pt = obs[t] - x;                               // lib.py:822-823
       per = period[t];
     }
@@ -77,33 +90,44 @@ k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
     }
     const double cv = carry + inc;
     carry += __shfl_sync(FULL, inc, 31);
-    if (valid) {
-      const double out = (t >= a.t_c0 && isn) ? CUDART_NAN : cv;
-      if (is_mean) {
+    const double out = (t >= a.t_c0 && isn) ? CUDART_NAN : cv;
+    if (valid && per == 1) {                         // inside the post-period (lib.py:966-1011)
+      pred_sum += x;
+      if (!isn) { eff_sum += pt; ++eff_cnt; }
+    }
+    if (is_mean) {
+      if (valid) {
         double* row = series + (size_t)t * IMP_SERIES_COLS;
         row[0] = x; row[3] = pt; row[6] = out;
-      } else {
-        cum[(size_t)r * Tc + (t - a.t_c0)] = out;
       }
-      if (per == 1) {                                // inside the post-period (lib.py:966-1011)
-        pred_sum += x;
-        if (!isn) { eff_sum += pt; ++eff_cnt; }
+      continue;
+    }
+    // transpose the chunk: [draw][t] -> [t][draw]
+    tile_raw[warp][lane] = raw;
+    tile_cum[warp][lane] = out;
+    __syncthreads();
+    {
+      const int tc = base + warp, rr = r0 + lane;    // warp <-> time step, lane <-> draw
+      if (tc < a.T && rr < a.S) {
+        trT[(size_t)tc * a.S + rr] = tile_raw[lane][warp];
+        if (tc >= a.t_c0) cumT[(size_t)(tc - a.t_c0) * a.S + rr] = tile_cum[lane][warp];
       }
     }
+    __syncthreads();
   }
   pred_sum = warp_sum(pred_sum);
   eff_sum = warp_sum(eff_sum);
   eff_cnt = __reduce_add_sync(FULL, eff_cnt);
-  if (lane == 0) {
+  if (lane == 0 && row_ok) {
     const double pm = pred_sum / (double)a.n_post;
     if (is_mean) {
       summ[18] = pm; summ[19] = pred_sum;
     } else {
-      double* st = stats + (size_t)r * IMP_STATS;
-      st[0] = pm; st[1] = pred_sum;
-      st[2] = eff_cnt > 0 ? eff_sum / (double)eff_cnt : CUDART_NAN;
-      st[3] = eff_sum;
-      st[4] = a.obs_sum / pred_sum - 1.0;            // lib.py:1010-1011
+      statsT[0 * (size_t)a.S + r] = pm;
+      statsT[1 * (size_t)a.S + r] = pred_sum;
+      statsT[2 * (size_t)a.S + r] = eff_cnt > 0 ? eff_sum / (double)eff_cnt : CUDART_NAN;
+      statsT[3 * (size_t)a.S + r] = eff_sum;
+      statsT[4 * (size_t)a.S + r] = a.obs_sum / pred_sum - 1.0;      // lib.py:1010-1011
     }
   }
 }
@@ -117,64 +141,78 @@ __device__ __forceinline__ double imp_lerp(double va, double vb, double g) {
   return r;
 }
 
-// One CTA per time step: prediction quantiles and point-effect quantiles from ONE read
-// of the column (posterior_processing.py:25-60 called at lib.py:760 and :886).
-template <typename R>
-__global__ void k_impact_cols(const R* __restrict__ traj, const double* __restrict__ obs,
-                              ImpactDev a, double* __restrict__ series) {
-  using Key = typename KeyOf<R>::type;
-  extern __shared__ __align__(16) unsigned char qsmem[];
-  Key* keys = reinterpret_cast<Key*>(qsmem);
-  __shared__ SelectShared<R> sh;
-  __shared__ int n_valid, s_nr;
-  __shared__ int slot[2][4];     // per quantile: lo, hi, mirrored lo, mirrored hi
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const int S = a.S, T = a.T;
-  const int n = load_column_keys<R>(traj, S, T, t, keys, &n_valid);
-  double* row = series + (size_t)t * IMP_SERIES_COLS;
-  if (t < a.t_c0 && tid == 0) { row[7] = 0.0; row[8] = 0.0; }   // cumulative effect is 0 before post
-  if (n == 0) {
-    if (tid == 0) { row[1] = row[2] = row[4] = row[5] = CUDART_NAN; }
-    return;
+// Contiguous column -> shared-memory keys; returns the number of non-NaN values.
+template <typename V>
+__device__ __forceinline__ int load_contig_keys(const V* __restrict__ col, int S,
+                                                typename KeyOf<V>::type* keys, int* n_valid) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) *n_valid = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int i = tid; i < S; i += nt) {
+    const V v = col[i];
+    const bool ok = (v == v);
+    keys[i] = ok ? KeyOf<V>::enc(v) : KeyOf<V>::nan_key();
+    cnt += ok ? 1 : 0;
   }
-  if (tid == 0) {
+  cnt = __reduce_add_sync(FULL, cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(n_valid, cnt);
+  __syncthreads();
+  return *n_valid;
+}
+
+// (q_lo, q_hi) quantiles of one contiguous column of V; MIRROR also selects the mirrored
+// ranks: the k-th smallest of (o - x) is o minus the k-th LARGEST x.  Results (as V
+// values, not yet un-scaled) in res[iq][0..3] = lo, hi, mirrored lo, mirrored hi; g[iq] =
+// interpolation weight.  Returns n (0 => no valid value).  Whole CTA.
+template <typename V, bool MIRROR>
+__device__ __forceinline__ int column_quantiles(const V* __restrict__ col, int S, double q_lo,
+                                                double q_hi, unsigned char* key_mem,
+                                                SelectShared<V>& sh, int* ibuf, double (&res)[2][4],
+                                                double (&g)[2]) {
+  using Key = typename KeyOf<V>::type;
+  Key* keys = reinterpret_cast<Key*>(key_mem);
+  int* n_valid = ibuf;                // [0]; [1] = number of ranks; [2..9] = slots
+  const int n = load_contig_keys<V>(col, S, keys, n_valid);
+  if (n == 0) return 0;
+  if (threadIdx.x == 0) {
     int nr = 0;
     for (int iq = 0; iq < 2; ++iq) {
-      const double pos = (iq == 0 ? a.q_lo : a.q_hi) * (double)(n - 1);
+      const double pos = (iq == 0 ? q_lo : q_hi) * (double)(n - 1);
       int lo = (int)floor(pos);
       lo = lo < 0 ? 0 : (lo > n - 1 ? n - 1 : lo);
       const int hi = lo + 1 < n ? lo + 1 : n - 1;
-      slot[iq][0] = add_rank(sh, nr, lo);
-      slot[iq][1] = add_rank(sh, nr, hi);
-      // k-th smallest of (o - x) = o - (k-th largest x)
-      slot[iq][2] = add_rank(sh, nr, n - 1 - lo);
-      slot[iq][3] = add_rank(sh, nr, n - 1 - hi);
+      ibuf[2 + 4 * iq + 0] = add_rank(sh, nr, lo);
+      ibuf[2 + 4 * iq + 1] = add_rank(sh, nr, hi);
+      if (MIRROR) {
+        ibuf[2 + 4 * iq + 2] = add_rank(sh, nr, n - 1 - lo);
+        ibuf[2 + 4 * iq + 3] = add_rank(sh, nr, n - 1 - hi);
+      }
     }
-    s_nr = nr;
+    ibuf[1] = nr;
   }
   __syncthreads();
-  radix_select_multi<R>(keys, S, s_nr, sh);
-  if (tid < 2) {
-    const int iq = tid;
-    const double pos = (iq == 0 ? a.q_lo : a.q_hi) * (double)(n - 1);
+  radix_select_multi<V>(keys, S, ibuf[1], sh);
+#pragma unroll
+  for (int iq = 0; iq < 2; ++iq) {
+    const double pos = (iq == 0 ? q_lo : q_hi) * (double)(n - 1);
     int lo = (int)floor(pos);
     lo = lo < 0 ? 0 : (lo > n - 1 ? n - 1 : lo);
-    const double g = pos - (double)lo;
-    auto val = [&](int s_) { return imp_unscale((double)KeyOf<R>::dec(sh.out[slot[iq][s_]]), a.scale, a.offset); };
-    row[1 + iq] = imp_lerp(val(0), val(1), g);
-    const double o = obs[t];
-    row[4 + iq] = (o == o) ? imp_lerp(o - val(2), o - val(3), g) : CUDART_NAN;
+    g[iq] = pos - (double)lo;
+#pragma unroll
+    for (int j = 0; j < (MIRROR ? 4 : 2); ++j)
+      res[iq][j] = (double)KeyOf<V>::dec(sh.out[ibuf[2 + 4 * iq + j]]);
   }
+  return n;
 }
 
 // sd (ddof = 1), mean relative effect and the tail counts of the p-value (lib.py:1021-1090).
 // One CTA, fixed reduction order: deterministic.
-__global__ void __launch_bounds__(1024)
-k_impact_summary(const double* __restrict__ stats, ImpactDev a, double* __restrict__ summ) {
-  __shared__ double red[32];
-  __shared__ double bc;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int S = a.S;
+__device__ __forceinline__ void impact_summary_block(const double* __restrict__ statsT,
+                                                     const ImpactDev& a, double* __restrict__ summ,
+                                                     double* red /*[33] shared*/) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int S = a.S, nw = nt >> 5;
   auto block_sum = [&](double v) -> double {
     v = warp_sum(v);
     __syncthreads();
@@ -182,19 +220,20 @@ k_impact_summary(const double* __restrict__ stats, ImpactDev a, double* __restri
     __syncthreads();
     if (tid == 0) {
       double tot = 0.0;
-      for (int w = 0; w < 32; ++w) tot += red[w];
-      bc = tot;
+      for (int w = 0; w < nw; ++w) tot += red[w];
+      red[32] = tot;
     }
     __syncthreads();
-    return bc;
+    return red[32];
   };
   for (int j = 0; j < IMP_STATS; ++j) {
+    const double* col = statsT + (size_t)j * S;
     double s = 0.0;
-    for (int i = tid; i < S; i += 1024) s += stats[(size_t)i * IMP_STATS + j];
+    for (int i = tid; i < S; i += nt) s += col[i];
     const double m = block_sum(s) / (double)S;
     double ss = 0.0;
-    for (int i = tid; i < S; i += 1024) {
-      const double d = stats[(size_t)i * IMP_STATS + j] - m;
+    for (int i = tid; i < S; i += nt) {
+      const double d = col[i] - m;
       ss += d * d;
     }
     const double tot = block_sum(ss);
@@ -204,14 +243,62 @@ k_impact_summary(const double* __restrict__ stats, ImpactDev a, double* __restri
     }
   }
   double le = 0.0, ge = 0.0;
-  for (int i = tid; i < S; i += 1024) {
-    const double ps = stats[(size_t)i * IMP_STATS + 1];
-    le += (a.obs_sum <= ps) ? 1.0 : 0.0;
-    ge += (a.obs_sum >= ps) ? 1.0 : 0.0;
+  const double* ps = statsT + (size_t)S;
+  for (int i = tid; i < S; i += nt) {
+    le += (a.obs_sum <= ps[i]) ? 1.0 : 0.0;
+    ge += (a.obs_sum >= ps[i]) ? 1.0 : 0.0;
   }
   const double tle = block_sum(le);
   const double tge = block_sum(ge);
   if (tid == 0) { summ[16] = tle; summ[17] = tge; }
+}
+
+// One CTA per column job (posterior_processing.py:25-60 called at lib.py:760, 886, 888 and
+// the quantiles of lib.py:1021-1075).  Heavy float64 jobs first.
+template <typename R>
+__global__ void k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
+                              const double* __restrict__ statsT, const double* __restrict__ obs,
+                              ImpactDev a, double* __restrict__ series, double* __restrict__ summ) {
+  extern __shared__ __align__(16) unsigned char key_mem[];
+  __shared__ __align__(16) unsigned char sel_raw[sizeof(SelectShared<double>)];
+  __shared__ int ibuf[10];
+  __shared__ double red[33];
+  const int Tc = a.T - a.t_c0, S = a.S;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double res[2][4], g[2];
+  if (b < Tc + IMP_STATS) {                         // cumulative-effect / per-draw statistic column
+    const bool is_cum = b < Tc;
+    const double* col = is_cum ? cumT + (size_t)b * S : statsT + (size_t)(b - Tc) * S;
+    SelectShared<double>& sh = *reinterpret_cast<SelectShared<double>*>(sel_raw);
+    const int n = column_quantiles<double, false>(col, S, a.q_lo, a.q_hi, key_mem, sh, ibuf, res, g);
+    if (tid == 0) {
+      double* out = is_cum ? series + (size_t)(a.t_c0 + b) * IMP_SERIES_COLS + 7
+                           : summ + 2 * (b - Tc);
+      for (int iq = 0; iq < 2; ++iq)
+        out[iq] = n ? imp_lerp(res[iq][0], res[iq][1], g[iq]) : CUDART_NAN;
+    }
+    return;
+  }
+  if (b < Tc + IMP_STATS + a.T) {                   // prediction + point-effect column
+    const int t = b - Tc - IMP_STATS;
+    SelectShared<R>& sh = *reinterpret_cast<SelectShared<R>*>(sel_raw);
+    const int n = column_quantiles<R, true>(trT + (size_t)t * S, S, a.q_lo, a.q_hi, key_mem, sh,
+                                            ibuf, res, g);
+    if (tid == 0) {
+      double* row = series + (size_t)t * IMP_SERIES_COLS;
+      if (t < a.t_c0) { row[7] = 0.0; row[8] = 0.0; }          // cumulative effect is 0 before post
+      const double o = obs[t];
+      for (int iq = 0; iq < 2; ++iq) {
+        if (n == 0) { row[1 + iq] = CUDART_NAN; row[4 + iq] = CUDART_NAN; continue; }
+        double v[4];
+        for (int j = 0; j < 4; ++j) v[j] = imp_unscale(res[iq][j], a.scale, a.offset);
+        row[1 + iq] = imp_lerp(v[0], v[1], g[iq]);
+        row[4 + iq] = (o == o) ? imp_lerp(o - v[2], o - v[3], g[iq]) : CUDART_NAN;
+      }
+    }
+    return;
+  }
+  impact_summary_block(statsT, a, summ, red);
 }
 
 }  // namespace ci
