@@ -52,11 +52,17 @@ def test_unexpected_kwargs_raise():                    # lib_test.py:231-240
 
 def test_unsupported_model_options_fail_loudly():
   data, pre, post = csv_data()
-  with pytest.raises(NotImplementedError):
+  with pytest.raises(ci.EngineError, match="state dimension"):       # 1 + 52 > one warp
     ci.fit_causalimpact(data, pre, post, seed=1,
-                        model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=7)]))
+                        model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=52)]))
   with pytest.raises(NotImplementedError):
     ci.fit_causalimpact(data, pre, post, seed=1, experimental_model=object())
+  # seasons themselves are supported (csrc/ci_seasonal.cuh): data.csv with a weekly component
+  res = ci.fit_causalimpact(data, pre, post, seed=1,
+                            model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=7)]),
+                            inference_options=ci.InferenceOptions(num_results=64))
+  assert res.posterior_samples.seasonal_levels.shape == (64, len(data), 1)
+  assert res.posterior_samples.weights.shape == (64, 3)
 
 
 @pytest.mark.parametrize("prior_level_sd", [0.01, 0.1, 0.5])

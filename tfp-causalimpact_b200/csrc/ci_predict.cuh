@@ -182,15 +182,14 @@ k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta, const R* __restrict__
 // ---------------------------------------------------------------------------
 // K5: one CTA per time column.  The column's S values are gathered into shared
 // memory as order-preserving integer keys; ALL needed order statistics (floor /
-// ceil rank of every quantile) are found together by an exact MSB-first RADIX
-// SELECT with 8-bit digits: one sweep over the keys per digit, whatever the
-// number of ranks -- ranks whose keys still share a prefix form a "group" with
-// its own 256-bin histogram, a key is counted in the group whose prefix it
-// matches (warp-aggregated shared-memory atomics: integer => deterministic),
-// one warp per group locates the bins, and the groups split as prefixes diverge.
-// 4 sweeps for float32, 8 for float64 (round 1: 3 / 6 sweeps PER RANK with 11-bit
-// digits and same-address atomic contention: 42 M bank conflicts per 10 000 x 2000
-// forecast, ncu run 22).  Interpolation is numpy's _lerp, bit for bit.
+// ceil rank of every quantile) are found together by an exact bit-wise bisection
+// on the key (bisect_select_impl below): 32 counting passes for float32, 64 for
+// float64, whatever the number of ranks.  History (B200, 10 000 draws per column):
+// bitonic sort -> per-rank radix select with 11-bit shared-memory histograms (same-
+// address atomics: 42 M bank conflicts per 10 000 x 2000 forecast, ~85 us per column
+// CTA, ncu run 22) -> multi-rank 8-bit radix with warp-aggregated atomics (~75 us: the
+// match.any and the serial regrouping cost what the saved sweeps gained, run 24) ->
+// bisection.  Interpolation is numpy's _lerp, bit for bit.
 // ---------------------------------------------------------------------------
 struct QuantArgs { double q[8]; int nq; };
 
@@ -220,96 +219,68 @@ template <> struct KeyOf<double> {
   static __device__ __forceinline__ unsigned long long nan_key() { return ~0ull; }
 };
 
-constexpr int QBINS = 256;     // 8-bit digits
 constexpr int QMAXR = 16;      // ranks selected together (8 quantiles x floor / ceil)
 
 template <typename R> struct SelectShared {
   using Key = typename KeyOf<R>::type;
-  int hist[QMAXR][QBINS];
-  Key g_prefix[QMAXR];         // prefix of each live group
   Key out[QMAXR];              // result: key of each rank
-  int rank[QMAXR];             // in: 0-based ranks (any order); during the select: residual ranks
-  int grp[QMAXR];              // group of each rank
-  int bin[QMAXR];
-  int n_groups;
+  int rank[QMAXR];             // in: 0-based ranks (any order, distinct)
+  int cnt[3][QMAXR];           // CTA-wide counts, rotating buffers
 };
 
-// Keys of the sh.rank[0..nr) smallest-rank order statistics of keys[0..n) -> sh.out[0..nr).
-// Executed by the whole CTA (blockDim a multiple of 32); ranks must be < n.
+// Keys of the sh.rank[0..nr) order statistics (0-based ranks, < n) of keys[0..n) ->
+// sh.out[0..nr).  BIT-WISE BISECTION on the key value, all ranks at once: the result is
+// built from the most significant bit down -- a bit is kept when the number of keys below
+// the trial value does not exceed the rank.  One pass over the shared-memory keys and ONE
+// barrier per bit; counting is compare + add in registers, warp totals by redux.sync, CTA
+// totals by 32 integer atomics per rank on a rotating triple buffer -- no histogram, no
+// same-address contention, deterministic.  Executed by the whole CTA.
+template <typename R, int NRT>
+__device__ __forceinline__ void bisect_select_impl(const typename KeyOf<R>::type* keys, int n,
+                                                   int nr, SelectShared<R>& sh) {
+  using Key = typename KeyOf<R>::type;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  constexpr int NB = (int)(8 * sizeof(Key));
+  Key result[NRT];
+  int rank[NRT];
+#pragma unroll
+  for (int r = 0; r < NRT; ++r) { result[r] = 0; rank[r] = r < nr ? sh.rank[r] : 0; }
+  if (tid < 3 * QMAXR) sh.cnt[tid / QMAXR][tid % QMAXR] = 0;
+  __syncthreads();
+  for (int bit = NB - 1, itn = 0; bit >= 0; --bit, ++itn) {
+    Key trial[NRT];
+    int c[NRT];
+#pragma unroll
+    for (int r = 0; r < NRT; ++r) { trial[r] = result[r] | ((Key)1 << bit); c[r] = 0; }
+    for (int i = tid; i < n; i += nt) {
+      const Key key = keys[i];
+#pragma unroll
+      for (int r = 0; r < NRT; ++r) c[r] += (key < trial[r]) ? 1 : 0;
+    }
+    int* cnt = sh.cnt[itn % 3];
+#pragma unroll
+    for (int r = 0; r < NRT; ++r) {
+      const int w = __reduce_add_sync(FULL, c[r]);
+      if (lane == r && r < nr && w) atomicAdd(&cnt[r], w);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NRT; ++r)
+      if (cnt[r] <= rank[r]) result[r] = trial[r];
+    if (tid < QMAXR) sh.cnt[(itn + 2) % 3][tid] = 0;     // used again two iterations from now
+  }
+#pragma unroll
+  for (int r = 0; r < NRT; ++r)
+    if (tid == 0 && r < nr) sh.out[r] = result[r];
+  __syncthreads();
+}
+
 template <typename R>
 __device__ void radix_select_multi(const typename KeyOf<R>::type* keys, int n, int nr,
                                    SelectShared<R>& sh) {
-  using Key = typename KeyOf<R>::type;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarps = nt >> 5;
-  if (tid == 0) { sh.n_groups = 1; sh.g_prefix[0] = 0; }
-  if (tid < nr) sh.grp[tid] = 0;
-  __syncthreads();
-  Key mask = 0;
-  for (int pass = 0; pass < KeyOf<R>::NPASS; ++pass) {
-    const int sh_bits = (int)(8 * sizeof(Key)) - 8 * (pass + 1);
-    const int ng = sh.n_groups;
-    for (int b = tid; b < ng * QBINS; b += nt) (&sh.hist[0][0])[b] = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += nt) {
-      const int i = i0 + tid;
-      int code = -1;
-      if (i < n) {
-        const Key key = keys[i];
-        const Key pre = key & mask;
-        int g = -1;
-        for (int gg = 0; gg < ng; ++gg)
-          if (pre == sh.g_prefix[gg]) g = gg;
-        if (g >= 0) code = g * QBINS + (int)((key >> sh_bits) & (Key)(QBINS - 1));
-      }
-      const unsigned peers = __match_any_sync(FULL, code);
-      if (code >= 0 && lane == __ffs(peers) - 1) atomicAdd(&(&sh.hist[0][0])[code], __popc(peers));
-    }
-    __syncthreads();
-    // warp w serves groups w, w + nwarps, ..: locate the bin of each of the group's ranks
-    for (int g = warp; g < ng; g += nwarps) {
-      const int per = QBINS / 32;
-      int loc = 0;
-#pragma unroll
-      for (int b = 0; b < per; ++b) loc += sh.hist[g][lane * per + b];
-      int inc = loc;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += t;
-      }
-      const int before = inc - loc;
-      for (int r = 0; r < nr; ++r) {
-        if (sh.grp[r] != g) continue;
-        const int rem = sh.rank[r];
-        if (rem >= before && rem < inc) {
-          int acc = before, b = lane * per;
-          while (acc + sh.hist[g][b] <= rem) { acc += sh.hist[g][b]; ++b; }
-          sh.bin[r] = b;
-          sh.rank[r] = rem - acc;
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {                         // split the groups along the new digit
-      Key np[QMAXR];
-      int ngn = 0;
-      for (int r = 0; r < nr; ++r) {
-        const Key pre = sh.g_prefix[sh.grp[r]] | ((Key)sh.bin[r] << sh_bits);
-        int g = -1;
-        for (int gg = 0; gg < ngn; ++gg)
-          if (np[gg] == pre) g = gg;
-        if (g < 0) { g = ngn; np[ngn++] = pre; }
-        sh.grp[r] = g;
-      }
-      for (int gg = 0; gg < ngn; ++gg) sh.g_prefix[gg] = np[gg];
-      sh.n_groups = ngn;
-    }
-    mask |= (Key)(QBINS - 1) << sh_bits;
-    __syncthreads();
-  }
-  if (tid < nr) sh.out[tid] = sh.g_prefix[sh.grp[tid]];
-  __syncthreads();
+  if (nr <= 4) bisect_select_impl<R, 4>(keys, n, nr, sh);
+  else if (nr <= 8) bisect_select_impl<R, 8>(keys, n, nr, sh);
+  else bisect_select_impl<R, 16>(keys, n, nr, sh);
 }
 
 // Gather column t of a [S,T] array into shared-memory keys; returns the number of non-NaN.
