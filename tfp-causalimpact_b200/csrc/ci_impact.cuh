@@ -256,7 +256,8 @@ __device__ __forceinline__ void impact_summary_block(const double* __restrict__ 
 // One CTA per column job (posterior_processing.py:25-60 called at lib.py:760, 886, 888 and
 // the quantiles of lib.py:1021-1075).  Heavy float64 jobs first.
 template <typename R>
-__global__ void k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
+__global__ void __launch_bounds__(1024)
+k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
                               const double* __restrict__ statsT, const double* __restrict__ obs,
                               ImpactDev a, double* __restrict__ series, double* __restrict__ summ) {
   extern __shared__ __align__(16) unsigned char key_mem[];

@@ -313,7 +313,8 @@ __device__ __forceinline__ int add_rank(SelectShared<R>& sh, int& nr, int k) {
 }
 
 template <typename R>
-__global__ void k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs qa,
+__global__ void __launch_bounds__(1024)
+k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs qa,
                                 R* __restrict__ out, int out_ld) {
   using Key = typename KeyOf<R>::type;
   extern __shared__ __align__(16) unsigned char qsmem[];
