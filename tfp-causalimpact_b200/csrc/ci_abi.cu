@@ -109,7 +109,7 @@ template <typename R> LltDev<R> make_lltdev(const ci_ctx* c) {
 }
 
 // static shared memory of the select kernels (16 x 256 histograms + bookkeeping), rounded up
-constexpr size_t QSTATIC = 20 * 1024;
+constexpr size_t QSTATIC = 28 * 1024;
 
 inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
