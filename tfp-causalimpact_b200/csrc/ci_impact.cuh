@@ -50,67 +50,83 @@ constexpr int IMP_TILE = 32;         // draws per CTA == time steps per chunk
 // Row r < S: draw r of traj (CTA b holds draws 32b .. 32b+31, warp w <-> draw, lane <-> t);
 // the LAST CTA's warp 0 handles the predictive mean (its cumulative path and post-period
 // mean / sum are the *_mean series columns and `predicted`).
+constexpr int IMP_CH = 2;            // 32-step chunks per loop iteration (loads overlap)
+
 template <typename R>
 __global__ void __launch_bounds__(32 * IMP_TILE)
 k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
               const double* __restrict__ obs, const uint8_t* __restrict__ period, ImpactDev a,
               R* __restrict__ trT, double* __restrict__ cumT, double* __restrict__ statsT,
               double* __restrict__ series, double* __restrict__ summ) {
-  __shared__ R tile_raw[IMP_TILE][IMP_TILE + 1];
-  __shared__ double tile_cum[IMP_TILE][IMP_TILE + 1];
+  __shared__ R tile_raw[IMP_TILE][IMP_CH * IMP_TILE + 1];
+  __shared__ double tile_cum[IMP_TILE][IMP_CH * IMP_TILE + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool mean_cta = blockIdx.x == gridDim.x - 1;
+  const bool is_mean = blockIdx.x == gridDim.x - 1;
   const int r0 = blockIdx.x * IMP_TILE;
-  const int r = mean_cta ? a.S : r0 + warp;
-  const bool is_mean = mean_cta;
-  if (mean_cta && warp != 0) return;                 // (no CTA-wide barrier on this path)
+  const int r = is_mean ? a.S : r0 + warp;
+  if (is_mean && warp != 0) return;                  // (no CTA-wide barrier on this path)
   const bool row_ok = is_mean || r < a.S;
   const R* src = is_mean ? mean : traj + (size_t)(row_ok ? r : 0) * a.T;
   double carry = 0.0, pred_sum = 0.0, eff_sum = 0.0;
   int eff_cnt = 0;
-  for (int base = 0; base < a.T; base += IMP_TILE) {
-    const int t = base + lane;
-    const bool valid = row_ok && t < a.T;
-    double x = 0.0, pt = CUDART_NAN;
-    R raw = 0;
-    int per = 0;
-    if (valid) {
-      raw = src[t];
-      x = imp_unscale((double)raw, a.scale, a.offset);
-      pt = obs[t] - x;                               // lib.py:822-823
-      per = period[t];
-    }
-    const bool isn = !(pt == pt);
-    // lib.py:826-831: effects before the post-period count as 0; NaNs are skipped, not spread
-    double inc = (valid && t >= a.t_c0 && !isn) ? pt : 0.0;
+  for (int base = 0; base < a.T; base += IMP_CH * IMP_TILE) {
+    R raw[IMP_CH];
+    double ob[IMP_CH];
+    int per[IMP_CH];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double up = __shfl_up_sync(FULL, inc, o);
-      if (lane >= o) inc += up;
+    for (int h = 0; h < IMP_CH; ++h) {               // all loads of the iteration first
+      const int t = base + h * IMP_TILE + lane;
+      const bool valid = row_ok && t < a.T;
+      raw[h] = valid ? src[t] : (R)0;
+      ob[h] = valid ? obs[t] : CUDART_NAN;
+      per[h] = valid ? (int)period[t] : 0;
     }
-    const double cv = carry + inc;
-    carry += __shfl_sync(FULL, inc, 31);
-    const double out = (t >= a.t_c0 && isn) ? CUDART_NAN : cv;
-    if (valid && per == 1) {                         // inside the post-period (lib.py:966-1011)
-      pred_sum += x;
-      if (!isn) { eff_sum += pt; ++eff_cnt; }
-    }
-    if (is_mean) {
-      if (valid) {
-        double* row = series + (size_t)t * IMP_SERIES_COLS;
-        row[0] = x; row[3] = pt; row[6] = out;
+    // nothing to accumulate before the post-period starts: cumulative effect is 0 there
+    const bool need_cum = base + IMP_CH * IMP_TILE > a.t_c0;
+#pragma unroll
+    for (int h = 0; h < IMP_CH; ++h) {
+      const int t = base + h * IMP_TILE + lane;
+      const bool valid = row_ok && t < a.T;
+      const double x = imp_unscale((double)raw[h], a.scale, a.offset);
+      const double pt = valid ? ob[h] - x : CUDART_NAN;            // lib.py:822-823
+      const bool isn = !(pt == pt);
+      double out = 0.0;
+      if (need_cum) {
+        // lib.py:826-831: effects before the post-period count as 0; NaNs are skipped
+        double inc = (valid && t >= a.t_c0 && !isn) ? pt : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += up;
+        }
+        const double cv = carry + inc;
+        carry += __shfl_sync(FULL, inc, 31);
+        out = (t >= a.t_c0 && isn) ? CUDART_NAN : cv;
       }
-      continue;
+      if (valid && per[h] == 1) {                    // inside the post-period (lib.py:966-1011)
+        pred_sum += x;
+        if (!isn) { eff_sum += pt; ++eff_cnt; }
+      }
+      if (is_mean) {
+        if (valid) {
+          double* row = series + (size_t)t * IMP_SERIES_COLS;
+          row[0] = x; row[3] = pt; row[6] = out;
+        }
+      } else {
+        tile_raw[warp][h * IMP_TILE + lane] = raw[h];
+        if (need_cum) tile_cum[warp][h * IMP_TILE + lane] = out;
+      }
     }
-    // transpose the chunk: [draw][t] -> [t][draw]
-    tile_raw[warp][lane] = raw;
-    tile_cum[warp][lane] = out;
+    if (is_mean) continue;
+    // transpose the chunk: [draw][t] -> [t][draw]; warp <-> time step, lane <-> draw
     __syncthreads();
-    {
-      const int tc = base + warp, rr = r0 + lane;    // warp <-> time step, lane <-> draw
+    const int rr = r0 + lane;
+#pragma unroll
+    for (int h = 0; h < IMP_CH; ++h) {
+      const int tc = base + h * IMP_TILE + warp;
       if (tc < a.T && rr < a.S) {
-        trT[(size_t)tc * a.S + rr] = tile_raw[lane][warp];
-        if (tc >= a.t_c0) cumT[(size_t)(tc - a.t_c0) * a.S + rr] = tile_cum[lane][warp];
+        trT[(size_t)tc * a.S + rr] = tile_raw[lane][h * IMP_TILE + warp];
+        if (tc >= a.t_c0) cumT[(size_t)(tc - a.t_c0) * a.S + rr] = tile_cum[lane][h * IMP_TILE + warp];
       }
     }
     __syncthreads();
