@@ -400,12 +400,25 @@ int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint
                           void* draws_d, void* level_d, void* traj_d, float* incl_d, void* latent_d,
                           void* seas_d, void* drift_d, cudaStream_t st) {
   const int p = c->prob.p, d = c->seas.d;
-  const uint32_t extra = (uint32_t)(2 * p * p + 5 * p + 8) + (uint32_t)(d * (d | 1) + d);
+  const uint32_t base_extra = (uint32_t)(2 * p * p + 5 * p + 8) + (uint32_t)(d * (d | 1) + d) +
+                              3u * (uint32_t)ci::TB;
+  const uint32_t scr_elems = (uint32_t)c->prob.T * (uint32_t)(d + 1);
   const uint32_t tail = (uint32_t)(p * p) * (uint32_t)c->esz + 16u;
   SmemCfg cfg;
-  int G = pick_G(c, C), rc = CI_OK;
-  for (; G >= 1; --G) {
-    rc = plan_smem(c, G, extra, &cfg, tail);
+  int G = pick_G(c, C), rc = CI_ERR_UNSUPPORTED;
+  bool scr_smem = false;
+  {  // first choice: the per-step scratch in shared memory with every tile resident
+    std::string keep = g_err;
+    for (int g = G; g >= 1 && rc != CI_OK; --g) {
+      SmemCfg t;
+      if (plan_smem(c, g, base_extra + scr_elems, &t, tail) == CI_OK && t.resident) {
+        cfg = t; G = g; rc = CI_OK; scr_smem = true;
+      }
+    }
+    g_err = keep;
+  }
+  for (; rc != CI_OK && G >= 1; --G) {
+    rc = plan_smem(c, G, base_extra, &cfg, tail);
     if (rc == CI_OK) break;
   }
   if (rc) return rc;
@@ -418,9 +431,12 @@ int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint
   GibbsDev<R> gd;
   gd.gram = static_cast<const R*>(c->gram.p); gd.xty0 = static_cast<const R*>(c->xty0.p);
   gd.yty0 = (R)c->yty0;
-  CU_TRY(c->s_scratch.reserve((size_t)C * c->prob.T * (d + 1) * sizeof(R)));
   SeasDev sz = c->seas;
-  sz.scratch = c->s_scratch.p;
+  sz.scratch = nullptr;                       // nullptr: the kernel's scratch is in shared memory
+  if (!scr_smem) {
+    CU_TRY(c->s_scratch.reserve((size_t)C * c->prob.T * (d + 1) * sizeof(R)));
+    sz.scratch = c->s_scratch.p;
+  }
   auto kern = k_gibbs_seasonal<R>;
   CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
   kern<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(

@@ -17,7 +17,8 @@
 // drift * N(0,1) * (e_j - 1/n) (zero-sum direction); prior of a block: sd^2 (I - 11'/n).
 //   pass A (forward):  simulate x+, y+ from the prior; Kalman filter on y* = r - y+ with
 //                      the d x d covariance in shared memory (row i in lane i): rank-1
-//                      downdates; gains K_t and e_t = v_t / F_t go to an L2-resident scratch
+//                      downdates; gains K_t and e_t = v_t / F_t go to a per-chain scratch
+//                      (shared memory when T (d+1) fits beside the tiles, else L2-resident)
 //   pass B (backward): r_{t-1} = r_t + h_t (e_t - K_t' r_t); r_t overwrites K_t
 //   pass C (forward):  xhat_0 = P_0 r_{-1}, xhat_{t+1} = xhat_t + Q_t r_t; x = x+ + xhat with
 //                      x+ REGENERATED from the same Philox counters (nothing stored);
@@ -93,7 +94,12 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   R* Ps = gs.vec + (p + 1);             // [d][LDP] state covariance, row i <-> lane i
   R* phs = Ps + d * LDP;                // [d]      P h of the current step
   R* Prow = Ps + (lane < d ? lane : 0) * LDP;
-  R* scr = static_cast<R*>(sz.scratch) + (size_t)c * T * (d + 1);
+  R* st_a = phs + d;                    // [TB] x3: per-step staging of the current tile
+  R* st_b = st_a + TB;
+  R* st_c = st_b + TB;
+  // per-step scratch (gains / r_t): in shared memory when the launch found room, else L2
+  const bool scr_smem = sz.scratch == nullptr;
+  R* scr = scr_smem ? st_c + TB : static_cast<R*>(sz.scratch) + (size_t)c * T * (d + 1);
   TilePipe<R> pipe = make_pipe(cs, cfg);
   const uint64_t gid = chain_id0 + (uint64_t)c;
   const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
@@ -103,7 +109,7 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   for (int k = 0; k < K; ++k)
     if (lane >= sz.off[k] && lane < sz.off[k] + sz.n[k]) { comp = k; my_n = sz.n[k]; my_off = sz.off[k]; }
   const R inv_n = (R)1 / (R)my_n;
-  const int src_off = lane < K ? sz.off[lane] : 0;   // lane l < K describes component l; lane K the level
+  const int my_coff = (lane >= 1 && lane <= K) ? sz.off[lane - 1] : 0;   // lane l in 1..K <-> component l-1
 
   // ---- initial state: the reference's (lib.py:566-581) ----
   double s_e = p > 0 ? 0.2 * (double)pr.P0 : (double)pr.P0;
@@ -129,16 +135,28 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
     }
     return out;
   };
-  // the step's schedule: per-lane source index (lane <= K), mask of observed columns, ends
-  auto step_sched = [&](int t, int& src, unsigned& cmask, int& em) {
+  // the step's schedule: cols[k] (uniform) = state index of the k-th observed column
+  // (k = 0: the level, k >= 1: component k-1's active season), mask of those columns, ends flags
+  auto step_sched = [&](int t, int (&cols)[MAX_SEAS + 1], unsigned& cmask, int& em) -> int {
     const uint8_t* sc = sz.sched + (size_t)t * (K + 1);
     em = sc[K];
-    src = lane < K ? src_off + (int)sc[lane] : 0;
-    cmask = __reduce_or_sync(FULL, lane <= K ? (1u << src) : 0u);
+    const int src = (lane >= 1 && lane <= K) ? my_coff + (int)sc[lane - 1] : 0;
+    cmask = 0u;
+#pragma unroll
+    for (int k = 0; k <= MAX_SEAS; ++k) {
+      cols[k] = __shfl_sync(FULL, src, k);
+      if (k <= K) cmask |= 1u << cols[k];
+    }
+    return src;      // lane l in 1..K: state index of component l-1's active season
   };
-  auto gather = [&](R v, int src) -> R {              // h' v
-    const R g = __shfl_sync(FULL, v, src);
-    return warp_sum(lane <= K ? g : (R)0);
+  auto gather = [&](R v, const int (&cols)[MAX_SEAS + 1]) -> R {      // h' v
+    R acc = 0;
+#pragma unroll
+    for (int k = 0; k <= MAX_SEAS; ++k) {
+      const R g = __shfl_sync(FULL, v, cols[k]);
+      if (k <= K) acc += g;
+    }
+    return acc;
   };
   auto drift_normal = [&](int t, int it, int k) -> R {
     const uint4 x = Philox::gen(seed, id_lo, RNG_S_DRIFT | id_hi8, (uint32_t)t,
@@ -178,71 +196,77 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       R xw[KS];
       blk_residuals_xw(B, xw, tile, ws.w, p, ld, lane);
       const int t0 = b * TB + lane * KS;
-      R zeta[KS], zeps[KS];
+      // stage the tile's per-step inputs (residual or NaN, level noise, observation noise) so
+      // that the sequential loop below stays ROLLED (an 8x unrolled body overflowed the
+      // instruction cache: 2200 cycles per step, run 22)
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
         const uint4 x = Philox::gen(seed, id_lo, RNG_S_PATH | id_hi8, (uint32_t)(t0 + kk), (uint32_t)it);
-        box_muller<R>(x.x, x.y, zeta[kk], zeps[kk]);
+        R ze, zo;
+        box_muller<R>(x.x, x.y, ze, zo);
+        st_a[lane * KS + kk] = ((B.obs >> kk) & 1u) ? B.r[kk] : Num<R>::nan();
+        st_b[lane * KS + kk] = ze;
+        st_c[lane * KS + kk] = zo;
       }
-      for (int L = 0; L < 32; ++L) {
-        if (b * TB + L * KS >= T) break;
+      __syncwarp();
+      const int nstep = min(TB, T - b * TB);
+#pragma unroll 1
+      for (int tl = 0; tl < nstep; ++tl) {
+        const int t = b * TB + tl;
+        const R r_t = st_a[tl], eta = st_b[tl], eps = st_c[tl];
+        int cols[MAX_SEAS + 1], em; unsigned cmask;
+        step_sched(t, cols, cmask, em);
+        R Kg = 0, e = 0;
+        if (r_t == r_t) {                                       // observed step
+          const R hxa = gather(xp + a, cols);
+          R Ph = 0;
+          if (lane < d) {
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {
-          const int t = b * TB + L * KS + kk;
-          const R r_t = __shfl_sync(FULL, B.r[kk], L);
-          const bool o = (__shfl_sync(FULL, B.obs, L) >> kk) & 1u;
-          const R eta = __shfl_sync(FULL, zeta[kk], L), eps = __shfl_sync(FULL, zeps[kk], L);
-          if (t < T) {
-            int src, em; unsigned cmask;
-            step_sched(t, src, cmask, em);
-            R Kg = 0, e = 0;
-            if (o) {
-              const R hxa = gather(xp + a, src);
-              R Ph = 0;
-              if (lane < d)
-                for (unsigned m = cmask; m; m &= m - 1) Ph += Prow[__ffs(m) - 1];
-              const R rF = Num<R>::rcp(gather(Ph, src) + se);
-              const R v = (r_t - sig_e * eps) - hxa;
-              e = v * rF; Kg = Ph * rF;
-              a = fma(Kg, v, a);
-              if (lane < d) phs[lane] = Ph;
-              __syncwarp();
-              if (lane < d)
-                for (int j = 0; j < d; ++j) Prow[j] = fma(-(Ph * phs[j]), rF, Prow[j]);
-              __syncwarp();
-            }
-            R* srow = scr + (size_t)t * (d + 1);
-            if (lane < d) srow[lane] = Kg;
-            if (lane == 0) srow[d] = e;
-            // x_{t+1} = x_t + noise_t
-            if (lane == 0) { Prow[0] += sh; xp = fma(sig_h, eta, xp); }
-            if (em) {
-              for (int k = 0; k < K; ++k) {
-                if (!((em >> k) & 1)) continue;
-                const int jk = __shfl_sync(FULL, src, k);
-                const R sdk = __shfl_sync(FULL, sdv, k);
-                const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
-                if (comp == k)
-                  for (int j = 0; j < my_n; ++j)
-                    Prow[my_off + j] = fma(sdk * ci, (my_off + j == jk ? (R)1 : (R)0) - inv_n,
-                                           Prow[my_off + j]);
-                xp = fma(Num<R>::sqrt(sdk) * drift_normal(t, it, k), ci, xp);
-              }
-              __syncwarp();
-            }
+            for (int k = 0; k <= MAX_SEAS; ++k)
+              if (k <= K) Ph += Prow[cols[k]];
           }
+          const R rF = Num<R>::rcp(gather(Ph, cols) + se);
+          const R v = (r_t - sig_e * eps) - hxa;
+          e = v * rF; Kg = Ph * rF;
+          a = fma(Kg, v, a);
+          if (lane < d) phs[lane] = Ph;
+          __syncwarp();
+          if (lane < d)
+            for (int j = 0; j < d; ++j) Prow[j] = fma(-(Ph * phs[j]), rF, Prow[j]);
+          __syncwarp();
+        }
+        R* srow = scr + (size_t)t * (d + 1);
+        if (lane < d) srow[lane] = Kg;
+        if (lane == 0) srow[d] = e;
+        // x_{t+1} = x_t + noise_t
+        if (lane == 0) { Prow[0] += sh; xp = fma(sig_h, eta, xp); }
+        if (em) {
+          for (int k = 0; k < K; ++k) {
+            if (!((em >> k) & 1)) continue;
+            const int jk = sz.off[k] + (int)sz.sched[(size_t)t * (K + 1) + k];
+            const R sdk = __shfl_sync(FULL, sdv, k);
+            const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
+            if (comp == k)
+              for (int j = 0; j < my_n; ++j)
+                Prow[my_off + j] = fma(sdk * ci, (my_off + j == jk ? (R)1 : (R)0) - inv_n,
+                                       Prow[my_off + j]);
+            xp = fma(Num<R>::sqrt(sdk) * drift_normal(t, it, k), ci, xp);
+          }
+          __syncwarp();
         }
       }
+      __syncwarp();
       pipe.release(lane);
     }
     __syncwarp();
     // ---- pass B ----
     R rr = 0;
+#pragma unroll 1
     for (int t = T - 1; t >= 0; --t) {
-      int src, em; unsigned cmask;
-      step_sched(t, src, cmask, em);
+      int cols[MAX_SEAS + 1], em; unsigned cmask;
+      step_sched(t, cols, cmask, em);
       R* srow = scr + (size_t)t * (d + 1);
-      if (t >= 4 && lane == 0) prefetch_l1(srow - 4 * (d + 1));
+      if (!scr_smem && t >= 4 && lane == 0) prefetch_l1(srow - 4 * (d + 1));
       const R Kg = lane < d ? srow[lane] : (R)0;
       const R e = srow[d];
       if (lane < d) srow[lane] = rr;                       // r_t, read back by pass C
@@ -276,63 +300,64 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       R xw[KS];
       blk_residuals_xw(B, xw, tile, ws.w, p, ld, lane);
       const int t0 = b * TB + lane * KS;
-      R zeta[KS], zp[KS];
+      R zp[KS];
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
         const uint4 x = Philox::gen(seed, id_lo, RNG_S_PATH | id_hi8, (uint32_t)(t0 + kk), (uint32_t)it);
-        R zeps;
-        box_muller<R>(x.x, x.y, zeta[kk], zeps);
-        box_muller<R>(x.z, x.w, zp[kk], zeps);
+        R ze, zo;
+        box_muller<R>(x.x, x.y, ze, zo);
+        st_a[lane * KS + kk] = ze;                          // level noise of the step
+        box_muller<R>(x.z, x.w, zp[kk], zo);
       }
-      R lv[KS], sc[KS];
-#pragma unroll
-      for (int kk = 0; kk < KS; ++kk) { lv[kk] = 0; sc[kk] = 0; }
-      for (int L = 0; L < 32; ++L) {
-        if (b * TB + L * KS >= T) break;
-#pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {
-          const int t = b * TB + L * KS + kk;
-          const R eta = __shfl_sync(FULL, zeta[kk], L);
-          if (t < T) {
-            int src, em; unsigned cmask;
-            step_sched(t, src, cmask, em);
-            const R* srow = scr + (size_t)t * (d + 1);
-            if (t + 4 < T && lane == 0) prefetch_l1(srow + 4 * (d + 1));
-            const R g = __shfl_sync(FULL, xt, src);        // lane k < K: contribution of component k
-            const R tot = warp_sum(lane <= K ? g : (R)0);  // level + all contributions
-            const R level_t = __shfl_sync(FULL, xt, 0);
-            if (lane == L) { lv[kk] = level_t; sc[kk] = tot - level_t; }
-            if (keep && seas_out && lane < K) seas_out[(out_row * T + t) * K + lane] = g;
-            if (t > 0) { const double dl = (double)(level_t - prev_level); d2 += dl * dl; }
-            prev_level = level_t;
-            if (t < T - 1) {
-              const R rt = lane < d ? srow[lane] : (R)0;
-              if (lane == 0) xt += fma(sh, rt, sig_h * eta);
-              if (em) {
-                for (int k = 0; k < K; ++k) {
-                  if (!((em >> k) & 1)) continue;
-                  const int jk = __shfl_sync(FULL, src, k);
-                  const R sdk = __shfl_sync(FULL, sdv, k);
-                  const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
-                  const R cr = __shfl_sync(FULL, rt, jk) -
-                               warp_sum(comp == k ? rt : (R)0) / (R)sz.n[k];
-                  const R u = fma(sdk, cr, Num<R>::sqrt(sdk) * drift_normal(t, it, k));
-                  xt = fma(u, ci, xt);
-                  if (lane == k) su2 += (double)u * (double)u;
-                }
-              }
+      __syncwarp();
+      const int nstep = min(TB, T - b * TB);
+#pragma unroll 1
+      for (int tl = 0; tl < nstep; ++tl) {
+        const int t = b * TB + tl;
+        const R eta = st_a[tl];
+        int cols[MAX_SEAS + 1], em; unsigned cmask;
+        const int src = step_sched(t, cols, cmask, em);
+        const R* srow = scr + (size_t)t * (d + 1);
+        if (!scr_smem && t + 4 < T && lane == 0) prefetch_l1(srow + 4 * (d + 1));
+        const R level_t = __shfl_sync(FULL, xt, 0);
+        const R tot = gather(xt, cols);                     // level + all contributions
+        const R mine = __shfl_sync(FULL, xt, src);          // lane l in 1..K: component l-1's share
+        if (lane == 0) { st_b[tl] = level_t; st_c[tl] = tot - level_t; }
+        if (keep && seas_out && lane >= 1 && lane <= K)
+          seas_out[(out_row * T + t) * K + (lane - 1)] = mine;
+        if (t > 0) { const double dl = (double)(level_t - prev_level); d2 += dl * dl; }
+        prev_level = level_t;
+        if (t < T - 1) {
+          const R rt = lane < d ? srow[lane] : (R)0;
+          if (lane == 0) xt += fma(sh, rt, sig_h * eta);
+          if (em) {
+            for (int k = 0; k < K; ++k) {
+              if (!((em >> k) & 1)) continue;
+              const int jk = sz.off[k] + (int)sz.sched[(size_t)t * (K + 1) + k];
+              const R sdk = __shfl_sync(FULL, sdv, k);
+              const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
+              const R cr = __shfl_sync(FULL, rt, jk) -
+                           warp_sum(comp == k ? rt : (R)0) / (R)sz.n[k];
+              const R u = fma(sdk, cr, Num<R>::sqrt(sdk) * drift_normal(t, it, k));
+              xt = fma(u, ci, xt);
+              if (lane == k) su2 += (double)u * (double)u;
             }
           }
         }
       }
+      __syncwarp();
+      R lv[KS], sc[KS];
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) { lv[kk] = st_b[lane * KS + kk]; sc[kk] = st_c[lane * KS + kk]; }
+      __syncwarp();
       // ---- per-lane epilogue for the tile's 8 owned steps (as k_gibbs) ----
       R tgt[KS];
       R ly = 0;
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
         const bool o = (B.obs >> kk) & 1u;
-        tgt[kk] = o ? (B.r[kk] - lv[kk] - sc[kk]) : (R)0;   // y - x.w - level - seasonal ... + x.w below
-        tgt[kk] = o ? tgt[kk] + xw[kk] : (R)0;              // targets of step A: y - level - seasonal
+        // targets of the next step A: y - level - seasonal on observed steps (B.r = y - x.w)
+        tgt[kk] = o ? (B.r[kk] + xw[kk]) - lv[kk] - sc[kk] : (R)0;
         ly = fma(tgt[kk], tgt[kk], ly);
       }
       n_yty += (double)ly;
