@@ -401,7 +401,7 @@ int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint
                           void* seas_d, void* drift_d, cudaStream_t st) {
   const int p = c->prob.p, d = c->seas.d;
   const uint32_t base_extra = (uint32_t)(2 * p * p + 5 * p + 8) + (uint32_t)(d * (d | 1) + d) +
-                              3u * (uint32_t)ci::TB;
+                              (3u + (uint32_t)c->seas.K) * (uint32_t)ci::TB;
   const uint32_t scr_elems = (uint32_t)c->prob.T * (uint32_t)(d + 1);
   const uint32_t tail = (uint32_t)(p * p) * (uint32_t)c->esz + 16u;
   SmemCfg cfg;

@@ -97,9 +97,10 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   R* st_a = phs + d;                    // [TB] x3: per-step staging of the current tile
   R* st_b = st_a + TB;
   R* st_c = st_b + TB;
+  R* st_d = st_c + TB;                  // [K][TB] drift normals of the tile's steps
   // per-step scratch (gains / r_t): in shared memory when the launch found room, else L2
   const bool scr_smem = sz.scratch == nullptr;
-  R* scr = scr_smem ? st_c + TB : static_cast<R*>(sz.scratch) + (size_t)c * T * (d + 1);
+  R* scr = scr_smem ? st_d + (size_t)K * TB : static_cast<R*>(sz.scratch) + (size_t)c * T * (d + 1);
   TilePipe<R> pipe = make_pipe(cs, cfg);
   const uint64_t gid = chain_id0 + (uint64_t)c;
   const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
@@ -158,12 +159,26 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
     }
     return acc;
   };
-  auto drift_normal = [&](int t, int it, int k) -> R {
-    const uint4 x = Philox::gen(seed, id_lo, RNG_S_DRIFT | id_hi8, (uint32_t)t,
-                                (uint32_t)it * 8u + (uint32_t)k);
-    R z0, z1;
-    box_muller<R>(x.x, x.y, z0, z1);
-    return z0;
+  // All normals of step t: level noise, observation noise of y+, predictive noise, and one
+  // drift normal per component.  Generated LANE-PARALLEL (a lane does its 8 steps of the
+  // tile) and staged in shared memory: run 28 showed the per-step, warp-redundant
+  // Philox + Box-Muller of the first version was 35 % of all instructions.
+  auto step_normals = [&](int t, int it, R& ze, R& zo, R& zpred, R (&dr)[MAX_SEAS]) {
+    const uint4 x = Philox::gen(seed, id_lo, RNG_S_PATH | id_hi8, (uint32_t)t, (uint32_t)it);
+    box_muller<R>(x.x, x.y, ze, zo);
+    box_muller<R>(x.z, x.w, zpred, dr[0]);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      if (K > 1 + 4 * m) {
+        const uint4 y = Philox::gen(seed, id_lo, RNG_S_DRIFT | id_hi8, (uint32_t)t,
+                                    (uint32_t)it * 2u + (uint32_t)m);
+        R q0, q1, q2, q3;
+        box_muller<R>(y.x, y.y, q0, q1);
+        box_muller<R>(y.z, y.w, q2, q3);
+        dr[1 + 4 * m] = q0; dr[2 + 4 * m] = q1;
+        if (m == 0) { dr[3] = q2; dr[4] = q3; }
+      }
+    }
   };
   auto init_xplus = [&](int it) -> R {
     const uint4 x = Philox::gen(seed, id_lo, RNG_S_INIT | id_hi8, (uint32_t)lane, (uint32_t)it);
@@ -180,6 +195,12 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
     // =================== B. (level, seasonal) | rest ===================
     const R se = (R)s_e, sh = (R)s_h, sig_e = (R)sqrt(s_e), sig_h = (R)sqrt(s_h);
     const R sdv = (R)sd_l;
+    R sig_d[MAX_SEAS], inv_nk[MAX_SEAS];                    // uniform: drift scale, 1/n per component
+#pragma unroll
+    for (int k = 0; k < MAX_SEAS; ++k) {
+      sig_d[k] = k < K ? Num<R>::sqrt(__shfl_sync(FULL, sdv, k)) : (R)0;
+      inv_nk[k] = k < K ? (R)1 / (R)sz.n[k] : (R)0;
+    }
     // ---- pass A ----
     if (lane < d) {
       for (int j = 0; j < d; ++j) Prow[j] = 0;
@@ -201,12 +222,14 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       // instruction cache: 2200 cycles per step, run 22)
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
-        const uint4 x = Philox::gen(seed, id_lo, RNG_S_PATH | id_hi8, (uint32_t)(t0 + kk), (uint32_t)it);
-        R ze, zo;
-        box_muller<R>(x.x, x.y, ze, zo);
+        R ze, zo, zpred, dr[MAX_SEAS];
+        step_normals(t0 + kk, it, ze, zo, zpred, dr);
         st_a[lane * KS + kk] = ((B.obs >> kk) & 1u) ? B.r[kk] : Num<R>::nan();
         st_b[lane * KS + kk] = ze;
         st_c[lane * KS + kk] = zo;
+#pragma unroll
+        for (int k = 0; k < MAX_SEAS; ++k)
+          if (k < K) st_d[k * TB + lane * KS + kk] = dr[k];
       }
       __syncwarp();
       const int nstep = min(TB, T - b * TB);
@@ -229,10 +252,13 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
           const R v = (r_t - sig_e * eps) - hxa;
           e = v * rF; Kg = Ph * rF;
           a = fma(Kg, v, a);
-          if (lane < d) phs[lane] = Ph;
-          __syncwarp();
-          if (lane < d)
-            for (int j = 0; j < d; ++j) Prow[j] = fma(-(Ph * phs[j]), rF, Prow[j]);
+          // P -= (P h)(P h)' / F: row i in lane i, (P h)_j by shuffle (symmetric in fp: the
+          // product Ph_i Ph_j commutes)
+#pragma unroll 4
+          for (int j = 0; j < d; ++j) {
+            const R pj = __shfl_sync(FULL, Ph, j);
+            if (lane < d) Prow[j] = fma(-(Ph * pj), rF, Prow[j]);
+          }
           __syncwarp();
         }
         R* srow = scr + (size_t)t * (d + 1);
@@ -241,16 +267,19 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
         // x_{t+1} = x_t + noise_t
         if (lane == 0) { Prow[0] += sh; xp = fma(sig_h, eta, xp); }
         if (em) {
-          for (int k = 0; k < K; ++k) {
-            if (!((em >> k) & 1)) continue;
-            const int jk = sz.off[k] + (int)sz.sched[(size_t)t * (K + 1) + k];
+#pragma unroll
+          for (int k = 0; k < MAX_SEAS; ++k) {
+            if (k >= K || !((em >> k) & 1)) continue;
+            const int jk = cols[k + 1];
             const R sdk = __shfl_sync(FULL, sdv, k);
             const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
-            if (comp == k)
-              for (int j = 0; j < my_n; ++j)
-                Prow[my_off + j] = fma(sdk * ci, (my_off + j == jk ? (R)1 : (R)0) - inv_n,
-                                       Prow[my_off + j]);
-            xp = fma(Num<R>::sqrt(sdk) * drift_normal(t, it, k), ci, xp);
+            if (comp == k) {
+              // P_block += sdk c c',  c = e_jk - 1/n:  row i gets  sdk c_i (e_jk - 1/n)'
+              const R f = sdk * ci, g0 = -f * inv_n;
+              for (int j = 0; j < my_n; ++j) Prow[my_off + j] += g0;
+              Prow[jk] += f;
+            }
+            xp = fma(sig_d[k] * st_d[k * TB + tl], ci, xp);
           }
           __syncwarp();
         }
@@ -303,11 +332,12 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       R zp[KS];
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
-        const uint4 x = Philox::gen(seed, id_lo, RNG_S_PATH | id_hi8, (uint32_t)(t0 + kk), (uint32_t)it);
-        R ze, zo;
-        box_muller<R>(x.x, x.y, ze, zo);
+        R ze, zo, dr[MAX_SEAS];
+        step_normals(t0 + kk, it, ze, zo, zp[kk], dr);      // the SAME normals as pass A
         st_a[lane * KS + kk] = ze;                          // level noise of the step
-        box_muller<R>(x.z, x.w, zp[kk], zo);
+#pragma unroll
+        for (int k = 0; k < MAX_SEAS; ++k)
+          if (k < K) st_d[k * TB + lane * KS + kk] = dr[k];
       }
       __syncwarp();
       const int nstep = min(TB, T - b * TB);
@@ -331,14 +361,15 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
           const R rt = lane < d ? srow[lane] : (R)0;
           if (lane == 0) xt += fma(sh, rt, sig_h * eta);
           if (em) {
-            for (int k = 0; k < K; ++k) {
-              if (!((em >> k) & 1)) continue;
-              const int jk = sz.off[k] + (int)sz.sched[(size_t)t * (K + 1) + k];
+#pragma unroll
+            for (int k = 0; k < MAX_SEAS; ++k) {
+              if (k >= K || !((em >> k) & 1)) continue;
+              const int jk = cols[k + 1];
               const R sdk = __shfl_sync(FULL, sdv, k);
               const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
               const R cr = __shfl_sync(FULL, rt, jk) -
-                           warp_sum(comp == k ? rt : (R)0) / (R)sz.n[k];
-              const R u = fma(sdk, cr, Num<R>::sqrt(sdk) * drift_normal(t, it, k));
+                           warp_sum(comp == k ? rt : (R)0) * inv_nk[k];
+              const R u = fma(sdk, cr, sig_d[k] * st_d[k * TB + tl]);
               xt = fma(u, ci, xt);
               if (lane == k) su2 += (double)u * (double)u;
             }
