@@ -145,18 +145,19 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
     cmask = 0u;
 #pragma unroll
     for (int k = 0; k <= MAX_SEAS; ++k) {
-      cols[k] = __shfl_sync(FULL, src, k);
-      if (k <= K) cmask |= 1u << cols[k];
+      cols[k] = 0;
+      if (k <= K) {                                   // K is uniform: no divergence
+        cols[k] = __shfl_sync(FULL, src, k);
+        cmask |= 1u << cols[k];
+      }
     }
     return src;      // lane l in 1..K: state index of component l-1's active season
   };
   auto gather = [&](R v, const int (&cols)[MAX_SEAS + 1]) -> R {      // h' v
     R acc = 0;
 #pragma unroll
-    for (int k = 0; k <= MAX_SEAS; ++k) {
-      const R g = __shfl_sync(FULL, v, cols[k]);
-      if (k <= K) acc += g;
-    }
+    for (int k = 0; k <= MAX_SEAS; ++k)
+      if (k <= K) acc += __shfl_sync(FULL, v, cols[k]);
     return acc;
   };
   // All normals of step t: level noise, observation noise of y+, predictive noise, and one
