@@ -80,6 +80,7 @@ struct ci_ctx {
   int force_G = 0;                   // CI_B200_G env override (tuning)
   int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
   int predict_team = 0;              // CI_B200_PREDICT_TEAM=1: team kernel for ci_posterior_predict
+  int team_sub = 1;                  // CI_B200_TEAM_SUB=0: no sub-tile (4 steps / lane) team kernels
 };
 
 namespace {
@@ -190,9 +191,15 @@ int pick_G(const ci_ctx* c, int C) {
 
 // Team mode (ci_team.cuh): one warp per tile, W = NB warps per chain.  Used when
 // the whole series is resident in shared memory and has 2..MAXW tiles.
+// `sub` (may be NULL): out, warps per tile -- 2 when the sub-tile kernels (ci_team4.cuh, 4 steps
+// per lane) apply: small p and at most MAXW/2 tiles; callers without sub-tile kernels pass NULL.
 template <typename R>
-bool plan_team(const ci_ctx* c, int C, int* GT, SmemCfg* cfg) {
-  const int W = c->NB;
+bool plan_team(const ci_ctx* c, int C, int* GT, SmemCfg* cfg, int* sub = nullptr) {
+  int W = c->NB;
+  if (sub) {
+    *sub = 1;
+    if (c->team_sub && 2 * W <= MAXW && c->prob.p <= PSMALL) { *sub = 2; W *= 2; }
+  }
   if (!c->team_mode || W < 2 || W > MAXW || c->prob.model != CI_MODEL_LOCAL_LEVEL) return false;
   int gt = (C >= 4 * c->sm_count) ? MAXW / W : 1;
   if (gt < 1) gt = 1;
@@ -238,12 +245,13 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
     c->launches++;
     return CI_OK;
   }
-  int GT = 0;
-  if (plan_team<R>(c, C, &GT, &cfg)) {
-    auto tk = k_logpost_team<R>;
+  int GT = 0, sub = 1;
+  if (plan_team<R>(c, C, &GT, &cfg, &sub)) {
+    const int W = c->NB * sub;
+    auto tk = sub == 2 ? k_logpost_teamq<R, 4> : k_logpost_team<R>;
     CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
-    tk<<<(C + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
-        make_probdev<R>(c), cfg, c->NB, static_cast<const R*>(theta_d), C,
+    tk<<<(C + GT - 1) / GT, 32 * (GT * W + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, W, static_cast<const R*>(theta_d), C,
         static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
     CU_TRY(cudaGetLastError());
     c->launches++;
@@ -338,12 +346,13 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
     c->launches++;
     return CI_OK;
   }
-  int GT = 0;
-  if (plan_team<R>(c, C, &GT, &cfg)) {
-    auto tk = k_hmc_team<R>;
+  int GT = 0, sub = 1;
+  if (plan_team<R>(c, C, &GT, &cfg, &sub)) {
+    const int W = c->NB * sub;
+    auto tk = sub == 2 ? k_hmc_teamq<R, 4> : k_hmc_team<R>;
     CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
-    tk<<<(C + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
-        make_probdev<R>(c), cfg, c->NB, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,
+    tk<<<(C + GT - 1) / GT, 32 * (GT * W + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, W, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,
         static_cast<R*>(draws_d), stats_d);
     CU_TRY(cudaGetLastError());
     c->launches++;
@@ -583,6 +592,7 @@ int ci_ctx_create(int device, ci_ctx** out) {
   if (const char* g = getenv("CI_B200_G")) c->force_G = atoi(g);
   if (const char* g = getenv("CI_B200_TEAM")) c->team_mode = atoi(g);
   if (const char* g = getenv("CI_B200_PREDICT_TEAM")) c->predict_team = atoi(g);
+  if (const char* g = getenv("CI_B200_TEAM_SUB")) c->team_sub = atoi(g);
   *out = c;
   return CI_OK;
 }
