@@ -80,7 +80,7 @@ struct ci_ctx {
   int force_G = 0;                   // CI_B200_G env override (tuning)
   int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
   int predict_team = 0;              // CI_B200_PREDICT_TEAM=1: team kernel for ci_posterior_predict
-  int team_sub = 1;                  // CI_B200_TEAM_SUB=0: no sub-tile (4 steps / lane) team kernels
+  int team_sub = 0;                  // CI_B200_TEAM_SUB=1: sub-tile (4 steps / lane) team kernels (experiment)
 };
 
 namespace {
@@ -1111,5 +1111,14 @@ int ci_impact(ci_ctx* c, const ci_impact_args* a, const void* traj, const void* 
   CU_TRY(cudaStreamSynchronize(c->stream));
   return CI_OK;
 }
+
+#ifdef CI_CLK
+// developer build only (-DCI_CLK): phase clocks of the last k_logpost_team launch
+int ci_debug_clocks(long long* out32) {
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpyFromSymbol(out32, ci::g_clk, sizeof(long long) * 32));
+  return CI_OK;
+}
+#endif
 
 }  // extern "C"

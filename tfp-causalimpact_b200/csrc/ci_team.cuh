@@ -20,6 +20,19 @@ namespace ci {
 
 constexpr int MAXW = 8;   // warps per team == max tiles in team mode
 
+// Developer instrumentation (-DCI_CLK): SM clock at the phase boundaries of team_eval, for
+// CTA 0, warps 0 and W-1, read back through ci_debug_clocks().  Compiled out by default.
+#ifdef CI_CLK
+__device__ long long g_clk[2][16];
+#define CI_CLK_MARK(i)                                                              \
+  do {                                                                              \
+    if (blockIdx.x == 0 && lane == 0 && (wt == 0 || wt == W - 1))                   \
+      g_clk[wt == 0 ? 0 : 1][i] = clock64();                                        \
+  } while (0)
+#else
+#define CI_CLK_MARK(i) do {} while (0)
+#endif
+
 // per-team exchange area in shared memory
 template <typename R> struct TeamShared {
   R aggM[MAXW][4];     // Moebius aggregate of each tile
@@ -45,8 +58,10 @@ __device__ __forceinline__ void team_eval(const R* __restrict__ tile, const Prob
                                           R (&gw)[JS]) {
   const int p = pr.p, ld = pr.ld;
   const int nthreads = 32 * W;
+  CI_CLK_MARK(1);
   Blk<R> B;
   blk_residuals(B, tile, w_s, p, ld, lane);
+  CI_CLK_MARK(2);
 
   // ---------------- F1: variance path, tile aggregate ----------------
   const R alpha = s_e + s_h, beta = s_e * s_h;
@@ -69,7 +84,9 @@ mob_scan_up(M, lane);
   if (lane == 31) { ts->aggM[wt][0] = M.a; ts->aggM[wt][1] = M.b; ts->aggM[wt][2] = M.c; ts->aggM[wt][3] = M.d; }
   Mob<R> E = mob_shfl_up(M, 1);
   if (lane == 0) { E.a = 1; E.b = 0; E.c = 0; E.d = 1; }
+  CI_CLK_MARK(3);
   team_sync(bar_id, nthreads);
+  CI_CLK_MARK(4);
 
   // ---------------- F2: carry-in P, sequential P; mean aggregate ----------------
   {
@@ -101,7 +118,9 @@ affine_scan_up(m, c, lane);
   if (lane == 31) { ts->aggA[wt][0] = m; ts->aggA[wt][1] = c; }
   R me = __shfl_up_sync(FULL, m, 1), ce = __shfl_up_sync(FULL, c, 1);
   if (lane == 0) { me = 1; ce = 0; }
+  CI_CLK_MARK(5);
   team_sync(bar_id, nthreads);
+  CI_CLK_MARK(6);
 
   // ---------------- F3: carry-in a, innovations, log-lik terms ----------------
   R a_in = pr.m0;
@@ -116,6 +135,7 @@ affine_scan_up(m, c, lane);
   const double ll_terms = warp_sum((double)blk_loglik_terms(B, s_e));
   const int n_obs = __reduce_add_sync(FULL, __popc(B.obs));
 
+  CI_CLK_MARK(7);
   R abn[KS], q[KS], dF[KS], rbar[KS];
   R lge = 0, lgh = 0;
   if (want_grad) {
@@ -131,7 +151,9 @@ affine_scan_down(m, c, lane);
     if (lane == 0) { ts->aggAB[wt][0] = m; ts->aggAB[wt][1] = c; }
     me = __shfl_down_sync(FULL, m, 1); ce = __shfl_down_sync(FULL, c, 1);
     if (lane == 31) { me = 1; ce = 0; }
+    CI_CLK_MARK(8);
     team_sync(bar_id, nthreads);
+    CI_CLK_MARK(9);
     R ab_in = 0;
     for (int t = W - 1; t > wt; --t) ab_in = fma(ts->aggAB[t][0], ab_in, ts->aggAB[t][1]);
     R ab = fma(me, ab_in, ce);
@@ -156,7 +178,9 @@ affine_scan_down(m, c, lane);
     if (lane == 0) { ts->aggPB[wt][0] = m; ts->aggPB[wt][1] = c; }
     me = __shfl_down_sync(FULL, m, 1); ce = __shfl_down_sync(FULL, c, 1);
     if (lane == 31) { me = 1; ce = 0; }
+    CI_CLK_MARK(10);
     team_sync(bar_id, nthreads);
+    CI_CLK_MARK(11);
     R pb_in = 0;
     for (int t = W - 1; t > wt; --t) pb_in = fma(ts->aggPB[t][0], pb_in, ts->aggPB[t][1]);
     R pb = fma(me, pb_in, ce);
@@ -169,6 +193,7 @@ affine_scan_down(m, c, lane);
       rbar[k] = fma(K, abn[k], -v * rF);
       pb = fma(omk * omk, pb, q[k]);
     }
+    CI_CLK_MARK(12);
     // ---------------- X^T rbar of this tile ----------------
     if (p > 0) {
       if (p <= PSMALL) {
@@ -209,6 +234,7 @@ affine_scan_down(m, c, lane);
       }
     }
   }
+  CI_CLK_MARK(13);
   const double ge_w = warp_sum((double)lge), gh_w = warp_sum((double)lgh);
   if (lane == 0) {
     ts->red[wt][0] = ll_terms; ts->red[wt][1] = ge_w; ts->red[wt][2] = gh_w;
@@ -233,6 +259,7 @@ affine_scan_down(m, c, lane);
   }
   // the exchange area is reused by the next evaluation
   team_sync(bar_id, nthreads);
+  CI_CLK_MARK(14);
 }
 
 // ---------------------------------------------------------------------------

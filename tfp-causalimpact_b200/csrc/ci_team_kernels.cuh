@@ -77,7 +77,13 @@ k_logpost_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, i
   const int lane = threadIdx.x & 31;
   const int n_warps = (blockDim.x >> 5) - 1;
   CtaShared<R> cs; int team, wt, c;
+#ifdef CI_CLK
+  const long long clk_entry = clock64();
+#endif
   if (!team_prologue(smem, cfg, pr, W, C, cs, team, wt, c)) return;
+#ifdef CI_CLK
+  if (blockIdx.x == 0 && lane == 0 && (wt == 0 || wt == W - 1)) g_clk[wt == 0 ? 0 : 1][0] = clk_entry;
+#endif
   const int p = pr.p, dim = pr.dim;
   const R* th = theta + (size_t)c * dim;
   const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, threadIdx.x >> 5);
@@ -109,6 +115,7 @@ k_logpost_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, i
     }
     if (lane == 0) { g[p] = (R)g_u; g[p + 1] = (R)g_l; }
   }
+  CI_CLK_MARK(15);
 }
 
 template <typename R>
