@@ -42,6 +42,10 @@ template <> struct Num<float> {
     return fmaf(r, fmaf(-x, r, 1.0f), r); }
   static __device__ __forceinline__ float rcp_fast(float x) {
     float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  // 2^-floor(log2 x) for normal x > 0: an EXACT power-of-two rescaling factor (3 integer ops
+  // instead of a MUFU.RCP on the critical path of every Moebius scan level)
+  static __device__ __forceinline__ float pow2_rescale(float x) {
+    return __int_as_float((254 - ((__float_as_int(x) >> 23) & 255)) << 23); }
   static __device__ __forceinline__ float log(float x) { return logf(x); }
   static __device__ __forceinline__ float exp(float x) { return expf(x); }
   static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
@@ -50,6 +54,8 @@ template <> struct Num<float> {
 template <> struct Num<double> {
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
   static __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ double pow2_rescale(double x) {
+    return __longlong_as_double((long long)(2046 - ((__double_as_longlong(x) >> 52) & 2047)) << 52); }
   static __device__ __forceinline__ double log(double x) { return ::log(x); }
   static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
@@ -65,6 +71,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
+}
+
+// Sum EACH of 16 per-lane values over the warp with 16 shuffles (a butterfly that halves the
+// number of live values per level) instead of 16 x 5.  On return v[0] of lane L holds the
+// warp total of value index L >> 1 (fixed order: deterministic).
+template <typename R> __device__ __forceinline__ void warp_multi_sum16(R (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const R send = up ? v[i] : v[i + half];
+      const R keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, off);
+    }
+  }
+  v[0] += __shfl_xor_sync(FULL, v[0], 1);
 }
 
 // ---------------------------------------------------------------------------

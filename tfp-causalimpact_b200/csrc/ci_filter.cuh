@@ -35,7 +35,7 @@ template <typename R> __device__ __forceinline__ Mob<R> mob_mul(const Mob<R>& L,
   Mob<R> o;
   o.a = L.a * E.a + L.b * E.c; o.b = L.a * E.b + L.b * E.d;
   o.c = L.c * E.a + L.d * E.c; o.d = L.c * E.b + L.d * E.d;
-  const R s = Num<R>::rcp_fast(o.a + o.b + o.c + o.d);
+  const R s = Num<R>::pow2_rescale(o.a + o.b + o.c + o.d);   // entries stay in [0, 2)
   o.a *= s; o.b *= s; o.c *= s; o.d *= s;
   return o;
 }

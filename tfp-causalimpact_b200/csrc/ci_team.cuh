@@ -41,6 +41,10 @@ template <typename R> struct TeamShared {
   R aggPB[MAXW][2];    // Pbar recursion (reverse)
   double red[MAXW][4]; // ll-terms, ge, gh, n_obs partials
   R gwpart[MAXW][MAX_DIM];
+  // log prior + Jacobian and its gradient, computed by the otherwise idle producer warp
+  // while the team filters (k_logpost_team): lp, d/du, d/dl, then d/dw
+  double prior[4];
+  R gwprior[MAX_DIM];
 };
 
 __device__ __forceinline__ void team_sync(int bar_id, int nthreads) {
@@ -66,8 +70,10 @@ __device__ __forceinline__ void team_eval(const R* __restrict__ tile, const Prob
   // ---------------- F1: variance path, tile aggregate ----------------
   const R alpha = s_e + s_h, beta = s_e * s_h;
   Mob<R> M{(R)1, (R)0, (R)0, (R)1};
+  Mob<R> Mx[KS];                       // lane-local map of the steps BEFORE step k
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
+    Mx[k] = M;
     const bool o = (B.obs >> k) & 1u;
     const R e1 = o ? alpha : (R)1, e2 = o ? beta : s_h;
     const R f1 = o ? (R)1 : (R)0, f2 = o ? s_e : (R)1;
@@ -97,15 +103,19 @@ mob_scan_up(M, lane);
     }
     E = mob_mul(E, Pre);
   }
-  R Pc = fma(E.a, pr.P0, E.b) * Num<R>::rcp(fma(E.c, pr.P0, E.d));
+  // The KS predicted variances of the lane, ALL AT ONCE: P_k is the Moebius image of P0 under
+  // (lane-local prefix before step k) o (everything before the lane) -- 8 independent
+  // compositions and reciprocals instead of a dependent chain of 8 (run 31: the sequential
+  // variance / gain pass was ~900 of the 14 000 cycles of an evaluation).
+  const R n0 = fma(E.a, pr.P0, E.b), d0 = fma(E.c, pr.P0, E.d);    // P at the lane's first step = n0/d0
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
-    B.P[k] = Pc;
+    const R num = fma(Mx[k].a, n0, Mx[k].b * d0), den = fma(Mx[k].c, n0, Mx[k].d * d0);
+    const R Pk = num * Num<R>::rcp(den);
+    B.P[k] = Pk;
     const bool o = (B.obs >> k) & 1u;
-    const R rF = o ? Num<R>::rcp(Pc + s_e) : (R)0;
-    const R K = Pc * rF;
-    B.rF[k] = rF; B.K[k] = K;
-    Pc = fma(-K, Pc, Pc) + s_h;
+    const R rF = o ? Num<R>::rcp(Pk + s_e) : (R)0;
+    B.rF[k] = rF; B.K[k] = Pk * rF;
   }
   R m = 1, c = 0;
 #pragma unroll
@@ -201,13 +211,9 @@ affine_scan_down(m, c, lane);
 #pragma unroll
         for (int j = 0; j < PSMALL; ++j) accw[j] = 0;
         blk_xt_rbar_small(tile, rbar, p, ld, lane, accw);
-#pragma unroll
-        for (int j = 0; j < PSMALL; ++j) {
-          if (j < p) {
-            const R tot = warp_sum(accw[j]);
-            if (lane == j) ts->gwpart[wt][j] = tot;
-          }
-        }
+        static_assert(PSMALL == 16, "warp_multi_sum16");
+        warp_multi_sum16(accw, lane);            // 16 shuffles for all covariates (was 5 each)
+        if (!(lane & 1) && (lane >> 1) < p) ts->gwpart[wt][lane >> 1] = accw[0];
       } else {
         const XtMap xm = xt_map(p, lane);
         R acc[JS];

@@ -74,19 +74,58 @@ __global__ void __launch_bounds__(32 * (MAXW + 1), 1)
 k_logpost_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, int C,
                R* __restrict__ value, R* __restrict__ grad, int flags) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_warps = (blockDim.x >> 5) - 1;
-  CtaShared<R> cs; int team, wt, c;
+  const int GT = n_warps / W;
+  const int p = pr.p, dim = pr.dim;
 #ifdef CI_CLK
   const long long clk_entry = clock64();
 #endif
-  if (!team_prologue(smem, cfg, pr, W, C, cs, team, wt, c)) return;
+  const CtaShared<R> cs = cta_prologue(smem, cfg, pr, 1);
+  if (warp == n_warps) {
+    // producer warp: start the bulk copies, then -- instead of idling -- evaluate the log
+    // prior + Jacobian of every chain of the CTA (it needs theta and Omega, not the series)
+    // and hand it to the team's warp 0 through a named barrier (run 31: the prior was a
+    // 1 800-cycle serial tail of the evaluation)
+    if (lane == 0) {
+      omega_fetch(cs, pr);
+      tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB,
+                    true, 0LL, [](long long) { return true; });
+    }
+    __syncwarp();
+    if (flags & 1) {
+      omega_wait(cs);
+      for (int t = 0; t < GT; ++t) {
+        const int cc = blockIdx.x * GT + t;
+        if (cc >= C) break;
+        const R* th = theta + (size_t)cc * dim;
+        const R u = th[p], l = th[p + 1];
+        const R s_e = Num<R>::exp(u), s_h = Num<R>::exp(l);
+        R gw[JS];
+#pragma unroll
+        for (int s = 0; s < JS; ++s) gw[s] = 0;
+        double g_u = 0.0, g_l = 0.0;
+        const double lp = chain_prior(pr, cs.omega, th, u, l, s_e, s_h, lane, gw, g_u, g_l);
+        TeamShared<R>* ts = team_area<R>(smem, cfg, n_warps, t);
+        if (lane == 0) { ts->prior[0] = lp; ts->prior[1] = g_u; ts->prior[2] = g_l; }
+#pragma unroll
+        for (int s = 0; s < JS; ++s) {
+          const int j = lane + 32 * s;
+          if (j < p) ts->gwprior[j] = gw[s];
+        }
+        asm volatile("bar.arrive %0, 64;" ::"r"(8 + t) : "memory");
+      }
+    }
+    return;
+  }
+  const int team = warp / W, wt = warp - team * W;
+  const int c = blockIdx.x * GT + team;
+  if (c >= C) return;
 #ifdef CI_CLK
   if (blockIdx.x == 0 && lane == 0 && (wt == 0 || wt == W - 1)) g_clk[wt == 0 ? 0 : 1][0] = clk_entry;
 #endif
-  const int p = pr.p, dim = pr.dim;
   const R* th = theta + (size_t)c * dim;
-  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, threadIdx.x >> 5);
+  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
   for (int j = lane; j < dim; j += 32) ws.w[j] = th[j];
   __syncwarp();
   const R u = ws.w[p], l = ws.w[p + 1];
@@ -96,14 +135,20 @@ k_logpost_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, i
   const bool want_grad = grad != nullptr;
   double ll, g_se, g_sh;
   R gw[JS];
-  team_eval(tile, pr, team_area<R>(smem, cfg, n_warps, team), ws.w, ws.rbuf, s_e, s_h, want_grad,
-            lane, wt, W, team + 1, ll, g_se, g_sh, gw);
+  TeamShared<R>* ts = team_area<R>(smem, cfg, n_warps, team);
+  team_eval(tile, pr, ts, ws.w, ws.rbuf, s_e, s_h, want_grad, lane, wt, W, team + 1, ll, g_se,
+            g_sh, gw);
   if (wt != 0) return;
   double val = ll;
   double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
   if (flags & 1) {
-    omega_wait(cs);
-    val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
+    asm volatile("bar.sync %0, 64;" ::"r"(8 + team) : "memory");
+    val += ts->prior[0]; g_u += ts->prior[1]; g_l += ts->prior[2];
+#pragma unroll
+    for (int s = 0; s < JS; ++s) {
+      const int j = lane + 32 * s;
+      if (j < p) gw[s] += ts->gwprior[j];
+    }
   }
   if (lane == 0) value[c] = (R)val;
   if (want_grad) {
