@@ -234,6 +234,28 @@ int ci_gibbs_seasonal_run_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t see
                             void* traj_d, float* incl_d, void* latent_d, void* seasonal_d,
                             void* drift_d, void* stream);
 
+/* ---- batches of independent series -------------------------
+ * The reference fits ONE series per fit_causalimpact call (single process, single chain;
+ * a user with thousands of geographies loops).  A batch holds N series that share their
+ * shape (T, p, dtype): data.py:77-137 output for each of them, uploaded together.
+ *   probs [N]      the model + priors of each series (m0, P0 and the prior scales differ)
+ *   y     [N,T]    X [N,T,p]    Omega [N,p,p]
+ * ci_gibbs_run_batch_d runs n_chains chains of EVERY series in one launch (grid.y = series).
+ * Every series uses the chain ids chain_id0 .. chain_id0 + n_chains - 1, so its draws are
+ * bit-identical to ci_gibbs_run on that series alone; outputs are series-major:
+ *   draws [N, rows, dim]   level / traj [N, rows, T]   incl [N, n_chains, p]
+ * with rows = n_chains * n_results ordered as opts->chain_major says.
+ * ci_batch_select makes one series of the batch the context's current problem, so that
+ * every single-series entry point (ci_predictive_mean_d, ci_logprob*, ci_hmc_run*,
+ * ci_posterior_predict*, ci_gibbs_run*) works on it without another upload.
+ */
+int ci_set_data_batch(ci_ctx* ctx, const ci_problem* probs, int n_series, const void* y,
+                      const void* X, const void* Omega);
+int ci_batch_select(ci_ctx* ctx, int series);
+int ci_gibbs_run_batch_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
+                         uint64_t chain_id0, int n_chains, void* draws_d, void* level_d,
+                         void* traj_d, float* incl_d, void* stream);
+
 /* Mean of the predictive mixture alone (lib.py:627): mean_t = avg_s level[s,t] + x_t . avg_s w_s,
  * for draws whose level paths are already on the device (the Gibbs kernel's output).
  * Deterministic: fixed summation order, float64 accumulation. */

@@ -126,3 +126,29 @@ def test_causalimpact_data_validation(csv):                        # data_test.p
   text = csv.copy(); text["x1"] = "a"
   with pytest.raises(ValueError, match="only numeric"):
     fr.CausalImpactData(text, pre, post)
+
+
+def test_seasonal_schedule_matches_oracle_and_reference_examples():
+  """model.build_seasonal (product, vectorised) vs oracle/seasonal_np.season_schedule (loop):
+  int / per-season tuple / per-cycle nested tuple run lengths, as the reference's own test
+  passes them (causalimpact_lib_test.py:741-755); priors of causalimpact_lib.py:471-474."""
+  import types
+  from causalimpact_b200 import model
+  from oracle import seasonal_np as S
+  cases = [(4, (2, 1, 1, 1)), (7, 1), (6, ((2, 2, 1, 1, 1, 1), (2, 2, 1, 1, 1, 1))),
+           (2, ((1, 2), (3, 1))), (7, 24), (3, (5, 1, 2))]
+  T = 211
+  seasons = [types.SimpleNamespace(num_seasons=n, num_steps_per_season=s) for n, s in cases]
+  sch = model.build_seasonal(seasons, T, 1.3)
+  assert sch.K == len(cases) and sch.active.shape == (len(cases), T)
+  for k, (n, s) in enumerate(cases):
+    idx, ends = S.season_schedule(n, s, T)
+    np.testing.assert_array_equal(sch.active[k], idx)
+    np.testing.assert_array_equal(sch.ends[k].astype(bool), ends)
+  assert sch.init_sd == 1.3 and sch.drift_conc == 0.005 and sch.drift_ub == 1.3
+  np.testing.assert_allclose(sch.drift_scale, 5e-7 * 1.3 ** 2)
+  assert model.build_seasonal([], T, 1.0) is None
+  for bad in ((4, (1, 2, 3)), (3, 0), (3, (1.5, 1, 1)), (1, 1)):
+    with pytest.raises(ValueError):
+      model.build_seasonal([types.SimpleNamespace(num_seasons=bad[0], num_steps_per_season=bad[1])],
+                           T, 1.0)

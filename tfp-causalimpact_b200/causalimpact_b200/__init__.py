@@ -8,7 +8,8 @@ __version__ = "0.1.0"
 
 from ._engine import DeviceArray, Engine, EngineError, ProblemSpec  # noqa: F401
 from .api import (CausalImpactAnalysis, CausalImpactPosteriorSamples, DataOptions,  # noqa: F401
-                  EngineOptions, InferenceOptions, ModelOptions, Seasons, fit_causalimpact)
+                  EngineOptions, InferenceOptions, ModelOptions, Seasons, fit_causalimpact,
+                  fit_causalimpact_many)
 from .frame import CausalImpactData, InputDateType  # noqa: F401
 from .model import build_problem, initial_theta  # noqa: F401
 from .report import plot, summary  # noqa: F401

@@ -75,6 +75,7 @@ EXPORTS = (
     "ci_hmc_run", "ci_hmc_run_d", "ci_gibbs_run", "ci_gibbs_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
     "ci_row_quantiles", "ci_row_quantiles_d", "ci_predictive_mean_d", "ci_impact", "ci_impact_d",
     "ci_set_seasonal", "ci_gibbs_seasonal_run", "ci_gibbs_seasonal_run_d",
+    "ci_set_data_batch", "ci_batch_select", "ci_gibbs_run_batch_d",
 )
 
 _lib = None
@@ -120,6 +121,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                                         vp, vp, vp]
   lib.ci_gibbs_seasonal_run_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp,
                                           vp, vp, vp, vp, vp]
+  lib.ci_set_data_batch.argtypes = [vp, C.POINTER(CiProblem), i32, vp, vp, vp]
+  lib.ci_batch_select.argtypes = [vp, i32]
+  lib.ci_gibbs_run_batch_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp, vp]
   _lib = lib
   return lib
 
@@ -210,6 +214,7 @@ class Engine:
     self.device = device
     self.spec: Optional[ProblemSpec] = None
     self.seasonal = None
+    self.batch_specs = None
     self._check(self._lib.ci_ctx_create(device, C.byref(self._ctx)))
 
   # -- plumbing ------------------------------------------------------------
@@ -243,17 +248,67 @@ class Engine:
   def set_data(self, spec: ProblemSpec):
     self.spec = spec
     self.seasonal = None
+    self.batch_specs = None
     dt = spec.np_dtype
     y = np.ascontiguousarray(spec.y, dtype=dt)
     X = None if spec.X is None else np.ascontiguousarray(spec.X, dtype=dt)
     Om = None if spec.Omega is None else np.ascontiguousarray(spec.Omega, dtype=dt)
-    pb = CiProblem(model=spec.model, dtype=spec.dtype, T=spec.T, p=spec.p,
-                   obs_conc=spec.obs_conc, obs_scale=spec.obs_scale, obs_ub=spec.obs_ub,
-                   lvl_conc=spec.lvl_conc, lvl_scale=spec.lvl_scale, lvl_ub=spec.lvl_ub,
-                   slope_conc=spec.slope_conc, slope_scale=spec.slope_scale,
-                   slope_ub=min(spec.slope_ub, 1e300), m0=spec.m0, P0=spec.P0,
-                   m0_slope=spec.m0_slope, P0_slope=spec.P0_slope)
+    pb = self._ci_problem(spec)
     self._check(self._lib.ci_set_data(self._ctx, C.byref(pb), _ptr(y), _ptr(X), _ptr(Om)))
+
+  @staticmethod
+  def _ci_problem(spec: ProblemSpec) -> CiProblem:
+    return CiProblem(model=spec.model, dtype=spec.dtype, T=spec.T, p=spec.p,
+                     obs_conc=spec.obs_conc, obs_scale=spec.obs_scale, obs_ub=spec.obs_ub,
+                     lvl_conc=spec.lvl_conc, lvl_scale=spec.lvl_scale, lvl_ub=spec.lvl_ub,
+                     slope_conc=spec.slope_conc, slope_scale=spec.slope_scale,
+                     slope_ub=min(spec.slope_ub, 1e300), m0=spec.m0, P0=spec.P0,
+                     m0_slope=spec.m0_slope, P0_slope=spec.P0_slope)
+
+  # -- batches of independent series -----------------------------
+  def set_data_batch(self, specs):
+    """ci_set_data_batch: N series sharing (T, p, dtype); series 0 becomes current."""
+    specs = list(specs)
+    s0 = specs[0]
+    dt = s0.np_dtype
+    for sp in specs:
+      if (sp.T, sp.p, sp.dtype, sp.model) != (s0.T, s0.p, s0.dtype, s0.model):
+        raise ValueError("the series of a batch must share T, the number of covariates and dtype")
+    probs = (CiProblem * len(specs))(*[self._ci_problem(sp) for sp in specs])
+    y = np.ascontiguousarray(np.stack([sp.y for sp in specs]), dtype=dt)
+    X = Om = None
+    if s0.p:
+      X = np.ascontiguousarray(np.stack([sp.X for sp in specs]), dtype=dt)
+      Om = np.ascontiguousarray(np.stack([sp.Omega for sp in specs]), dtype=dt)
+    self.spec, self.seasonal, self.batch_specs = s0, None, specs
+    self._check(self._lib.ci_set_data_batch(self._ctx, probs, len(specs), _ptr(y), _ptr(X), _ptr(Om)))
+
+  def batch_select(self, i: int, spec: Optional[ProblemSpec] = None):
+    """ci_batch_select: series i of the batch becomes the current problem."""
+    self._check(self._lib.ci_batch_select(self._ctx, int(i)))
+    self.spec = spec if spec is not None else self.batch_specs[i]
+    self.seasonal = None
+
+  def gibbs_run_batch_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
+                        chain_id0: int = 0, sparse: bool = True,
+                        nonzero_prob: Optional[float] = None):
+    """ci_gibbs_run_batch_d, chain-major: device tensors theta [N, R, dim], level [N, R, T],
+    traj [N, R, T] (R = n_chains * n_results) and incl [N, n_chains, p] ndarray."""
+    torch, dev = self._torch_dev()
+    sp, dt, N = self.spec, self._tdtype(torch), len(self.batch_specs)
+    if nonzero_prob is None:
+      nonzero_prob = min(1.0, 3.0 / sp.p) if sp.p else 1.0     # lib.py:449-450
+    rows = n_chains * n_results
+    draws = torch.empty((N, rows, sp.dim), dtype=dt, device=dev)
+    level = torch.empty((N, rows, sp.T), dtype=dt, device=dev)
+    traj = torch.empty((N, rows, sp.T), dtype=dt, device=dev)
+    incl = torch.zeros((N, n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
+    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
+                       nonzero_prob=float(nonzero_prob))
+    self._check(self._lib.ci_gibbs_run_batch_d(
+        self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, draws.data_ptr(),
+        level.data_ptr(), traj.data_ptr(), incl.data_ptr(), self._stream(torch)))
+    return draws, level, traj, incl.cpu().numpy()[:, :, :sp.p]
 
   def set_seasonal(self, sched):
     """ci_set_seasonal: ``sched`` is a model.SeasonalSchedule (or None to remove)."""

@@ -297,27 +297,34 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   # for any GPU count
   mean_t = eng.predictive_mean_t(theta_t, parts[3] if sched is not None else level_t)
 
+  samples = _package_samples(eng, theta_t, level_t, p, T, np_dt, wh,
+                             (parts[4], parts[5], K) if sched is not None else None)
+  samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
+  return samples, DeviceArray(mean_t), DeviceArray(traj_t)
+
+
+def _package_samples(eng, theta_t, level_t, p, T, np_dt, wh=None, seasonal=None):
+  """Device draws -> the reference's posterior-sample record (host arrays)."""
   theta = eng.to_host(theta_t).astype(np.float64)
   level = eng.to_host(level_t)
   z = theta[:, :p]
   weights = wh.to_weights(z) if wh is not None else z
   S = theta.shape[0]
-  if sched is not None:
+  if seasonal is not None:
     # each component's contribution at every step: what the reference extracts as the
     # 0-th element of the component's latent (lib.py:299-317), [S, T, K]
-    seas_levels = eng.to_host(parts[4]).reshape(S, T, K).astype(np_dt, copy=False)
-    drift_scales = np.exp(0.5 * eng.to_host(parts[5]).astype(np.float64)).astype(np_dt)
+    seas_t, drift_t, K = seasonal
+    seas_levels = eng.to_host(seas_t).reshape(S, T, K).astype(np_dt, copy=False)
+    drift_scales = np.exp(0.5 * eng.to_host(drift_t).astype(np.float64)).astype(np_dt)
   else:
     seas_levels, drift_scales = np.zeros((S, T, 0), np_dt), np.zeros((S, 0), np_dt)
-  samples = CausalImpactPosteriorSamples(
+  return CausalImpactPosteriorSamples(
       observation_noise_scale=Samples(np.exp(0.5 * theta[:, p]).astype(np_dt)),
       level_scale=Samples(np.exp(0.5 * theta[:, p + 1]).astype(np_dt)),
       level=Samples(level.astype(np_dt, copy=False)),
       weights=Samples(weights.astype(np_dt)) if p else Samples(np.zeros((S, 0), np_dt)),
       seasonal_drift_scales=Samples(drift_scales),
       seasonal_levels=Samples(seas_levels))
-  samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
-  return samples, DeviceArray(mean_t), DeviceArray(traj_t)
 
 
 def fit_causalimpact(data: pd.DataFrame,
@@ -357,6 +364,10 @@ def fit_causalimpact(data: pd.DataFrame,
       experimental_tf_function_cache_key_addition=cache_key, engine_options=engine_options)
   eng = _resolve_engine(engine_options)
   series, summary = _impact.compute_impact(means, trajectories, ci_data, alpha, eng.impact)
+  return _analysis(series, summary, samples)
+
+
+def _analysis(series, summary, samples) -> CausalImpactAnalysis:
   stats = getattr(samples, "hmc_stats", None)
   result_samples = CausalImpactPosteriorSamples(
       observation_noise_scale=samples.observation_noise_scale,
@@ -366,3 +377,69 @@ def fit_causalimpact(data: pd.DataFrame,
                              if samples.seasonal_drift_scales.shape[-1] > 0 else None),   # :332-334
       seasonal_levels=samples.seasonal_levels)
   return CausalImpactAnalysis(series, summary, result_samples, stats)
+
+
+def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, seed=None,
+                          data_options: Optional[DataOptions] = None,
+                          model_options: Optional[ModelOptions] = None,
+                          inference_options: Optional[InferenceOptions] = None,
+                          engine_options: Optional[EngineOptions] = None):
+  """Fit MANY independent series in one go (the "thousands of
+  geographies" use case the reference serves with a Python loop of single-chain fits).
+
+  ``datas``: sequence of DataFrames with a common shape -- same index, periods and number of
+  covariates.  Every series is prepared exactly as ``fit_causalimpact`` does (data.py:77-137),
+  all of them are uploaded together (``ci_set_data_batch``) and ONE launch of the reference's
+  sampler (``ci_gibbs_run_batch_d``: spike-and-slab Gibbs, grid.y = series) draws every chain
+  of every series; predictive mean and impact follow per series on the device.  Result i is
+  bit-identical to ``fit_causalimpact(datas[i], ..., engine_options=EngineOptions(
+  sampler="gibbs"))`` with the same seed.
+
+  Multi-GPU: series are sharded over the ranks of an initialised process group (contiguous
+  ranges, no collective: series are independent); a rank returns ``None`` for the series it
+  does not own.  Seasonal components are not batched (NotImplementedError).
+  """
+  data_options = data_options if data_options is not None else DataOptions()
+  model_options = model_options if model_options is not None else ModelOptions()
+  inference_options = inference_options if inference_options is not None else InferenceOptions()
+  opts = engine_options or EngineOptions()
+  if model_options.seasons:
+    raise NotImplementedError("seasonal components are not batched: use fit_causalimpact")
+  if opts.sampler == "hmc":
+    raise NotImplementedError("the batched path runs the Gibbs kernel")
+  np_dt = _np_dtype(data_options.dtype)
+  seed64 = _seed_to_u64(seed)
+  datas = list(datas)
+  rank, ws = _shard.world()
+  s0, n_local = _shard.split_range(len(datas), ws, rank)
+  out = [None] * len(datas)
+  if n_local == 0:
+    return out
+  eng = _resolve_engine(opts)
+  cids, specs = [], []
+  for d in datas[s0:s0 + n_local]:
+    cid = _frame.CausalImpactData(data=d, pre_period=pre_period, post_period=post_period,
+                                  outcome_column=data_options.outcome_column,
+                                  standardize_data=data_options.standardize_data, dtype=np_dt)
+    y_ext, design, outcome_sd = cid.engine_inputs(np_dt)
+    specs.append(build_problem(y_ext, design, prior_level_sd=model_options.prior_level_sd,
+                               outcome_sd=outcome_sd, dtype=np_dt))
+    cids.append(cid)
+  p, T = specs[0].p, specs[0].T
+  eng.set_data_batch(specs)
+  num_results = inference_options.num_results
+  C = max(int(opts.num_chains), 1)
+  n_per = max(1, math.ceil(num_results / C))
+  n_warm = max(int(inference_options.num_warmup_steps), int(opts.gibbs_min_warmup))
+  theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
+                                                   seed=seed64, chain_id0=0, sparse=True)
+  for i, cid in enumerate(cids):
+    eng.batch_select(i, specs[i])
+    th_i, lv_i, tr_i = (t[i][:num_results] for t in (theta, level, traj))
+    mean_i = eng.predictive_mean_t(th_i, lv_i)
+    samples = _package_samples(eng, th_i, lv_i, p, T, np_dt)
+    samples.hmc_stats = {"sampler": "gibbs", "inclusion": incl[i]}
+    series, summary = _impact.compute_impact(DeviceArray(mean_i), DeviceArray(tr_i), cid, alpha,
+                                             eng.impact)
+    out[s0 + i] = _analysis(series, summary, samples)
+  return out

@@ -74,6 +74,17 @@ struct ci_ctx {
   DevBuf i_cum, i_stats, i_meta, i_series, i_summ, i_trT;   // ci_impact workspaces
   DevBuf s_sched, s_scratch, w_latent, w_seas, w_drift;   // seasonal components
   ci::SeasDev seas{};                // seas.K == 0: no seasonal components
+  // views of the CURRENT series: the context's own buffers after ci_set_data, a slice of the
+  // batch buffers after ci_batch_select
+  const void* v_tiles = nullptr; const void* v_omega = nullptr;
+  const void* v_gram = nullptr; const void* v_xty = nullptr;
+  // batch of independent series (ci_set_data_batch)
+  int batch_n = 0;
+  DevBuf b_tiles, b_omega, b_gram, b_xty, b_dev;
+  size_t b_tile_stride = 0, b_omega_stride = 0, b_gram_stride = 0, b_xty_stride = 0;   // bytes
+  std::vector<ci_problem> b_prob;
+  std::vector<double> b_yty;
+  std::vector<int> b_nobs;
   double yty0 = 0.0;
   int n_obs = 0;
   int64_t launches = 0;
@@ -89,8 +100,8 @@ using namespace ci;
 
 template <typename R> ProbDev<R> make_probdev(const ci_ctx* c) {
   ProbDev<R> pr;
-  pr.tiles = static_cast<const R*>(c->tiles.p);
-  pr.omega = static_cast<const R*>(c->omega.p);
+  pr.tiles = static_cast<const R*>(c->v_tiles);
+  pr.omega = static_cast<const R*>(c->v_omega);
   pr.T = c->prob.T; pr.p = c->prob.p; pr.ld = c->ld; pr.NB = c->NB; pr.dim = c->dim;
   pr.model = c->prob.model;
   pr.m0 = (R)c->prob.m0; pr.P0 = (R)c->prob.P0;
@@ -374,12 +385,15 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
 
 template <typename R>
 int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0, int C,
-                 void* draws_d, void* level_d, void* traj_d, float* incl_d, cudaStream_t st) {
+                 void* draws_d, void* level_d, void* traj_d, float* incl_d, cudaStream_t st,
+                 bool batch = false) {
   const int p = c->prob.p;
   const uint32_t extra = (uint32_t)(2 * p * p + 5 * p + 8);
   const uint32_t tail = (uint32_t)(p * p) * (uint32_t)c->esz + 16u;
   SmemCfg cfg;
-  int G = pick_G(c, C), rc = CI_OK;
+  // a batch runs C chains of EVERY series (grid.y = series): size CTAs for the whole grid
+  int G = batch ? pick_G(c, C * c->batch_n) : pick_G(c, C), rc = CI_OK;
+  if (G > C) G = C;
   for (; G >= 1; --G) {            // wide problems: fewer chains per CTA
     rc = plan_smem(c, G, extra, &cfg, tail);
     if (rc == CI_OK) break;
@@ -392,13 +406,15 @@ int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
   plan.logit_pi = (plan.sparse && pi < 1.0) ? std::log(pi) - std::log1p(-pi) : 1e30;
   if (!(pi < 1.0)) plan.sparse = 0;
   GibbsDev<R> gd;
-  gd.gram = static_cast<const R*>(c->gram.p); gd.xty0 = static_cast<const R*>(c->xty0.p);
+  gd.gram = static_cast<const R*>(c->v_gram); gd.xty0 = static_cast<const R*>(c->v_xty);
   gd.yty0 = (R)c->yty0;
   auto kern = k_gibbs<R>;
   CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
-  kern<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+  const dim3 grid((C + G - 1) / G, batch ? c->batch_n : 1);
+  kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(
       make_probdev<R>(c), gd, cfg, plan, seed, chain_id0, C, static_cast<R*>(draws_d),
-      static_cast<R*>(level_d), static_cast<R*>(traj_d), incl_d);
+      static_cast<R*>(level_d), static_cast<R*>(traj_d), incl_d,
+      batch ? static_cast<const BatchDev<R>*>(c->b_dev.p) : nullptr);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;
@@ -438,7 +454,7 @@ int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint
   plan.logit_pi = (plan.sparse && pi < 1.0) ? std::log(pi) - std::log1p(-pi) : 1e30;
   if (!(pi < 1.0)) plan.sparse = 0;
   GibbsDev<R> gd;
-  gd.gram = static_cast<const R*>(c->gram.p); gd.xty0 = static_cast<const R*>(c->xty0.p);
+  gd.gram = static_cast<const R*>(c->v_gram); gd.xty0 = static_cast<const R*>(c->v_xty);
   gd.yty0 = (R)c->yty0;
   SeasDev sz = c->seas;
   sz.scratch = nullptr;                       // nullptr: the kernel's scratch is in shared memory
@@ -555,6 +571,75 @@ int launch_impact(ci_ctx* c, const ImpactDev& a, const void* traj_d, const void*
 
 }  // namespace
 
+namespace {
+template <typename R>
+int upload_batch(ci_ctx* c, const ci_problem* probs, int N, const void* y_, const void* X_,
+                 const void* Om_) {
+  const int T = probs[0].T, p = probs[0].p;
+  const size_t te = (size_t)ci::tile_elems(p);
+  const size_t tile_stride = (size_t)c->NB * te;                        // elements per series
+  const size_t om_stride = (((size_t)p * p * sizeof(R) + 15) & ~(size_t)15) / sizeof(R) + 16 / sizeof(R);
+  std::vector<R> tiles(tile_stride * N), om(om_stride * N, (R)0), gram((size_t)p * p * N + 4),
+      xty((size_t)(p > 0 ? p : 1) * N + 4);
+  c->b_prob.assign(probs, probs + N);
+  c->b_yty.assign(N, 0.0); c->b_nobs.assign(N, 0);
+  const R* y = static_cast<const R*>(y_);
+  const R* X = static_cast<const R*>(X_);
+  const R* Om = static_cast<const R*>(Om_);
+  std::vector<R> one;
+  for (int s = 0; s < N; ++s) {
+    build_tiles<R>(&probs[s], y + (size_t)s * T, p ? X + (size_t)s * T * p : nullptr, c->NB, c->ld, one);
+    std::copy(one.begin(), one.end(), tiles.begin() + tile_stride * s);
+    if (p) std::copy(Om + (size_t)s * p * p, Om + (size_t)(s + 1) * p * p, om.begin() + om_stride * s);
+    // sufficient statistics over observed rows, float64 on the host (as ci_set_data)
+    std::vector<double> g((size_t)p * p, 0.0), b((size_t)(p > 0 ? p : 1), 0.0);
+    double yty = 0.0; int nobs = 0;
+    for (int t = 0; t < T; ++t) {
+      const double yt = (double)y[(size_t)s * T + t];
+      if (!(yt == yt)) continue;
+      ++nobs; yty += yt * yt;
+      const R* xr = X + ((size_t)s * T + t) * p;
+      for (int i = 0; i < p; ++i) {
+        b[i] += (double)xr[i] * yt;
+        for (int j = 0; j <= i; ++j) g[(size_t)i * p + j] += (double)xr[i] * (double)xr[j];
+      }
+    }
+    for (int i = 0; i < p; ++i)
+      for (int j = i + 1; j < p; ++j) g[(size_t)i * p + j] = g[(size_t)j * p + i];
+    for (int i = 0; i < p * p; ++i) gram[(size_t)s * p * p + i] = (R)g[i];
+    for (int i = 0; i < p; ++i) xty[(size_t)s * p + i] = (R)b[i];
+    c->b_yty[s] = yty; c->b_nobs[s] = nobs;
+  }
+  c->b_tile_stride = tile_stride * sizeof(R); c->b_omega_stride = om_stride * sizeof(R);
+  c->b_gram_stride = (size_t)p * p * sizeof(R); c->b_xty_stride = (size_t)p * sizeof(R);
+  CU_TRY(c->b_tiles.reserve(tiles.size() * sizeof(R)));
+  CU_TRY(c->b_omega.reserve(om.size() * sizeof(R)));
+  CU_TRY(c->b_gram.reserve(gram.size() * sizeof(R)));
+  CU_TRY(c->b_xty.reserve(xty.size() * sizeof(R)));
+  CU_TRY(cudaMemcpyAsync(c->b_tiles.p, tiles.data(), tiles.size() * sizeof(R), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(c->b_omega.p, om.data(), om.size() * sizeof(R), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(c->b_gram.p, gram.data(), gram.size() * sizeof(R), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(c->b_xty.p, xty.data(), xty.size() * sizeof(R), cudaMemcpyHostToDevice, c->stream));
+  // per-series device descriptors of the batched kernels
+  std::vector<ci::BatchDev<R>> dev(N);
+  for (int s = 0; s < N; ++s) {
+    c->prob = probs[s];
+    c->v_tiles = static_cast<char*>(c->b_tiles.p) + c->b_tile_stride * s;
+    c->v_omega = static_cast<char*>(c->b_omega.p) + c->b_omega_stride * s;
+    dev[s].pr = make_probdev<R>(c);
+    dev[s].gd.gram = reinterpret_cast<const R*>(static_cast<char*>(c->b_gram.p) + c->b_gram_stride * s);
+    dev[s].gd.xty0 = reinterpret_cast<const R*>(static_cast<char*>(c->b_xty.p) + c->b_xty_stride * s);
+    dev[s].gd.yty0 = (R)c->b_yty[s];
+    dev[s].n_obs = c->b_nobs[s];
+  }
+  CU_TRY(c->b_dev.reserve(dev.size() * sizeof(ci::BatchDev<R>)));
+  CU_TRY(cudaMemcpyAsync(c->b_dev.p, dev.data(), dev.size() * sizeof(ci::BatchDev<R>),
+                         cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+}  // namespace
+
 // ===========================================================================
 extern "C" {
 
@@ -605,6 +690,7 @@ int ci_ctx_destroy(ci_ctx* c) {
   c->w_theta.release(); c->w_value.release(); c->w_grad.release();
   c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release(); c->w_incl.release();
   c->gram.release(); c->xty0.release();
+  c->b_tiles.release(); c->b_omega.release(); c->b_gram.release(); c->b_xty.release(); c->b_dev.release();
   c->s_sched.release(); c->s_scratch.release(); c->w_latent.release(); c->w_seas.release(); c->w_drift.release();
   c->i_trT.release(); c->i_cum.release(); c->i_stats.release(); c->i_meta.release(); c->i_series.release(); c->i_summ.release();
   delete c;
@@ -691,12 +777,84 @@ int ci_set_data(ci_ctx* c, const ci_problem* pb, const void* y, const void* X, c
       }
     }
   }
+  c->v_tiles = c->tiles.p; c->v_omega = c->omega.p; c->v_gram = c->gram.p; c->v_xty = c->xty0.p;
+  c->batch_n = 0;
   // validate that the pipeline fits before accepting the problem
   ci::SmemCfg cfg;
   int rc = plan_smem(c, 1, 0, &cfg);
   if (rc) return rc;
   c->has_data = true;
   return CI_OK;
+}
+
+// ---- batches of independent series -------------------------------------
+int ci_batch_select(ci_ctx* c, int s) {
+  if (!c) return fail(CI_ERR_INVALID, "null argument");
+  if (c->batch_n < 1) return fail(CI_ERR_STATE, "ci_set_data_batch has not been called");
+  if (s < 0 || s >= c->batch_n) return fail(CI_ERR_INVALID, "series %d out of range [0,%d)", s, c->batch_n);
+  c->prob = c->b_prob[s];
+  c->v_tiles = static_cast<char*>(c->b_tiles.p) + c->b_tile_stride * s;
+  c->v_omega = static_cast<char*>(c->b_omega.p) + c->b_omega_stride * s;
+  c->v_gram = static_cast<char*>(c->b_gram.p) + c->b_gram_stride * s;
+  c->v_xty = static_cast<char*>(c->b_xty.p) + c->b_xty_stride * s;
+  c->yty0 = c->b_yty[s]; c->n_obs = c->b_nobs[s];
+  c->seas = ci::SeasDev{};
+  c->has_data = true;
+  return CI_OK;
+}
+
+int ci_set_data_batch(ci_ctx* c, const ci_problem* probs, int N, const void* y, const void* X,
+                      const void* Omega) {
+  if (!c || !probs || !y) return fail(CI_ERR_INVALID, "null argument");
+  if (N < 1) return fail(CI_ERR_INVALID, "n_series must be >= 1");
+  const ci_problem& p0 = probs[0];
+  if (p0.T < 1 || p0.p < 0) return fail(CI_ERR_INVALID, "bad T / p");
+  if (p0.p > 0 && (!X || !Omega)) return fail(CI_ERR_INVALID, "X and Omega are required when p > 0");
+  if (p0.dtype != CI_F32 && p0.dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  if (p0.model != CI_MODEL_LOCAL_LEVEL)
+    return fail(CI_ERR_UNSUPPORTED, "batches are local-level only (as the reference's model)");
+  if (p0.p + 2 > ci::MAX_DIM) return fail(CI_ERR_UNSUPPORTED, "p=%d exceeds the supported maximum", p0.p);
+  for (int s = 0; s < N; ++s) {
+    if (probs[s].T != p0.T || probs[s].p != p0.p || probs[s].dtype != p0.dtype || probs[s].model != p0.model)
+      return fail(CI_ERR_INVALID, "series %d differs in T / p / dtype / model: a batch shares its shape", s);
+    if (!(probs[s].P0 > 0)) return fail(CI_ERR_INVALID, "P0 must be positive (series %d)", s);
+  }
+  CU_TRY(cudaSetDevice(c->device));
+  c->has_data = false;
+  c->seas = ci::SeasDev{};
+  c->prob = p0;
+  c->esz = p0.dtype == CI_F64 ? 8 : 4;
+  c->NB = (p0.T + ci::TB - 1) / ci::TB;
+  c->ld = ci::tile_ld(p0.p);
+  c->dim = p0.p + 2;
+  int rc = p0.dtype == CI_F64 ? upload_batch<double>(c, probs, N, y, X, Omega)
+                              : upload_batch<float>(c, probs, N, y, X, Omega);
+  if (rc) return rc;
+  c->batch_n = N;
+  rc = ci_batch_select(c, 0);
+  if (rc) return rc;
+  ci::SmemCfg cfg;
+  rc = plan_smem(c, 1, 0, &cfg);
+  if (rc) { c->has_data = false; c->batch_n = 0; return rc; }
+  return CI_OK;
+}
+
+int ci_gibbs_run_batch_d(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0,
+                         int Cs, void* draws_d, void* level_d, void* traj_d, float* incl_d,
+                         void* stream) {
+  if (!c || !o || !draws_d) return fail(CI_ERR_INVALID, "null argument");
+  if (c->batch_n < 1) return fail(CI_ERR_STATE, "ci_set_data_batch has not been called");
+  if (Cs < 1 || o->n_results < 1 || o->n_warmup < 0)
+    return fail(CI_ERR_INVALID, "n_chains >= 1, n_results >= 1, n_warmup >= 0 required");
+  if (o->sparse && !(o->nonzero_prob > 0.0 && o->nonzero_prob <= 1.0))
+    return fail(CI_ERR_INVALID, "nonzero_prob must be in (0, 1]");
+  for (int s = 0; s < c->batch_n; ++s)
+    if (c->b_nobs[s] < 2) return fail(CI_ERR_INVALID, "series %d has fewer than 2 observed points", s);
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prob.dtype == CI_F64)
+    return launch_gibbs<double>(c, o, seed, chain_id0, Cs, draws_d, level_d, traj_d, incl_d, st, true);
+  return launch_gibbs<float>(c, o, seed, chain_id0, Cs, draws_d, level_d, traj_d, incl_d, st, true);
 }
 
 int ci_logprob_grad_d(ci_ctx* c, const void* theta_d, int C, void* value_d, void* grad_d,

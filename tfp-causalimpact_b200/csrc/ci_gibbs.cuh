@@ -38,6 +38,14 @@ template <typename R> struct GibbsDev {
   R yty0;          //        y'y over observed rows
 };
 
+// One entry per series of a batch (ci_set_data_batch): the kernel of CTA
+// row blockIdx.y works on series blockIdx.y -- its own tiles, priors and sufficient statistics.
+template <typename R> struct BatchDev {
+  ProbDev<R> pr;
+  GibbsDev<R> gd;
+  int n_obs;
+};
+
 // per-warp dense-algebra scratch (elements of R)
 template <typename R> struct GibbsScratch {
   R* bvec;   // [p]        X'(y - level)
@@ -216,8 +224,16 @@ template <typename R>
 __global__ void __launch_bounds__(32 * (MAXG + 1), 1)
 k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t seed,
         uint64_t chain_id0, int C, R* __restrict__ draws, R* __restrict__ level_out,
-        R* __restrict__ traj_out, float* __restrict__ incl_out) {
+        R* __restrict__ traj_out, float* __restrict__ incl_out,
+        const BatchDev<R>* __restrict__ batch) {
   extern __shared__ __align__(128) unsigned char smem[];
+  // batched launch: grid.y = series; every series has C chains with the SAME global chain
+  // ids (so a series' draws equal those of a single-series run), outputs are series-major
+  const size_t series_row0 = batch ? (size_t)blockIdx.y * C * plan.n_results : 0;
+  const size_t series_chain0 = batch ? (size_t)blockIdx.y * C : 0;
+  if (batch) {
+    pr = batch[blockIdx.y].pr; gd = batch[blockIdx.y].gd; plan.n_obs = batch[blockIdx.y].n_obs;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = (blockDim.x >> 5) - 1;
   const int chain0 = blockIdx.x * G;
@@ -282,8 +298,8 @@ k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t see
     __syncwarp();
     const bool keep = it >= plan.n_warmup;
     const size_t out_row = !keep ? 0
-        : plan.chain_major ? ((size_t)c * plan.n_results + (size_t)(it - plan.n_warmup))
-                           : ((size_t)(it - plan.n_warmup) * C + c);
+        : series_row0 + (plan.chain_major ? ((size_t)c * plan.n_results + (size_t)(it - plan.n_warmup))
+                                          : ((size_t)(it - plan.n_warmup) * C + c));
     const XtMap xm = xt_map(p, lane);
     const bool small_p = p <= PSMALL;
     R accw[PSMALL];
@@ -403,7 +419,7 @@ affine_scan_down(m, cc, lane);
 #pragma unroll
     for (int wd = 0; wd < DSLOTS; ++wd) {
       const int j = lane + 32 * wd;
-      if (j < p) incl_out[(size_t)c * p + j] = (float)(incl_cnt[wd] / (plan.n_results > 0 ? plan.n_results : 1));
+      if (j < p) incl_out[(series_chain0 + (size_t)c) * p + j] = (float)(incl_cnt[wd] / (plan.n_results > 0 ? plan.n_results : 1));
     }
   }
 }
