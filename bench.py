@@ -362,6 +362,48 @@ def main():
   sync_all()
   t_impact = float(p0.elapsed_time(p1)) / 10.0
 
+  # ---- BASELINE configs[4] shape on this GPU: 10 000-draw posterior forecast, T = 2000, 10
+  # covariates -- simulation smoother + predictive draws + mean + the whole impact stage,
+  # device resident (the second headline quantity: posterior draws/s) ----
+  from conftest import make_series as _mk
+  y5, X5, _ = _mk(2000, 10, 20245)
+  eng5 = cib.Engine(local)
+  eng5.set_data(cib.build_problem(y5, X5))
+  S5 = 10000
+  th5 = torch.from_numpy(np.ascontiguousarray(np.tile(th_np, (S5 // C + 1, 1))[:S5])).to(dev)
+  per5 = np.zeros(2000, np.uint8); per5[1400:] = 1
+  obs5 = np.random.Generator(np.random.PCG64(6)).normal(size=2000)
+  meta5 = types.SimpleNamespace(observed=obs5, period=per5, scale=2.0, offset=100.0, q_lo=0.025,
+                                q_hi=0.975, obs_sum=float(obs5[1400:].sum()))
+  def forecast():
+    lv5, tr5 = eng5.posterior_predict_t(th5, seed=11, draw_id0=rank * S5)
+    mu5 = eng5.predictive_mean_t(th5, lv5)
+    return eng5.impact(tr5, mu5, meta5)          # ends with the D2H of series + summary
+  for _ in range(3):
+    forecast()
+  sync_all()
+  tq = time.perf_counter()
+  for _ in range(5):
+    forecast()
+  sync_all()
+  t_fc = (time.perf_counter() - tq) / 5 * 1e3
+  eng5.close()
+
+  # ---- batch of independent series: one launch, grid.y = series ----
+  specs_b = []
+  for sb in range(128):
+    yb, Xb, _ = _mk(300, 2, 3000 + sb)
+    specs_b.append(cib.build_problem(yb, Xb))
+  engb = cib.Engine(local)
+  engb.set_data_batch(specs_b)
+  engb.gibbs_run_batch_t(8, n_warmup=2, n_results=2, seed=1)
+  sync_all()
+  tq = time.perf_counter()
+  engb.gibbs_run_batch_t(8, n_warmup=100, n_results=50, seed=1)
+  sync_all()
+  t_batch = (time.perf_counter() - tq) * 1e3
+  engb.close()
+
   # ---- the reference's own sampler on the GPU: Gibbs sweeps/s (spike-and-slab, 256 chains)
   eng.gibbs_run(C, n_warmup=2, n_results=2, seed=1, chain_id0=rank * C, want_level=False,
                 want_traj=False)
@@ -447,6 +489,16 @@ def main():
                   "fit_causalimpact_quickstart_ms": t_fit,
                   "fit_note": "T=100, 1 covariate, 900 draws, 64 chains, 2nd call; reference "
                               "publishes 5170 ms for this call (other hardware, incl. tracing)",
+                  "forecast_10000_draws_T2000_ms": t_fc,
+                  "forecast_draws_per_sec": S5 * world / (t_fc * 1e-3),
+                  "forecast_note": "BASELINE configs[4] shape per GPU: ci_posterior_predict_d + "
+                                   "ci_predictive_mean_d + ci_impact_d for 10 000 draws, T=2000, 10 "
+                                   "covariates, wall clock incl. the D2H of series + summary",
+                  "batch_gibbs": {"series": 128, "T": 300, "chains_per_series": 8, "sweeps": 150,
+                                  "wall_ms": t_batch,
+                                  "sweeps_per_sec": 128 * 8 * 150 * world / (t_batch * 1e-3),
+                                  "note": "ci_gibbs_run_batch_d: every chain of every series in "
+                                          "one launch (rank 0's time)"},
                   "impact_ms": t_impact,
                   "impact_note": f"ci_impact_d on {S_pred} draws x T={cfg['T']}: effect paths, 3 per-time "
                                  "quantile families, post-period summary; device resident "
