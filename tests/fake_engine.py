@@ -95,6 +95,24 @@ class FakeEngine:
       m = m + self.prob.X @ th[:, :self.spec.p].mean(axis=0)
     return torch.from_numpy(m.astype(self.spec.np_dtype))
 
+  # ---- batches of independent series (fit_causalimpact_many) ----
+  def set_data_batch(self, specs):
+    self.batch_specs = list(specs)
+    self.set_data(self.batch_specs[0])
+
+  def batch_select(self, i, spec=None):
+    self.set_data(spec if spec is not None else self.batch_specs[i])
+
+  def gibbs_run_batch_t(self, n_chains, **kw):
+    import torch
+    outs = []
+    for i in range(len(self.batch_specs)):
+      self.batch_select(i)
+      outs.append(self.gibbs_run_t(n_chains, **kw))
+    self.batch_select(0)
+    return (torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]),
+            torch.stack([o[2] for o in outs]), np.stack([o[3] for o in outs]))
+
   def to_host(self, t):
     return t.detach().cpu().numpy()
 

@@ -84,3 +84,60 @@ def test_world2_gloo_equals_single_process(tmp_path, n_cov):
   for k in one:
     assert np.array_equal(one[k], two[k], equal_nan=True), k
   assert one["level"].shape == (22, 60)
+
+
+MANY_WORKER = r'''
+import os, pickle, sys
+import numpy as np, pandas as pd
+ROOT = sys.argv[1]
+for p in (ROOT, os.path.join(ROOT, "tfp-causalimpact_b200"), os.path.join(ROOT, "tests")):
+  sys.path.insert(0, p)
+import torch.distributed as dist
+from fake_engine import FakeEngine
+import causalimpact_b200 as cib
+from causalimpact_b200 import api
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+  dist.init_process_group("gloo")
+fake = FakeEngine()
+api._resolve_engine = lambda opts: fake
+rng = np.random.default_rng(5)
+idx = pd.date_range("2021-01-01", periods=50)
+dfs = []
+for s in range(5):
+  x = 100 + np.cumsum(rng.normal(size=50)); y = (1 + 0.2 * s) * x + rng.normal(size=50); y[35:] += 3 + s
+  dfs.append(pd.DataFrame({"y": y, "x": x}, index=idx))
+res = cib.fit_causalimpact_many(dfs, (idx[0], idx[34]), (idx[35], idx[-1]), seed=(1, 2),
+    inference_options=cib.InferenceOptions(num_results=12),
+    engine_options=cib.EngineOptions(num_chains=3, gibbs_min_warmup=8))
+mine = {i: dict(series=r.series[[c for c in r.series.columns if not c.endswith(("_start", "_end"))]].values,
+                summary=r.summary.values) for i, r in enumerate(res) if r is not None}
+pickle.dump(mine, open(sys.argv[2] + "." + os.environ.get("RANK", "0"), "wb"))
+if world > 1:
+  dist.destroy_process_group()
+'''
+
+
+def test_many_series_are_sharded_by_series_without_a_collective(tmp_path):
+  """fit_causalimpact_many under a 2-rank gloo group: rank r owns a contiguous range of the
+  series (None elsewhere), and every owned result equals the single-process one bit for bit."""
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  script = str(tmp_path / "many_worker.py")
+  open(script, "w").write(MANY_WORKER)
+  env = dict(os.environ, OMP_NUM_THREADS="1")
+  one, two = str(tmp_path / "one"), str(tmp_path / "two")
+  r = subprocess.run([sys.executable, script, root, one], capture_output=True, text=True, env=env,
+                     timeout=600)
+  assert r.returncode == 0, r.stderr[-3000:]
+  r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                      "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29733",
+                      script, root, two], capture_output=True, text=True, env=env, timeout=600)
+  assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+  ref = pickle.load(open(one + ".0", "rb"))
+  parts = [pickle.load(open(f"{two}.{k}", "rb")) for k in (0, 1)]
+  assert sorted(ref) == [0, 1, 2, 3, 4]
+  assert sorted(parts[0]) == [0, 1, 2] and sorted(parts[1]) == [3, 4]      # split_range(5, 2, r)
+  for part in parts:
+    for i, got in part.items():
+      np.testing.assert_array_equal(got["series"], ref[i]["series"])
+      np.testing.assert_array_equal(got["summary"], ref[i]["summary"])
