@@ -152,3 +152,15 @@ def test_seasonal_schedule_matches_oracle_and_reference_examples():
     with pytest.raises(ValueError):
       model.build_seasonal([types.SimpleNamespace(num_seasons=bad[0], num_steps_per_season=bad[1])],
                            T, 1.0)
+
+
+def test_split_rhat():
+  from causalimpact_b200.api import split_rhat
+  rng = np.random.default_rng(0)
+  good = rng.normal(size=(16, 200, 3))
+  r = split_rhat(good)
+  assert r.shape == (3,) and np.all(np.abs(r - 1.0) < 0.02)
+  bad = good.copy(); bad[:8, :, 1] += 3.0                  # half of the chains sit elsewhere
+  r = split_rhat(bad)
+  assert r[1] > 1.5 and abs(r[0] - 1.0) < 0.02
+  assert np.isnan(split_rhat(rng.normal(size=(4, 3, 2)))).all()

@@ -299,8 +299,31 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
 
   samples = _package_samples(eng, theta_t, level_t, p, T, np_dt, wh,
                              (parts[4], parts[5], K) if sched is not None else None)
+  if stats is not None:
+    # convergence across the parallel chains: split-R-hat of (log sigma_obs^2, log sigma_level^2)
+    # over the complete chains among the kept draws (rows are chain-major)
+    full = (theta_t.shape[0] // n_per) * n_per
+    if full >= 2 * n_per:
+      th = eng.to_host(theta_t[:full, p:p + 2]).reshape(full // n_per, n_per, 2)
+      stats["rhat_log_variances"] = split_rhat(th)
   samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
   return samples, DeviceArray(mean_t), DeviceArray(traj_t)
+
+
+def split_rhat(x: np.ndarray) -> np.ndarray:
+  """Split-R-hat (Gelman et al. 2013) of draws [chains, iterations, k] -> [k].  The reference
+  returns no convergence diagnostics; with many short chains this is the
+  natural one.  NaN when a chain has fewer than 4 iterations."""
+  x = np.asarray(x, dtype=np.float64)
+  c, n = x.shape[:2]
+  if n < 4 or c < 1:
+    return np.full(x.shape[2:], np.nan)
+  h = n // 2
+  halves = np.concatenate([x[:, :h], x[:, n - h:]], axis=0)            # [2c, h, k]
+  w = halves.var(axis=1, ddof=1).mean(axis=0)
+  b = h * halves.mean(axis=1).var(axis=0, ddof=1)
+  with np.errstate(divide="ignore", invalid="ignore"):
+    return np.sqrt(((h - 1) / h * w + b / h) / w)
 
 
 def _package_samples(eng, theta_t, level_t, p, T, np_dt, wh=None, seasonal=None):
