@@ -297,3 +297,48 @@ def test_auto_sampler_reproduces_reference_spike_and_slab_posterior():
     assert abs(a - b) < 0.05 * sd_y, (col, a, b)
   ratio = res.summary.loc["average", "abs_effect_sd"] / sum_o.loc["average", "abs_effect_sd"]
   assert 0.75 < ratio < 1.33, ratio
+
+
+def test_shortest_period_after_pre_period():           # lib_test.py:222-229
+  data, _, _ = csv_data()
+  res = ci.fit_causalimpact(data, (data.index[0], data.index[-2]), (data.index[-1], data.index[-1]),
+                            inference_options=ci.InferenceOptions(num_results=10), seed=(1, 2))
+  assert res is not None and res.series.shape[0] == data.shape[0]
+  assert np.isfinite(res.summary.loc["average", "abs_effect"])
+
+
+def test_no_datetime_index_succeeds():                 # lib_test.py:273-284
+  data, _, _ = csv_data()
+  data = data.copy(); data.index = np.arange(data.shape[0])
+  res = ci.fit_causalimpact(data, (data.index[0], data.index[19]), (data.index[20], data.index[-1]),
+                            inference_options=ci.InferenceOptions(num_results=10), seed=(0, 0))
+  assert res is not None and res.series.index.equals(data.index)
+
+
+def test_non_aligned_start_time():                     # lib_test.py:537-562
+  rng = np.random.default_rng(2)
+  y = rng.normal(size=100, scale=0.0001); y[50:] += 5.0
+  df = pd.DataFrame({"y": y}, index=pd.date_range("2018-01-07", periods=100, freq="W"))
+  res = ci.fit_causalimpact(df, pre_period=("2018-01-10", "2018-01-30"),
+                            post_period=("2018-02-02", "2018-02-23"), seed=1,
+                            inference_options=ci.InferenceOptions(num_results=10))
+  assert res.series.loc[pd.to_datetime("2018-01-28"), "cumulative_effects_mean"] == 0
+  assert res.series.loc[pd.to_datetime("2018-02-04"), "cumulative_effects_mean"] != 0
+
+
+def test_missing_and_healthy_input():                  # lib_test.py:793-811, 778-788
+  with pytest.raises(TypeError):
+    ci.fit_causalimpact()                              # pylint: disable=no-value-for-parameter
+  rng = np.random.default_rng(3)
+  data = pd.DataFrame({"y": rng.normal(size=200), "x1": rng.normal(size=200),
+                       "x2": rng.normal(size=200)})
+  res = ci.fit_causalimpact(data, pre_period=(0, 100), post_period=(101, 199), seed=4,
+                            inference_options=ci.InferenceOptions(num_results=10))
+  assert data.shape[0] == res.series.shape[0]
+  assert "Posterior Inference" in ci.summary(res)
+  assert "Posterior Inference" in ci.summary(res, output_format="summary")
+  assert "Analysis report" in ci.summary(res, output_format="report")
+  assert "Analysis report" in ci.summary(res, "report")
+  with pytest.raises(ValueError):
+    ci.summary(res, output_format="foo")
+  assert res.diagnostics["rhat_log_variances"].shape == (2,)
