@@ -164,3 +164,41 @@ def test_split_rhat():
   r = split_rhat(bad)
   assert r[1] > 1.5 and abs(r[0] - 1.0) < 0.02
   assert np.isnan(split_rhat(rng.normal(size=(4, 3, 2)))).all()
+
+
+def test_prepare_panel_matches_the_pandas_data_prep():
+  """panel.prepare_panel (vectorised numpy over N series) vs CausalImpactData.engine_inputs
+  (the mirror of data.py:77-137) series by series: the engine inputs agree to one ulp of the
+  engine dtype; validation errors are the reference's."""
+  import causalimpact_b200 as ci
+  rng = np.random.default_rng(0)
+  N, T, k = 6, 120, 2
+  idx = pd.date_range("2021-01-01", periods=T, freq="D")
+  vals = np.empty((N, T, 1 + k))
+  for s in range(N):
+    xs = 100 + np.cumsum(rng.normal(size=(T, k)), axis=0) * 0.3
+    y = xs[:, 0] + rng.normal(size=T); y[90:] += 3
+    if s % 2:
+      y[4 + s] = np.nan
+    vals[s] = np.column_stack([y, xs])
+  pre, post = (idx[0], idx[89]), (idx[95], idx[-3])
+  prep = ci.prepare_panel(vals, idx, pre, post)
+  assert prep["y_ext"].shape == (N, T) and prep["design"].shape == (N, T, k + 1)
+  eps = np.finfo(np.float32).eps
+  for s in range(N):
+    cid = fr.CausalImpactData(pd.DataFrame(vals[s], index=idx, columns=["y", "a", "b"]), pre, post)
+    y_ext, design, sd = cid.engine_inputs(np.float32)
+    np.testing.assert_allclose(prep["y_ext"][s], y_ext, rtol=2 * eps, atol=2 * eps, equal_nan=True)
+    np.testing.assert_allclose(prep["design"][s], design, rtol=2 * eps, atol=2 * eps)
+    np.testing.assert_allclose(prep["outcome_sd"][s], sd, rtol=2 * eps)
+    np.testing.assert_allclose(prep["y_scale"][s], float(cid.outcome_scaler.stddev_), rtol=1e-14)
+    np.testing.assert_allclose(prep["y_offset"][s], float(cid.outcome_scaler.mean_), rtol=1e-14)
+  no_cov = ci.prepare_panel(vals[:, :, :1], idx, pre, post)
+  assert no_cov["design"] is None
+  raw = ci.prepare_panel(vals, idx, pre, post, standardize_data=False)
+  np.testing.assert_array_equal(raw["y_scale"], 1.0)
+  with pytest.raises(ValueError, match="missing"):
+    bad = vals.copy(); bad[1, 5, 1] = np.nan
+    ci.prepare_panel(bad, idx, pre, post)
+  with pytest.raises(ValueError, match="overlap"):
+    ci.prepare_panel(vals, idx, (idx[0], idx[50]), (idx[40], idx[-1]))

@@ -95,3 +95,36 @@ def test_no_covariates_batch():
                               engine_options=ci.EngineOptions(sampler="gibbs"))
     pd.testing.assert_frame_equal(got.series, one.series)
     assert got.posterior_samples.weights is None
+
+
+def test_panel_arrays_match_the_frame_path():
+  """fit_causalimpact_panel (vectorised numpy prep, one read-back, arrays out) vs
+  fit_causalimpact_many (pandas per series): same kernels and Philox keys; the inputs can differ
+  by one float64 ulp in the pre-period mean / sd, so agreement is to rounding (rtol 2e-4 on the
+  original scale), with the dense prior (<= 2 covariates) where the sweep is continuous in its
+  inputs."""
+  dfs = panel(5, 120, 2, 11, 90)
+  idx = dfs[0].index
+  pre, post = (idx[0], idx[89]), (idx[92], idx[-2])          # a gap and a tail
+  kw = dict(seed=7, inference_options=ci.InferenceOptions(num_results=120),
+            engine_options=ci.EngineOptions(num_chains=10))
+  many = ci.fit_causalimpact_many(dfs, pre, post, **kw)
+  values = np.stack([d.values for d in dfs])
+  res = ci.fit_causalimpact_panel(values, idx, pre, post, keep_level=True, **kw)
+  assert res.series.shape == (5, 120, 10) and res.summary.shape == (5, 2, 15)
+  assert res.level.shape == (5, 120, 120) and res.weights.shape == (5, 120, 3)
+  vals = ci.impact.SERIES_VALUE_COLUMNS
+  for i, one in enumerate(many):
+    want = one.series[vals].values.astype(float)
+    scale = np.nanmax(np.abs(want))
+    np.testing.assert_allclose(res.series[i], want, rtol=2e-4, atol=2e-4 * scale, equal_nan=True)
+    np.testing.assert_array_equal(np.isnan(res.series[i]), np.isnan(want))
+    np.testing.assert_allclose(res.summary[i], one.summary.values.astype(float), rtol=2e-4,
+                               atol=2e-4 * scale)
+    ser, summ = res.frames(i)
+    assert list(ser.columns) == list(one.series.columns)
+    assert list(summ.columns) == list(one.summary.columns)
+    np.testing.assert_allclose(res.level[i], one.posterior_samples.level, rtol=2e-3, atol=2e-3)
+  with pytest.raises(ValueError, match="constant"):
+    bad = values.copy(); bad[2, :, 0] = 1.0
+    ci.fit_causalimpact_panel(bad, idx, pre, post, **kw)

@@ -12,4 +12,5 @@ from .api import (CausalImpactAnalysis, CausalImpactPosteriorSamples, DataOption
                   fit_causalimpact_many)
 from .frame import CausalImpactData, InputDateType  # noqa: F401
 from .model import build_problem, initial_theta  # noqa: F401
+from .panel import PanelResult, fit_causalimpact_panel, prepare_panel  # noqa: F401
 from .report import plot, summary  # noqa: F401

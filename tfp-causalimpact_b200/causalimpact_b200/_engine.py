@@ -549,11 +549,13 @@ class Engine:
     return t.cpu().numpy()
 
   # -- impact series + summary -----------------------------------
-  def impact(self, traj, mean, meta) -> Tuple[np.ndarray, np.ndarray]:
+  def impact(self, traj, mean, meta, out=None) -> Tuple[np.ndarray, np.ndarray]:
     """ci_impact: (series [T,9], summary [20]) float64 from predictive draws [S,T] and mean [T]
     on the standardized scale.  ``traj`` / ``mean`` may be DeviceArray / torch CUDA tensors
     (no copy: ci_impact_d) or host arrays (ci_impact uploads them once).  ``meta``:
-    impact.ImpactMeta."""
+    impact.ImpactMeta.  With ``out`` (a float64 device tensor of T*9 + 20 elements, device
+    inputs only) the result is left there and nothing is synchronised or returned -- the
+    panel path queues one call per series and reads everything back once."""
     if isinstance(traj, DeviceArray):
       traj = traj.tensor
     if isinstance(mean, DeviceArray):
@@ -582,11 +584,18 @@ class Engine:
     args = CiImpactArgs(S=S, T=T, dtype=dt, reserved=0, scale=meta.scale, offset=meta.offset,
                         q_lo=meta.q_lo, q_hi=meta.q_hi, obs_sum=meta.obs_sum)
     if on_dev:
-      out = torch.empty(T * IMPACT_SERIES_COLS + IMPACT_SUMMARY_LEN, dtype=torch.float64,
-                        device=dev)
+      queued = out is not None
+      if not queued:
+        out = torch.empty(T * IMPACT_SERIES_COLS + IMPACT_SUMMARY_LEN, dtype=torch.float64,
+                          device=dev)
+      elif out.numel() != T * IMPACT_SERIES_COLS + IMPACT_SUMMARY_LEN or \
+          out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 tensor of T*9 + 20 elements")
       self._check(self._lib.ci_impact_d(
           self._ctx, C.byref(args), traj.data_ptr(), mean_t.data_ptr(), _ptr(obs), _ptr(per),
           out.data_ptr(), out.data_ptr() + 8 * T * IMPACT_SERIES_COLS, self._stream(torch)))
+      if queued:
+        return None
       out = out.cpu().numpy()
       return out[:T * IMPACT_SERIES_COLS].reshape(T, IMPACT_SERIES_COLS), \
           out[T * IMPACT_SERIES_COLS:]

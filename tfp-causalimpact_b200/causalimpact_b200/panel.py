@@ -1,0 +1,205 @@
+"""Panels of independent series without per-series pandas.
+
+``fit_causalimpact_panel`` takes ONE array ``values [N, T, 1 + k]`` (column 0 = outcome) with a
+shared index and shared periods -- the "thousands of geographies" shape -- and returns arrays.
+Everything the reference does per series in pandas (data.py:77-137: split, nan-aware
+standardisation with the pre-period statistics, intercept column, masked outcome; then
+causalimpact_lib.py:892-931 / :1021-1091: series and summary frames) is done once for the whole
+panel with vectorised numpy; sampling is one batched launch (``ci_gibbs_run_batch_d``), predictive
+mean and impact are queued per series on the device and read back with a single copy.  Frames
+are built only on demand (``PanelResult.analysis(i)``).
+
+The arithmetic per series is the one of ``fit_causalimpact``; only the summation order inside the
+pre-period mean / sd can differ from pandas' (1 ulp in float64 before the cast to the engine
+dtype), so results agree with ``fit_causalimpact_many`` to rounding, not bit for bit
+(tests/test_gpu_batch.py).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Optional
+
+import numpy as np
+import pandas as pd
+
+from . import frame as _frame
+from . import impact as _impact
+from . import shard as _shard
+from .model import build_problem
+
+SUMMARY_COLUMNS = ["actual", "predicted", "predicted_lower", "predicted_upper", "predicted_sd",
+                   "abs_effect", "abs_effect_lower", "abs_effect_upper", "abs_effect_sd",
+                   "rel_effect", "rel_effect_lower", "rel_effect_upper", "rel_effect_sd", "p_value",
+                   "alpha"]
+
+
+@dataclasses.dataclass
+class PanelResult:
+  """Arrays for the series this rank owns (``series_ids``); frames on demand."""
+  index: pd.Index                 # the caller's index
+  series_ids: np.ndarray          # [n] positions in the input panel
+  series: np.ndarray              # [n, len(index), 10] float64, impact.SERIES_VALUE_COLUMNS
+  summary: np.ndarray             # [n, 2, 15] float64: (average, cumulative) x SUMMARY_COLUMNS
+  observation_noise_scale: np.ndarray   # [n, S]
+  level_scale: np.ndarray         # [n, S]
+  weights: Optional[np.ndarray]   # [n, S, k + 1] or None
+  level: Optional[np.ndarray]     # [n, S, T_model] when keep_level
+  pre_period: tuple
+  post_period: tuple
+  inclusion: np.ndarray           # [n, chains, k + 1]
+
+  def frames(self, i: int):
+    """(series, summary) DataFrames of the i-th owned series, as fit_causalimpact returns."""
+    ser = pd.DataFrame(self.series[i], index=self.index, columns=_impact.SERIES_VALUE_COLUMNS)
+    ser["pre_period_start"] = self.pre_period[0]
+    ser["pre_period_end"] = self.pre_period[1]
+    ser["post_period_start"] = self.post_period[0]
+    ser["post_period_end"] = self.post_period[1]
+    summ = pd.DataFrame(self.summary[i], index=["average", "cumulative"], columns=SUMMARY_COLUMNS)
+    return ser, summ
+
+
+def prepare_panel(values, index, pre_period, post_period, standardize_data=True, dtype=np.float32):
+  """Vectorised data.py:77-137 for N series at once.
+
+  Returns dict: y_ext [N, Tm] (float64 view of the dtype-rounded standardized outcome, NaN where
+  masked), design [N, Tm, k+1] or None, outcome_sd [N], y_scale / y_offset [N], model rows
+  (positions of the modelled span in ``index``), periods, observed-scale outcome [N, Tm]."""
+  values = np.asarray(values, dtype=np.float64)
+  if values.ndim != 3 or values.shape[2] < 1:
+    raise ValueError("values must be [n_series, T, 1 + n_covariates]")
+  index = pd.Index(index)
+  N, T, ncol = values.shape
+  if len(index) != T:
+    raise ValueError("index length differs from values.shape[1]")
+  probe = pd.DataFrame({"y": np.zeros(T)}, index=index)
+  pre, post = _frame.parse_and_validate_date_data(probe, pre_period, post_period)
+  in_pre = np.asarray((index >= pre[0]) & (index <= pre[1]))
+  after = np.asarray(index > pre[1])
+  rows = np.flatnonzero(in_pre | after)                 # the modelled span, in index order
+  n_pre = int(in_pre.sum())
+  y_all = values[:, :, 0]
+  # input validation of data.py:140-190, for every series
+  with np.errstate(invalid="ignore"):
+    if np.any(np.nanstd(y_all, axis=1) == 0):
+      raise ValueError("Input response cannot be constant.")
+  if np.any(np.sum(~np.isnan(y_all), axis=1) < 3):
+    raise ValueError("Input data must have at least 3 observations.")
+  if ncol > 1 and np.isnan(values[:, :, 1:]).any():
+    raise ValueError("Input data cannot have any missing values.")
+  pre_vals = values[:, in_pre, :]                       # [N, n_pre, ncol]
+  model_vals = values[:, rows, :]                       # [N, Tm, ncol]
+  if standardize_data:
+    mean = np.nanmean(pre_vals, axis=1)                 # standardize.py:42-47 (ddof = 1)
+    std = np.nanstd(pre_vals, axis=1, ddof=1)
+    ok = std > 0
+    scaled = np.where(ok[:, None, :], (model_vals - mean[:, None, :]) / np.where(ok, std, 1.0)[:, None, :],
+                      model_vals)
+    y_scale, y_offset = std[:, 0].copy(), mean[:, 0].copy()
+  else:
+    scaled = model_vals
+    y_scale, y_offset = np.ones(N), np.zeros(N)
+  np_dt = np.dtype(dtype)
+  y_pre = scaled[:, :n_pre, 0].astype(np_dt)
+  y_ext = np.concatenate([y_pre, np.full((N, len(rows) - n_pre), np.nan, dtype=np_dt)], axis=1)
+  design = None
+  if ncol > 1:
+    design = np.concatenate([scaled[:, :, 1:], np.ones((N, len(rows), 1))], axis=2).astype(np_dt)
+  outcome_sd = np.nanstd(y_pre, axis=1, ddof=1).astype(np_dt).astype(np.float64)   # lib.py:563-564
+  return dict(y_ext=y_ext.astype(np.float64), design=None if design is None else design.astype(np.float64),
+              outcome_sd=outcome_sd, y_scale=y_scale, y_offset=y_offset, rows=rows, n_pre=n_pre,
+              pre=pre, post=post, y_model=model_vals[:, :, 0], index=index)
+
+
+def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float = 0.05, seed=None,
+                           data_options=None, model_options=None, inference_options=None,
+                           engine_options=None, keep_level: bool = False) -> PanelResult:
+  """Fit every series of ``values [N, T, 1 + k]`` (shared ``index`` and periods); see module
+  docstring.  Series are sharded over the ranks of an initialised process group (contiguous
+  ranges, no collective); the result holds this rank's series (``series_ids``)."""
+  from . import api as _api
+  data_options = data_options if data_options is not None else _api.DataOptions()
+  model_options = model_options if model_options is not None else _api.ModelOptions()
+  inference_options = inference_options if inference_options is not None else _api.InferenceOptions()
+  opts = engine_options or _api.EngineOptions()
+  if model_options.seasons:
+    raise NotImplementedError("seasonal components are not batched: use fit_causalimpact")
+  if not 0 < alpha < 1:
+    raise ValueError("`alpha` must be between 0 and 1.")
+  np_dt = _api._np_dtype(data_options.dtype)
+  seed64 = _api._seed_to_u64(seed)
+  values = np.asarray(values)
+  rank, ws = _shard.world()
+  s0, n_local = _shard.split_range(values.shape[0], ws, rank)
+  prep = prepare_panel(values[s0:s0 + n_local], index, pre_period, post_period,
+                       data_options.standardize_data, np_dt)
+  N, Tm = prep["y_ext"].shape
+  specs = [build_problem(prep["y_ext"][i], None if prep["design"] is None else prep["design"][i],
+                         prior_level_sd=model_options.prior_level_sd,
+                         outcome_sd=float(prep["outcome_sd"][i]), dtype=np_dt) for i in range(N)]
+  p = specs[0].p
+  eng = _api._resolve_engine(opts)
+  eng.set_data_batch(specs)
+  S = inference_options.num_results
+  C = max(int(opts.num_chains), 1)
+  n_per = max(1, math.ceil(S / C))
+  n_warm = max(int(inference_options.num_warmup_steps), int(opts.gibbs_min_warmup))
+  theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
+                                                   seed=seed64, chain_id0=0, sparse=True)
+  S = min(S, C * n_per)
+
+  # ---- O(T) metadata of the impact stage, shared / vectorised (impact.prepare per series) ----
+  mi = prep["index"][prep["rows"]]
+  pre, post = prep["pre"], prep["post"]
+  in_pre = np.asarray(mi <= pre[1])
+  in_post = np.asarray((mi >= post[0]) & (mi <= post[1]))
+  period = np.where(np.asarray(mi < post[0]), 0, np.where(in_post, 1, 2)).astype(np.uint8)
+  observed = np.where((in_pre | in_post)[None, :], prep["y_model"], np.nan)      # [N, Tm]
+  hide = np.asarray(((mi > pre[1]) & (mi < post[0])) | (mi > post[1]))[None, :] | np.isnan(observed)
+  y_post = observed[:, in_post]
+  obs_mean, obs_sum = np.nanmean(y_post, axis=1), np.nansum(y_post, axis=1)
+  q_lo, q_hi = _impact._percentile_q(alpha / 2.0), _impact._percentile_q(1.0 - alpha / 2.0)
+
+  import torch
+  out = torch.empty((N, Tm * 9 + 20), dtype=torch.float64, device=theta.device)
+  for i in range(N):
+    eng.batch_select(i, specs[i])
+    th_i, lv_i, tr_i = theta[i, :S], level[i, :S], traj[i, :S]
+    mean_i = eng.predictive_mean_t(th_i, lv_i)
+    meta = _impact.ImpactMeta(index=mi, observed=observed[i], period=period, hide=hide[i],
+                              scale=float(prep["y_scale"][i]), offset=float(prep["y_offset"][i]),
+                              q_lo=q_lo, q_hi=q_hi, obs_mean=float(obs_mean[i]),
+                              obs_sum=float(obs_sum[i]))
+    eng.impact(tr_i, mean_i, meta, out=out[i])
+  res = eng.to_host(out)                                             # ONE read-back
+  series9 = res[:, :Tm * 9].reshape(N, Tm, 9)
+  summ = res[:, Tm * 9:]
+
+  # ---- lib.py:892-931 for all series: NaN rules, re-index to the caller's index ----
+  cols = np.concatenate([observed[:, :, None], series9], axis=2)     # [N, Tm, 10]
+  cols[:, :, 4:][hide] = np.nan
+  full = np.full((N, len(prep["index"]), 10), np.nan)
+  full[:, prep["rows"], :] = cols
+  full[:, :, 0] = values[s0:s0 + n_local, :, 0]                      # `observed` = the input column
+  # ---- lib.py:1021-1091 for all series ----
+  qd = summ[:, 0:10].reshape(N, 5, 2); sd = summ[:, 10:15]
+  avg_pred, cum_pred, rel_mean = summ[:, 18], summ[:, 19], summ[:, 15]
+  table = np.empty((N, 2, 15))
+  for r, (act, pred, k_pred, k_eff) in enumerate(((obs_mean, avg_pred, 0, 2), (obs_sum, cum_pred, 1, 3))):
+    table[:, r, 0] = act; table[:, r, 1] = pred
+    table[:, r, 2] = qd[:, k_pred, 0]; table[:, r, 3] = qd[:, k_pred, 1]; table[:, r, 4] = sd[:, k_pred]
+    table[:, r, 5] = act - pred
+    table[:, r, 6] = qd[:, k_eff, 0]; table[:, r, 7] = qd[:, k_eff, 1]; table[:, r, 8] = sd[:, k_eff]
+    table[:, r, 9] = rel_mean
+    table[:, r, 10] = qd[:, 4, 0]; table[:, r, 11] = qd[:, 4, 1]; table[:, r, 12] = sd[:, 4]
+    table[:, r, 13] = np.minimum((summ[:, 16] + 1.0) / (S + 1.0), (summ[:, 17] + 1.0) / (S + 1.0))
+    table[:, r, 14] = alpha
+  th = eng.to_host(theta[:, :S]).astype(np.float64)
+  return PanelResult(
+      index=prep["index"], series_ids=np.arange(s0, s0 + n_local), series=full, summary=table,
+      observation_noise_scale=np.exp(0.5 * th[:, :, p]).astype(np_dt),
+      level_scale=np.exp(0.5 * th[:, :, p + 1]).astype(np_dt),
+      weights=th[:, :, :p].astype(np_dt) if p else None,
+      level=eng.to_host(level[:, :S]).astype(np_dt, copy=False) if keep_level else None,
+      pre_period=pre, post_period=post, inclusion=incl)

@@ -38,3 +38,10 @@ eng.gibbs_run_batch_t(8, n_warmup=2, n_results=2, seed=1); torch.cuda.synchroniz
 t0 = time.perf_counter(); eng.gibbs_run_batch_t(8, n_warmup=100, n_results=50, seed=1); torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 print(f"ci_gibbs_run_batch_d: {N} series x 8 chains x 150 sweeps in {dt*1e3:.1f} ms = {N*8*150/dt/1e6:.2f} M sweeps/s")
+vals = np.stack([d.values for d in dfs])
+cib.fit_causalimpact_panel(vals[:4], idx, pre, post, **kw)
+t0 = time.perf_counter(); res = cib.fit_causalimpact_panel(vals, idx, pre, post, **kw); dt = time.perf_counter() - t0
+print(f"fit_causalimpact_panel: {N} series in {dt*1e3:.0f} ms = {N/dt:.0f} series/s")
+import cProfile, pstats, io
+pr = cProfile.Profile(); pr.enable(); cib.fit_causalimpact_panel(vals, idx, pre, post, **kw); pr.disable()
+st = pstats.Stats(pr); st.sort_stats("cumulative"); buf = io.StringIO(); st.stream = buf; st.print_stats(14); print("\n".join(buf.getvalue().splitlines()[6:24]))
