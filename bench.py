@@ -257,19 +257,8 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
-  # L2 flush between timed steps: 256 MB of streaming stores.  BENCH_FLUSH=torch uses
-  # tensor.zero_(); the default is the library's own store kernel (ci_l2_flush_d), which asks
-  # for the same shared-memory carveout as the engine's kernels -- see the note in config.l2.
-  own_flush = os.environ.get("BENCH_FLUSH", "own") != "torch"
-  def do_flush():
-    if own_flush:
-      rc = eng._lib.ci_l2_flush_d(eng._ctx, flush.data_ptr(), flush.numel() * flush.element_size(),
-                                   stream.cuda_stream)
-      assert rc == 0, eng._lib.ci_last_error()
-    else:
-      flush.zero_()
   for _ in range(args.warmup):
-    do_flush(); step()
+    flush.zero_(); step()
   sync_all()
   l0 = eng.launch_count
 
@@ -279,7 +268,7 @@ def main():
   with ClockSampler(local) as clk:
     sync_all()
     for i in range(args.steps):
-      do_flush()
+      flush.zero_()
       starts[i].record(stream); step(); stops[i].record(stream)
     sync_all()
     # hot-L2 back-to-back (no flush) for reference
@@ -493,10 +482,7 @@ def main():
                    "variant": ("associative scan, TEAM mode: warp-shuffle scan per 256-step tile, one "
                                "warp per tile (4 warps per chain), tile aggregates exchanged via smem")
                               if team else "associative scan, one warp per chain (CI_B200_TEAM=0)",
-                   "l2": ("flushed between timed steps: 256 MB of streaming stores by ci_l2_flush_d "
-                          "(same shared-memory carveout as the timed kernel; BENCH_FLUSH=torch "
-                          "flushes with tensor.zero_() instead)") if own_flush else
-                         "flushed (256 MB tensor.zero_()) between timed steps",
+                   "l2": "flushed (256 MB memset) between timed steps",
                    "timing": "CUDA events per step on the launching stream"},
         "e2e": {"value": total / (t_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(th_np.nbytes),

@@ -256,13 +256,6 @@ int ci_gibbs_run_batch_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
                          uint64_t chain_id0, int n_chains, void* draws_d, void* level_d,
                          void* traj_d, float* incl_d, void* stream);
 
-/* Benchmark utility: overwrite `bytes` (a multiple of 16, 16-byte aligned device buffer) with
- * zeros by plain streaming stores -- an L2 flush when the buffer is larger than the L2.  The
- * kernel asks for the same shared-memory carveout as the engine's kernels, so flushing between
- * two timed launches does not make every SM re-partition its L1 / shared memory twice per step
- * (no reference counterpart). */
-int ci_l2_flush_d(ci_ctx* ctx, void* buf_d, size_t bytes, void* stream);
-
 /* Mean of the predictive mixture alone (lib.py:627): mean_t = avg_s level[s,t] + x_t . avg_s w_s,
  * for draws whose level paths are already on the device (the Gibbs kernel's output).
  * Deterministic: fixed summation order, float64 accumulation. */

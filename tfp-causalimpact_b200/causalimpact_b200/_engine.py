@@ -75,7 +75,7 @@ EXPORTS = (
     "ci_hmc_run", "ci_hmc_run_d", "ci_gibbs_run", "ci_gibbs_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
     "ci_row_quantiles", "ci_row_quantiles_d", "ci_predictive_mean_d", "ci_impact", "ci_impact_d",
     "ci_set_seasonal", "ci_gibbs_seasonal_run", "ci_gibbs_seasonal_run_d",
-    "ci_set_data_batch", "ci_batch_select", "ci_gibbs_run_batch_d", "ci_l2_flush_d",
+    "ci_set_data_batch", "ci_batch_select", "ci_gibbs_run_batch_d",
 )
 
 _lib = None
@@ -121,7 +121,6 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                                         vp, vp, vp]
   lib.ci_gibbs_seasonal_run_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp,
                                           vp, vp, vp, vp, vp]
-  lib.ci_l2_flush_d.argtypes = [vp, vp, C.c_size_t, vp]
   lib.ci_set_data_batch.argtypes = [vp, C.POINTER(CiProblem), i32, vp, vp, vp]
   lib.ci_batch_select.argtypes = [vp, i32]
   lib.ci_gibbs_run_batch_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp, vp]

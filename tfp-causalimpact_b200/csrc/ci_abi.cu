@@ -282,16 +282,6 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
   return CI_OK;
 }
 
-// Plain streaming stores over a buffer: the L2 flush of the benchmark (bench.py).  Launched with
-// the same shared-memory carveout preference as the engine's kernels, so that a flush between
-// two timed launches does not make the SMs re-partition L1 / shared memory twice per step.
-__global__ void k_l2_flush(uint4* __restrict__ buf, size_t n16) {
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
-       i += (size_t)gridDim.x * blockDim.x)
-    buf[i] = z;
-}
-
 template <typename R>
 void build_tiles(const ci_problem* pb, const void* y_, const void* X_, int NB, int ld,
                  std::vector<R>& out) {
@@ -1182,22 +1172,6 @@ int ci_gibbs_seasonal_run(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint
     CU_TRY(cudaMemcpyAsync(incl, c->w_incl.p, (size_t)C * c->prob.p * sizeof(float),
                            cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
-  return CI_OK;
-}
-
-int ci_l2_flush_d(ci_ctx* c, void* buf_d, size_t bytes, void* stream) {
-  if (!c || !buf_d) return fail(CI_ERR_INVALID, "null argument");
-  if ((reinterpret_cast<uintptr_t>(buf_d) & 15u) != 0) return fail(CI_ERR_INVALID, "buffer must be 16-byte aligned");
-  CU_TRY(cudaSetDevice(c->device));
-  static thread_local bool configured = false;
-  if (!configured) {
-    CU_TRY(cudaFuncSetAttribute(k_l2_flush, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                (int)cudaSharedmemCarveoutMaxShared));
-    configured = true;
-  }
-  k_l2_flush<<<c->sm_count * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<uint4*>(buf_d), bytes / 16);
-  CU_TRY(cudaGetLastError());
   return CI_OK;
 }
 
