@@ -34,24 +34,16 @@ template <typename R> struct TeamEval {
     const int p = pr.p;
     const R u = ws.w[p], l = ws.w[p + 1];
     const R s_e = Num<R>::exp(u), s_h = Num<R>::exp(l);
-    // the prior needs only theta and Omega: issued BEFORE the filter so that its shared-memory
-    // loads, divisions and reduction overlap the filter's first loads instead of forming a
-    // serial tail after the last team barrier (run 31: ~1 800 cycles of a 14 000-cycle evaluation)
-    R gwp[JS];
-#pragma unroll
-    for (int s = 0; s < JS; ++s) gwp[s] = 0;
-    double gp_u = 0.0, gp_l = 0.0;
-    const double lprior = chain_prior(pr, omega, ws.w, u, l, s_e, s_h, lane, gwp, gp_u, gp_l);
     double ll, g_se, g_sh;
     R gw[JS];
     team_eval(tile, pr, ts, ws.w, ws.rbuf, s_e, s_h, true, lane, wt, W, bar_id, ll, g_se, g_sh,
               gw);
-    const double g_u = g_se * (double)s_e + gp_u, g_l = g_sh * (double)s_h + gp_l;
-    lp = ll + lprior;
+    double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
+    lp = ll + chain_prior(pr, omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
 #pragma unroll
     for (int s = 0; s < DSLOTS; ++s) {
       const int i = lane + 32 * s;
-      g[s] = i < p ? gw[s] + gwp[s] : (i == p ? (R)g_u : (i == p + 1 ? (R)g_l : (R)0));
+      g[s] = i < p ? gw[s] : (i == p ? (R)g_u : (i == p + 1 ? (R)g_l : (R)0));
     }
   }
 };
