@@ -285,7 +285,7 @@ int ci_predictive_mean_d(ci_ctx* ctx, const void* theta_draws_d, const void* lev
  *     [10..14] their sample standard deviations (ddof = 1)
  *     [15]     mean relative effect          [16],[17]  #draws with obs_sum <= / >= summed prediction
  *     [18],[19] post-period mean / sum of the predictive mean
- * S is limited to what one column of float64 keys fits in shared memory (~25 000).
+ * Columns of up to ~25 000 draws are selected in shared memory, longer ones from global memory.
  */
 #define CI_IMPACT_SERIES_COLS 9
 #define CI_IMPACT_SUMMARY_LEN 20

@@ -139,8 +139,17 @@ def test_rejects_bad_input(engine):
   bad = types.SimpleNamespace(**vars(m)); bad.q_hi = 1.5
   with pytest.raises(EngineError, match="quantiles"):
     engine.impact(traj, traj[0], bad)
-  with pytest.raises(EngineError, match="exceeds"):
-    engine.impact(np.zeros((40000, 30), np.float32), traj[0], m)
+
+
+def test_more_draws_than_shared_memory_holds(engine):
+  """40 000 draws: the cumulative-effect columns (float64 keys) no longer fit shared memory and
+  every column job selects from global memory -- same result as the oracle."""
+  rng = np.random.default_rng(12)
+  S, T = 40000, 24
+  m = make_meta(T, 14, 15, 22, rng, nan_obs=2)
+  traj = rng.normal(size=(S, T)).astype(np.float32)
+  mean = traj.mean(axis=0).astype(np.float32)
+  check(engine.impact(traj, mean, m), oracle(traj, mean, m), rtol=1e-10, atol=1e-9)
 
 
 def test_fit_keeps_trajectories_on_device():

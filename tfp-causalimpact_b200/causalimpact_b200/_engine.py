@@ -609,16 +609,13 @@ class Engine:
   def row_quantiles(self, a, q) -> np.ndarray:
     """Per-time quantiles of a [S, T] draw-major array -> [T, len(q)].
 
-    The kernel keeps one column per CTA in shared memory (exact radix select): up to
-    ~25 000 draws in float64, ~50 900 in float32.  A float64 input between those limits
-    is selected in float32 (quantiles then carry float32 rounding); beyond, EngineError."""
+    Columns of up to ~50 900 (float32) / ~25 000 (float64) draws are selected in shared memory;
+    longer ones straight from global memory (slower per draw, no size limit)."""
     a = np.ascontiguousarray(a)
     if a.dtype not in (np.float32, np.float64):
       a = a.astype(np.float64)
     S, T = a.shape
     out_dtype = a.dtype
-    if a.dtype == np.float64 and 25000 < S <= 50900:
-      a = a.astype(np.float32)
     q = np.ascontiguousarray(q, dtype=np.float64)
     out = np.empty((T, q.shape[0]), dtype=a.dtype)
     self._check(self._lib.ci_row_quantiles(

@@ -525,11 +525,11 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
 template <typename R>
 int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, int nq,
                      void* out_d, cudaStream_t st, int out_ld = 0) {
-  // the whole column lives in shared memory as integer keys
-  const size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
-  if (bytes + QSTATIC > (size_t)c->smem_optin)
-    return fail(CI_ERR_UNSUPPORTED, "ci_row_quantiles: S=%d does not fit the shared-memory select "
-                "(max %d draws for this dtype)", S, (int)((c->smem_optin - QSTATIC) / sizeof(R)));
+  // the whole column lives in shared memory as integer keys when it fits; longer columns are
+  // selected straight from global memory (every sweep re-reads them through L2)
+  size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
+  const int in_smem = bytes + QSTATIC <= (size_t)c->smem_optin;
+  if (!in_smem) bytes = 0;
   QuantArgs qa;
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q[i];
@@ -538,7 +538,7 @@ int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, 
   int nt = 1024;
   while (nt > 64 && nt / 2 >= S) nt >>= 1;
   kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, qa, static_cast<R*>(out_d),
-                             out_ld > 0 ? out_ld : nq);
+                             out_ld > 0 ? out_ld : nq, in_smem);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;
@@ -558,12 +558,15 @@ int launch_impact(ci_ctx* c, const ImpactDev& a, const void* traj_d, const void*
       statsT, series_d, summ_d);
   CU_TRY(cudaGetLastError());
   c->launches++;
-  const size_t bytes = (((size_t)S * sizeof(double)) + 15) & ~(size_t)15;   // float64 jobs
+  size_t bytes = (((size_t)S * sizeof(double)) + 15) & ~(size_t)15;   // float64 jobs
+  const int in_smem = bytes + QSTATIC <= (size_t)c->smem_optin;       // else: select from global memory
+  if (!in_smem) bytes = 0;
   auto kern = k_impact_jobs<R>;
   CU_TRY(set_smem(kern, (uint32_t)bytes));
   int nt = 1024;
   while (nt > 64 && nt / 2 >= S) nt >>= 1;
-  kern<<<Tc + IMP_STATS + T + 1, nt, bytes, st>>>(trT, cumT, statsT, obs_d, a, series_d, summ_d);
+  kern<<<Tc + IMP_STATS + T + 1, nt, bytes, st>>>(trT, cumT, statsT, obs_d, a, series_d, summ_d,
+                                                   in_smem);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;
@@ -1221,10 +1224,6 @@ int ci_impact_d(ci_ctx* c, const ci_impact_args* a, const void* traj_d, const vo
     d.n_post += period[t] == 1;
   }
   if (d.n_post < 1) return fail(CI_ERR_INVALID, "the post-period is empty");
-  const size_t keyb = (size_t)S * sizeof(double);
-  if (keyb + QSTATIC > (size_t)c->smem_optin)
-    return fail(CI_ERR_UNSUPPORTED, "ci_impact: S=%d exceeds the shared-memory select (max %d draws)",
-                S, (int)((c->smem_optin - QSTATIC) / sizeof(double)));
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Tc = T - d.t_c0;

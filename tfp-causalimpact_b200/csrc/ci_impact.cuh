@@ -183,13 +183,15 @@ __device__ __forceinline__ int load_contig_keys(const V* __restrict__ col, int S
 // interpolation weight.  Returns n (0 => no valid value).  Whole CTA.
 template <typename V, bool MIRROR>
 __device__ __forceinline__ int column_quantiles(const V* __restrict__ col, int S, double q_lo,
-                                                double q_hi, unsigned char* key_mem,
+                                                double q_hi, unsigned char* key_mem, int in_smem,
                                                 SelectShared<V>& sh, int* ibuf, double (&res)[2][4],
                                                 double (&g)[2]) {
   using Key = typename KeyOf<V>::type;
   Key* keys = reinterpret_cast<Key*>(key_mem);
   int* n_valid = ibuf;                // [0]; [1] = number of ranks; [2..9] = slots
-  const int n = load_contig_keys<V>(col, S, keys, n_valid);
+  const GlobalKeys<V> gkeys{col, (size_t)1};
+  const int n = in_smem ? load_contig_keys<V>(col, S, keys, n_valid)
+                        : count_valid_keys<V>(gkeys, S, n_valid);
   if (n == 0) return 0;
   if (threadIdx.x == 0) {
     int nr = 0;
@@ -208,7 +210,8 @@ __device__ __forceinline__ int column_quantiles(const V* __restrict__ col, int S
     ibuf[1] = nr;
   }
   __syncthreads();
-  radix_select_multi<V>(keys, S, ibuf[1], sh);
+  if (in_smem) radix_select_multi<V>(SmemKeys<V>{keys}, S, ibuf[1], sh);
+  else radix_select_multi<V>(gkeys, S, ibuf[1], sh);
 #pragma unroll
   for (int iq = 0; iq < 2; ++iq) {
     const double pos = (iq == 0 ? q_lo : q_hi) * (double)(n - 1);
@@ -275,7 +278,8 @@ template <typename R>
 __global__ void __launch_bounds__(1024)
 k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
                               const double* __restrict__ statsT, const double* __restrict__ obs,
-                              ImpactDev a, double* __restrict__ series, double* __restrict__ summ) {
+                              ImpactDev a, double* __restrict__ series, double* __restrict__ summ,
+                              int in_smem) {
   extern __shared__ __align__(16) unsigned char key_mem[];
   __shared__ __align__(16) unsigned char sel_raw[sizeof(SelectShared<double>)];
   __shared__ int ibuf[10];
@@ -287,7 +291,7 @@ k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
     const bool is_cum = b < Tc;
     const double* col = is_cum ? cumT + (size_t)b * S : statsT + (size_t)(b - Tc) * S;
     SelectShared<double>& sh = *reinterpret_cast<SelectShared<double>*>(sel_raw);
-    const int n = column_quantiles<double, false>(col, S, a.q_lo, a.q_hi, key_mem, sh, ibuf, res, g);
+    const int n = column_quantiles<double, false>(col, S, a.q_lo, a.q_hi, key_mem, in_smem, sh, ibuf, res, g);
     if (tid == 0) {
       double* out = is_cum ? series + (size_t)(a.t_c0 + b) * IMP_SERIES_COLS + 7
                            : summ + 2 * (b - Tc);
@@ -299,8 +303,8 @@ k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
   if (b < Tc + IMP_STATS + a.T) {                   // prediction + point-effect column
     const int t = b - Tc - IMP_STATS;
     SelectShared<R>& sh = *reinterpret_cast<SelectShared<R>*>(sel_raw);
-    const int n = column_quantiles<R, true>(trT + (size_t)t * S, S, a.q_lo, a.q_hi, key_mem, sh,
-                                            ibuf, res, g);
+    const int n = column_quantiles<R, true>(trT + (size_t)t * S, S, a.q_lo, a.q_hi, key_mem, in_smem,
+                                            sh, ibuf, res, g);
     if (tid == 0) {
       double* row = series + (size_t)t * IMP_SERIES_COLS;
       if (t < a.t_c0) { row[7] = 0.0; row[8] = 0.0; }          // cumulative effect is 0 before post

@@ -241,6 +241,22 @@ template <typename R> struct SelectShared {
   Key kmin, kmax;
 };
 
+// Where the select reads its keys from: shared memory (the column was encoded once), or --
+// for columns too long for shared memory -- straight from global memory, encoding on the fly
+// (every sweep re-reads the column through L2; same results, no size limit).
+template <typename R> struct SmemKeys {
+  const typename KeyOf<R>::type* k;
+  __device__ __forceinline__ typename KeyOf<R>::type operator()(int i) const { return k[i]; }
+};
+template <typename R> struct GlobalKeys {
+  const R* base;
+  size_t stride;
+  __device__ __forceinline__ typename KeyOf<R>::type operator()(int i) const {
+    const R v = base[(size_t)i * stride];
+    return (v == v) ? KeyOf<R>::enc(v) : KeyOf<R>::nan_key();
+  }
+};
+
 // Keys of the sh.rank[0..nr) order statistics (0-based ranks, < n) of keys[0..n) ->
 // sh.out[0..nr).  BIT-WISE BISECTION on the key value, all ranks at once: the result is
 // built from the most significant bit down -- a bit is kept when the number of keys below
@@ -248,9 +264,9 @@ template <typename R> struct SelectShared {
 // barrier per bit; counting is compare + add in registers, warp totals by redux.sync, CTA
 // totals by 32 integer atomics per rank on a rotating triple buffer -- no histogram, no
 // same-address contention, deterministic.  Executed by the whole CTA.
-template <typename R, int NRT>
-__device__ __forceinline__ void bisect_select_impl(const typename KeyOf<R>::type* keys, int n,
-                                                   int nr, SelectShared<R>& sh) {
+template <typename R, int NRT, typename KeyAt>
+__device__ __forceinline__ void bisect_select_impl(const KeyAt keys, int n, int nr,
+                                                   SelectShared<R>& sh) {
   using Key = typename KeyOf<R>::type;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   constexpr int NB = (int)(8 * sizeof(Key));
@@ -266,7 +282,7 @@ __device__ __forceinline__ void bisect_select_impl(const typename KeyOf<R>::type
 #pragma unroll
     for (int r = 0; r < NRT; ++r) { trial[r] = result[r] | ((Key)1 << bit); c[r] = 0; }
     for (int i = tid; i < n; i += nt) {
-      const Key key = keys[i];
+      const Key key = keys(i);
 #pragma unroll
       for (int r = 0; r < NRT; ++r) c[r] += (key < trial[r]) ? 1 : 0;
     }
@@ -297,8 +313,8 @@ __device__ __forceinline__ void bisect_select_impl(const typename KeyOf<R>::type
 // instructions per key instead of a pass per digit / bit.  Returns false -- nothing
 // selected -- when the column defeats the binning (infinities, a bin with more than LCAP
 // keys: heavy ties or extreme outliers); the caller then runs the bisection.
-template <typename R>
-__device__ __forceinline__ bool binned_select(const typename KeyOf<R>::type* keys, int n, int nr,
+template <typename R, typename KeyAt>
+__device__ __forceinline__ bool binned_select(const KeyAt keys, int n, int nr,
                                               SelectShared<R>& sh) {
   using Key = typename KeyOf<R>::type;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -311,7 +327,7 @@ __device__ __forceinline__ bool binned_select(const typename KeyOf<R>::type* key
   {
     Key mn = NANK, mx = 0;
     for (int i = tid; i < n; i += nt) {
-      const Key k = keys[i];
+      const Key k = keys(i);
       if (k != NANK) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
     }
 #pragma unroll
@@ -337,7 +353,7 @@ __device__ __forceinline__ bool binned_select(const typename KeyOf<R>::type* key
     return b < LBINS - 1 ? b : LBINS - 1;
   };
   for (int i = tid; i < n; i += nt) {
-    const Key k = keys[i];
+    const Key k = keys(i);
     if (k != NANK) atomicAdd(&sh.hist[bin_of(k)], 1);
   }
   __syncthreads();
@@ -383,7 +399,7 @@ __device__ __forceinline__ bool binned_select(const typename KeyOf<R>::type* key
   if (sh.fallback) return false;
   const int ng = sh.ngroups;
   for (int i = tid; i < n; i += nt) {
-    const Key k = keys[i];
+    const Key k = keys(i);
     if (k == NANK) continue;
     const int b = bin_of(k);
     for (int g = 0; g < ng; ++g)
@@ -406,13 +422,26 @@ __device__ __forceinline__ bool binned_select(const typename KeyOf<R>::type* key
   return true;
 }
 
-template <typename R>
-__device__ void radix_select_multi(const typename KeyOf<R>::type* keys, int n, int nr,
-                                   SelectShared<R>& sh) {
+template <typename R, typename KeyAt>
+__device__ void radix_select_multi(const KeyAt keys, int n, int nr, SelectShared<R>& sh) {
   if (binned_select<R>(keys, n, nr, sh)) return;
   if (nr <= 4) bisect_select_impl<R, 4>(keys, n, nr, sh);
   else if (nr <= 8) bisect_select_impl<R, 8>(keys, n, nr, sh);
   else bisect_select_impl<R, 16>(keys, n, nr, sh);
+}
+
+// Number of non-NaN keys of an accessor (the global-memory path has no load pass to count in).
+template <typename R, typename KeyAt>
+__device__ __forceinline__ int count_valid_keys(const KeyAt keys, int n, int* n_valid) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) *n_valid = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int i = tid; i < n; i += nt) cnt += keys(i) != KeyOf<R>::nan_key() ? 1 : 0;
+  cnt = __reduce_add_sync(FULL, cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(n_valid, cnt);
+  __syncthreads();
+  return *n_valid;
 }
 
 // Gather column t of a [S,T] array into shared-memory keys; returns the number of non-NaN.
@@ -447,7 +476,7 @@ __device__ __forceinline__ int add_rank(SelectShared<R>& sh, int& nr, int k) {
 template <typename R>
 __global__ void __launch_bounds__(1024)
 k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs qa,
-                                R* __restrict__ out, int out_ld) {
+                                R* __restrict__ out, int out_ld, int in_smem) {
   using Key = typename KeyOf<R>::type;
   extern __shared__ __align__(16) unsigned char qsmem[];
   Key* keys = reinterpret_cast<Key*>(qsmem);
@@ -455,7 +484,9 @@ k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs qa,
   __shared__ int n_valid, s_nr;
   __shared__ int slot_lo[8], slot_hi[8];
   const int t = blockIdx.x, tid = threadIdx.x;
-  const int n = load_column_keys<R>(a, S, T, t, keys, &n_valid);
+  const GlobalKeys<R> gkeys{a + t, (size_t)T};
+  const int n = in_smem ? load_column_keys<R>(a, S, T, t, keys, &n_valid)
+                        : count_valid_keys<R>(gkeys, S, &n_valid);
   if (n == 0) {
     if (tid < qa.nq) out[(size_t)t * out_ld + tid] = Num<R>::nan();
     return;
@@ -473,7 +504,8 @@ k_row_quantiles(const R* __restrict__ a, int S, int T, QuantArgs qa,
     s_nr = nr;
   }
   __syncthreads();
-  radix_select_multi<R>(keys, S, s_nr, sh);
+  if (in_smem) radix_select_multi<R>(SmemKeys<R>{keys}, S, s_nr, sh);
+  else radix_select_multi<R>(gkeys, S, s_nr, sh);
   if (tid < qa.nq) {
     const double pos = qa.q[tid] * (double)(n - 1);
     int lo = (int)floor(pos);
