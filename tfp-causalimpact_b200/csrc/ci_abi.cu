@@ -211,7 +211,9 @@ bool plan_team(const ci_ctx* c, int C, int* GT, SmemCfg* cfg, int* sub = nullptr
     *sub = 1;
     if (c->team_sub && 2 * W <= MAXW && c->prob.p <= PSMALL) { *sub = 2; W *= 2; }
   }
-  if (!c->team_mode || W < 2 || W > MAXW || c->prob.model != CI_MODEL_LOCAL_LEVEL) return false;
+  // (W = 1, a single tile, is a team of one: same kernel, no checkpoint replay between the
+  // forward and the adjoint sweep)
+  if (!c->team_mode || W < 1 || W > MAXW || c->prob.model != CI_MODEL_LOCAL_LEVEL) return false;
   int gt = (C >= 4 * c->sm_count) ? MAXW / W : 1;
   if (gt < 1) gt = 1;
   if (c->force_G > 0) gt = c->force_G * W <= MAXW ? c->force_G : 1;
