@@ -105,7 +105,8 @@ class Scaler:
     # plain ndarray arithmetic: the same IEEE operations as the frame expression
     # (frame - mean) / std, without building three intermediate DataFrames
     vals = np.asarray(frame, dtype=np.float64) if not isinstance(frame, np.ndarray) else frame
-    scaled = np.where(self.stddev_ > 0, (vals - self.mean_) / self.stddev_, vals)
+    with np.errstate(divide="ignore", invalid="ignore"):       # zero-variance columns pass through
+      scaled = np.where(self.stddev_ > 0, (vals - self.mean_) / self.stddev_, vals)
     return pd.DataFrame(scaled, index=frame.index, columns=frame.columns)
 
   def fit_transform(self, frame: pd.DataFrame) -> pd.DataFrame:
