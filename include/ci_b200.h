@@ -255,6 +255,17 @@ int ci_batch_select(ci_ctx* ctx, int series);
 int ci_gibbs_run_batch_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
                          uint64_t chain_id0, int n_chains, void* draws_d, void* level_d,
                          void* traj_d, float* incl_d, void* stream);
+/* The same with seasonal components.  ci_set_seasonal_batch (after ci_set_data_batch) gives the
+ * season calendar of the WHOLE panel (every series has the same T) and, per series, the priors
+ * that scale with the series' own outcome sd (lib.py:472-489): init_sd [N], drift_scale [N],
+ * drift_ub [N] (HOST arrays; the scalar fields of `seas` are ignored by the batched kernel).
+ * Outputs as ci_gibbs_seasonal_run, series-major; bit-identical per series to the single run. */
+int ci_set_seasonal_batch(ci_ctx* ctx, const ci_seasonal* seas, const double* init_sd,
+                          const double* drift_scale, const double* drift_ub);
+int ci_gibbs_seasonal_run_batch_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
+                                  uint64_t chain_id0, int n_chains, void* draws_d,
+                                  void* level_d, void* traj_d, float* incl_d, void* latent_d,
+                                  void* seasonal_d, void* drift_d, void* stream);
 
 /* Mean of the predictive mixture alone (lib.py:627): mean_t = avg_s level[s,t] + x_t . avg_s w_s,
  * for draws whose level paths are already on the device (the Gibbs kernel's output).

@@ -128,3 +128,42 @@ def test_panel_arrays_match_the_frame_path():
   with pytest.raises(ValueError, match="constant"):
     bad = values.copy(); bad[2, :, 0] = 1.0
     ci.fit_causalimpact_panel(bad, idx, pre, post, **kw)
+
+
+def test_seasonal_panel_and_many_equal_single_seasonal_fits():
+  """Seasonal components in the batched paths: fit_causalimpact_many is bit-identical to the
+  single seasonal fits (per-series prior scales travel with the batch), the panel agrees to
+  rounding."""
+  rng = np.random.default_rng(21)
+  n = 140
+  idx = pd.date_range("2022-01-03", periods=n, freq="D")
+  pat = np.array([1.0, 4.0, 5.0, 2.0, -1.0, -2.0, -3.0])
+  dfs = []
+  for s in range(3):
+    x = 100 + np.cumsum(rng.normal(size=n)) * 0.3
+    y = x + (0.5 + 0.2 * s) * pat[np.arange(n) % 7] + 0.3 * rng.normal(size=n)
+    y[100:] += 2.0
+    dfs.append(pd.DataFrame({"y": y, "x": x}, index=idx))
+  pre, post = (idx[0], idx[99]), (idx[100], idx[-1])
+  mo = ci.ModelOptions(seasons=[ci.Seasons(num_seasons=7)])
+  kw = dict(seed=5, model_options=mo, inference_options=ci.InferenceOptions(num_results=96),
+            engine_options=ci.EngineOptions(num_chains=8))
+  many = ci.fit_causalimpact_many(dfs, pre, post, **kw)
+  res = ci.fit_causalimpact_panel(np.stack([d.values for d in dfs]), idx, pre, post,
+                                  keep_level=True, **kw)
+  assert res.seasonal_levels.shape == (3, 96, n, 1) and res.seasonal_drift_scales.shape == (3, 96, 1)
+  vals = ci.impact.SERIES_VALUE_COLUMNS
+  for i, df in enumerate(dfs):
+    one = ci.fit_causalimpact(df, pre, post, **kw)
+    pd.testing.assert_frame_equal(many[i].series, one.series)
+    pd.testing.assert_frame_equal(many[i].summary, one.summary)
+    np.testing.assert_array_equal(many[i].posterior_samples.seasonal_levels,
+                                  one.posterior_samples.seasonal_levels)
+    np.testing.assert_array_equal(many[i].posterior_samples.seasonal_drift_scales,
+                                  one.posterior_samples.seasonal_drift_scales)
+    want = one.series[vals].values.astype(float)
+    np.testing.assert_allclose(res.series[i], want, rtol=5e-4, atol=5e-4 * np.nanmax(np.abs(want)),
+                               equal_nan=True)
+    # the weekly pattern is found in every series
+    contrib = one.posterior_samples.seasonal_levels.numpy()[:, :98, 0].mean(0).reshape(14, 7).mean(0)
+    assert np.corrcoef(contrib, pat)[0, 1] > 0.95

@@ -75,7 +75,8 @@ EXPORTS = (
     "ci_hmc_run", "ci_hmc_run_d", "ci_gibbs_run", "ci_gibbs_run_d", "ci_posterior_predict", "ci_posterior_predict_d",
     "ci_row_quantiles", "ci_row_quantiles_d", "ci_predictive_mean_d", "ci_impact", "ci_impact_d",
     "ci_set_seasonal", "ci_gibbs_seasonal_run", "ci_gibbs_seasonal_run_d",
-    "ci_set_data_batch", "ci_batch_select", "ci_gibbs_run_batch_d",
+    "ci_set_data_batch", "ci_batch_select", "ci_gibbs_run_batch_d", "ci_set_seasonal_batch",
+    "ci_gibbs_seasonal_run_batch_d",
 )
 
 _lib = None
@@ -121,6 +122,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                                         vp, vp, vp]
   lib.ci_gibbs_seasonal_run_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp,
                                           vp, vp, vp, vp, vp]
+  lib.ci_set_seasonal_batch.argtypes = [vp, C.POINTER(CiSeasonal), vp, vp, vp]
+  lib.ci_gibbs_seasonal_run_batch_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp,
+                                                vp, vp, vp, vp, vp, vp]
   lib.ci_set_data_batch.argtypes = [vp, C.POINTER(CiProblem), i32, vp, vp, vp]
   lib.ci_batch_select.argtypes = [vp, i32]
   lib.ci_gibbs_run_batch_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp, vp]
@@ -287,7 +291,6 @@ class Engine:
     """ci_batch_select: series i of the batch becomes the current problem."""
     self._check(self._lib.ci_batch_select(self._ctx, int(i)))
     self.spec = spec if spec is not None else self.batch_specs[i]
-    self.seasonal = None
 
   def gibbs_run_batch_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
                         chain_id0: int = 0, sparse: bool = True,
@@ -309,6 +312,47 @@ class Engine:
         self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, draws.data_ptr(),
         level.data_ptr(), traj.data_ptr(), incl.data_ptr(), self._stream(torch)))
     return draws, level, traj, incl.cpu().numpy()[:, :, :sp.p]
+
+  def set_seasonal_batch(self, scheds):
+    """ci_set_seasonal_batch: one model.SeasonalSchedule per series of the batch (same calendar,
+    per-series prior scales)."""
+    scheds = list(scheds)
+    s0 = scheds[0]
+    act = np.ascontiguousarray(s0.active, dtype=np.uint8)
+    ends = np.ascontiguousarray(s0.ends, dtype=np.uint8)
+    cs = CiSeasonal(n_components=s0.K, active=act.ctypes.data, ends=ends.ctypes.data,
+                    init_sd=s0.init_sd, drift_conc=s0.drift_conc, drift_scale=s0.drift_scale,
+                    drift_ub=s0.drift_ub)
+    for k, n in enumerate(s0.num_seasons):
+      cs.num_seasons[k] = int(n)
+    a = np.ascontiguousarray([sc.init_sd for sc in scheds], dtype=np.float64)
+    b = np.ascontiguousarray([sc.drift_scale for sc in scheds], dtype=np.float64)
+    u = np.ascontiguousarray([sc.drift_ub for sc in scheds], dtype=np.float64)
+    self._check(self._lib.ci_set_seasonal_batch(self._ctx, C.byref(cs), _ptr(a), _ptr(b), _ptr(u)))
+    self.seasonal = s0
+
+  def gibbs_seasonal_run_batch_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
+                                 chain_id0: int = 0, sparse: bool = True,
+                                 nonzero_prob: Optional[float] = None):
+    """ci_gibbs_seasonal_run_batch_d, chain-major device tensors with a leading series axis:
+    (theta [N,R,dim], level, latent, traj [N,R,T], seasonal [N,R,T,K], log drift variance
+    [N,R,K], incl [N,C,p] ndarray)."""
+    torch, dev = self._torch_dev()
+    sp, dt, K, N = self.spec, self._tdtype(torch), self.seasonal.K, len(self.batch_specs)
+    if nonzero_prob is None:
+      nonzero_prob = min(1.0, 3.0 / sp.p) if sp.p else 1.0
+    rows = n_chains * n_results
+    mk = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+    draws, level, latent, traj = mk(N, rows, sp.dim), mk(N, rows, sp.T), mk(N, rows, sp.T), mk(N, rows, sp.T)
+    seas, drift = mk(N, rows, sp.T, K), mk(N, rows, K)
+    incl = torch.zeros((N, n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
+    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
+                       nonzero_prob=float(nonzero_prob))
+    self._check(self._lib.ci_gibbs_seasonal_run_batch_d(
+        self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, draws.data_ptr(),
+        level.data_ptr(), traj.data_ptr(), incl.data_ptr(), latent.data_ptr(), seas.data_ptr(),
+        drift.data_ptr(), self._stream(torch)))
+    return draws, level, latent, traj, seas, drift, incl.cpu().numpy()[:, :, :sp.p]
 
   def set_seasonal(self, sched):
     """ci_set_seasonal: ``sched`` is a model.SeasonalSchedule (or None to remove)."""

@@ -420,16 +420,15 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
 
   Multi-GPU: series are sharded over the ranks of an initialised process group (contiguous
   ranges, no collective: series are independent); a rank returns ``None`` for the series it
-  does not own.  Seasonal components are not batched (NotImplementedError).
+  does not own.  ``ModelOptions.seasons`` are supported (one season calendar for the panel).
   """
   data_options = data_options if data_options is not None else DataOptions()
   model_options = model_options if model_options is not None else ModelOptions()
   inference_options = inference_options if inference_options is not None else InferenceOptions()
   opts = engine_options or EngineOptions()
-  if model_options.seasons:
-    raise NotImplementedError("seasonal components are not batched: use fit_causalimpact")
   if opts.sampler == "hmc":
     raise NotImplementedError("the batched path runs the Gibbs kernel")
+  seasons = list(model_options.seasons or ())
   np_dt = _np_dtype(data_options.dtype)
   seed64 = _seed_to_u64(seed)
   datas = list(datas)
@@ -439,7 +438,7 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
   if n_local == 0:
     return out
   eng = _resolve_engine(opts)
-  cids, specs = [], []
+  cids, specs, scheds = [], [], []
   for d in datas[s0:s0 + n_local]:
     cid = _frame.CausalImpactData(data=d, pre_period=pre_period, post_period=post_period,
                                   outcome_column=data_options.outcome_column,
@@ -447,20 +446,32 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
     y_ext, design, outcome_sd = cid.engine_inputs(np_dt)
     specs.append(build_problem(y_ext, design, prior_level_sd=model_options.prior_level_sd,
                                outcome_sd=outcome_sd, dtype=np_dt))
+    scheds.append(build_seasonal(seasons, specs[-1].T, outcome_sd))
     cids.append(cid)
   p, T = specs[0].p, specs[0].T
   eng.set_data_batch(specs)
+  K = 0
+  if seasons:
+    eng.set_seasonal_batch(scheds)
+    K = scheds[0].K
   num_results = inference_options.num_results
   C = max(int(opts.num_chains), 1)
   n_per = max(1, math.ceil(num_results / C))
   n_warm = max(int(inference_options.num_warmup_steps), int(opts.gibbs_min_warmup))
-  theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
-                                                   seed=seed64, chain_id0=0, sparse=True)
+  if seasons:
+    theta, level, latent, traj, seas, drift, incl = eng.gibbs_seasonal_run_batch_t(
+        C, n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=0, sparse=True)
+  else:
+    theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
+                                                     seed=seed64, chain_id0=0, sparse=True)
+    latent = level
   for i, cid in enumerate(cids):
     eng.batch_select(i, specs[i])
-    th_i, lv_i, tr_i = (t[i][:num_results] for t in (theta, level, traj))
-    mean_i = eng.predictive_mean_t(th_i, lv_i)
-    samples = _package_samples(eng, th_i, lv_i, p, T, np_dt)
+    th_i, lv_i, tr_i, la_i = (t[i][:num_results] for t in (theta, level, traj, latent))
+    mean_i = eng.predictive_mean_t(th_i, la_i)
+    samples = _package_samples(
+        eng, th_i, lv_i, p, T, np_dt,
+        seasonal=(seas[i][:num_results], drift[i][:num_results], K) if seasons else None)
     samples.hmc_stats = {"sampler": "gibbs", "inclusion": incl[i]}
     series, summary = _impact.compute_impact(DeviceArray(mean_i), DeviceArray(tr_i), cid, alpha,
                                              eng.impact)

@@ -26,7 +26,7 @@ import pandas as pd
 from . import frame as _frame
 from . import impact as _impact
 from . import shard as _shard
-from .model import build_problem
+from .model import build_problem, build_seasonal
 
 SUMMARY_COLUMNS = ["actual", "predicted", "predicted_lower", "predicted_upper", "predicted_sd",
                    "abs_effect", "abs_effect_lower", "abs_effect_upper", "abs_effect_sd",
@@ -45,6 +45,8 @@ class PanelResult:
   level_scale: np.ndarray         # [n, S]
   weights: Optional[np.ndarray]   # [n, S, k + 1] or None
   level: Optional[np.ndarray]     # [n, S, T_model] when keep_level
+  seasonal_levels: Optional[np.ndarray]         # [n, S, T_model, K] when keep_level and seasons
+  seasonal_drift_scales: Optional[np.ndarray]   # [n, S, K] with seasons
   pre_period: tuple
   post_period: tuple
   inclusion: np.ndarray           # [n, chains, k + 1]
@@ -123,8 +125,7 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
   model_options = model_options if model_options is not None else _api.ModelOptions()
   inference_options = inference_options if inference_options is not None else _api.InferenceOptions()
   opts = engine_options or _api.EngineOptions()
-  if model_options.seasons:
-    raise NotImplementedError("seasonal components are not batched: use fit_causalimpact")
+  seasons = list(model_options.seasons or ())
   if not 0 < alpha < 1:
     raise ValueError("`alpha` must be between 0 and 1.")
   np_dt = _api._np_dtype(data_options.dtype)
@@ -145,8 +146,16 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
   C = max(int(opts.num_chains), 1)
   n_per = max(1, math.ceil(S / C))
   n_warm = max(int(inference_options.num_warmup_steps), int(opts.gibbs_min_warmup))
-  theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
-                                                   seed=seed64, chain_id0=0, sparse=True)
+  seas = drift = None
+  if seasons:
+    eng.set_seasonal_batch([build_seasonal(seasons, Tm, float(prep["outcome_sd"][i]))
+                            for i in range(N)])
+    theta, level, latent, traj, seas, drift, incl = eng.gibbs_seasonal_run_batch_t(
+        C, n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=0, sparse=True)
+  else:
+    theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
+                                                     seed=seed64, chain_id0=0, sparse=True)
+    latent = level
   S = min(S, C * n_per)
 
   # ---- O(T) metadata of the impact stage, shared / vectorised (impact.prepare per series) ----
@@ -165,8 +174,8 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
   out = torch.empty((N, Tm * 9 + 20), dtype=torch.float64, device=theta.device)
   for i in range(N):
     eng.batch_select(i, specs[i])
-    th_i, lv_i, tr_i = theta[i, :S], level[i, :S], traj[i, :S]
-    mean_i = eng.predictive_mean_t(th_i, lv_i)
+    th_i, tr_i = theta[i, :S], traj[i, :S]
+    mean_i = eng.predictive_mean_t(th_i, latent[i, :S])
     meta = _impact.ImpactMeta(index=mi, observed=observed[i], period=period, hide=hide[i],
                               scale=float(prep["y_scale"][i]), offset=float(prep["y_offset"][i]),
                               q_lo=q_lo, q_hi=q_hi, obs_mean=float(obs_mean[i]),
@@ -202,4 +211,8 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
       level_scale=np.exp(0.5 * th[:, :, p + 1]).astype(np_dt),
       weights=th[:, :, :p].astype(np_dt) if p else None,
       level=eng.to_host(level[:, :S]).astype(np_dt, copy=False) if keep_level else None,
+      seasonal_levels=(eng.to_host(seas[:, :S]).astype(np_dt, copy=False)
+                       if (seasons and keep_level) else None),
+      seasonal_drift_scales=(np.exp(0.5 * eng.to_host(drift[:, :S]).astype(np.float64)).astype(np_dt)
+                             if seasons else None),
       pre_period=pre, post_period=post, inclusion=incl)

@@ -72,7 +72,7 @@ struct ci_ctx {
   DevBuf w_level, w_traj, w_mean, w_q, w_draws, w_stats, w_incl;
   DevBuf gram, xty0;                 // X'X, X'y over observed rows (Gibbs regression step)
   DevBuf i_cum, i_stats, i_meta, i_series, i_summ, i_trT;   // ci_impact workspaces
-  DevBuf s_sched, s_scratch, w_latent, w_seas, w_drift;   // seasonal components
+  DevBuf s_sched, s_scratch, s_series, w_latent, w_seas, w_drift;   // seasonal components
   ci::SeasDev seas{};                // seas.K == 0: no seasonal components
   // views of the CURRENT series: the context's own buffers after ci_set_data, a slice of the
   // batch buffers after ci_batch_select
@@ -425,14 +425,15 @@ int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
 template <typename R>
 int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0, int C,
                           void* draws_d, void* level_d, void* traj_d, float* incl_d, void* latent_d,
-                          void* seas_d, void* drift_d, cudaStream_t st) {
+                          void* seas_d, void* drift_d, cudaStream_t st, bool batch = false) {
   const int p = c->prob.p, d = c->seas.d;
   const uint32_t base_extra = (uint32_t)(2 * p * p + 5 * p + 8) + (uint32_t)(d * (d | 1) + d) +
                               (3u + (uint32_t)c->seas.K) * (uint32_t)ci::TB;
   const uint32_t scr_elems = (uint32_t)c->prob.T * (uint32_t)(d + 1);
   const uint32_t tail = (uint32_t)(p * p) * (uint32_t)c->esz + 16u;
   SmemCfg cfg;
-  int G = pick_G(c, C), rc = CI_ERR_UNSUPPORTED;
+  int G = batch ? pick_G(c, C * c->batch_n) : pick_G(c, C), rc = CI_ERR_UNSUPPORTED;
+  if (G > C) G = C;
   bool scr_smem = false;
   {  // first choice: the per-step scratch in shared memory with every tile resident
     std::string keep = g_err;
@@ -461,15 +462,17 @@ int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint
   SeasDev sz = c->seas;
   sz.scratch = nullptr;                       // nullptr: the kernel's scratch is in shared memory
   if (!scr_smem) {
-    CU_TRY(c->s_scratch.reserve((size_t)C * c->prob.T * (d + 1) * sizeof(R)));
+    CU_TRY(c->s_scratch.reserve((size_t)C * (batch ? c->batch_n : 1) * c->prob.T * (d + 1) * sizeof(R)));
     sz.scratch = c->s_scratch.p;
   }
   auto kern = k_gibbs_seasonal<R>;
   CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
-  kern<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+  const dim3 grid((C + G - 1) / G, batch ? c->batch_n : 1);
+  kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(
       make_probdev<R>(c), gd, sz, cfg, plan, seed, chain_id0, C, static_cast<R*>(draws_d),
       static_cast<R*>(level_d), static_cast<R*>(traj_d), static_cast<R*>(latent_d),
-      static_cast<R*>(seas_d), static_cast<R*>(drift_d), incl_d);
+      static_cast<R*>(seas_d), static_cast<R*>(drift_d), incl_d,
+      batch ? static_cast<const BatchDev<R>*>(c->b_dev.p) : nullptr);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;
@@ -696,7 +699,7 @@ int ci_ctx_destroy(ci_ctx* c) {
   c->w_level.release(); c->w_traj.release(); c->w_mean.release(); c->w_q.release(); c->w_draws.release(); c->w_stats.release(); c->w_incl.release();
   c->gram.release(); c->xty0.release();
   c->b_tiles.release(); c->b_omega.release(); c->b_gram.release(); c->b_xty.release(); c->b_dev.release();
-  c->s_sched.release(); c->s_scratch.release(); c->w_latent.release(); c->w_seas.release(); c->w_drift.release();
+  c->s_sched.release(); c->s_scratch.release(); c->s_series.release(); c->w_latent.release(); c->w_seas.release(); c->w_drift.release();
   c->i_trT.release(); c->i_cum.release(); c->i_stats.release(); c->i_meta.release(); c->i_series.release(); c->i_summ.release();
   delete c;
   return CI_OK;
@@ -803,7 +806,8 @@ int ci_batch_select(ci_ctx* c, int s) {
   c->v_gram = static_cast<char*>(c->b_gram.p) + c->b_gram_stride * s;
   c->v_xty = static_cast<char*>(c->b_xty.p) + c->b_xty_stride * s;
   c->yty0 = c->b_yty[s]; c->n_obs = c->b_nobs[s];
-  c->seas = ci::SeasDev{};
+  // (a season calendar set with ci_set_seasonal after ci_set_data_batch belongs to the whole
+  // panel -- same T for every series -- and survives the selection)
   c->has_data = true;
   return CI_OK;
 }
@@ -842,6 +846,50 @@ int ci_set_data_batch(ci_ctx* c, const ci_problem* probs, int N, const void* y, 
   rc = plan_smem(c, 1, 0, &cfg);
   if (rc) { c->has_data = false; c->batch_n = 0; return rc; }
   return CI_OK;
+}
+
+int ci_set_seasonal_batch(ci_ctx* c, const ci_seasonal* sp, const double* init_sd,
+                          const double* drift_scale, const double* drift_ub) {
+  if (!c || !sp || !init_sd || !drift_scale || !drift_ub) return fail(CI_ERR_INVALID, "null argument");
+  if (c->batch_n < 1) return fail(CI_ERR_STATE, "ci_set_data_batch has not been called");
+  int rc = ci_set_seasonal(c, sp);
+  if (rc) return rc;
+  const int N = c->batch_n;
+  std::vector<double> h((size_t)3 * N);
+  for (int s = 0; s < N; ++s) {
+    if (!(init_sd[s] > 0) || !(drift_scale[s] > 0) || !(drift_ub[s] > 0)) {
+      c->seas = ci::SeasDev{};
+      return fail(CI_ERR_INVALID, "init_sd, drift_scale, drift_ub must be positive (series %d)", s);
+    }
+    h[3 * s] = init_sd[s] * init_sd[s]; h[3 * s + 1] = drift_scale[s]; h[3 * s + 2] = drift_ub[s];
+  }
+  CU_TRY(c->s_series.reserve(h.size() * sizeof(double)));
+  CU_TRY(cudaMemcpyAsync(c->s_series.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->seas.per_series = static_cast<const double*>(c->s_series.p);
+  return CI_OK;
+}
+
+int ci_gibbs_seasonal_run_batch_d(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed,
+                                  uint64_t chain_id0, int Cs, void* draws_d, void* level_d,
+                                  void* traj_d, float* incl_d, void* latent_d, void* seas_d,
+                                  void* drift_d, void* stream) {
+  if (!c || !o || !draws_d) return fail(CI_ERR_INVALID, "null argument");
+  if (c->batch_n < 1) return fail(CI_ERR_STATE, "ci_set_data_batch has not been called");
+  if (c->seas.K < 1) return fail(CI_ERR_STATE, "ci_set_seasonal has not been called");
+  if (Cs < 1 || o->n_results < 1 || o->n_warmup < 0)
+    return fail(CI_ERR_INVALID, "n_chains >= 1, n_results >= 1, n_warmup >= 0 required");
+  if (o->sparse && !(o->nonzero_prob > 0.0 && o->nonzero_prob <= 1.0))
+    return fail(CI_ERR_INVALID, "nonzero_prob must be in (0, 1]");
+  for (int s = 0; s < c->batch_n; ++s)
+    if (c->b_nobs[s] < 2) return fail(CI_ERR_INVALID, "series %d has fewer than 2 observed points", s);
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prob.dtype == CI_F64)
+    return launch_gibbs_seasonal<double>(c, o, seed, chain_id0, Cs, draws_d, level_d, traj_d, incl_d,
+                                         latent_d, seas_d, drift_d, st, true);
+  return launch_gibbs_seasonal<float>(c, o, seed, chain_id0, Cs, draws_d, level_d, traj_d, incl_d,
+                                      latent_d, seas_d, drift_d, st, true);
 }
 
 int ci_gibbs_run_batch_d(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chain_id0,

@@ -41,6 +41,7 @@ struct SeasDev {
   double init_var;              // initial_effect_prior variance (lib.py:489: sd^2)
   double drift_conc, drift_scale, drift_ub;   // InverseGamma on the drift variance (lib.py:472-474)
   void* scratch;                // [C][T][d+1] elements of R
+  const double* per_series;     // batch only: [N][3] = init_var, drift_scale, drift_ub of every series
 };
 
 // Gamma(shape, 1) for any shape > 0 (boost for shape < 1: G(a) = G(a+1) U^(1/a)).
@@ -62,8 +63,18 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
                  uint64_t seed, uint64_t chain_id0, int C, R* __restrict__ draws,
                  R* __restrict__ level_out, R* __restrict__ traj_out, R* __restrict__ latent_out,
                  R* __restrict__ seas_out, R* __restrict__ drift_out,
-                 float* __restrict__ incl_out) {
+                 float* __restrict__ incl_out, const BatchDev<R>* __restrict__ batch) {
   extern __shared__ __align__(128) unsigned char smem[];
+  // batched launch (grid.y = series; the season calendar is shared by the panel): as k_gibbs
+  const size_t series_row0 = batch ? (size_t)blockIdx.y * C * plan.n_results : 0;
+  const size_t series_chain0 = batch ? (size_t)blockIdx.y * C : 0;
+  if (batch) {
+    pr = batch[blockIdx.y].pr; gd = batch[blockIdx.y].gd; plan.n_obs = batch[blockIdx.y].n_obs;
+    if (sz.per_series) {        // the priors scale with each series' own outcome sd (lib.py:472-489)
+      const double* ps = sz.per_series + 3 * (size_t)blockIdx.y;
+      sz.init_var = ps[0]; sz.drift_scale = ps[1]; sz.drift_ub = ps[2];
+    }
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = (blockDim.x >> 5) - 1;
   const int chain0 = blockIdx.x * G;
@@ -100,7 +111,7 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   R* st_d = st_c + TB;                  // [K][TB] drift normals of the tile's steps
   // per-step scratch (gains / r_t): in shared memory when the launch found room, else L2
   const bool scr_smem = sz.scratch == nullptr;
-  R* scr = scr_smem ? st_d + (size_t)K * TB : static_cast<R*>(sz.scratch) + (size_t)c * T * (d + 1);
+  R* scr = scr_smem ? st_d + (size_t)K * TB : static_cast<R*>(sz.scratch) + (series_chain0 + (size_t)c) * T * (d + 1);
   TilePipe<R> pipe = make_pipe(cs, cfg);
   const uint64_t gid = chain_id0 + (uint64_t)c;
   const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
@@ -307,8 +318,8 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
     // ---- pass C ----
     const bool keep = it >= plan.n_warmup;
     const size_t out_row = !keep ? 0
-        : plan.chain_major ? ((size_t)c * plan.n_results + (size_t)(it - plan.n_warmup))
-                           : ((size_t)(it - plan.n_warmup) * C + c);
+        : series_row0 + (plan.chain_major ? ((size_t)c * plan.n_results + (size_t)(it - plan.n_warmup))
+                                          : ((size_t)(it - plan.n_warmup) * C + c));
     R xt = init_xplus(it);                                 // x = x+ + xhat, element `lane`
     {
       const R rc = block_centered(rr);
@@ -468,7 +479,7 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
 #pragma unroll
     for (int wd = 0; wd < DSLOTS; ++wd) {
       const int j = lane + 32 * wd;
-      if (j < p) incl_out[(size_t)c * p + j] = (float)(incl_cnt[wd] / (plan.n_results > 0 ? plan.n_results : 1));
+      if (j < p) incl_out[(series_chain0 + (size_t)c) * p + j] = (float)(incl_cnt[wd] / (plan.n_results > 0 ? plan.n_results : 1));
     }
   }
 }
