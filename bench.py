@@ -490,8 +490,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # dram__bytes_read+write per launch, ncu --set full (profiles/r01_k_logpost_*_ncu.md)
-                     "traffic": 137216 if team else 133888,
+                     # dram__bytes_read+write per launch, ncu --set full (profiles/r01_k_logpost_*_ncu.md, run 33)
+                     "traffic": 140288 if team else 133888,
                      "kernel": "k_logpost_team<float>" if team else "k_logpost_scan<float>",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": C * B,
