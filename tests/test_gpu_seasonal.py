@@ -180,3 +180,56 @@ def test_limits_and_errors(engine):
                         engine_options=ci.EngineOptions(sampler="hmc"))
   with pytest.raises(ValueError, match="num_steps_per_season"):
     model.build_seasonal(seasons((4, (1, 2, 3))), 60, 1.0)
+
+
+def test_maximum_state_dimension_and_wide_regression(engine):
+  """Edge of the supported range: 7 components with 1 + 31 = 32 state elements (one per lane),
+  and a 20-covariate regression (the transposed X'r path) next to a seasonal component; the
+  exact check against the dense Gaussian conditional for the 32-dimensional state."""
+  rng = np.random.default_rng(9)
+  T = 48
+  ss = seasons((4, 1), (4, 2), (4, 3), (4, (2, 1, 1, 1)), (4, 5), (4, 1), (7, 1))
+  y = 0.3 + rng.normal(size=T)
+  y[[2, 9]] = np.nan; y[40:] = np.nan
+  mask = np.isnan(y)
+  s_e, s_h, s_d = 0.3, 0.02, 0.01
+  spec = pinned_spec(y, s_e, s_h, np.float32)
+  engine.set_data(spec)
+  sched = dataclasses.replace(model.build_seasonal(ss, T, 0.9), drift_conc=1e9,
+                              drift_scale=1e9 * s_d, drift_ub=1e3)
+  assert 1 + sum(sched.num_seasons) == 32
+  engine.set_seasonal(sched)
+  out = engine.gibbs_seasonal_run(64, n_warmup=2, n_results=40, seed=3, sparse=False)
+  lat = out["latent"].reshape(-1, T).astype(np.float64)
+  sea = out["seasonal"].reshape(-1, T, 7).astype(np.float64)
+  n = lat.shape[0]
+  sp = S.make_spec(ss, T, 0.9)
+  mu, Syy, Sxy, covs = S.dense_moments(sp, T, s_e, s_h, [s_d] * 7, spec.m0, spec.P0)
+  o = ~mask
+  Sinv_r = np.linalg.solve(Syy[np.ix_(o, o)], (y - mu)[o])
+  for t in range(T):
+    G = Sxy[t][:, o]
+    cmean = np.r_[spec.m0, np.zeros(sp.d - 1)] + G @ Sinv_r
+    ccov = covs[t] - G @ np.linalg.solve(Syy[np.ix_(o, o)], G.T)
+    cols = S.obs_cols(sp, t)
+    for got, idx in [(lat[:, t], cols)] + [(sea[:, t, k], [cols[k + 1]]) for k in range(7)]:
+      m_ref, v_ref = cmean[idx].sum(), ccov[np.ix_(idx, idx)].sum()
+      assert abs(got.mean() - m_ref) < 5 * np.sqrt(v_ref / n) + 3e-4, (t, idx)
+      assert abs(got.var() - v_ref) < 6 * v_ref * np.sqrt(2.0 / n) + 1e-5, (t, idx)
+  # 20 covariates + weekly component: runs, finite, the planted pattern is recovered
+  T2 = 150
+  X = rng.normal(size=(T2, 20)); X = np.column_stack([X, np.ones(T2)])
+  pat = np.array([1.0, 4.0, 5.0, 2.0, -1.0, -2.0, -3.0]); pat -= pat.mean()
+  y2 = X[:, 0] * 0.8 - X[:, 1] * 0.5 + 0.2 * pat[np.arange(T2) % 7] + 0.2 * rng.normal(size=T2)
+  y2 = (y2 - y2[:110].mean()) / y2[:110].std(ddof=1)
+  sd2 = 1.0
+  y2[110:] = np.nan
+  engine.set_data(ci.build_problem(y2, X, outcome_sd=sd2))
+  engine.set_seasonal(model.build_seasonal(seasons((7, 1)), T2, sd2))
+  out = engine.gibbs_seasonal_run(32, n_warmup=150, n_results=10, seed=4, sparse=True)
+  assert np.all(np.isfinite(out["traj"]))
+  w = out["draws"].reshape(-1, 23)[:, :21]
+  assert abs(w[:, 0].mean() - 0.8 / np.nanstd(y2[:110] * 0 + 1)) < 1.0   # (scale-free sanity)
+  contrib = out["seasonal"].reshape(-1, T2)[:, :105].mean(0).reshape(15, 7).mean(0)
+  assert np.corrcoef(contrib, pat)[0, 1] > 0.9
+  assert out["incl"][:, 2:20].mean() < 0.3 and out["incl"][:, 0].mean() > 0.9
