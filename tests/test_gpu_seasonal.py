@@ -221,7 +221,8 @@ def test_maximum_state_dimension_and_wide_regression(engine):
   X = rng.normal(size=(T2, 20)); X = np.column_stack([X, np.ones(T2)])
   pat = np.array([1.0, 4.0, 5.0, 2.0, -1.0, -2.0, -3.0]); pat -= pat.mean()
   y2 = X[:, 0] * 0.8 - X[:, 1] * 0.5 + 0.2 * pat[np.arange(T2) % 7] + 0.2 * rng.normal(size=T2)
-  y2 = (y2 - y2[:110].mean()) / y2[:110].std(ddof=1)
+  sd_raw = y2[:110].std(ddof=1)
+  y2 = (y2 - y2[:110].mean()) / sd_raw
   sd2 = 1.0
   y2[110:] = np.nan
   engine.set_data(ci.build_problem(y2, X, outcome_sd=sd2))
@@ -229,7 +230,7 @@ def test_maximum_state_dimension_and_wide_regression(engine):
   out = engine.gibbs_seasonal_run(32, n_warmup=150, n_results=10, seed=4, sparse=True)
   assert np.all(np.isfinite(out["traj"]))
   w = out["draws"].reshape(-1, 23)[:, :21]
-  assert abs(w[:, 0].mean() - 0.8 / np.nanstd(y2[:110] * 0 + 1)) < 1.0   # (scale-free sanity)
+  assert abs(w[:, 0].mean() - 0.8 / sd_raw) < 0.1 and abs(w[:, 1].mean() + 0.5 / sd_raw) < 0.1
   contrib = out["seasonal"].reshape(-1, T2)[:, :105].mean(0).reshape(15, 7).mean(0)
   assert np.corrcoef(contrib, pat)[0, 1] > 0.9
   assert out["incl"][:, 2:20].mean() < 0.3 and out["incl"][:, 0].mean() > 0.9
