@@ -116,6 +116,12 @@ class FakeEngine:
   def to_host(self, t):
     return t.detach().cpu().numpy()
 
-  def impact(self, traj, mean, meta):
-    return impact_np.impact_arrays(np.asarray(traj), np.asarray(mean), meta.observed, meta.period,
-                                   meta.scale, meta.offset, meta.q_lo, meta.q_hi, meta.obs_sum)
+  def impact(self, traj, mean, meta, out=None):
+    s9, summ = impact_np.impact_arrays(np.asarray(traj), np.asarray(mean), meta.observed,
+                                       meta.period, meta.scale, meta.offset, meta.q_lo, meta.q_hi,
+                                       meta.obs_sum)
+    if out is None:
+      return s9, summ
+    import torch
+    out.copy_(torch.from_numpy(np.concatenate([s9.reshape(-1), summ])))
+    return None

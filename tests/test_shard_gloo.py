@@ -141,3 +141,39 @@ def test_many_series_are_sharded_by_series_without_a_collective(tmp_path):
     for i, got in part.items():
       np.testing.assert_array_equal(got["series"], ref[i]["series"])
       np.testing.assert_array_equal(got["summary"], ref[i]["summary"])
+
+
+def test_panel_host_logic_matches_the_frame_path(monkeypatch):
+  """fit_causalimpact_panel's vectorised packaging (NaN rules, re-indexing, summary table) vs
+  the pandas packaging of fit_causalimpact_many, both on the oracle-backed FakeEngine (CPU):
+  a gap between the periods, a tail after the post-period, a missing pre-period point."""
+  from fake_engine import FakeEngine
+  import causalimpact_b200 as cib
+  from causalimpact_b200 import api
+  fake = FakeEngine()
+  monkeypatch.setattr(api, "_resolve_engine", lambda opts: fake)
+  rng = np.random.default_rng(8)
+  idx = pd.date_range("2021-03-01", periods=60)
+  dfs = []
+  for s in range(3):
+    x = 100 + np.cumsum(rng.normal(size=60)); y = (1 + 0.3 * s) * x + rng.normal(size=60)
+    y[40:] += 4
+    if s == 1:
+      y[5] = np.nan
+    dfs.append(pd.DataFrame({"y": y, "x": x}, index=idx))
+  pre, post = (idx[0], idx[37]), (idx[41], idx[55])
+  kw = dict(seed=(3, 1), inference_options=cib.InferenceOptions(num_results=10),
+            engine_options=cib.EngineOptions(num_chains=2, gibbs_min_warmup=6))
+  many = cib.fit_causalimpact_many(dfs, pre, post, **kw)
+  res = cib.fit_causalimpact_panel(np.stack([d.values for d in dfs]), idx, pre, post,
+                                   keep_level=True, **kw)
+  vals = cib.impact.SERIES_VALUE_COLUMNS
+  for i, one in enumerate(many):
+    want = one.series[vals].values.astype(float)
+    np.testing.assert_array_equal(np.isnan(res.series[i]), np.isnan(want))
+    np.testing.assert_allclose(res.series[i], want, rtol=1e-5, atol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(res.summary[i], one.summary.values.astype(float), rtol=1e-5, atol=1e-6)
+    ser, summ = res.frames(i)
+    assert list(ser.columns) == list(one.series.columns) and ser.index.equals(one.series.index)
+    assert list(summ.columns) == list(one.summary.columns) and list(summ.index) == list(one.summary.index)
+    np.testing.assert_allclose(res.level[i], one.posterior_samples.level, rtol=1e-4, atol=1e-4)
