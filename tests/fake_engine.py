@@ -15,7 +15,7 @@ from oracle import smoother_np as SM
 
 class FakeEngine:
   def __init__(self, device=0):
-    self.device, self.spec, self.prob = device, None, None
+    self.device, self.spec, self.prob, self.seasonal = device, None, None, None
 
   def set_data(self, spec):
     self.spec = spec
@@ -94,6 +94,37 @@ class FakeEngine:
     if self.spec.p:
       m = m + self.prob.X @ th[:, :self.spec.p].mean(axis=0)
     return torch.from_numpy(m.astype(self.spec.np_dtype))
+
+  # ---- seasonal components: the restated seasonal sweep (oracle/seasonal_np.py) ----
+  def set_seasonal(self, sched):
+    self.seasonal = sched
+
+  def gibbs_seasonal_run_t(self, n_chains, *, n_warmup, n_results, seed, chain_id0=0, sparse=True,
+                           nonzero_prob=None):
+    import torch
+    from oracle import seasonal_np as S
+    sp, dt, sc = self.spec, self.spec.np_dtype, self.seasonal
+    ssp = S.SeasonalSpec(n=list(sc.num_seasons), idx=np.asarray(sc.active, np.int64),
+                         ends=np.asarray(sc.ends, bool), init_sd=sc.init_sd,
+                         drift_conc=sc.drift_conc, drift_scale=sc.drift_scale, drift_ub=sc.drift_ub)
+    K, R = ssp.K, n_chains * n_results
+    th = np.empty((R, sp.dim), dt); lv = np.empty((R, sp.T), dt); la = np.empty((R, sp.T), dt)
+    tr = np.empty((R, sp.T), dt); se = np.empty((R, sp.T, K), dt); dr = np.empty((R, K), dt)
+    incl = np.zeros((n_chains, max(sp.p, 1)), np.float32)
+    for c in range(n_chains):
+      g = S.run(self.prob, ssp, n_results=n_results, n_warmup=n_warmup,
+                seed=(int(seed) % (2 ** 31)) * 1000003 + chain_id0 + c, sparse=sparse and sp.p > 3)
+      rows = slice(c * n_results, (c + 1) * n_results)
+      th[rows, :sp.p] = g["w"]; th[rows, sp.p] = np.log(g["s_e"]); th[rows, sp.p + 1] = np.log(g["s_h"])
+      lv[rows] = g["level"]; se[rows] = g["seasonal"]; dr[rows] = np.log(g["s_d"])
+      la[rows] = g["level"] + g["seasonal"].sum(-1)
+      rng = np.random.default_rng(chain_id0 + c)
+      loc = la[rows] + (g["w"] @ self.prob.X.T if sp.p else 0.0)
+      tr[rows] = loc + np.sqrt(g["s_e"])[:, None] * rng.normal(size=loc.shape)
+      if sp.p:
+        incl[c, :sp.p] = (g["w"] != 0).mean(0)
+    t = torch.from_numpy
+    return t(th), t(lv), t(la), t(tr), t(se), t(dr), incl[:, :sp.p]
 
   # ---- batches of independent series (fit_causalimpact_many) ----
   def set_data_batch(self, specs):

@@ -31,35 +31,41 @@ api._resolve_engine = lambda opts: fake
 rng = np.random.default_rng(3)
 n = 60
 n_cov = int(sys.argv[3])
+seasonal = len(sys.argv) > 4 and sys.argv[4] == "seasonal"
 xs = 100 + np.cumsum(rng.normal(size=(n, n_cov)), axis=0); y = 1.2 * xs[:, 0] + rng.normal(size=n); y[40:] += 4
 df = pd.DataFrame(np.column_stack([y, xs]), columns=["y"] + [f"x{i}" for i in range(n_cov)],
                   index=pd.date_range("2021-01-01", periods=n))
+mo = cib.ModelOptions(seasons=[cib.Seasons(num_seasons=4), cib.Seasons(num_seasons=3, num_steps_per_season=2)]) \
+    if seasonal else None
 ci = cib.fit_causalimpact(df, (df.index[0], df.index[39]), (df.index[40], df.index[-1]), seed=(1, 2),
-    inference_options=cib.InferenceOptions(num_results=22),
+    model_options=mo, inference_options=cib.InferenceOptions(num_results=22),
     engine_options=cib.EngineOptions(num_chains=5, min_warmup=25, max_leapfrog=3,
                                      gibbs_min_warmup=10))
 if int(os.environ.get("RANK", "0")) == 0:
   vals = [c for c in ci.series.columns if not c.endswith(("_start", "_end"))]
   pickle.dump(dict(series=ci.series[vals].values, summary=ci.summary.values,
                    level=np.asarray(ci.posterior_samples.level),
-                   weights=np.asarray(ci.posterior_samples.weights)), open(sys.argv[2], "wb"))
+                   weights=np.asarray(ci.posterior_samples.weights),
+                   seasonal=np.asarray(ci.posterior_samples.seasonal_levels),
+                   drift=None if ci.posterior_samples.seasonal_drift_scales is None
+                   else np.asarray(ci.posterior_samples.seasonal_drift_scales)), open(sys.argv[2], "wb"))
 if world > 1:
   dist.destroy_process_group()
 '''
 
 
-def _run(world, out, n_cov=1):
+def _run(world, out, n_cov=1, mode=""):
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
     f.write(WORKER)
     script = f.name
   env = dict(os.environ, OMP_NUM_THREADS="1")
   if world == 1:
-    cmd = [sys.executable, script, root, out, str(n_cov)]
+    cmd = [sys.executable, script, root, out, str(n_cov), mode]
   else:
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29731",
-           script, root, out, str(n_cov)]
+           script, root, out, str(n_cov), mode]
   res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
   os.unlink(script)
   assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
@@ -81,9 +87,20 @@ def test_world2_gloo_equals_single_process(tmp_path, n_cov):
   """n_cov = 1 -> sampler auto = HMC; n_cov = 4 (p = 5 > 3) -> the Gibbs kernel path."""
   one = _run(1, str(tmp_path / "w1.pkl"), n_cov)
   two = _run(2, str(tmp_path / "w2.pkl"), n_cov)
+  assert one.pop("drift") is None and two.pop("drift") is None      # no seasonal components
   for k in one:
     assert np.array_equal(one[k], two[k], equal_nan=True), k
   assert one["level"].shape == (22, 60)
+
+
+def test_world2_gloo_equals_single_process_with_seasonal_components(tmp_path):
+  """The seasonal branch of the fit (six gathered parts: theta, level, trajectory, latent,
+  per-component contributions, drift variances) under a 2-rank gloo group == single process."""
+  one = _run(1, str(tmp_path / "s1.pkl"), 1, "seasonal")
+  two = _run(2, str(tmp_path / "s2.pkl"), 1, "seasonal")
+  for k in one:
+    assert np.array_equal(one[k], two[k], equal_nan=True), k
+  assert one["seasonal"].shape == (22, 60, 2) and one["drift"].shape == (22, 2)
 
 
 MANY_WORKER = r'''
