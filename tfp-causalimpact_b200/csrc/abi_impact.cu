@@ -1,0 +1,108 @@
+// abi_impact.cu -- impact series + summary entry points.
+#include "ci_host.cuh"
+#include "ci_impact.cuh"
+
+namespace {
+
+using namespace ci;
+
+template <typename R>
+int launch_impact(ci_ctx* c, const ImpactDev& a, const void* traj_d, const void* mean_d,
+                  const double* obs_d, const uint8_t* period_d, double* series_d, double* summ_d,
+                  cudaStream_t st) {
+  const int S = a.S, T = a.T, Tc = T - a.t_c0;
+  R* trT = static_cast<R*>(c->i_trT.p);
+  double* cumT = static_cast<double*>(c->i_cum.p);
+  double* statsT = static_cast<double*>(c->i_stats.p);
+  const int row_ctas = (S + IMP_TILE - 1) / IMP_TILE + 1;            // + the predictive mean
+  k_impact_rows<R><<<row_ctas, 32 * IMP_TILE, 0, st>>>(
+      static_cast<const R*>(traj_d), static_cast<const R*>(mean_d), obs_d, period_d, a, trT, cumT,
+      statsT, series_d, summ_d);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  size_t bytes = (((size_t)S * sizeof(double)) + 15) & ~(size_t)15;   // float64 jobs
+  const int in_smem = bytes + QSTATIC <= (size_t)c->smem_optin;       // else: select from global memory
+  if (!in_smem) bytes = 0;
+  auto kern = k_impact_jobs<R>;
+  CU_TRY(set_smem(kern, (uint32_t)bytes));
+  int nt = 1024;
+  while (nt > 64 && nt / 2 >= S) nt >>= 1;
+  kern<<<Tc + IMP_STATS + T + 1, nt, bytes, st>>>(trT, cumT, statsT, obs_d, a, series_d, summ_d,
+                                                   in_smem);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ci_impact_d(ci_ctx* c, const ci_impact_args* a, const void* traj_d, const void* mean_d,
+                const double* observed, const uint8_t* period, double* series_d, double* summ_d,
+                void* stream) {
+  if (!c || !a || !traj_d || !mean_d || !observed || !period || !series_d || !summ_d)
+    return fail(CI_ERR_INVALID, "null argument");
+  if (a->S < 1 || a->T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (a->dtype != CI_F32 && a->dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  if (!(a->q_lo >= 0.0 && a->q_lo <= 1.0 && a->q_hi >= 0.0 && a->q_hi <= 1.0))
+    return fail(CI_ERR_INVALID, "quantiles must be in [0,1]");
+  if (!(a->scale > 0.0)) return fail(CI_ERR_INVALID, "scale must be positive");
+  const int S = a->S, T = a->T;
+  ci::ImpactDev d{};
+  d.S = S; d.T = T; d.scale = a->scale; d.offset = a->offset; d.q_lo = a->q_lo; d.q_hi = a->q_hi;
+  d.obs_sum = a->obs_sum;
+  d.t_c0 = T; d.n_post = 0;
+  for (int t = 0; t < T; ++t) {
+    if (period[t] > 2 || (t > 0 && period[t] < period[t - 1]))
+      return fail(CI_ERR_INVALID, "period[] must be non-decreasing values in {0,1,2}");
+    if (period[t] != 0 && d.t_c0 == T) d.t_c0 = t;
+    d.n_post += period[t] == 1;
+  }
+  if (d.n_post < 1) return fail(CI_ERR_INVALID, "the post-period is empty");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Tc = T - d.t_c0;
+  CU_TRY(c->i_cum.reserve((size_t)S * (Tc > 0 ? Tc : 1) * sizeof(double)));
+  CU_TRY(c->i_stats.reserve((size_t)S * ci::IMP_STATS * sizeof(double)));
+  CU_TRY(c->i_trT.reserve((size_t)S * T * (a->dtype == CI_F64 ? 8 : 4)));
+  const size_t ob = (size_t)T * sizeof(double);
+  CU_TRY(c->i_meta.reserve(ob + (size_t)T));
+  CU_TRY(cudaMemcpyAsync(c->i_meta.p, observed, ob, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(static_cast<char*>(c->i_meta.p) + ob, period, (size_t)T,
+                         cudaMemcpyHostToDevice, st));
+  const double* obs_d = static_cast<const double*>(c->i_meta.p);
+  const uint8_t* per_d = reinterpret_cast<const uint8_t*>(static_cast<char*>(c->i_meta.p) + ob);
+  if (a->dtype == CI_F64)
+    return launch_impact<double>(c, d, traj_d, mean_d, obs_d, per_d, series_d, summ_d, st);
+  return launch_impact<float>(c, d, traj_d, mean_d, obs_d, per_d, series_d, summ_d, st);
+}
+
+int ci_impact(ci_ctx* c, const ci_impact_args* a, const void* traj, const void* mean,
+              const double* observed, const uint8_t* period, double* series, double* summary) {
+  if (!c || !a || !traj || !mean || !observed || !period || !series || !summary)
+    return fail(CI_ERR_INVALID, "null argument");
+  if (a->S < 1 || a->T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (a->dtype != CI_F32 && a->dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t es = a->dtype == CI_F64 ? 8 : 4;
+  const size_t tb = (size_t)a->S * a->T * es, mb = (size_t)a->T * es;
+  const size_t sb = (size_t)a->T * CI_IMPACT_SERIES_COLS * sizeof(double);
+  const size_t ub = CI_IMPACT_SUMMARY_LEN * sizeof(double);
+  CU_TRY(c->w_traj.reserve(tb));
+  CU_TRY(c->w_mean.reserve(mb));
+  CU_TRY(c->i_series.reserve(sb));
+  CU_TRY(c->i_summ.reserve(ub));
+  CU_TRY(cudaMemcpyAsync(c->w_traj.p, traj, tb, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(c->w_mean.p, mean, mb, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_impact_d(c, a, c->w_traj.p, c->w_mean.p, observed, period,
+                       static_cast<double*>(c->i_series.p), static_cast<double*>(c->i_summ.p),
+                       c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(series, c->i_series.p, sb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(summary, c->i_summ.p, ub, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+}  // extern "C"

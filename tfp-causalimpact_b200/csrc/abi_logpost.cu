@@ -1,0 +1,140 @@
+// abi_logpost.cu -- K1/K2/K3 entry points: Kalman log-prob (+ gradient) kernels.
+#include "ci_host.cuh"
+#include "ci_team_kernels.cuh"
+#include "ci_seq.cuh"
+#include "ci_llt_kernels.cuh"
+
+namespace {
+
+using namespace ci;
+
+template <typename R>
+int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* grad_d, int variant,
+                   int flags, cudaStream_t st) {
+  if (variant != CI_VARIANT_SCAN && variant != CI_VARIANT_SEQ)
+    return fail(CI_ERR_INVALID, "unknown variant %d", variant);
+  SmemCfg cfg;
+  if (c->prob.model == CI_MODEL_LOCAL_LINEAR_TREND) {
+    if (variant != CI_VARIANT_SCAN)
+      return fail(CI_ERR_UNSUPPORTED, "the local linear trend model has only the scan variant");
+    const int G = pick_G(c, C);
+    int rc = plan_smem(c, G, 0, &cfg);
+    if (rc) return rc;
+    auto lk = k_logpost_llt<R>;
+    CU_TRY(set_smem(lk, (uint32_t)cfg.total_bytes));
+    lk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), make_lltdev<R>(c), cfg, static_cast<const R*>(theta_d), C,
+        static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
+  if (variant == CI_VARIANT_SEQ) {
+    const int G = pick_G(c, C);
+    int rc = plan_smem(c, G, 2u * (uint32_t)c->NB * (uint32_t)GROUPS_PER_TILE, &cfg);
+    if (rc) return rc;
+    auto sk = k_logpost_seq<R>;
+    CU_TRY(set_smem(sk, (uint32_t)cfg.total_bytes));
+    sk<<<(C + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, static_cast<const R*>(theta_d), C, static_cast<R*>(value_d),
+        static_cast<R*>(grad_d), flags);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
+  int GT = 0;
+  if (plan_team<R>(c, C, &GT, &cfg)) {
+    const int W = c->NB;
+    auto tk = k_logpost_team<R>;
+    CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
+    tk<<<(C + GT - 1) / GT, 32 * (GT * W + 1), cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, W, static_cast<const R*>(theta_d), C,
+        static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
+  const int G = pick_G(c, C);
+  int rc = plan_smem(c, G, 0, &cfg);
+  if (rc) return rc;
+  auto kern = k_logpost_scan<R>;
+  CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
+  const int grid = (C + G - 1) / G;
+  kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(
+      make_probdev<R>(c), cfg, static_cast<const R*>(theta_d), C, static_cast<R*>(value_d),
+      static_cast<R*>(grad_d), flags);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ci_logprob_grad_d(ci_ctx* c, const void* theta_d, int C, void* value_d, void* grad_d,
+                      int variant, int flags, void* stream) {
+  if (!c || !theta_d || !value_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (C < 1) return fail(CI_ERR_INVALID, "n_chains must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prob.dtype == CI_F64)
+    return launch_logpost<double>(c, theta_d, C, value_d, grad_d, variant, flags, st);
+  return launch_logpost<float>(c, theta_d, C, value_d, grad_d, variant, flags, st);
+}
+
+// Device-visible alias of a PINNED host buffer (cudaHostAlloc / cudaHostRegister),
+// or nullptr for pageable memory.
+static void* pinned_alias(const void* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return at.devicePointer;
+}
+
+int ci_logprob_grad(ci_ctx* c, const void* theta, int C, void* value, void* grad, int variant,
+                    int flags) {
+  if (!c || !theta || !value) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (C < 1) return fail(CI_ERR_INVALID, "n_chains must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t tb = (size_t)C * c->dim * c->esz, vb = (size_t)C * c->esz;
+  // Pinned caller buffers: the kernel reads theta and writes value / grad straight
+  // over PCIe (zero-copy) -- one launch + one sync instead of three staged copies.
+  void* th_a = pinned_alias(theta);
+  void* va_a = th_a ? pinned_alias(value) : nullptr;
+  void* gr_a = (va_a && grad) ? pinned_alias(grad) : nullptr;
+  if (th_a && va_a && (!grad || gr_a) && tb <= (1u << 20)) {
+    int rc = ci_logprob_grad_d(c, th_a, C, va_a, gr_a, variant, flags, c->stream);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CI_OK;
+  }
+  CU_TRY(c->w_theta.reserve(tb));
+  CU_TRY(c->w_value.reserve(vb));
+  if (grad) CU_TRY(c->w_grad.reserve(tb));
+  CU_TRY(cudaMemcpyAsync(c->w_theta.p, theta, tb, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_logprob_grad_d(c, c->w_theta.p, C, c->w_value.p, grad ? c->w_grad.p : nullptr,
+                             variant, flags, c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(value, c->w_value.p, vb, cudaMemcpyDeviceToHost, c->stream));
+  if (grad) CU_TRY(cudaMemcpyAsync(grad, c->w_grad.p, tb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_logprob(ci_ctx* c, const void* theta, int C, void* value, int variant, int flags) {
+  return ci_logprob_grad(c, theta, C, value, nullptr, variant, flags);
+}
+
+#ifdef CI_CLK
+// developer build only (-DCI_CLK): phase clocks of the last k_logpost_team launch
+int ci_debug_clocks(long long* out32) {
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpyFromSymbol(out32, ci::g_clk, sizeof(long long) * 32));
+  return CI_OK;
+}
+#endif
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// abi_predict.cu -- K4 / K5 entry points: simulation smoother, predictive mean, per-time quantiles.
+#include "ci_host.cuh"
+#include "ci_predict.cuh"
+#include "ci_team_kernels.cuh"
+
+namespace {
+
+using namespace ci;
+
+template <typename R>
+int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_t draw_id0,
+                   void* level_d, void* traj_d, void* mean_d, cudaStream_t st) {
+  SmemCfg cfg;
+  const ProbDev<R> prt = make_probdev<R>(c);
+  int GT = 0;
+  // The kernel choice must NOT depend on S: a draw has to come out bit-identical however
+  // the batch is split over calls / GPUs.  The one-warp kernel is the default (better
+  // occupancy at thousands of draws: 21.5 vs 20.0 M draws/s at S=4096, run 8); the team
+  // kernel (lower latency for a handful of draws) is opt-in via CI_B200_PREDICT_TEAM=1.
+  if (c->predict_team && plan_team<R>(c, S, &GT, &cfg)) {
+    auto tk = k_predict_team<R>;
+    CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
+    tk<<<(S + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
+        prt, cfg, c->NB, static_cast<const R*>(theta_d), S, seed, draw_id0,
+        static_cast<R*>(level_d), static_cast<R*>(traj_d));
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    if (mean_d) {
+      k_predict_mean<R><<<(c->prob.T + MEAN_COLS - 1) / MEAN_COLS, dim3(MEAN_COLS, MEAN_ROWS), 0, st>>>(
+          prt, static_cast<const R*>(theta_d), static_cast<const R*>(level_d), S,
+          static_cast<R*>(mean_d));
+      CU_TRY(cudaGetLastError());
+      c->launches++;
+    }
+    return CI_OK;
+  }
+  const int G = pick_G(c, S);
+  int rc = plan_smem(c, G, 0, &cfg);
+  if (rc) return rc;
+  auto kern = k_predict<R>;
+  CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
+  const int grid = (S + G - 1) / G;
+  const ProbDev<R> pr = make_probdev<R>(c);
+  kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(pr, cfg, static_cast<const R*>(theta_d), S,
+                                                     seed, draw_id0, static_cast<R*>(level_d),
+                                                     static_cast<R*>(traj_d));
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  if (mean_d) {
+    k_predict_mean<R><<<(c->prob.T + MEAN_COLS - 1) / MEAN_COLS, dim3(MEAN_COLS, MEAN_ROWS), 0, st>>>(
+        pr, static_cast<const R*>(theta_d), static_cast<const R*>(level_d), S,
+        static_cast<R*>(mean_d));
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  return CI_OK;
+}
+
+template <typename R>
+int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, int nq,
+                     void* out_d, cudaStream_t st, int out_ld = 0) {
+  // the whole column lives in shared memory as integer keys when it fits; longer columns are
+  // selected straight from global memory (every sweep re-reads them through L2)
+  size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
+  const int in_smem = bytes + QSTATIC <= (size_t)c->smem_optin;
+  if (!in_smem) bytes = 0;
+  QuantArgs qa;
+  qa.nq = nq;
+  for (int i = 0; i < nq; ++i) qa.q[i] = q[i];
+  auto kern = k_row_quantiles<R>;
+  CU_TRY(set_smem(kern, (uint32_t)bytes));
+  int nt = 1024;
+  while (nt > 64 && nt / 2 >= S) nt >>= 1;
+  kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, qa, static_cast<R*>(out_d),
+                             out_ld > 0 ? out_ld : nq, in_smem);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ci_posterior_predict_d(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_t draw_id0,
+                           void* level_d, void* traj_d, void* mean_d, void* stream) {
+  if (!c || !theta_d || !traj_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
+  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
+    return fail(CI_ERR_UNSUPPORTED, "ci_posterior_predict: local level only (the reference has "
+                "no slope component, causalimpact_lib.py:496)");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!level_d && mean_d) {   // the mean needs the level paths: use the workspace
+    CU_TRY(c->w_level.reserve((size_t)S * c->prob.T * c->esz));
+    level_d = c->w_level.p;
+  }
+  if (c->prob.dtype == CI_F64)
+    return launch_predict<double>(c, theta_d, S, seed, draw_id0, level_d, traj_d, mean_d, st);
+  return launch_predict<float>(c, theta_d, S, seed, draw_id0, level_d, traj_d, mean_d, st);
+}
+
+int ci_posterior_predict(ci_ctx* c, const void* theta, int S, uint64_t seed, uint64_t draw_id0,
+                         void* level, void* traj, void* mean) {
+  if (!c || !theta || !traj) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t tb = (size_t)S * c->dim * c->esz, st_b = (size_t)S * c->prob.T * c->esz;
+  const size_t mb = (size_t)c->prob.T * c->esz;
+  CU_TRY(c->w_theta.reserve(tb));
+  CU_TRY(c->w_level.reserve(st_b));
+  CU_TRY(c->w_traj.reserve(st_b));
+  CU_TRY(c->w_mean.reserve(mb));
+  CU_TRY(cudaMemcpyAsync(c->w_theta.p, theta, tb, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_posterior_predict_d(c, c->w_theta.p, S, seed, draw_id0, c->w_level.p, c->w_traj.p,
+                                  mean ? c->w_mean.p : nullptr, c->stream);
+  if (rc) return rc;
+  if (level) CU_TRY(cudaMemcpyAsync(level, c->w_level.p, st_b, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(traj, c->w_traj.p, st_b, cudaMemcpyDeviceToHost, c->stream));
+  if (mean) CU_TRY(cudaMemcpyAsync(mean, c->w_mean.p, mb, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_row_quantiles_d(ci_ctx* c, const void* a_d, int S, int T, int dtype, const double* q,
+                       int nq, void* out_d, void* stream) {
+  if (!c || !a_d || !q || !out_d) return fail(CI_ERR_INVALID, "null argument");
+  if (S < 1 || T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (nq < 1 || nq > 8) return fail(CI_ERR_INVALID, "nq must be in [1,8]");
+  for (int i = 0; i < nq; ++i)
+    if (!(q[i] >= 0.0 && q[i] <= 1.0)) return fail(CI_ERR_INVALID, "quantile %d out of [0,1]", i);
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == CI_F64) return launch_quantiles<double>(c, a_d, S, T, q, nq, out_d, st);
+  if (dtype == CI_F32) return launch_quantiles<float>(c, a_d, S, T, q, nq, out_d, st);
+  return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+}
+
+int ci_row_quantiles(ci_ctx* c, const void* a, int S, int T, int dtype, const double* q, int nq,
+                     void* out) {
+  if (!c || !a || !q || !out) return fail(CI_ERR_INVALID, "null argument");
+  if (S < 1 || T < 1) return fail(CI_ERR_INVALID, "S and T must be >= 1");
+  if (dtype != CI_F32 && dtype != CI_F64) return fail(CI_ERR_INVALID, "dtype must be 0 or 1");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t es = dtype == CI_F64 ? 8 : 4;
+  const size_t ab = (size_t)S * T * es, ob = (size_t)T * nq * es;
+  CU_TRY(c->w_traj.reserve(ab));
+  CU_TRY(c->w_q.reserve(ob > 0 ? ob : 16));
+  CU_TRY(cudaMemcpyAsync(c->w_traj.p, a, ab, cudaMemcpyHostToDevice, c->stream));
+  int rc = ci_row_quantiles_d(c, c->w_traj.p, S, T, dtype, q, nq, c->w_q.p, c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(out, c->w_q.p, ob, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return CI_OK;
+}
+
+int ci_predictive_mean_d(ci_ctx* c, const void* theta_d, const void* level_d, int S, void* mean_d,
+                         void* stream) {
+  if (!c || !theta_d || !level_d || !mean_d) return fail(CI_ERR_INVALID, "null argument");
+  if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
+  if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
+  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
+    return fail(CI_ERR_UNSUPPORTED, "ci_predictive_mean: local level only");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 blk(ci::MEAN_COLS, ci::MEAN_ROWS);
+  const int grid = (c->prob.T + ci::MEAN_COLS - 1) / ci::MEAN_COLS;
+  if (c->prob.dtype == CI_F64)
+    ci::k_predict_mean<double><<<grid, blk, 0, st>>>(
+        make_probdev<double>(c), static_cast<const double*>(theta_d),
+        static_cast<const double*>(level_d), S, static_cast<double*>(mean_d));
+  else
+    ci::k_predict_mean<float><<<grid, blk, 0, st>>>(
+        make_probdev<float>(c), static_cast<const float*>(theta_d),
+        static_cast<const float*>(level_d), S, static_cast<float*>(mean_d));
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return CI_OK;
+}
+
+}  // extern "C"

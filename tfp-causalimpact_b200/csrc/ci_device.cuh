@@ -18,6 +18,20 @@ template <typename R> struct ProbDev {
   R lvl_conc, lvl_scale, lvl_ub;
 };
 
+// Seasonal components as the kernels see them (ci_set_seasonal; kernel in ci_seasonal.cuh).
+constexpr int MAX_SEAS = 7;     // components (the "season ends" flags of a step are one byte)
+constexpr int SEAS_MAXD = 32;   // 1 + sum of num_seasons
+
+struct SeasDev {
+  int K, d;
+  int n[MAX_SEAS], off[MAX_SEAS], n_ends[MAX_SEAS];
+  const uint8_t* sched;         // [T][K+1]: active season of each component, then the ends mask
+  double init_var;              // initial_effect_prior variance (lib.py:489: sd^2)
+  double drift_conc, drift_scale, drift_ub;   // InverseGamma on the drift variance (lib.py:472-474)
+  void* scratch;                // [C][T][d+1] elements of R
+  const double* per_series;     // batch only: [N][3] = init_var, drift_scale, drift_ub of every series
+};
+
 // Dynamic shared memory layout (byte offsets), computed on the host.
 struct SmemCfg {
   uint32_t stage_elems;  // elements per stage (== tile_elems)

@@ -31,19 +31,6 @@
 namespace ci {
 
 enum : uint32_t { RNG_S_PATH = 9, RNG_S_INIT = 10, RNG_S_DRIFT = 11, RNG_S_GAMMA_U = 12 };
-constexpr int MAX_SEAS = 7;     // components (the "season ends" flags of a step are one byte)
-constexpr int SEAS_MAXD = 32;   // 1 + sum of num_seasons
-
-struct SeasDev {
-  int K, d;
-  int n[MAX_SEAS], off[MAX_SEAS], n_ends[MAX_SEAS];
-  const uint8_t* sched;         // [T][K+1]: active season of each component, then the ends mask
-  double init_var;              // initial_effect_prior variance (lib.py:489: sd^2)
-  double drift_conc, drift_scale, drift_ub;   // InverseGamma on the drift variance (lib.py:472-474)
-  void* scratch;                // [C][T][d+1] elements of R
-  const double* per_series;     // batch only: [N][3] = init_var, drift_scale, drift_ub of every series
-};
-
 // Gamma(shape, 1) for any shape > 0 (boost for shape < 1: G(a) = G(a+1) U^(1/a)).
 __device__ __forceinline__ double gamma_draw_any(double shape, uint64_t seed, uint32_t c0,
                                                  uint32_t c1, uint32_t it, uint32_t site) {

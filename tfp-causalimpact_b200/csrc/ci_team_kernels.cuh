@@ -4,7 +4,6 @@
 #pragma once
 #include "ci_hmc.cuh"
 #include "ci_team.cuh"
-#include "ci_team4.cuh"
 
 namespace ci {
 
@@ -204,107 +203,6 @@ k_predict_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, i
   team_predict(tile, pr, team_area<R>(smem, cfg, n_warps, team), ws.w, s_e, s_h,
                Num<R>::sqrt(s_e), seed, draw_id0 + (uint64_t)s, lane, wt, W, team + 1,
                level ? level + row : nullptr, traj + row);
-}
-
-// ---------------------------------------------------------------------------
-// Sub-tile team kernels (ci_team4.cuh): W = NB * (8 / KQ) warps per chain, warp wt owns
-// rows (wt % SUB) * 32 KQ .. of tile wt / SUB.
-// ---------------------------------------------------------------------------
-template <typename R, int KQ> struct TeamEvalQ {
-  const R* tile; const ProbDev<R>& pr; TeamShared<R>* ts; const WarpScratch<R>& ws;
-  const R* omega; int lane, wt, W, bar_id, row_base;
-  __device__ __forceinline__ bool writer() const { return wt == 0; }
-  __device__ __forceinline__ void publish(const R (&t)[DSLOTS]) {
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < DSLOTS; ++s) {
-      const int i = lane + 32 * s;
-      if (i < pr.dim) ws.w[i] = t[s];
-    }
-    __syncwarp();
-  }
-  __device__ __forceinline__ void eval(double& lp, R (&g)[DSLOTS]) {
-    const int p = pr.p;
-    const R u = ws.w[p], l = ws.w[p + 1];
-    const R s_e = Num<R>::exp(u), s_h = Num<R>::exp(l);
-    double ll, g_se, g_sh;
-    R gw[JS];
-    team_eval_q<R, KQ>(tile, pr, ts, ws.w, ws.rbuf, s_e, s_h, true, lane, wt, W, bar_id, row_base,
-                       ll, g_se, g_sh, gw);
-    double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
-    lp = ll + chain_prior(pr, omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
-#pragma unroll
-    for (int s = 0; s < DSLOTS; ++s) {
-      const int i = lane + 32 * s;
-      g[s] = i < p ? gw[s] : (i == p ? (R)g_u : (i == p + 1 ? (R)g_l : (R)0));
-    }
-  }
-};
-
-template <typename R, int KQ>
-__global__ void __launch_bounds__(32 * (MAXW + 1), 1)
-k_logpost_teamq(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, int C,
-                R* __restrict__ value, R* __restrict__ grad, int flags) {
-  constexpr int SUB = KS / KQ;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int lane = threadIdx.x & 31;
-  const int n_warps = (blockDim.x >> 5) - 1;
-  CtaShared<R> cs; int team, wt, c;
-  if (!team_prologue(smem, cfg, pr, W, C, cs, team, wt, c)) return;
-  const int p = pr.p, dim = pr.dim;
-  const R* th = theta + (size_t)c * dim;
-  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, threadIdx.x >> 5);
-  for (int j = lane; j < dim; j += 32) ws.w[j] = th[j];
-  __syncwarp();
-  const R u = ws.w[p], l = ws.w[p + 1];
-  const R s_e = Num<R>::exp(u), s_h = Num<R>::exp(l);
-  const int tix = wt / SUB;
-  mbar_wait(&cs.full[tix], 0u);
-  const R* tile = cs.stage0 + (size_t)tix * cfg.stage_elems;
-  const bool want_grad = grad != nullptr;
-  double ll, g_se, g_sh;
-  R gw[JS];
-  team_eval_q<R, KQ>(tile, pr, team_area<R>(smem, cfg, n_warps, team), ws.w, ws.rbuf, s_e, s_h,
-                     want_grad, lane, wt, W, team + 1, (wt % SUB) * 32 * KQ, ll, g_se, g_sh, gw);
-  if (wt != 0) return;
-  double val = ll;
-  double g_u = g_se * (double)s_e, g_l = g_sh * (double)s_h;
-  if (flags & 1) {
-    omega_wait(cs);
-    val += chain_prior(pr, cs.omega, ws.w, u, l, s_e, s_h, lane, gw, g_u, g_l);
-  }
-  if (lane == 0) value[c] = (R)val;
-  if (want_grad) {
-    R* g = grad + (size_t)c * dim;
-#pragma unroll
-    for (int s = 0; s < JS; ++s) {
-      const int j = lane + 32 * s;
-      if (j < p) g[j] = gw[s];
-    }
-    if (lane == 0) { g[p] = (R)g_u; g[p + 1] = (R)g_l; }
-  }
-}
-
-template <typename R, int KQ>
-__global__ void __launch_bounds__(32 * (MAXW + 1), 1)
-k_hmc_teamq(ProbDev<R> pr, SmemCfg cfg, int W, HmcPlan plan, uint64_t seed, uint64_t chain_id0,
-            const R* __restrict__ theta0, int C, R* __restrict__ draws,
-            ci_hmc_stats* __restrict__ stats) {
-  constexpr int SUB = KS / KQ;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int lane = threadIdx.x & 31;
-  const int n_warps = (blockDim.x >> 5) - 1;
-  CtaShared<R> cs; int team, wt, c;
-  if (!team_prologue(smem, cfg, pr, W, C, cs, team, wt, c)) return;
-  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, threadIdx.x >> 5);
-  const int tix = wt / SUB;
-  mbar_wait(&cs.full[tix], 0u);
-  const R* tile = cs.stage0 + (size_t)tix * cfg.stage_elems;
-  omega_wait(cs);
-  TeamEvalQ<R, KQ> ev{tile, pr, team_area<R>(smem, cfg, n_warps, team), ws, cs.omega, lane, wt, W,
-                      team + 1, (wt % SUB) * 32 * KQ};
-  hmc_chain<R>(ev, plan, seed, chain_id0 + (uint64_t)c, theta0 + (size_t)c * pr.dim, pr.dim, lane,
-               c, C, draws, stats);
 }
 
 }  // namespace ci
