@@ -82,6 +82,17 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
     c->launches++;
     return CI_OK;
   }
+  int TW = 0;
+  if (plan_tstream<R>(c, C, &GT, &TW, &cfg)) {
+    auto sk = k_hmc_tstream<R>;
+    CU_TRY(set_smem(sk, (uint32_t)cfg.total_bytes));
+    sk<<<(C + GT - 1) / GT, 32 * GT * TW, cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, TW, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,
+        static_cast<R*>(draws_d), stats_d);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
   const int G = pick_G(c, C);
   int rc = plan_smem(c, G, 0, &cfg);
   if (rc) return rc;

@@ -54,6 +54,17 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
     c->launches++;
     return CI_OK;
   }
+  int TW = 0;
+  if (plan_tstream<R>(c, C, &GT, &TW, &cfg)) {
+    auto sk = k_logpost_tstream<R>;
+    CU_TRY(set_smem(sk, (uint32_t)cfg.total_bytes));
+    sk<<<(C + GT - 1) / GT, 32 * GT * TW, cfg.total_bytes, st>>>(
+        make_probdev<R>(c), cfg, TW, static_cast<const R*>(theta_d), C,
+        static_cast<R*>(value_d), static_cast<R*>(grad_d), flags);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CI_OK;
+  }
   const int G = pick_G(c, C);
   int rc = plan_smem(c, G, 0, &cfg);
   if (rc) return rc;

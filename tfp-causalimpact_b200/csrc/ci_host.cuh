@@ -14,6 +14,7 @@
 #include "../../include/ci_b200.h"
 #include "ci_kernels.cuh"
 #include "ci_team.cuh"
+#include "ci_team_stream.cuh"
 #include "ci_llt.cuh"
 
 // thread-local message of the last failure (defined in abi_core.cu; ONE instance for the library)
@@ -110,6 +111,8 @@ struct ci_ctx {
   int force_G = 0;                   // CI_B200_G env override (tuning)
   int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
   int predict_team = 0;              // CI_B200_PREDICT_TEAM=1: team kernel for ci_posterior_predict
+  int tstream_mode = 1;              // CI_B200_TSTREAM=0 disables the long-series team kernels
+  int tstream_W = 0;                 // CI_B200_TSW: warps per chain of the long-series team kernels (tuning)
 };
 
 namespace {
@@ -171,8 +174,10 @@ template <typename Kern> cudaError_t set_smem(Kern kern, uint32_t bytes) {
 
 // Shared-memory plan for a kernel with G consumer warps and `extra_elems`
 // kernel-specific per-warp scratch elements.
+// `ckpt_elems` < 0: the per-tile checkpoints of the one-warp kernels (6 NB); `max_stages`:
+// ring depth when the series is streamed.
 int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
-              uint32_t tail_bytes = 0) {
+              uint32_t tail_bytes = 0, int ckpt_elems = -1, uint32_t max_stages = 8) {
   const uint32_t esz = (uint32_t)c->esz;
   const int p = c->prob.p, NB = c->NB;
   SmemCfg cfg{};
@@ -182,7 +187,7 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
   uint32_t e = 0;
   cfg.w_off = e;     e += align_up((uint32_t)(p + 4), 4);   // holds the full theta in the HMC kernel
   cfg.rbuf_off = e;  e += TB + 8;
-  cfg.ckpt_off = e;  e += align_up(6u * (uint32_t)NB, 4);    // (a,P) or the 5-value trend state
+  cfg.ckpt_off = e;  e += align_up(ckpt_elems < 0 ? 6u * (uint32_t)NB : (uint32_t)ckpt_elems, 4);    // (a,P) or the 5-value trend state
   cfg.extra_off = e; e += align_up(extra_elems, 4);
   cfg.warp_bytes = align_up(e * esz, 16);
   const uint32_t omega_bytes = align_up((uint32_t)(p * p) * esz, 16);
@@ -196,7 +201,7 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
                 stage_bytes);
   uint32_t nst = (budget - fixed - 128u) / (stage_bytes + 16u);
   if (nst >= (uint32_t)NB) { nst = (uint32_t)NB; cfg.resident = 1; }
-  else { cfg.resident = 0; if (nst > 8) nst = 8; }
+  else { cfg.resident = 0; if (nst > max_stages) nst = max_stages; }
   cfg.nstage = nst;
   uint32_t off = align_up(nst * stage_bytes, 128);
   cfg.off_full = off;   off += nst * 8;
@@ -236,5 +241,39 @@ bool plan_team(const ci_ctx* c, int C, int* GT, SmemCfg* cfg) {
   return true;
 }
 
+
+// Long-series team mode (ci_team_stream.cuh): W warps per chain walking the series in rounds
+// of W tiles.  Used for the local level model when the series has more tiles than a resident
+// team can hold (NB > MAXW, or the tiles do not fit in shared memory).  GT teams per CTA.
+template <typename R>
+bool plan_tstream(const ci_ctx* c, int C, int* GT, int* Wout, SmemCfg* cfg) {
+  if (!c->team_mode || !c->tstream_mode || c->prob.model != CI_MODEL_LOCAL_LEVEL) return false;
+  const int NB = c->NB;
+  if (NB < 2) return false;
+  int W = c->tstream_W > 0 ? c->tstream_W : 4;
+  if (W > MAXW) W = MAXW;
+  if (W > NB) W = NB;
+  if (W < 2) return false;
+  // teams per CTA: enough warps per SM to hide the scan latencies (up to TS_MAXWARPS), but no
+  // more CTAs' worth of chains than there are
+  int gt = c->force_G > 0 ? c->force_G : (C + c->sm_count - 1) / c->sm_count;
+  if (gt < 1) gt = 1;
+  if (gt * W > TS_MAXWARPS) gt = TS_MAXWARPS / W;
+  if (gt > 8) gt = 8;
+  std::string keep = cih_err();
+  for (; gt >= 1; --gt) {
+    const uint32_t tail = (uint32_t)gt * (uint32_t)tstream_team_bytes<R>(NB) + 16u;
+    // streaming needs a ring of at least two rounds: finishing a tile triggers the copy of the
+    // tile nstage - W positions ahead, which must reach into the next round
+    if (plan_smem(c, gt * W, 0, cfg, tail, 0, 3u * (uint32_t)W) == CI_OK &&
+        (cfg->resident || cfg->nstage >= 2u * (uint32_t)W)) {
+      cih_err() = keep;
+      *GT = gt; *Wout = W;
+      return true;
+    }
+  }
+  cih_err() = keep;
+  return false;
+}
 
 }  // namespace
