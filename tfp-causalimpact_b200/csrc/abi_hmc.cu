@@ -84,7 +84,8 @@ int launch_hmc(ci_ctx* c, const ci_hmc_opts* o, uint64_t seed, uint64_t chain_id
   }
   int TW = 0;
   if (plan_tstream<R>(c, C, &GT, &TW, &cfg)) {
-    auto sk = k_hmc_tstream<R>;
+    auto sk = TW != TS_W ? k_hmc_tstream<R, 0, 0>
+              : (c->prob.p == 2 ? k_hmc_tstream<R, 2, TS_W> : k_hmc_tstream<R, 0, TS_W>);
     CU_TRY(set_smem(sk, (uint32_t)cfg.total_bytes));
     sk<<<(C + GT - 1) / GT, 32 * GT * TW, cfg.total_bytes, st>>>(
         make_probdev<R>(c), cfg, TW, plan, seed, chain_id0, static_cast<const R*>(theta0_d), C,

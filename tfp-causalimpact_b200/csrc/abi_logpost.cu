@@ -56,7 +56,10 @@ int launch_logpost(ci_ctx* c, const void* theta_d, int C, void* value_d, void* g
   }
   int TW = 0;
   if (plan_tstream<R>(c, C, &GT, &TW, &cfg)) {
-    auto sk = k_logpost_tstream<R>;
+    // instantiations: the tuned team width with the column count known (1 covariate + intercept:
+    // BASELINE configs[3]) or not; anything else (CI_B200_TSW overrides) runs the generic kernel
+    auto sk = TW != TS_W ? k_logpost_tstream<R, 0, 0>
+              : (c->prob.p == 2 ? k_logpost_tstream<R, 2, TS_W> : k_logpost_tstream<R, 0, TS_W>);
     CU_TRY(set_smem(sk, (uint32_t)cfg.total_bytes));
     sk<<<(C + GT - 1) / GT, 32 * GT * TW, cfg.total_bytes, st>>>(
         make_probdev<R>(c), cfg, TW, static_cast<const R*>(theta_d), C,

@@ -47,6 +47,7 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float pow2_rescale(float x) {
     return __int_as_float((254 - ((__float_as_int(x) >> 23) & 255)) << 23); }
   static __device__ __forceinline__ float log(float x) { return logf(x); }
+  static __device__ __forceinline__ float log_fast(float x) { return __logf(x); }
   static __device__ __forceinline__ float exp(float x) { return expf(x); }
   static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
   static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
@@ -57,6 +58,7 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double pow2_rescale(double x) {
     return __longlong_as_double((long long)(2046 - ((__double_as_longlong(x) >> 52) & 2047)) << 52); }
   static __device__ __forceinline__ double log(double x) { return ::log(x); }
+  static __device__ __forceinline__ double log_fast(double x) { return ::log(x); }
   static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
   static __device__ __forceinline__ double nan() { return CUDART_NAN; }

@@ -250,7 +250,7 @@ bool plan_tstream(const ci_ctx* c, int C, int* GT, int* Wout, SmemCfg* cfg) {
   if (!c->team_mode || !c->tstream_mode || c->prob.model != CI_MODEL_LOCAL_LEVEL) return false;
   const int NB = c->NB;
   if (NB < 2) return false;
-  int W = c->tstream_W > 0 ? c->tstream_W : 4;
+  int W = c->tstream_W > 0 ? c->tstream_W : TS_W;
   if (W > MAXW) W = MAXW;
   if (W > NB) W = NB;
   if (W < 2) return false;

@@ -22,7 +22,7 @@ for r in rows:
     cur = r[1]; sect[cur] = []
   elif cur is not None:
     sect[cur].append(r)
-name = [k for k in sect if kern in k and ("<%s>" % tmpl) in k]
+name = [k for k in sect if kern in k and ("<%s" % tmpl) in k]
 if not name:
   name = [k for k in sect if kern in k]
 name = name[0]
@@ -38,13 +38,14 @@ for r in body[1:]:
 with tempfile.TemporaryDirectory() as td:
   subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=td, capture_output=True)
   lines = None
-  mangled = "%d%sI%sE" % (len(kern), kern, {"float": "f", "double": "d"}[tmpl])
+  mangled = "%d%sI%s" % (len(kern), kern, {"float": "f", "double": "d"}[tmpl])
+  extra = sys.argv[5] if len(sys.argv) > 5 else ""     # e.g. Li2ELi4 to pick one instantiation
   for f in sorted(os.listdir(td)):
     out = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(td, f)], capture_output=True, text=True).stdout
     if mangled not in out:
       continue
     # cut the function's text section
-    m = re.search(r"\.section\s+\.text\.[^\n]*%s[^\n]*\n" % re.escape(mangled), out)
+    m = re.search(r"\.section\s+\.text\.[^\n]*%s[^\n]*\n" % (re.escape(mangled) + re.escape(extra)), out)
     if not m:
       continue
     seg = out[m.end():]
