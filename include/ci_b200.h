@@ -51,12 +51,20 @@ enum { CI_WITH_PRIOR = 1     /* add log prior + Jacobian: value is the HMC targe
 
 /* The model + priors.  Replaces the TFP StructuralTimeSeries object built by
  * _build_default_gibbs_model (causalimpact/causalimpact_lib.py:398-500):
- *   obs_*   InverseGamma(conc, scale) on sigma_obs^2, obs_ub bounds the SCALE
- *           sigma_obs                                   (lib.py:434-443)
+ *   obs_*   InverseGamma(conc, scale) on sigma_obs^2; obs_ub is the `upper_bound`
+ *           attribute the reference hangs on that prior (lib.py:434-443)
  *   lvl_*   same for the local-level random walk        (lib.py:424-432)
  *   slope_* same for the trend slope (extension; the reference has no slope,
  *           lib.py:496) -- ignored when model == 0
  *   m0, P0  initial level ~ N(m0, P0)                   (lib.py:467-469)
+ *   ub_on_scale  what the *_ub bounds (and ci_seasonal.drift_ub) limit.  The reference sets
+ *           `prior.upper_bound = sd` on InverseGamma priors OVER VARIANCES (lib.py:432,
+ *           442-443, 474) and TFP's Gibbs sampler clips the sampled variance:
+ *           sample_parameters.sample_with_optional_upper_bound and the spike-and-slab
+ *           sampler's observation_noise_variance_upper_bound both do min(variance, bound).
+ *             0 (default)  bound on the VARIANCE: sigma^2 <= ub           (TFP semantics)
+ *             1            bound on the SCALE:    sigma   <= ub           (round-1 behaviour)
+ *           Gibbs kernels clip the draw, the HMC target truncates the prior at the bound.
  */
 typedef struct {
   int32_t model;    /* CI_MODEL_*                                            */
@@ -69,6 +77,8 @@ typedef struct {
   double slope_conc, slope_scale, slope_ub;
   double m0, P0;
   double m0_slope, P0_slope;
+  int32_t ub_on_scale;  /* 0: *_ub limit variances (TFP), 1: they limit scales         */
+  int32_t reserved;
 } ci_problem;
 
 /* HMC driver options (replaces num_results / num_warmup_steps handed to
@@ -159,6 +169,15 @@ typedef struct {
                              1: outputs [C, n_results, .] -- every chain's draws contiguous,
                                 the layout the multi-GPU all-gather wants             */
   double nonzero_prob;
+  int32_t ssvs_order;     /* order in which a sweep visits the features' inclusion indicators:
+                             0 = a fresh random permutation per sweep (Philox; TFP's sampler
+                                 permutes the features), 1 = index order 0..p-1             */
+  int32_t reserved;
+  uint64_t series_stride; /* batched runs only: series s uses the global chain ids
+                             chain_id0 + s * series_stride + c.  0 = every series consumes the
+                             SAME random streams (bit-identical to a single-series run, but the
+                             Monte-Carlo errors of the series are then perfectly correlated);
+                             >= n_chains gives every series its own streams                */
 } ci_gibbs_opts;
 
 int ci_gibbs_run(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,

@@ -37,8 +37,10 @@ def logpost_grad(prob, theta, with_prior=True, want_grad=True, nthreads=0):
   y = np.ascontiguousarray(prob.y, np.float64)
   X = np.ascontiguousarray(prob.X if p else np.zeros((prob.T, 0)), np.float64)
   Om = np.ascontiguousarray(prob.Omega if p else np.zeros((0, 0)), np.float64)
-  prior = np.array([prob.m0, prob.P0, prob.obs_conc, prob.obs_scale, prob.obs_ub,
-                    prob.lvl_conc, prob.lvl_scale, prob.lvl_ub], np.float64)
+  # (the C port bounds the scale: hand it the square root of the variance bound)
+  prior = np.array([prob.m0, prob.P0, prob.obs_conc, prob.obs_scale,
+                    np.sqrt(prob.ub_var(prob.obs_ub)), prob.lvl_conc, prob.lvl_scale,
+                    np.sqrt(prob.ub_var(prob.lvl_ub))], np.float64)
   val = np.empty(n); grad = np.empty_like(theta) if want_grad else None
   used = lib.ci_oracle_logpost_grad(_dp(y), _dp(X), _dp(Om), prob.T, p, _dp(prior), _dp(theta),
                                     n, _dp(val), _dp(grad), int(with_prior), nthreads)

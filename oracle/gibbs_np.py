@@ -98,7 +98,7 @@ def run(prob, *, n_results, n_warmup, seed, prior_level_sd=0.01, sparse=False):
       else:
         sse = yty
       s_e = 1.0 / rng.gamma(prob.obs_conc + 0.5 * n_obs, 1.0 / (prob.obs_scale + 0.5 * sse))
-      s_e = min(s_e, prob.obs_ub ** 2)
+      s_e = min(s_e, prob.ub_var(prob.obs_ub))
       if idx.size:
         w[idx] = wbar + np.sqrt(s_e) * np.linalg.solve(Lc.T, rng.normal(size=idx.size))
       r = prob.y - prob.X @ w
@@ -108,7 +108,7 @@ def run(prob, *, n_results, n_warmup, seed, prior_level_sd=0.01, sparse=False):
       wbar = np.linalg.solve(Lam, b)
       sse = float(targ @ targ - wbar @ Lam @ wbar)
       s_e = 1.0 / rng.gamma(prob.obs_conc + 0.5 * n_obs, 1.0 / (prob.obs_scale + 0.5 * sse))
-      s_e = min(s_e, prob.obs_ub ** 2)
+      s_e = min(s_e, prob.ub_var(prob.obs_ub))
       w = wbar + np.sqrt(s_e) * np.linalg.solve(Lam_chol.T, rng.normal(size=p))
       r = prob.y - prob.X @ w
     else:
@@ -117,11 +117,11 @@ def run(prob, *, n_results, n_warmup, seed, prior_level_sd=0.01, sparse=False):
     level = SM.ffbs_path(m, Cv, s_h, rng.normal(size=T))
     dl = np.diff(level)
     s_h = 1.0 / rng.gamma(prob.lvl_conc + 0.5 * (T - 1), 1.0 / (prob.lvl_scale + 0.5 * dl @ dl))
-    s_h = min(s_h, prob.lvl_ub ** 2)
+    s_h = min(s_h, prob.ub_var(prob.lvl_ub))
     if not p:
       e = (prob.y - level)[obs]
       s_e = 1.0 / rng.gamma(prob.obs_conc + 0.5 * n_obs, 1.0 / (prob.obs_scale + 0.5 * e @ e))
-      s_e = min(s_e, prob.obs_ub ** 2)
+      s_e = min(s_e, prob.ub_var(prob.obs_ub))
     if it >= n_warmup:
       out["w"].append(w.copy()); out["s_e"].append(s_e); out["s_h"].append(s_h)
       out["level"].append(level.copy())

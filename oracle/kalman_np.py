@@ -47,15 +47,22 @@ class Problem:
   P0: float                     # initial level variance = sd^2
   obs_conc: float               # InvGamma on sigma_obs^2      (lib.py:434-441)
   obs_scale: float
-  obs_ub: float                 # upper bound on the SCALE sigma_obs (lib.py:442-443)
+  obs_ub: float                 # the prior's `upper_bound` (lib.py:442-443); see ub_on_scale
   lvl_conc: float               # InvGamma on sigma_level^2    (lib.py:424-431)
   lvl_scale: float
-  lvl_ub: float                 # upper bound on sigma_level   (lib.py:432)
+  lvl_ub: float                 # the prior's `upper_bound` (lib.py:432)
   slope_conc: float = 16.0      # extension: no reference counterpart (lib.py:496)
   slope_scale: float = 0.0
   slope_ub: float = np.inf
   m0_slope: float = 0.0
   P0_slope: float = 1.0
+  # what the *_ub limit: the reference puts `upper_bound` on InverseGamma priors over VARIANCES
+  # and TFP clips the variance draw (min(variance, upper_bound)) -> False; True = the scale
+  ub_on_scale: bool = False
+
+  def ub_var(self, ub: float) -> float:
+    """The bound expressed on the variance."""
+    return ub * ub if self.ub_on_scale else ub
 
   @property
   def T(self) -> int:
@@ -296,9 +303,9 @@ def _unpack(prob: Problem, theta: np.ndarray):
 def in_support(prob: Problem, theta) -> np.ndarray:
   """upper_bound clamps of the reference (lib.py:432, 442-443) as a truncation."""
   theta, W, s_e, s_h, s_z = _unpack(prob, theta)
-  ok = (np.sqrt(s_e) <= prob.obs_ub) & (np.sqrt(s_h) <= prob.lvl_ub)
+  ok = (s_e <= prob.ub_var(prob.obs_ub)) & (s_h <= prob.ub_var(prob.lvl_ub))
   if s_z is not None:
-    ok &= np.sqrt(s_z) <= prob.slope_ub
+    ok &= s_z <= prob.ub_var(prob.slope_ub)
   return ok & np.all(np.isfinite(theta), axis=1)
 
 

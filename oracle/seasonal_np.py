@@ -78,7 +78,7 @@ class SeasonalSpec:
   init_sd: float               # initial_effect_prior scale (lib.py:489: outcome_sd)
   drift_conc: float            # InverseGamma on the drift VARIANCE (lib.py:472-473)
   drift_scale: float
-  drift_ub: float              # upper bound (lib.py:474), applied as min(scale, ub) like gibbs_np
+  drift_ub: float              # the prior's upper_bound (lib.py:474), applied like gibbs_np (Problem.ub_on_scale)
 
   @property
   def K(self):
@@ -322,14 +322,14 @@ def run(prob, sp: SeasonalSpec, *, n_results, n_warmup, seed, prior_level_sd=0.0
         wbar = np.linalg.solve(Lg, Xty[idx])
         sse = yty - wbar @ Lg @ wbar
       s_e = min(1.0 / rng.gamma(prob.obs_conc + 0.5 * n_obs, 1.0 / (prob.obs_scale + 0.5 * sse)),
-                prob.obs_ub ** 2)
+                prob.ub_var(prob.obs_ub))
       if idx.size:
         w[idx] = wbar + np.sqrt(s_e) * np.linalg.solve(Lc.T, rng.normal(size=idx.size))
       r = prob.y - prob.X @ w
     else:
       # no covariates: sigma_obs^2 from y - level - seasonal (sweep 0: latent = 0)
       s_e = min(1.0 / rng.gamma(prob.obs_conc + 0.5 * n_obs, 1.0 / (prob.obs_scale + 0.5 * yty)),
-                prob.obs_ub ** 2)
+                prob.ub_var(prob.obs_ub))
       r = prob.y
     x = posterior_state_draw(sp, np.where(obs, r, 0.0), prob.mask, s_e, s_h, s_d, prob.m0, prob.P0,
                              rng)
@@ -339,14 +339,14 @@ def run(prob, sp: SeasonalSpec, *, n_results, n_warmup, seed, prior_level_sd=0.0
     latent = level + seas.sum(axis=1)
     dl = np.diff(level)
     s_h = min(1.0 / rng.gamma(prob.lvl_conc + 0.5 * (T - 1), 1.0 / (prob.lvl_scale + 0.5 * dl @ dl)),
-              prob.lvl_ub ** 2)
+              prob.ub_var(prob.lvl_ub))
     for k in range(K):
       # the season-end increment is u * C e_j; its j-th entry is u (1 - 1/n)
       tt = np.flatnonzero(sp.ends[k, :T - 1])
       j = sp.offsets[k] + sp.idx[k, tt]
       u = (x[tt + 1, j] - x[tt, j]) / (1.0 - 1.0 / sp.n[k])
       s_d[k] = min(1.0 / rng.gamma(sp.drift_conc + 0.5 * n_ends[k],
-                                   1.0 / (sp.drift_scale + 0.5 * u @ u)), sp.drift_ub ** 2)
+                                   1.0 / (sp.drift_scale + 0.5 * u @ u)), prob.ub_var(sp.drift_ub))
     if it >= n_warmup:
       out["w"].append(w.copy()); out["s_e"].append(s_e); out["s_h"].append(s_h)
       out["s_d"].append(s_d.copy()); out["level"].append(level.copy()); out["seasonal"].append(seas)

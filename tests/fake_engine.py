@@ -24,7 +24,8 @@ class FakeEngine:
         X=None if spec.X is None else np.asarray(spec.X, float),
         Omega=None if spec.Omega is None else np.asarray(spec.Omega, float),
         m0=spec.m0, P0=spec.P0, obs_conc=spec.obs_conc, obs_scale=spec.obs_scale,
-        obs_ub=spec.obs_ub, lvl_conc=spec.lvl_conc, lvl_scale=spec.lvl_scale, lvl_ub=spec.lvl_ub)
+        obs_ub=spec.obs_ub, lvl_conc=spec.lvl_conc, lvl_scale=spec.lvl_scale, lvl_ub=spec.lvl_ub,
+        ub_on_scale=bool(getattr(spec, "ub_on_scale", False)))
 
   def hmc_run(self, theta0, *, n_warmup, n_results, seed, chain_id0=0, max_leapfrog=8,
               init_step=0.05, target_accept=0.8, adapt_mass=True):
@@ -37,7 +38,7 @@ class FakeEngine:
     return draws.astype(self.spec.np_dtype), stats
 
   def gibbs_run(self, n_chains, *, n_warmup, n_results, seed, chain_id0=0, sparse=True,
-                nonzero_prob=None, want_level=True, want_traj=True):
+                nonzero_prob=None, want_level=True, want_traj=True, ssvs_order="random"):
     from oracle import gibbs_np as G
     sp, dt = self.spec, self.spec.np_dtype
     draws = np.empty((n_results, n_chains, sp.dim), dt)
@@ -100,7 +101,7 @@ class FakeEngine:
     self.seasonal = sched
 
   def gibbs_seasonal_run_t(self, n_chains, *, n_warmup, n_results, seed, chain_id0=0, sparse=True,
-                           nonzero_prob=None):
+                           nonzero_prob=None, ssvs_order="random"):
     import torch
     from oracle import seasonal_np as S
     sp, dt, sc = self.spec, self.spec.np_dtype, self.seasonal
@@ -134,12 +135,13 @@ class FakeEngine:
   def batch_select(self, i, spec=None):
     self.set_data(spec if spec is not None else self.batch_specs[i])
 
-  def gibbs_run_batch_t(self, n_chains, **kw):
+  def gibbs_run_batch_t(self, n_chains, series_stride=0, chain_id0=0, **kw):
     import torch
     outs = []
     for i in range(len(self.batch_specs)):
       self.batch_select(i)
-      outs.append(self.gibbs_run_t(n_chains, **kw))
+      # series i uses the global chain ids chain_id0 + i * series_stride + c (ci_gibbs_opts)
+      outs.append(self.gibbs_run_t(n_chains, chain_id0=chain_id0 + i * series_stride, **kw))
     self.batch_select(0)
     return (torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]),
             torch.stack([o[2] for o in outs]), np.stack([o[3] for o in outs]))

@@ -27,10 +27,10 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
   import ctypes
   from causalimpact_b200 import _engine
-  assert ctypes.sizeof(_engine.CiProblem) == 4 * 4 + 13 * 8
+  assert ctypes.sizeof(_engine.CiProblem) == 4 * 4 + 13 * 8 + 2 * 4
   assert ctypes.sizeof(_engine.CiHmcOpts) == 4 * 4 + 2 * 8
   assert ctypes.sizeof(_engine.CiHmcStats) == 16 == _engine.HMC_STATS_DTYPE.itemsize
-  assert ctypes.sizeof(_engine.CiGibbsOpts) == 4 * 4 + 8
+  assert ctypes.sizeof(_engine.CiGibbsOpts) == 4 * 4 + 8 + 2 * 4 + 8
   assert ctypes.sizeof(_engine.CiImpactArgs) == 4 * 4 + 5 * 8
   assert ctypes.sizeof(_engine.CiSeasonal) == 8 * 4 + 2 * 8 + 4 * 8
   assert _engine.MAX_SEASONAL == 7 and _engine.IMPACT_SERIES_COLS == 9

@@ -34,7 +34,7 @@ def test_many_equals_one_by_one(n_cov):
   dfs = panel(5, 120, n_cov, 3, 90)
   pre, post = (dfs[0].index[0], dfs[0].index[89]), (dfs[0].index[90], dfs[0].index[-1])
   kw = dict(seed=(2, 5), inference_options=ci.InferenceOptions(num_results=150))
-  eo = ci.EngineOptions(num_chains=12, sampler="gibbs")
+  eo = ci.EngineOptions(num_chains=12, sampler="gibbs", decorrelate_series=False)
   many = ci.fit_causalimpact_many(dfs, pre, post, engine_options=eo, **kw)
   assert len(many) == 5
   for df, got in zip(dfs, many):
@@ -88,7 +88,8 @@ def test_no_covariates_batch():
   for d in dfs:
     d.iloc[70:, 0] += 3
   many = ci.fit_causalimpact_many(dfs, (idx[0], idx[69]), (idx[70], idx[-1]), seed=1,
-                                  inference_options=ci.InferenceOptions(num_results=64))
+                                  inference_options=ci.InferenceOptions(num_results=64),
+                                  engine_options=ci.EngineOptions(decorrelate_series=False))
   for df, got in zip(dfs, many):
     one = ci.fit_causalimpact(df, (idx[0], idx[69]), (idx[70], idx[-1]), seed=1,
                               inference_options=ci.InferenceOptions(num_results=64),
@@ -147,7 +148,7 @@ def test_seasonal_panel_and_many_equal_single_seasonal_fits():
   pre, post = (idx[0], idx[99]), (idx[100], idx[-1])
   mo = ci.ModelOptions(seasons=[ci.Seasons(num_seasons=7)])
   kw = dict(seed=5, model_options=mo, inference_options=ci.InferenceOptions(num_results=96),
-            engine_options=ci.EngineOptions(num_chains=8))
+            engine_options=ci.EngineOptions(num_chains=8, decorrelate_series=False))
   many = ci.fit_causalimpact_many(dfs, pre, post, **kw)
   res = ci.fit_causalimpact_panel(np.stack([d.values for d in dfs]), idx, pre, post,
                                   keep_level=True, **kw)

@@ -46,8 +46,9 @@ def test_spike_and_slab_matches_restated_reference_sampler(engine):
                      (np.exp(d[:, spec.p + 1] / 2), np.sqrt(ob["s_h"]), "sigma_level")):
     ok, info = _close(a, b, 2e-3)
     assert ok, (name, info)
-  assert np.all(np.exp(d[:, spec.p] / 2) <= spec.obs_ub * (1 + 1e-6))
-  assert np.all(np.exp(d[:, spec.p + 1] / 2) <= spec.lvl_ub * (1 + 1e-6))
+  # the reference's upper bounds limit the VARIANCES (ci_problem.ub_on_scale = 0)
+  assert np.all(np.exp(d[:, spec.p]) <= spec.obs_ub * (1 + 1e-6))
+  assert np.all(np.exp(d[:, spec.p + 1]) <= spec.lvl_ub * (1 + 1e-6))
   # counterfactual (level + X w) over the masked post-period
   post = np.isnan(y); post[:210] = False
   loc_gpu = (level.reshape(-1, spec.T) + w @ X.T)[:, post].mean(1)

@@ -63,7 +63,7 @@ def test_out_of_support_and_bad_inputs(engine):
   spec = cib.build_problem(y, X)
   engine.set_data(spec)
   th = make_thetas(spec.dim, spec.p, 4, 1)
-  th[0, spec.p] = np.log((spec.obs_ub * 1.05) ** 2)
+  th[0, spec.p] = np.log(spec.ub_variance(spec.obs_ub) * 1.1)
   v = engine.logprob(th, with_prior=True)
   assert np.isneginf(v[0]) and np.all(np.isfinite(v[1:]))
   with pytest.raises(ValueError):

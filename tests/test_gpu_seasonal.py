@@ -167,8 +167,8 @@ def test_limits_and_errors(engine):
   rng = np.random.default_rng(1)
   y = rng.normal(size=80); y[60:] = np.nan
   engine.set_data(ci.build_problem(y, None, outcome_sd=1.0))
-  with pytest.raises(EngineError, match="state dimension"):
-    engine.set_seasonal(model.build_seasonal(seasons((24, 1), (12, 2)), 80, 1.0))
+  with pytest.raises(ValueError, match="state dimension"):       # checked on the host, loudly
+    model.build_seasonal(seasons((24, 1), (12, 2)), 80, 1.0)
   engine.set_seasonal(None)
   with pytest.raises(EngineError, match="ci_set_seasonal"):
     engine.seasonal = model.build_seasonal(seasons((7, 1)), 80, 1.0)

@@ -12,7 +12,7 @@ def test_c_port_equals_numpy_oracle(T, n_cov):
   y, X, _ = make_series(T, n_cov, 3)
   prob = K.default_problem(y, X)
   th = make_thetas(prob.dim, prob.p, 9, 2)
-  th[0, prob.p] = np.log((prob.obs_ub * 1.1) ** 2)        # out of support
+  th[0, prob.p] = np.log(prob.ub_var(prob.obs_ub) * 1.2)        # out of support
   v, g, used = c_port.logpost_grad(prob, th)
   ov, og = K.log_post_grad(prob, th)
   np.testing.assert_allclose(v, ov, rtol=1e-12, atol=1e-10)

@@ -77,8 +77,8 @@ def test_scan_formulation_equals_sequential():
 
 def test_out_of_support_is_minus_inf():
   prob, th = _toy(0)
-  th[0, prob.p] = np.log((prob.obs_ub * 1.01) ** 2)
-  th[1, prob.p + 1] = np.log((prob.lvl_ub * 1.01) ** 2)
+  th[0, prob.p] = np.log(prob.ub_var(prob.obs_ub) * 1.02)
+  th[1, prob.p + 1] = np.log(prob.ub_var(prob.lvl_ub) * 1.02)
   v = K.log_post(prob, th)
   assert np.isneginf(v[0]) and np.isneginf(v[1]) and np.isfinite(v[2])
 

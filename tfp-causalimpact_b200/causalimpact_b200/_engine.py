@@ -31,7 +31,8 @@ class CiProblem(C.Structure):
               ("lvl_conc", C.c_double), ("lvl_scale", C.c_double), ("lvl_ub", C.c_double),
               ("slope_conc", C.c_double), ("slope_scale", C.c_double), ("slope_ub", C.c_double),
               ("m0", C.c_double), ("P0", C.c_double),
-              ("m0_slope", C.c_double), ("P0_slope", C.c_double)]
+              ("m0_slope", C.c_double), ("P0_slope", C.c_double),
+              ("ub_on_scale", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CiHmcOpts(C.Structure):
@@ -41,7 +42,10 @@ class CiHmcOpts(C.Structure):
 
 class CiGibbsOpts(C.Structure):
   _fields_ = [("n_warmup", C.c_int32), ("n_results", C.c_int32), ("sparse", C.c_int32),
-              ("chain_major", C.c_int32), ("nonzero_prob", C.c_double)]
+              ("chain_major", C.c_int32), ("nonzero_prob", C.c_double),
+              ("ssvs_order", C.c_int32), ("reserved", C.c_int32), ("series_stride", C.c_uint64)]
+
+SSVS_ORDER = {"random": 0, "index": 1}
 
 
 class CiImpactArgs(C.Structure):
@@ -153,6 +157,11 @@ class ProblemSpec:
   slope_ub: float = float("inf")
   m0_slope: float = 0.0
   P0_slope: float = 1.0
+  ub_on_scale: bool = False           # False: the *_ub bound VARIANCES (TFP), True: scales
+
+  def ub_variance(self, ub: float) -> float:
+    """The bound `ub` expressed on the variance."""
+    return float(ub) ** 2 if self.ub_on_scale else float(ub)
 
   @property
   def T(self) -> int:
@@ -267,7 +276,8 @@ class Engine:
                      lvl_conc=spec.lvl_conc, lvl_scale=spec.lvl_scale, lvl_ub=spec.lvl_ub,
                      slope_conc=spec.slope_conc, slope_scale=spec.slope_scale,
                      slope_ub=min(spec.slope_ub, 1e300), m0=spec.m0, P0=spec.P0,
-                     m0_slope=spec.m0_slope, P0_slope=spec.P0_slope)
+                     m0_slope=spec.m0_slope, P0_slope=spec.P0_slope,
+                     ub_on_scale=int(bool(spec.ub_on_scale)), reserved=0)
 
   # -- batches of independent series -----------------------------
   def set_data_batch(self, specs):
@@ -294,7 +304,8 @@ class Engine:
 
   def gibbs_run_batch_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
                         chain_id0: int = 0, sparse: bool = True,
-                        nonzero_prob: Optional[float] = None):
+                        nonzero_prob: Optional[float] = None, ssvs_order: str = "random",
+                        series_stride: int = 0):
     """ci_gibbs_run_batch_d, chain-major: device tensors theta [N, R, dim], level [N, R, T],
     traj [N, R, T] (R = n_chains * n_results) and incl [N, n_chains, p] ndarray."""
     torch, dev = self._torch_dev()
@@ -307,7 +318,8 @@ class Engine:
     traj = torch.empty((N, rows, sp.T), dtype=dt, device=dev)
     incl = torch.zeros((N, n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
     opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
-                       nonzero_prob=float(nonzero_prob))
+                       nonzero_prob=float(nonzero_prob), ssvs_order=SSVS_ORDER[ssvs_order],
+                       reserved=0, series_stride=int(series_stride))
     self._check(self._lib.ci_gibbs_run_batch_d(
         self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, draws.data_ptr(),
         level.data_ptr(), traj.data_ptr(), incl.data_ptr(), self._stream(torch)))
@@ -333,7 +345,8 @@ class Engine:
 
   def gibbs_seasonal_run_batch_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
                                  chain_id0: int = 0, sparse: bool = True,
-                                 nonzero_prob: Optional[float] = None):
+                                 nonzero_prob: Optional[float] = None, ssvs_order: str = "random",
+                                 series_stride: int = 0):
     """ci_gibbs_seasonal_run_batch_d, chain-major device tensors with a leading series axis:
     (theta [N,R,dim], level, latent, traj [N,R,T], seasonal [N,R,T,K], log drift variance
     [N,R,K], incl [N,C,p] ndarray)."""
@@ -347,7 +360,8 @@ class Engine:
     seas, drift = mk(N, rows, sp.T, K), mk(N, rows, K)
     incl = torch.zeros((N, n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
     opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
-                       nonzero_prob=float(nonzero_prob))
+                       nonzero_prob=float(nonzero_prob), ssvs_order=SSVS_ORDER[ssvs_order],
+                       reserved=0, series_stride=int(series_stride))
     self._check(self._lib.ci_gibbs_seasonal_run_batch_d(
         self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, draws.data_ptr(),
         level.data_ptr(), traj.data_ptr(), incl.data_ptr(), latent.data_ptr(), seas.data_ptr(),
@@ -376,7 +390,7 @@ class Engine:
 
   def gibbs_seasonal_run(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
                          chain_id0: int = 0, sparse: bool = True,
-                         nonzero_prob: Optional[float] = None):
+                         nonzero_prob: Optional[float] = None, ssvs_order: str = "random"):
     """Host-buffer ci_gibbs_seasonal_run.  Returns dict: draws [n_results, C, dim], level,
     latent, traj [n_results, C, T], seasonal [n_results, C, T, K], drift [n_results, C, K]
     (drift SCALES), incl [C, p]."""
@@ -390,7 +404,8 @@ class Engine:
                seasonal=np.empty(shp + (sp.T, K), dt), drift=np.empty(shp + (K,), dt))
     incl = np.zeros((n_chains, max(sp.p, 1)), dtype=np.float32)
     opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=0,
-                       nonzero_prob=float(nonzero_prob))
+                       nonzero_prob=float(nonzero_prob), ssvs_order=SSVS_ORDER[ssvs_order],
+                       reserved=0, series_stride=0)
     self._check(self._lib.ci_gibbs_seasonal_run(
         self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, _ptr(out["draws"]),
         _ptr(out["level"]), _ptr(out["traj"]), _ptr(incl), _ptr(out["latent"]),
@@ -401,7 +416,7 @@ class Engine:
 
   def gibbs_seasonal_run_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
                            chain_id0: int = 0, sparse: bool = True,
-                           nonzero_prob: Optional[float] = None):
+                           nonzero_prob: Optional[float] = None, ssvs_order: str = "random"):
     """ci_gibbs_seasonal_run_d, chain-major device tensors: (theta [R, dim], level [R, T],
     latent [R, T], traj [R, T], seasonal [R, T, K], log drift variance [R, K], incl ndarray),
     R = C * n_results."""
@@ -415,7 +430,8 @@ class Engine:
     seas, drift = mk(rows, sp.T, K), mk(rows, K)
     incl = torch.zeros((n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
     opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
-                       nonzero_prob=float(nonzero_prob))
+                       nonzero_prob=float(nonzero_prob), ssvs_order=SSVS_ORDER[ssvs_order],
+                       reserved=0, series_stride=0)
     self._check(self._lib.ci_gibbs_seasonal_run_d(
         self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0, n_chains, draws.data_ptr(),
         level.data_ptr(), traj.data_ptr(), incl.data_ptr(), latent.data_ptr(), seas.data_ptr(),
@@ -474,7 +490,7 @@ class Engine:
   # -- the reference's Gibbs sampler (spike-and-slab) --------------------------
   def gibbs_run(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
                 chain_id0: int = 0, sparse: bool = True, nonzero_prob: Optional[float] = None,
-                want_level: bool = True, want_traj: bool = True):
+                want_level: bool = True, want_traj: bool = True, ssvs_order: str = "random"):
     """Returns draws [n_results, C, dim], level, traj [n_results, C, T], incl [C, p]."""
     sp = self.spec
     if nonzero_prob is None:
@@ -484,8 +500,9 @@ class Engine:
     level = np.empty((n_results, n_chains, sp.T), dtype=dt) if want_level else None
     traj = np.empty((n_results, n_chains, sp.T), dtype=dt) if want_traj else None
     incl = np.zeros((n_chains, max(sp.p, 1)), dtype=np.float32)
-    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), reserved=0,
-                       nonzero_prob=float(nonzero_prob))
+    opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=0,
+                       nonzero_prob=float(nonzero_prob), ssvs_order=SSVS_ORDER[ssvs_order],
+                       reserved=0, series_stride=0)
     self._check(self._lib.ci_gibbs_run(self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0,
                                        n_chains, _ptr(draws), _ptr(level), _ptr(traj),
                                        _ptr(incl)))
@@ -507,6 +524,10 @@ class Engine:
   def _torch_dev(self):
     import torch
     return torch, torch.device("cuda", self.device)
+
+  def torch_device(self):
+    """torch.device of this engine's GPU."""
+    return self._torch_dev()[1]
 
   def _tdtype(self, torch):
     return torch.float64 if self.spec.dtype == F64 else torch.float32
@@ -539,7 +560,8 @@ class Engine:
     return draws, stats.cpu().numpy().view(HMC_STATS_DTYPE)
 
   def gibbs_run_t(self, n_chains: int, *, n_warmup: int, n_results: int, seed: int,
-                  chain_id0: int = 0, sparse: bool = True, nonzero_prob: Optional[float] = None):
+                  chain_id0: int = 0, sparse: bool = True, nonzero_prob: Optional[float] = None,
+                  ssvs_order: str = "random"):
     """ci_gibbs_run_d, chain-major: returns (theta [C*n_results, dim], level [C*n_results, T],
     traj [C*n_results, T]) device tensors -- row c*n_results + i is kept sweep i of chain c --
     and incl [C, p] ndarray."""
@@ -553,7 +575,8 @@ class Engine:
     traj = torch.empty((rows, sp.T), dtype=dt, device=dev)
     incl = torch.zeros((n_chains, max(sp.p, 1)), dtype=torch.float32, device=dev)
     opts = CiGibbsOpts(n_warmup=n_warmup, n_results=n_results, sparse=int(sparse), chain_major=1,
-                       nonzero_prob=float(nonzero_prob))
+                       nonzero_prob=float(nonzero_prob), ssvs_order=SSVS_ORDER[ssvs_order],
+                       reserved=0, series_stride=0)
     self._check(self._lib.ci_gibbs_run_d(self._ctx, C.byref(opts), seed & (2**64 - 1), chain_id0,
                                          n_chains, draws.data_ptr(), level.data_ptr(),
                                          traj.data_ptr(), incl.data_ptr(), self._stream(torch)))

@@ -109,6 +109,15 @@ class EngineOptions:
     is then the continuous slab and HMC targets exactly the reference's posterior),
     the GPU Gibbs kernel with spike-and-slab otherwise; "hmc" forces HMC on the
     slab-only model, "gibbs" forces the Gibbs kernel.
+  upper_bound_on: what the reference's ``prior.upper_bound`` attributes (lib.py:432,
+    442-443, 474) limit: "variance" (default; TFP clips the sampled variance with
+    ``min(variance, upper_bound)``) or "scale" (sigma <= bound; the round-1 reading).
+  ssvs_order: order in which a Gibbs sweep visits the spike-and-slab inclusion indicators:
+    "random" (a fresh Philox permutation per sweep, like TFP's sampler) or "index".
+  decorrelate_series: batched fits (``fit_causalimpact_many`` / ``_panel``) give series i the
+    global chain ids ``i * num_chains + c``, so the Monte-Carlo errors of different series are
+    independent and panel aggregates average them out.  False: every series consumes the same
+    streams and result i is bit-identical to ``fit_causalimpact(datas[i], sampler="gibbs")``.
   """
   num_chains: int = 64
   sampler: str = "auto"
@@ -119,6 +128,9 @@ class EngineOptions:
   target_accept: float = 0.8
   device: Optional[int] = None
   whiten: bool = True
+  upper_bound_on: str = "variance"
+  ssvs_order: str = "random"
+  decorrelate_series: bool = True
 
 
 _ENGINES = {}
@@ -205,10 +217,14 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
 
   rank, ws = _shard.world()
   eng = _resolve_engine(opts)
+  if seed is None and ws > 1:          # fresh entropy: every rank must use rank 0's
+    seed64 = _shard.broadcast_u64(seed64, getattr(eng, "torch_device", lambda: None)())
 
   y_ext, design, outcome_sd = ci_data.engine_inputs(np_dt)
+  if opts.upper_bound_on not in ("variance", "scale"):
+    raise ValueError(f"EngineOptions.upper_bound_on must be variance|scale, got {opts.upper_bound_on!r}")
   spec = build_problem(y_ext, design, prior_level_sd=prior_level_sd, outcome_sd=outcome_sd,
-                       dtype=np_dt)
+                       dtype=np_dt, ub_on_scale=opts.upper_bound_on == "scale")
   p, T = spec.p, spec.T
   if opts.sampler not in ("auto", "hmc", "gibbs"):
     raise ValueError(f"EngineOptions.sampler must be auto|hmc|gibbs, got {opts.sampler!r}")
@@ -239,7 +255,7 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
     n_warm = max(int(num_warmup_steps), int(opts.gibbs_min_warmup))
     theta_l, level_l, latent_l, traj_l, seas_l, drift_l, incl = eng.gibbs_seasonal_run_t(
         max(c_local, 1), n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=c0,
-        sparse=True)
+        sparse=True, ssvs_order=opts.ssvs_order)
     extra_l = [latent_l, seas_l.reshape(seas_l.shape[0], T * K), drift_l]
     stats = {"sampler": "gibbs", "inclusion": incl[:c_local]}
   elif use_gibbs:
@@ -248,7 +264,8 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
     n_warm = max(int(num_warmup_steps), int(opts.gibbs_min_warmup))
     theta_l, level_l, traj_l, incl = eng.gibbs_run_t(max(c_local, 1), n_warmup=n_warm,
                                                      n_results=n_per, seed=seed64,
-                                                     chain_id0=c0, sparse=True)
+                                                     chain_id0=c0, sparse=True,
+                                                     ssvs_order=opts.ssvs_order)
     stats = {"sampler": "gibbs", "inclusion": incl[:c_local]}
   else:
     rng = np.random.Generator(np.random.Philox(key=seed64))
@@ -261,8 +278,8 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
     theta0[:, p:] += 0.1 * rng.normal(size=(C, spec.dim - p))
     # keep every start strictly inside the truncated support (lib.py:432, 442-443):
     # a chain that starts at log-density -inf could never move
-    theta0[:, p] = np.minimum(theta0[:, p], 2.0 * np.log(0.9 * spec.obs_ub))
-    theta0[:, p + 1] = np.minimum(theta0[:, p + 1], 2.0 * np.log(0.9 * spec.lvl_ub))
+    theta0[:, p] = np.minimum(theta0[:, p], np.log(0.8 * spec.ub_variance(spec.obs_ub)))
+    theta0[:, p + 1] = np.minimum(theta0[:, p + 1], np.log(0.8 * spec.ub_variance(spec.lvl_ub)))
     n_warm = max(int(num_warmup_steps), int(opts.min_warmup))
     # a rank without chains (more ranks than chains) still runs one throw-away chain so
     # that every rank holds tensors of the right width for the all-gather
@@ -414,9 +431,11 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
   covariates.  Every series is prepared exactly as ``fit_causalimpact`` does (data.py:77-137),
   all of them are uploaded together (``ci_set_data_batch``) and ONE launch of the reference's
   sampler (``ci_gibbs_run_batch_d``: spike-and-slab Gibbs, grid.y = series) draws every chain
-  of every series; predictive mean and impact follow per series on the device.  Result i is
-  bit-identical to ``fit_causalimpact(datas[i], ..., engine_options=EngineOptions(
-  sampler="gibbs"))`` with the same seed.
+  of every series; predictive mean and impact follow per series on the device.  The batched
+  path always runs the Gibbs kernel (``fit_causalimpact(sampler="auto")`` picks HMC for <= 2
+  covariates).  With ``EngineOptions(decorrelate_series=False)`` result i is bit-identical to
+  ``fit_causalimpact(datas[i], ..., engine_options=EngineOptions(sampler="gibbs"))`` with the
+  same seed; by default every series draws from its own Philox streams.
 
   Multi-GPU: series are sharded over the ranks of an initialised process group (contiguous
   ranges, no collective: series are independent); a rank returns ``None`` for the series it
@@ -435,9 +454,11 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
   rank, ws = _shard.world()
   s0, n_local = _shard.split_range(len(datas), ws, rank)
   out = [None] * len(datas)
+  eng = _resolve_engine(opts)
+  if seed is None and ws > 1:
+    seed64 = _shard.broadcast_u64(seed64, getattr(eng, "torch_device", lambda: None)())
   if n_local == 0:
     return out
-  eng = _resolve_engine(opts)
   cids, specs, scheds = [], [], []
   for d in datas[s0:s0 + n_local]:
     cid = _frame.CausalImpactData(data=d, pre_period=pre_period, post_period=post_period,
@@ -445,7 +466,8 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
                                   standardize_data=data_options.standardize_data, dtype=np_dt)
     y_ext, design, outcome_sd = cid.engine_inputs(np_dt)
     specs.append(build_problem(y_ext, design, prior_level_sd=model_options.prior_level_sd,
-                               outcome_sd=outcome_sd, dtype=np_dt))
+                               outcome_sd=outcome_sd, dtype=np_dt,
+                               ub_on_scale=opts.upper_bound_on == "scale"))
     scheds.append(build_seasonal(seasons, specs[-1].T, outcome_sd))
     cids.append(cid)
   p, T = specs[0].p, specs[0].T
@@ -458,12 +480,14 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
   C = max(int(opts.num_chains), 1)
   n_per = max(1, math.ceil(num_results / C))
   n_warm = max(int(inference_options.num_warmup_steps), int(opts.gibbs_min_warmup))
+  # series i of the WHOLE input (not of this rank's shard) owns the chain ids i * C .. i * C + C - 1
+  stride = C if opts.decorrelate_series else 0
+  bkw = dict(n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=s0 * stride, sparse=True,
+             ssvs_order=opts.ssvs_order, series_stride=stride)
   if seasons:
-    theta, level, latent, traj, seas, drift, incl = eng.gibbs_seasonal_run_batch_t(
-        C, n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=0, sparse=True)
+    theta, level, latent, traj, seas, drift, incl = eng.gibbs_seasonal_run_batch_t(C, **bkw)
   else:
-    theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
-                                                     seed=seed64, chain_id0=0, sparse=True)
+    theta, level, traj, incl = eng.gibbs_run_batch_t(C, **bkw)
     latent = level
   for i, cid in enumerate(cids):
     eng.batch_select(i, specs[i])

@@ -27,7 +27,7 @@ def slab_precision(design: np.ndarray) -> np.ndarray:
 
 def build_problem(y_ext, design: Optional[np.ndarray], *, prior_level_sd: float = 0.01,
                   outcome_sd: Optional[float] = None, model: int = MODEL_LOCAL_LEVEL,
-                  dtype=np.float32) -> ProblemSpec:
+                  dtype=np.float32, ub_on_scale: bool = False) -> ProblemSpec:
   """Assemble the ``ci_problem`` the reference would hand to its sampler.
 
   Args:
@@ -39,6 +39,10 @@ def build_problem(y_ext, design: Optional[np.ndarray], *, prior_level_sd: float 
     prior_level_sd: ModelOptions.prior_level_sd (causalimpact_lib.py:202).
     outcome_sd: nanstd(pre y, ddof=1) (causalimpact_lib.py:563-564); computed
       from ``y_ext`` when omitted.
+    ub_on_scale: what the reference's ``prior.upper_bound`` attributes (:432, 442-443,
+      474) limit.  They sit on InverseGamma priors over VARIANCES and TFP's samplers clip
+      the variance draw (``min(variance, upper_bound)``), so the default is False: e.g.
+      sigma_obs^2 <= 1.2 sd.  True bounds the scale instead (sigma_obs <= 1.2 sd).
   """
   y_ext = np.asarray(y_ext, dtype=np.float64)
   seen = y_ext[~np.isnan(y_ext)]
@@ -66,7 +70,7 @@ def build_problem(y_ext, design: Optional[np.ndarray], *, prior_level_sd: float 
       lvl_conc=16.0, lvl_scale=16.0 * level0 * level0,           # :424-431
       lvl_ub=sd,                                                 # :432
       slope_conc=16.0, slope_scale=16.0 * level0 * level0, slope_ub=sd,
-      m0_slope=0.0, P0_slope=sd * sd)
+      m0_slope=0.0, P0_slope=sd * sd, ub_on_scale=bool(ub_on_scale))
 
 
 def initial_theta(spec: ProblemSpec, prior_level_sd: float = 0.01) -> np.ndarray:
@@ -84,6 +88,10 @@ def initial_theta(spec: ProblemSpec, prior_level_sd: float = 0.01) -> np.ndarray
 # ---------------------------------------------------------------------------
 # seasonal components (ModelOptions.seasons; causalimpact_lib.py:162-180, 471-489)
 # ---------------------------------------------------------------------------
+MAX_SEASONAL_COMPONENTS = 7     # csrc/ci_device.cuh: MAX_SEAS
+MAX_SEASONAL_STATE = 32         # csrc/ci_device.cuh: SEAS_MAXD (level + every seasonal effect)
+
+
 @dataclasses.dataclass
 class SeasonalSchedule:
   """What ``ci_set_seasonal`` needs: per component the active season of every step and
@@ -124,6 +132,15 @@ def build_seasonal(seasons: Sequence, T: int, outcome_sd: float) -> Optional[Sea
   if not seasons:
     return None
   K = len(seasons)
+  # the engine's limits (csrc/ci_device.cuh: MAX_SEAS, SEAS_MAXD), checked here with a clear
+  # message before anything is packed into uint8 calendars
+  if K > MAX_SEASONAL_COMPONENTS:
+    raise ValueError(f"at most {MAX_SEASONAL_COMPONENTS} seasonal components are supported, got {K}")
+  total = 1 + sum(int(s.num_seasons) for s in seasons)
+  if total > MAX_SEASONAL_STATE:
+    raise ValueError(
+        f"1 + sum(num_seasons) = {total} exceeds the seasonal state dimension the engine "
+        f"supports ({MAX_SEASONAL_STATE}): e.g. Seasons(num_seasons=52) is not available")
   active = np.zeros((K, T), np.uint8)
   ends = np.zeros((K, T), np.uint8)
   ns = []

@@ -114,6 +114,22 @@ def prepare_panel(values, index, pre_period, post_period, standardize_data=True,
               pre=pre, post=post, y_model=model_vals[:, :, 0], index=index)
 
 
+def _empty_result(values, index, pre_period, post_period, np_dt, seasons, keep_level) -> PanelResult:
+  """The result of a rank that owns no series (more ranks than series)."""
+  index = pd.Index(index)
+  probe = pd.DataFrame({"y": np.zeros(len(index))}, index=index)
+  pre, post = _frame.parse_and_validate_date_data(probe, pre_period, post_period)
+  k1 = values.shape[2]                       # covariates + intercept
+  z = lambda *shape: np.zeros(shape, np_dt)
+  return PanelResult(
+      index=index, series_ids=np.zeros(0, np.int64), series=np.zeros((0, len(index), 10)),
+      summary=np.zeros((0, 2, 15)), observation_noise_scale=z(0, 0), level_scale=z(0, 0),
+      weights=z(0, 0, k1) if k1 > 1 else None, level=z(0, 0, 0) if keep_level else None,
+      seasonal_levels=z(0, 0, 0, 0) if (seasons and keep_level) else None,
+      seasonal_drift_scales=z(0, 0, 0) if seasons else None, pre_period=pre, post_period=post,
+      inclusion=np.zeros((0, 0, k1 if k1 > 1 else 0), np.float32))
+
+
 def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float = 0.05, seed=None,
                            data_options=None, model_options=None, inference_options=None,
                            engine_options=None, keep_level: bool = False) -> PanelResult:
@@ -133,28 +149,34 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
   values = np.asarray(values)
   rank, ws = _shard.world()
   s0, n_local = _shard.split_range(values.shape[0], ws, rank)
+  eng = _api._resolve_engine(opts)
+  if seed is None and ws > 1:          # fresh entropy: every rank must use rank 0's
+    seed64 = _shard.broadcast_u64(seed64, getattr(eng, "torch_device", lambda: None)())
+  if n_local == 0:                     # more ranks than series: nothing to fit on this one
+    return _empty_result(values, index, pre_period, post_period, np_dt, bool(seasons), keep_level)
   prep = prepare_panel(values[s0:s0 + n_local], index, pre_period, post_period,
                        data_options.standardize_data, np_dt)
   N, Tm = prep["y_ext"].shape
   specs = [build_problem(prep["y_ext"][i], None if prep["design"] is None else prep["design"][i],
                          prior_level_sd=model_options.prior_level_sd,
-                         outcome_sd=float(prep["outcome_sd"][i]), dtype=np_dt) for i in range(N)]
+                         outcome_sd=float(prep["outcome_sd"][i]), dtype=np_dt,
+                         ub_on_scale=opts.upper_bound_on == "scale") for i in range(N)]
   p = specs[0].p
-  eng = _api._resolve_engine(opts)
   eng.set_data_batch(specs)
   S = inference_options.num_results
   C = max(int(opts.num_chains), 1)
   n_per = max(1, math.ceil(S / C))
   n_warm = max(int(inference_options.num_warmup_steps), int(opts.gibbs_min_warmup))
   seas = drift = None
+  stride = C if opts.decorrelate_series else 0          # see EngineOptions.decorrelate_series
+  bkw = dict(n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=s0 * stride, sparse=True,
+             ssvs_order=opts.ssvs_order, series_stride=stride)
   if seasons:
     eng.set_seasonal_batch([build_seasonal(seasons, Tm, float(prep["outcome_sd"][i]))
                             for i in range(N)])
-    theta, level, latent, traj, seas, drift, incl = eng.gibbs_seasonal_run_batch_t(
-        C, n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=0, sparse=True)
+    theta, level, latent, traj, seas, drift, incl = eng.gibbs_seasonal_run_batch_t(C, **bkw)
   else:
-    theta, level, traj, incl = eng.gibbs_run_batch_t(C, n_warmup=n_warm, n_results=n_per,
-                                                     seed=seed64, chain_id0=0, sparse=True)
+    theta, level, traj, incl = eng.gibbs_run_batch_t(C, **bkw)
     latent = level
   S = min(S, C * n_per)
 

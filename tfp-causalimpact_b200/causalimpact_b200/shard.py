@@ -24,6 +24,26 @@ def world() -> Tuple[int, int]:
   return 0, 1
 
 
+def broadcast_u64(value: int, device=None) -> int:
+  """Rank 0's 64-bit value on every rank (one tiny broadcast; identity without a group).
+  Used for ``seed=None``: every rank of a sharded fit must key its Philox streams with the
+  SAME fresh seed."""
+  rank, ws = world()
+  if ws == 1:
+    return int(value)
+  import torch
+  import torch.distributed as dist
+  if dist.get_backend() == "nccl":
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+  else:
+    dev = torch.device("cpu")
+  v = int(value) & (2**64 - 1)
+  t = torch.tensor([v >> 32, v & 0xFFFFFFFF], dtype=torch.int64, device=dev)
+  dist.broadcast(t, src=0)
+  hi, lo = (int(x) for x in t.tolist())
+  return (hi << 32) | lo
+
+
 def split_range(n: int, world_size: int, rank: int) -> Tuple[int, int]:
   """Contiguous balanced split of range(n): returns (start, count)."""
   base, extra = divmod(n, world_size)
@@ -50,7 +70,11 @@ def all_gather_rows(local, n_items: int, rows_per_item: int = 1):
   cap = max(counts)
   on_gpu = dist.get_backend() == "nccl"
   home = local.device
-  dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+  if on_gpu and not local.is_cuda:
+    raise ValueError("all_gather_rows over NCCL needs the rows on this rank's GPU")
+  # stage on the device the rows live on (the engine's), NOT torch.cuda.current_device(): a
+  # caller that never ran torch.cuda.set_device(LOCAL_RANK) would put every rank on cuda:0
+  dev = home if on_gpu else torch.device("cpu")
   send = torch.zeros((cap, width), dtype=local.dtype, device=dev)
   send[:local.shape[0]] = local.to(dev)
   recv = torch.empty((ws * cap, width), dtype=send.dtype, device=dev)

@@ -315,7 +315,8 @@ int ci_set_seasonal_batch(ci_ctx* c, const ci_seasonal* sp, const double* init_s
       c->seas = ci::SeasDev{};
       return fail(CI_ERR_INVALID, "init_sd, drift_scale, drift_ub must be positive (series %d)", s);
     }
-    h[3 * s] = init_sd[s] * init_sd[s]; h[3 * s + 1] = drift_scale[s]; h[3 * s + 2] = drift_ub[s];
+    h[3 * s] = init_sd[s] * init_sd[s]; h[3 * s + 1] = drift_scale[s];
+    h[3 * s + 2] = ub_variance(drift_ub[s], c->b_prob[s].ub_on_scale);
   }
   CU_TRY(c->s_series.reserve(h.size() * sizeof(double)));
   CU_TRY(cudaMemcpyAsync(c->s_series.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -360,7 +361,7 @@ int ci_set_seasonal(ci_ctx* c, const ci_seasonal* sp) {
     sched[(size_t)t * (K + 1) + K] = em;
   }
   sz.init_var = sp->init_sd * sp->init_sd;
-  sz.drift_conc = sp->drift_conc; sz.drift_scale = sp->drift_scale; sz.drift_ub = sp->drift_ub;
+  sz.drift_conc = sp->drift_conc; sz.drift_scale = sp->drift_scale; sz.drift_ub = ub_variance(sp->drift_ub, c->prob.ub_on_scale);
   CU_TRY(cudaSetDevice(c->device));
   CU_TRY(c->s_sched.reserve(sched.size()));
   CU_TRY(cudaMemcpyAsync(c->s_sched.p, sched.data(), sched.size(), cudaMemcpyHostToDevice, c->stream));

@@ -11,7 +11,7 @@ int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
                  void* draws_d, void* level_d, void* traj_d, float* incl_d, cudaStream_t st,
                  bool batch = false) {
   const int p = c->prob.p;
-  const uint32_t extra = (uint32_t)(2 * p * p + 5 * p + 8);
+  const uint32_t extra = (uint32_t)(2 * p * p + 6 * p + 8);
   const uint32_t tail = (uint32_t)(p * p) * (uint32_t)c->esz + 16u;
   SmemCfg cfg;
   // a batch runs C chains of EVERY series (grid.y = series): size CTAs for the whole grid
@@ -25,6 +25,7 @@ int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
   GibbsPlan plan;
   plan.n_warmup = o->n_warmup; plan.n_results = o->n_results; plan.sparse = o->sparse ? 1 : 0;
   plan.n_obs = c->n_obs; plan.chain_major = o->chain_major ? 1 : 0;
+  plan.ssvs_random = o->ssvs_order == 0 ? 1 : 0; plan.series_stride = o->series_stride;
   const double pi = o->nonzero_prob;
   plan.logit_pi = (plan.sparse && pi < 1.0) ? std::log(pi) - std::log1p(-pi) : 1e30;
   if (!(pi < 1.0)) plan.sparse = 0;
@@ -56,6 +57,7 @@ int ci_gibbs_run_batch_d(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint6
     return fail(CI_ERR_INVALID, "n_chains >= 1, n_results >= 1, n_warmup >= 0 required");
   if (o->sparse && !(o->nonzero_prob > 0.0 && o->nonzero_prob <= 1.0))
     return fail(CI_ERR_INVALID, "nonzero_prob must be in (0, 1]");
+  if (o->ssvs_order != 0 && o->ssvs_order != 1) return fail(CI_ERR_INVALID, "ssvs_order must be 0 or 1");
   for (int s = 0; s < c->batch_n; ++s)
     if (c->b_nobs[s] < 2) return fail(CI_ERR_INVALID, "series %d has fewer than 2 observed points", s);
   CU_TRY(cudaSetDevice(c->device));
@@ -75,6 +77,7 @@ int ci_gibbs_run_d(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t ch
     return fail(CI_ERR_INVALID, "n_chains >= 1, n_results >= 1, n_warmup >= 0 required");
   if (o->sparse && !(o->nonzero_prob > 0.0 && o->nonzero_prob <= 1.0))
     return fail(CI_ERR_INVALID, "nonzero_prob must be in (0, 1]");
+  if (o->ssvs_order != 0 && o->ssvs_order != 1) return fail(CI_ERR_INVALID, "ssvs_order must be 0 or 1");
   if (c->n_obs < 2) return fail(CI_ERR_INVALID, "need at least 2 observed points");
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);

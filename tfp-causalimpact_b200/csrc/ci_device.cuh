@@ -14,7 +14,7 @@ template <typename R> struct ProbDev {
   const R* omega;   // [p,p] slab precision
   int T, p, ld, NB, dim, model;
   R m0, P0;
-  R obs_conc, obs_scale, obs_ub;
+  R obs_conc, obs_scale, obs_ub;   // *_ub: bound on the VARIANCE (the host converts a scale bound)
   R lvl_conc, lvl_scale, lvl_ub;
 };
 
@@ -27,7 +27,7 @@ struct SeasDev {
   int n[MAX_SEAS], off[MAX_SEAS], n_ends[MAX_SEAS];
   const uint8_t* sched;         // [T][K+1]: active season of each component, then the ends mask
   double init_var;              // initial_effect_prior variance (lib.py:489: sd^2)
-  double drift_conc, drift_scale, drift_ub;   // InverseGamma on the drift variance (lib.py:472-474)
+  double drift_conc, drift_scale, drift_ub;   // InverseGamma on the drift variance (lib.py:472-474); drift_ub bounds the VARIANCE
   void* scratch;                // [C][T][d+1] elements of R
   const double* per_series;     // batch only: [N][3] = init_var, drift_scale, drift_ub of every series
 };
@@ -184,7 +184,7 @@ __device__ __forceinline__ double chain_prior(const ProbDev<R>& pr, const R* om_
     lp += -0.5 * p * (double)u - 0.5 * (double)q * rse;
     g_u += -0.5 * p + 0.5 * (double)q * rse;
   }
-  const bool ok = (Num<R>::sqrt(s_e) <= pr.obs_ub) && (Num<R>::sqrt(s_h) <= pr.lvl_ub) &&
+  const bool ok = (s_e <= pr.obs_ub) && (s_h <= pr.lvl_ub) &&
                   (u == u) && (l == l);
   return ok ? lp : -CUDART_INF;
 }

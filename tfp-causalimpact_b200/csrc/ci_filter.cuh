@@ -63,6 +63,26 @@ template <typename R> __device__ __forceinline__ void affine_scan_down(R& m, R& 
     c = fma(m, co, c); m = m * mo;
   }
 }
+// float32: the combine is PREDICATED instead of selecting the identity (one setp + two predicated
+// ops per level instead of a compare, two selects and two ops); still no divergence region.
+template <> __device__ __forceinline__ void affine_scan_up<float>(float& m, float& c, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float mo = __shfl_up_sync(FULL, m, off), co = __shfl_up_sync(FULL, c, off);
+    asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %2, %3;\n\t@q fma.rn.f32 %0, %1, %5, %0;\n\t"
+        "@q mul.f32 %1, %1, %4;\n\t}"
+        : "+f"(c), "+f"(m) : "r"(lane), "r"(off), "f"(mo), "f"(co));
+  }
+}
+template <> __device__ __forceinline__ void affine_scan_down<float>(float& m, float& c, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float mo = __shfl_down_sync(FULL, m, off), co = __shfl_down_sync(FULL, c, off);
+    asm("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %2, %3;\n\t@q fma.rn.f32 %0, %1, %5, %0;\n\t"
+        "@q mul.f32 %1, %1, %4;\n\t}"
+        : "+f"(c), "+f"(m) : "r"(lane), "r"(32 - off), "f"(mo), "f"(co));
+  }
+}
 template <typename R> __device__ __forceinline__ void mob_scan_up(Mob<R>& M, int lane) {
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {

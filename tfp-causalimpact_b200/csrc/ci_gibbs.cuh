@@ -25,10 +25,12 @@
 
 namespace ci {
 
-enum : uint32_t { RNG_G_INCL = 6, RNG_G_GAMMA = 7, RNG_G_W = 8 };
+enum : uint32_t { RNG_G_INCL = 6, RNG_G_GAMMA = 7, RNG_G_W = 8, RNG_G_PERM = 13 };
 
 struct GibbsPlan {
   int n_warmup, n_results, sparse, n_obs, chain_major;
+  int ssvs_random;                     // visit the features in a fresh random order every sweep
+  unsigned long long series_stride;    // batch: chain ids of series s start at chain_id0 + s * stride
   double logit_pi;
 };
 
@@ -53,6 +55,7 @@ template <typename R> struct GibbsScratch {
   R* Lo;     // [p^2]      Cholesky of Omega_gamma
   R* idx;    // [p]        active feature list (stored as R, exact for p <= 128)
   R* vec;    // [p+1]      work vector
+  R* perm;   // [p]        visiting order of the sweep (ssvs_random)
 };
 
 // Gamma(shape, 1), shape >= 1 (Marsaglia & Tsang 2000); every lane computes the same draw.
@@ -163,7 +166,21 @@ template <typename R> struct GibbsReg {
     if (p > 0) {
       double lm_cur = log_marginal(gam, yty, k, ss);
       if (plan.sparse) {
-        for (int j = 0; j < p; ++j) {
+        if (plan.ssvs_random) {
+          // one Fisher-Yates shuffle per sweep, keyed like every other draw of the chain
+          for (int j = lane; j < p; j += 32) gs.perm[j] = (R)j;
+          __syncwarp();
+          if (lane == 0) {
+            for (int i = p - 1; i > 0; --i) {
+              const uint4 x = Philox::gen(seed, id_lo, RNG_G_PERM | id_hi8, (uint32_t)it, (uint32_t)i);
+              const int k2 = (int)(((uint64_t)x.x * (uint64_t)(i + 1)) >> 32);
+              const R t = gs.perm[i]; gs.perm[i] = gs.perm[k2]; gs.perm[k2] = t;
+            }
+          }
+          __syncwarp();
+        }
+        for (int jj = 0; jj < p; ++jj) {
+          const int j = plan.ssvs_random ? (int)gs.perm[jj] : jj;
           uint32_t gf[4] = {gam[0], gam[1], gam[2], gam[3]};
           gf[j >> 5] ^= 1u << (j & 31);
           int kf; double ssf;
@@ -181,7 +198,7 @@ template <typename R> struct GibbsReg {
     {
       const double g = gamma_draw(conc_e, seed, id_lo, RNG_G_GAMMA | id_hi8, (uint32_t)it, 0u);
       s_e = ((double)pr.obs_scale + 0.5 * ss) / g;
-      const double ub2 = (double)pr.obs_ub * (double)pr.obs_ub;
+      const double ub2 = (double)pr.obs_ub;                            // variance bound
       if (s_e > ub2) s_e = ub2;                                        // lib.py:442-443
     }
     if (p > 0) {
@@ -260,9 +277,9 @@ k_gibbs(ProbDev<R> pr, GibbsDev<R> gd, SmemCfg cfg, GibbsPlan plan, uint64_t see
   const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
   GibbsScratch<R> gs;
   gs.bvec = ws.extra; gs.La = gs.bvec + p; gs.Lo = gs.La + (p + 1) * (p + 1);
-  gs.idx = gs.Lo + p * p; gs.vec = gs.idx + p;
+  gs.idx = gs.Lo + p * p; gs.vec = gs.idx + p; gs.perm = gs.vec + (p + 1);
   TilePipe<R> pipe = make_pipe(cs, cfg);
-  const uint64_t gid = chain_id0 + (uint64_t)c;
+  const uint64_t gid = chain_id0 + (uint64_t)c + (batch ? (uint64_t)blockIdx.y * plan.series_stride : 0ull);
   const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
 
   // ---- initial state: the reference's (lib.py:566-581) ----
@@ -404,7 +421,7 @@ affine_scan_down(m, cc, lane);
       const double g = gamma_draw((double)pr.lvl_conc + 0.5 * (T - 1), seed, id_lo,
                                   RNG_G_GAMMA | id_hi8, (uint32_t)it, 1u);
       s_h = ((double)pr.lvl_scale + 0.5 * d2) / g;
-      const double ub2 = (double)pr.lvl_ub * (double)pr.lvl_ub;
+      const double ub2 = (double)pr.lvl_ub;                            // variance bound
       if (s_h > ub2) s_h = ub2;                                        // lib.py:432
     }
     if (keep) {

@@ -119,6 +119,13 @@ namespace {
 
 using namespace ci;
 
+// the kernels compare VARIANCES with their bound: a bound on the scale is squared here
+// (ci_problem.ub_on_scale, include/ci_b200.h)
+inline double ub_variance(double ub, int on_scale) {
+  if (!on_scale) return ub;
+  return ub > 1e150 ? ub : ub * ub;
+}
+
 template <typename R> ProbDev<R> make_probdev(const ci_ctx* c) {
   ProbDev<R> pr;
   pr.tiles = static_cast<const R*>(c->v_tiles);
@@ -127,16 +134,17 @@ template <typename R> ProbDev<R> make_probdev(const ci_ctx* c) {
   pr.model = c->prob.model;
   pr.m0 = (R)c->prob.m0; pr.P0 = (R)c->prob.P0;
   pr.obs_conc = (R)c->prob.obs_conc; pr.obs_scale = (R)c->prob.obs_scale;
-  pr.obs_ub = (R)c->prob.obs_ub;
+  pr.obs_ub = (R)ub_variance(c->prob.obs_ub, c->prob.ub_on_scale);
   pr.lvl_conc = (R)c->prob.lvl_conc; pr.lvl_scale = (R)c->prob.lvl_scale;
-  pr.lvl_ub = (R)c->prob.lvl_ub;
+  pr.lvl_ub = (R)ub_variance(c->prob.lvl_ub, c->prob.ub_on_scale);
   return pr;
 }
 
 template <typename R> LltDev<R> make_lltdev(const ci_ctx* c) {
   LltDev<R> d;
   d.q_conc = (R)c->prob.slope_conc; d.q_scale = (R)c->prob.slope_scale;
-  d.q_ub = (R)(c->prob.slope_ub > 1e30 ? 1e30 : c->prob.slope_ub);
+  const double qv = ub_variance(c->prob.slope_ub, c->prob.ub_on_scale);
+  d.q_ub = (R)(qv > 1e30 ? 1e30 : qv);
   d.m0s = (R)c->prob.m0_slope; d.P0s = (R)c->prob.P0_slope;
   return d;
 }

@@ -108,7 +108,7 @@ __device__ __forceinline__ St2<R> el2_apply(const El2<R>& e, const St2<R>& s) {
 
 // slope-related problem constants (ProbDev carries the level ones)
 template <typename R> struct LltDev {
-  R q_conc, q_scale, q_ub;   // InvGamma on sigma_slope^2, bound on sigma_slope
+  R q_conc, q_scale, q_ub;   // InvGamma on sigma_slope^2, bound on the slope VARIANCE
   R m0s, P0s;                // initial slope ~ N(m0s, P0s)
 };
 
@@ -403,7 +403,7 @@ template <typename R>
 __device__ __forceinline__ double llt_slope_prior(const LltDev<R>& ld2, R s, R q2, double& g_s) {
   const R rq = (R)1 / q2;
   g_s += -((double)ld2.q_conc + 1.0) + (double)ld2.q_scale * rq + 1.0;
-  const bool ok = (Num<R>::sqrt(q2) <= ld2.q_ub) && (s == s);
+  const bool ok = (q2 <= ld2.q_ub) && (s == s);
   const double lp = -((double)ld2.q_conc + 1.0) * s - (double)ld2.q_scale * rq + s;
   return ok ? lp : -CUDART_INF;
 }

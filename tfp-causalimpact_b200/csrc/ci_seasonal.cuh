@@ -87,9 +87,9 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
   GibbsScratch<R> gs;
   gs.bvec = ws.extra; gs.La = gs.bvec + p; gs.Lo = gs.La + (p + 1) * (p + 1);
-  gs.idx = gs.Lo + p * p; gs.vec = gs.idx + p;
+  gs.idx = gs.Lo + p * p; gs.vec = gs.idx + p; gs.perm = gs.vec + (p + 1);
   const int d = sz.d, K = sz.K, LDP = d | 1;
-  R* Ps = gs.vec + (p + 1);             // [d][LDP] state covariance, row i <-> lane i
+  R* Ps = gs.perm + p;                  // [d][LDP] state covariance, row i <-> lane i
   R* phs = Ps + d * LDP;                // [d]      P h of the current step
   R* Prow = Ps + (lane < d ? lane : 0) * LDP;
   R* st_a = phs + d;                    // [TB] x3: per-step staging of the current tile
@@ -100,7 +100,7 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   const bool scr_smem = sz.scratch == nullptr;
   R* scr = scr_smem ? st_d + (size_t)K * TB : static_cast<R*>(sz.scratch) + (series_chain0 + (size_t)c) * T * (d + 1);
   TilePipe<R> pipe = make_pipe(cs, cfg);
-  const uint64_t gid = chain_id0 + (uint64_t)c;
+  const uint64_t gid = chain_id0 + (uint64_t)c + (batch ? (uint64_t)blockIdx.y * plan.series_stride : 0ull);
   const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
 
   // which block element `lane` belongs to: -1 level, k component, -2 unused lane
@@ -441,7 +441,7 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       const double g = gamma_draw((double)pr.lvl_conc + 0.5 * (T - 1), seed, id_lo,
                                   RNG_G_GAMMA | id_hi8, (uint32_t)it, 1u);
       s_h = ((double)pr.lvl_scale + 0.5 * d2) / g;
-      const double ub2 = (double)pr.lvl_ub * (double)pr.lvl_ub;
+      const double ub2 = (double)pr.lvl_ub;                            // variance bound
       if (s_h > ub2) s_h = ub2;                                        // lib.py:432
     }
     for (int k = 0; k < K; ++k) {
@@ -449,7 +449,7 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       const double g = gamma_draw_any(sz.drift_conc + 0.5 * sz.n_ends[k], seed, id_lo,
                                       RNG_G_GAMMA | id_hi8, (uint32_t)it, 2u + (uint32_t)k);
       double v = (sz.drift_scale + 0.5 * u2) / g;
-      const double ub2 = sz.drift_ub * sz.drift_ub;
+      const double ub2 = sz.drift_ub;                                  // variance bound
       if (v > ub2) v = ub2;                                            // lib.py:474
       if (lane == k) sd_l = v;
     }
