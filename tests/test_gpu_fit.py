@@ -52,7 +52,7 @@ def test_unexpected_kwargs_raise():                    # lib_test.py:231-240
 
 def test_unsupported_model_options_fail_loudly():
   data, pre, post = csv_data()
-  with pytest.raises(ci.EngineError, match="state dimension"):       # 1 + 52 > one warp
+  with pytest.raises(ValueError, match="state dimension"):           # 1 + 52 > one warp
     ci.fit_causalimpact(data, pre, post, seed=1,
                         model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=52)]))
   with pytest.raises(NotImplementedError):

@@ -139,3 +139,53 @@ def test_gibbs_rejects_bad_options(engine):
     engine.gibbs_run(2, n_warmup=5, n_results=0, seed=1)
   with pytest.raises(cib.EngineError):
     engine.gibbs_run(2, n_warmup=5, n_results=2, seed=1, nonzero_prob=1.5)
+
+
+def test_team_and_one_warp_gibbs_paths_agree(monkeypatch):
+  """T <= 2048 runs the TEAM sweep (one warp per tile, speculative inclusion draws); with
+  CI_B200_GIBBS_TEAM=0 the same problem runs one warp per chain.  Same Philox keys, same
+  decisions: the two differ only by the summation order of the sufficient statistics, so the
+  first sweeps agree to float32 rounding (later ones drift apart chaotically) and long runs
+  agree in distribution.  Checked with the spike-and-slab prior and both visiting orders."""
+  y, X, _ = make_series(700, 10, 2030, nan_frac=0.02)
+  spec = cib.build_problem(y, X)
+  res = {}
+  for mode in ("1", "0"):
+    monkeypatch.setenv("CI_B200_GIBBS_TEAM", mode)
+    eng = cib.Engine(0)
+    eng.set_data(spec)
+    res[mode] = dict(
+        short=eng.gibbs_run(24, n_warmup=0, n_results=2, seed=5, sparse=True),
+        short_idx=eng.gibbs_run(24, n_warmup=0, n_results=2, seed=5, sparse=True, ssvs_order="index"),
+        long=eng.gibbs_run(48, n_warmup=200, n_results=100, seed=9, sparse=True))
+    eng.close()
+  for key in ("short", "short_idx"):
+    a, b = res["1"][key], res["0"][key]
+    np.testing.assert_array_equal(a[0][..., :spec.p] != 0, b[0][..., :spec.p] != 0)   # same inclusions
+    np.testing.assert_allclose(a[0], b[0], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(a[1], b[1], rtol=2e-3, atol=5e-3)                      # level paths
+    np.testing.assert_array_equal(a[3], b[3])
+  a, b = res["1"]["long"], res["0"]["long"]
+  np.testing.assert_allclose(a[3].mean(0), b[3].mean(0), atol=0.08)                   # inclusion freq
+  da, db = a[0].reshape(-1, spec.dim), b[0].reshape(-1, spec.dim)
+  for j in (0, 1, 2, spec.p, spec.p + 1):
+    ok, info = _close(da[:, j], db[:, j], 5e-3)
+    assert ok, (j, info)
+
+
+def test_team_gibbs_edge_shapes(engine):
+  """Team sweep at its limits: a single tile (W = 1), 8 tiles (T = 2048), a ragged last tile,
+  no covariates, float64; finite draws, clamps respected, deterministic."""
+  for T, n_cov, dt in ((200, 3, np.float32), (2048, 2, np.float32), (1800, 0, np.float32),
+                       (600, 12, np.float64)):
+    y, X, _ = make_series(T, n_cov, 40 + T)
+    spec = cib.build_problem(y, X, dtype=dt)
+    engine.set_data(spec)
+    a = engine.gibbs_run(9, n_warmup=15, n_results=5, seed=3)
+    b = engine.gibbs_run(9, n_warmup=15, n_results=5, seed=3)
+    for x, z in zip(a, b):
+      assert np.array_equal(x, z)
+    assert all(np.all(np.isfinite(x)) for x in a[:3])
+    assert np.all(np.exp(a[0][..., spec.p]) <= spec.obs_ub * (1 + 1e-6))
+    lo = engine.gibbs_run(4, n_warmup=15, n_results=5, seed=3)
+    assert np.array_equal(a[0][:, :4], lo[0]) and np.array_equal(a[1][:, :4], lo[1])

@@ -142,6 +142,7 @@ int ci_ctx_create(int device, ci_ctx** out) {
   if (const char* g = getenv("CI_B200_TEAM")) c->team_mode = atoi(g);
   if (const char* g = getenv("CI_B200_PREDICT_TEAM")) c->predict_team = atoi(g);
   if (const char* g = getenv("CI_B200_TSTREAM")) c->tstream_mode = atoi(g);
+  if (const char* g = getenv("CI_B200_GIBBS_TEAM")) c->gibbs_team = atoi(g);
   if (const char* g = getenv("CI_B200_TSW")) c->tstream_W = atoi(g);
   *out = c;
   return CI_OK;

@@ -1,6 +1,7 @@
 // abi_gibbs.cu -- Gibbs (spike-and-slab) entry points, single series and batched.
 #include "ci_host.cuh"
 #include "ci_gibbs.cuh"
+#include "ci_gibbs_team.cuh"
 
 namespace {
 
@@ -32,6 +33,35 @@ int launch_gibbs(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint64_t chai
   GibbsDev<R> gd;
   gd.gram = static_cast<const R*>(c->v_gram); gd.xty0 = static_cast<const R*>(c->v_xty);
   gd.yty0 = (R)c->yty0;
+  // team mode (ci_gibbs_team.cuh): one warp per tile when the series is resident in shared memory
+  if (c->team_mode && c->gibbs_team && c->NB >= 1 && c->NB <= MAXW) {
+    const int W = c->NB;
+    const int total = batch ? C * c->batch_n : C;
+    int gt = c->force_G > 0 ? c->force_G : (total + c->sm_count - 1) / c->sm_count;
+    if (gt < 1) gt = 1;
+    if (gt * W > GT_MAXWARPS) gt = GT_MAXWARPS / W;
+    if (gt > C) gt = C;
+    if (gt > 8) gt = 8;
+    std::string keep = cih_err();
+    for (; gt >= 1; --gt) {
+      const uint32_t ttail = (uint32_t)gt * (uint32_t)sizeof(GibbsTeamShared<R>) + tail + 32u;
+      SmemCfg tcfg;
+      if (plan_smem(c, gt * W, extra, &tcfg, ttail, 0) == CI_OK && tcfg.resident) {
+        cih_err() = keep;
+        auto tk = k_gibbs_team<R>;
+        CU_TRY(set_smem(tk, (uint32_t)tcfg.total_bytes));
+        const dim3 tgrid((C + gt - 1) / gt, batch ? c->batch_n : 1);
+        tk<<<tgrid, 32 * gt * W, tcfg.total_bytes, st>>>(
+            make_probdev<R>(c), gd, tcfg, plan, W, seed, chain_id0, C, static_cast<R*>(draws_d),
+            static_cast<R*>(level_d), static_cast<R*>(traj_d), incl_d,
+            batch ? static_cast<const BatchDev<R>*>(c->b_dev.p) : nullptr);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        return CI_OK;
+      }
+    }
+    cih_err() = keep;
+  }
   auto kern = k_gibbs<R>;
   CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
   const dim3 grid((C + G - 1) / G, batch ? c->batch_n : 1);

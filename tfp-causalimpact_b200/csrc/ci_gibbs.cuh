@@ -157,44 +157,38 @@ template <typename R> struct GibbsReg {
     return ld_om - ld_lam - conc_e * log((double)pr.obs_scale + 0.5 * ss);
   }
 
-  // One regression step: inclusion indicators (gam), sigma_obs^2 (s_e), weights -> w_s.
-  // Inputs: gs.bvec = X'(targets), yty = |targets|^2 over observed steps.
-  __device__ __forceinline__ void step(int it, const GibbsPlan& plan, uint32_t (&gam)[4], double yty,
-                                       double& s_e, R* w_s) const {
-    double ss = yty;
-    int k = 0;
-    if (p > 0) {
-      double lm_cur = log_marginal(gam, yty, k, ss);
-      if (plan.sparse) {
-        if (plan.ssvs_random) {
-          // one Fisher-Yates shuffle per sweep, keyed like every other draw of the chain
-          for (int j = lane; j < p; j += 32) gs.perm[j] = (R)j;
-          __syncwarp();
-          if (lane == 0) {
-            for (int i = p - 1; i > 0; --i) {
-              const uint4 x = Philox::gen(seed, id_lo, RNG_G_PERM | id_hi8, (uint32_t)it, (uint32_t)i);
-              const int k2 = (int)(((uint64_t)x.x * (uint64_t)(i + 1)) >> 32);
-              const R t = gs.perm[i]; gs.perm[i] = gs.perm[k2]; gs.perm[k2] = t;
-            }
-          }
-          __syncwarp();
-        }
-        for (int jj = 0; jj < p; ++jj) {
-          const int j = plan.ssvs_random ? (int)gs.perm[jj] : jj;
-          uint32_t gf[4] = {gam[0], gam[1], gam[2], gam[3]};
-          gf[j >> 5] ^= 1u << (j & 31);
-          int kf; double ssf;
-          const double lm_new = log_marginal(gf, yty, kf, ssf);
-          const bool cur = (gam[j >> 5] >> (j & 31)) & 1u;
-          const double d = (cur ? lm_cur - lm_new : lm_new - lm_cur) + plan.logit_pi;
-          const uint4 x = Philox::gen(seed, id_lo, RNG_G_INCL | id_hi8, (uint32_t)it, (uint32_t)j);
-          const bool take = u01<double>(x.x) < 1.0 / (1.0 + exp(-d));
-          if (take != cur) { gam[j >> 5] ^= 1u << (j & 31); lm_cur = lm_new; }
-        }
-        lm_cur = log_marginal(gam, yty, k, ss);      // factor of the final configuration
+  // visiting order of the sweep's inclusion draws -> gs.perm (ssvs_random): one Fisher-Yates
+  // shuffle per sweep, keyed like every other draw of the chain
+  __device__ __forceinline__ void make_order(int it, const GibbsPlan& plan) const {
+    if (!plan.ssvs_random) return;
+    for (int j = lane; j < p; j += 32) gs.perm[j] = (R)j;
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = p - 1; i > 0; --i) {
+        const uint4 x = Philox::gen(seed, id_lo, RNG_G_PERM | id_hi8, (uint32_t)it, (uint32_t)i);
+        const int k2 = (int)(((uint64_t)x.x * (uint64_t)(i + 1)) >> 32);
+        const R t = gs.perm[i]; gs.perm[i] = gs.perm[k2]; gs.perm[k2] = t;
       }
-      (void)lm_cur;
     }
+    __syncwarp();
+  }
+  __device__ __forceinline__ int order(int jj, const GibbsPlan& plan) const {
+    return plan.ssvs_random ? (int)gs.perm[jj] : jj;
+  }
+  // the inclusion draw of feature j given the log-marginals of the current configuration and of
+  // the one with j flipped; returns true when the indicator changes
+  __device__ __forceinline__ bool flips(int it, int j, bool cur, double lm_cur, double lm_new,
+                                        const GibbsPlan& plan) const {
+    const double d = (cur ? lm_cur - lm_new : lm_new - lm_cur) + plan.logit_pi;
+    const uint4 x = Philox::gen(seed, id_lo, RNG_G_INCL | id_hi8, (uint32_t)it, (uint32_t)j);
+    const bool take = u01<double>(x.x) < 1.0 / (1.0 + exp(-d));
+    return take != cur;
+  }
+
+  // sigma_obs^2 | gam  and the active weights | sigma_obs^2, gam  -> s_e, w_s.  Needs the factor
+  // of the final configuration in gs.La (log_marginal(gam, ...) was the last factorisation):
+  // k active features, residual sum of squares ss.
+  __device__ __forceinline__ void draw(int it, int k, double ss, double& s_e, R* w_s) const {
     {
       const double g = gamma_draw(conc_e, seed, id_lo, RNG_G_GAMMA | id_hi8, (uint32_t)it, 0u);
       s_e = ((double)pr.obs_scale + 0.5 * ss) / g;
@@ -234,6 +228,32 @@ template <typename R> struct GibbsReg {
       for (int a = lane; a < k; a += 32) w_s[(int)gs.idx[a]] = gs.vec[a];
       __syncwarp();
     }
+  }
+
+  // One regression step: inclusion indicators (gam), sigma_obs^2 (s_e), weights -> w_s.
+  // Inputs: gs.bvec = X'(targets), yty = |targets|^2 over observed steps.
+  __device__ __forceinline__ void step(int it, const GibbsPlan& plan, uint32_t (&gam)[4], double yty,
+                                       double& s_e, R* w_s) const {
+    double ss = yty;
+    int k = 0;
+    if (p > 0) {
+      double lm_cur = log_marginal(gam, yty, k, ss);
+      if (plan.sparse) {
+        make_order(it, plan);
+        for (int jj = 0; jj < p; ++jj) {
+          const int j = order(jj, plan);
+          uint32_t gf[4] = {gam[0], gam[1], gam[2], gam[3]};
+          gf[j >> 5] ^= 1u << (j & 31);
+          int kf; double ssf;
+          const double lm_new = log_marginal(gf, yty, kf, ssf);
+          const bool cur = (gam[j >> 5] >> (j & 31)) & 1u;
+          if (flips(it, j, cur, lm_cur, lm_new, plan)) { gam[j >> 5] ^= 1u << (j & 31); lm_cur = lm_new; }
+        }
+        lm_cur = log_marginal(gam, yty, k, ss);      // factor of the final configuration
+      }
+      (void)lm_cur;
+    }
+    draw(it, k, ss, s_e, w_s);
   }
 };
 
