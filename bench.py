@@ -3,17 +3,24 @@
 
   python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A *step* is one pass of the hot path over one batch: one Kalman log-prob +
-gradient evaluation of every chain of BASELINE.json configs[1] (local level +
-10 covariates, T=1000, 256 chains per GPU).  Prints ONE JSON line.
+A *step* is one pass of the hot path over one batch: one Kalman log-prob + gradient evaluation
+of every chain of BASELINE.json configs[1] (local level + 10 covariates, T=1000, 256 chains per
+GPU).  Prints ONE JSON line.  `extra.configs` carries the same measurement block (device-timed
+value, kernel time, roofline, CPU baseline, host-buffer e2e) for EVERY GPU config of
+BASELINE.json -- configs[1..4] -- and `extra.posterior_draws` the metric's second quantity
+(posterior draws/s); `extra.saturation` is the chains-per-launch curve; `extra.sharded_fit`
+times the product call `fit_causalimpact` with its chains sharded over the ranks and the ONE
+all-gather inside the timed region (strong scaling, BASELINE configs[4] shape).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
@@ -22,9 +29,25 @@ for _p in (ROOT, os.path.join(ROOT, "tfp-causalimpact_b200"), os.path.join(ROOT,
   if _p not in sys.path:
     sys.path.insert(0, _p)
 
-WORKLOAD = dict(T=1000, n_cov=10, chains=256)       # BASELINE.json configs[1]
 METRIC = "kalman_logprob_grad_evals_per_sec"
 UNIT = "evals/s"
+
+# BASELINE.json configs[1..4]; seeds 20240 + index as BASELINE.md section 4
+CONFIGS = [
+    dict(key="configs[1]", idx=1, kind="logprob", model=0, T=1000, n_cov=10, chains=256,
+         workload="local-level + 10 covariates, T=1000, 256 chains per GPU (BASELINE.json configs[1]); "
+                  "value+gradient, prior included"),
+    dict(key="configs[2]", idx=2, kind="logprob", model=1, T=5000, n_cov=50, chains=1024,
+         workload="local-linear-trend + 50 covariates, T=5000, 1024 chains (BASELINE.json configs[2]); "
+                  "value+gradient, prior included"),
+    dict(key="configs[3]", idx=3, kind="logprob", model=0, T=20000, n_cov=1, chains=512,
+         workload="T=20000 long series, 1 covariate, associative-scan filter path, 512 chains "
+                  "(BASELINE.json configs[3]); value+gradient, prior included"),
+    dict(key="configs[4]", idx=4, kind="forecast", model=0, T=2000, n_cov=10, draws=10000,
+         workload="10000-draw posterior forecast, T=2000, 10 covariates (BASELINE.json configs[4]): "
+                  "simulation smoother + predictive draws + mean + impact quantiles"),
+]
+WORKLOAD = CONFIGS[0]
 
 
 def bytes_per_eval(T, p, d=1):
@@ -32,11 +55,20 @@ def bytes_per_eval(T, p, d=1):
   return 8 * T * (p + 1) + 4 * (2 * (p + 1 + d) + 1)
 
 
-def make_inputs(cfg, seed=20242):
+def bytes_per_draw(T, p, t_post):
+  """B_draw = 4 T (p+1) + 4 T (write traj) + 4 T (read it for the per-time
+  quantiles) + 8 T_post (cumulative-effect pass)."""
+  return 4 * T * (p + 1) + 8 * T + 8 * t_post
+
+
+def make_inputs(cfg, seed=None, chains=None):
   from conftest import make_series, make_thetas
+  seed = 20240 + cfg["idx"] + 1 if seed is None else seed      # configs[1] -> 20242 (round-1 seed)
   y, X, _ = make_series(cfg["T"], cfg["n_cov"], seed)
   p = 0 if X is None else X.shape[1]
-  th = make_thetas(p + 2, p, cfg["chains"], seed + 1)
+  d = 2 if cfg.get("model") == 1 else 1
+  n = chains if chains is not None else cfg.get("chains", cfg.get("draws"))
+  th = make_thetas(p + 1 + d, p, n, seed + 1, d=d)
   return y, X, th
 
 
@@ -48,6 +80,18 @@ def measured_peak_hbm():
     except Exception:   # pylint: disable=broad-except
       pass
   return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_traffic(kernel):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
+  ncu summary profiles/r02_traffic.json (written by tools/ncu_traffic.py from ncu --set full
+  captures); None when the kernel has no capture."""
+  try:
+    tab = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    e = tab.get(kernel)
+    return None if e is None else int(e["dram_bytes_read"] + e["dram_bytes_write"])
+  except Exception:   # pylint: disable=broad-except
+    return None
 
 
 class ClockSampler:
@@ -76,11 +120,15 @@ class ClockSampler:
       r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
     except Exception:   # pylint: disable=broad-except
       r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+    try:
+      util = n.nvmlDeviceGetUtilizationRates(self._h).gpu
+    except Exception:   # pylint: disable=broad-except
+      util = -1
     act = lambda bit: "Active" if (r & bit) else "Not Active"
     self.rows.append([str(sm), str(mx), act(n.nvmlClocksThrottleReasonHwSlowdown),
                       act(n.nvmlClocksThrottleReasonHwThermalSlowdown),
                       act(n.nvmlClocksThrottleReasonSwThermalSlowdown),
-                      act(n.nvmlClocksThrottleReasonSwPowerCap)])
+                      act(n.nvmlClocksThrottleReasonSwPowerCap), util])
 
   def _run(self):
     while not self._stop.is_set():
@@ -92,7 +140,7 @@ class ClockSampler:
                                 "--format=csv,noheader,nounits"], capture_output=True, text=True,
                                timeout=5).stdout.strip()
           if out:
-            self.rows.append([c.strip() for c in out.split(",")])
+            self.rows.append([c.strip() for c in out.split(",")] + [-1])
       except Exception:   # pylint: disable=broad-except
         pass
       self._stop.wait(0.005 if self._nvml is not None else 0.1)
@@ -113,8 +161,10 @@ class ClockSampler:
     mx = max(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
+    busy = [r for r in self.rows if isinstance(r[6], int) and r[6] > 0]
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-            "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
+            "samples": len(self.rows), "samples_under_load": len(busy),
+            "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 _BEST_THREADS = None
@@ -132,61 +182,97 @@ def usable_cpus():
   return n
 
 
-def cpu_port_rate(cfg, seconds=10.0, nthreads=None):
-  """Times oracle/_ref (C port of the oracle, float64, OpenMP over chains) on a
-  bounded sample of the SAME workload; returns evals/s and a description.
-
-  The thread count is CALIBRATED once (0.3 s each for n, n/2, n/4, ... of the
-  usable CPUs, best kept): torchrun exports OMP_NUM_THREADS=1, and on a shared
-  box 128 spinning threads ran 180x slower than 64 (run 12) -- the baseline must
-  be the fastest the host can do, not an accident of the environment."""
-  global _BEST_THREADS
-  os.environ.setdefault("OMP_WAIT_POLICY", "passive")
-  from oracle import c_port
+def _oracle_problem(cfg, y, X):
   from oracle import kalman_np as K
+  return K.default_problem(y, X, model=cfg.get("model", 0))
+
+
+def best_threads():
+  """The thread count that runs the C port fastest, CALIBRATED once on configs[1] (0.3 s each for
+  n, n/2, n/4, ... of the usable CPUs): torchrun exports OMP_NUM_THREADS=1, and on a shared box
+  128 spinning threads ran 180x slower than 64 (round 1, run 12) -- the baseline must be the
+  fastest the host can do, not an accident of the environment."""
+  global _BEST_THREADS
+  if _BEST_THREADS is None:
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    from oracle import c_port
+    y, X, th = make_inputs(WORKLOAD)
+    prob = _oracle_problem(WORKLOAD, y, X)
+    c_port.logpost_grad(prob, th[:8])                     # load + warm
+    best, n, cand = (0.0, 1), usable_cpus(), []
+    while n >= 1:
+      cand.append(n); n //= 2
+    for nt in cand:
+      t0 = time.perf_counter(); k = 0
+      while time.perf_counter() - t0 < 0.3:
+        c_port.logpost_grad(prob, th, nthreads=nt); k += th.shape[0]
+      rate = k / (time.perf_counter() - t0)
+      if rate > best[0]:
+        best = (rate, nt)
+    _BEST_THREADS = best[1]
+  return _BEST_THREADS
+
+
+def cpu_logprob_rate(cfg, seconds=10.0, max_chains=None):
+  """oracle/_ref (C port of the oracle: float64, OpenMP over chains) on a BOUNDED sample of the
+  workload: repeated value+gradient passes over (a slice of) the config's chain batch for
+  `seconds`.  Returns (evals/s, threads, description)."""
+  from oracle import c_port
+  nt = best_threads()
   y, X, th = make_inputs(cfg)
-  prob = K.default_problem(y, X)
-  c_port.logpost_grad(prob, th[:8])                     # load + warm
-  if nthreads is None:
-    if _BEST_THREADS is None:
-      best, n = (0.0, 1), usable_cpus()
-      cand = []
-      while n >= 1:
-        cand.append(n); n //= 2
-      for nt in cand:
-        t0 = time.perf_counter(); k = 0
-        while time.perf_counter() - t0 < 0.3:
-          c_port.logpost_grad(prob, th, nthreads=nt); k += th.shape[0]
-        rate = k / (time.perf_counter() - t0)
-        if rate > best[0]:
-          best = (rate, nt)
-      _BEST_THREADS = best[1]
-    nthreads = _BEST_THREADS
-  t0 = time.perf_counter(); n = 0; used = 1
+  if max_chains is not None:
+    th = th[:max_chains]
+  prob = _oracle_problem(cfg, y, X)
+  c_port.logpost_grad(prob, th[:min(8, len(th))], nthreads=nt)
+  t0 = time.perf_counter(); n = 0; used = nt
   while True:
-    _, _, used = c_port.logpost_grad(prob, th, nthreads=nthreads)
+    _, _, used = c_port.logpost_grad(prob, th, nthreads=nt)
     n += th.shape[0]
     dt = time.perf_counter() - t0
     if dt >= seconds:
       break
-  return n / dt, used, (f"{n} value+grad evals of the workload ({n // th.shape[0]} passes, "
-                        f"{dt:.1f} s; {used} threads chosen by calibration out of "
-                        f"{usable_cpus()} usable CPUs)")
+  return n / dt, used, (f"{n} value+grad evals of the workload ({n // th.shape[0]} passes over "
+                        f"{th.shape[0]} chains, {dt:.1f} s; {used} threads chosen by calibration "
+                        f"out of {usable_cpus()} usable CPUs)")
+
+
+def cpu_forecast_rate(cfg, n_draws=1024):
+  """CPU baseline of posterior draws/s on a bounded sample of configs[4]: the C port of the
+  simulation smoother + predictive draws (OpenMP over draws) followed by the oracle's float64
+  numpy impact stage (per-time quantiles of three families + summary: oracle/impact_np.py) on
+  `n_draws` draws.  Returns (draws/s, threads, description)."""
+  from oracle import c_port, impact_np
+  nt = best_threads()
+  y, X, th = make_inputs(cfg, chains=n_draws)
+  prob = _oracle_problem(cfg, y, X)
+  T = cfg["T"]; t_pre = int(round(0.7 * T))
+  per = np.zeros(T, np.uint8); per[t_pre:] = 1
+  obs = np.random.Generator(np.random.PCG64(6)).normal(size=T)
+  c_port.posterior_predict(prob, th[:8], seed=11, nthreads=nt)
+  t0 = time.perf_counter()
+  _, traj, mean, used = c_port.posterior_predict(prob, th, seed=11, want_level=False, nthreads=nt)
+  t1 = time.perf_counter()
+  impact_np.impact_arrays(traj, mean, obs, per, 2.0, 100.0, 0.025, 0.975, float(obs[t_pre:].sum()))
+  t2 = time.perf_counter()
+  dt = t2 - t0
+  return n_draws / dt, used, (f"{n_draws} of the {cfg['draws']} draws: C smoother + predictive draws "
+                              f"{(t1 - t0) * 1e3:.0f} ms on {used} threads, numpy float64 impact stage "
+                              f"{(t2 - t1) * 1e3:.0f} ms on 1 thread")
 
 
 def run_reference(args):
-  """--impl reference: the reference's CPU path for this metric.  The reference
-  delegates to TensorFlow Probability, which is not installable here (no
-  network, not in /opt/wheelhouse), so per the task's tier rules this arm times
-  the oracle's C port of that algorithm on the host cores."""
+  """--impl reference: the reference's CPU path for this metric.  The reference delegates to
+  TensorFlow Probability, which is not installable here (no network, not in /opt/wheelhouse), so
+  per the task's tier rules this arm times the oracle's C port of that algorithm on the host
+  cores, on the SAME config / metric / unit as the GPU arm."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  cfg = dict(WORKLOAD)
+  cfg = WORKLOAD
   per_step = max(0.2, min(8.0, 90.0 / max(1, args.steps + args.warmup)))   # whole arm <= ~1.5 min
   rates = []
   for i in range(args.warmup + args.steps):
-    r, used, sample = cpu_port_rate(cfg, seconds=per_step)
+    r, used, sample = cpu_logprob_rate(cfg, seconds=per_step)
     if i >= args.warmup:
       rates.append(r)
   val = float(np.mean(rates))
@@ -195,12 +281,345 @@ def run_reference(args):
       "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": 1e3 * cfg["chains"] / val, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-      "config": {"workload": "local-level + 10 covariates, T=1000, 256 chains (configs[1])",
-                 "note": "TFP is not installable here; C port of the oracle, OpenMP over chains"},
+      "config": {"workload": cfg["workload"],
+                 "note": "TFP is not installable here; C port of the oracle, OpenMP over chains, "
+                         "each step a bounded sample (repeated passes over the 256-chain batch)"},
       "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port",
                        "sample": sample},
       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU measurements
+# ------------------------------------------------------------------------------------------
+class Gpu:
+  def __init__(self, local):
+    import torch
+    self.torch = torch
+    self.dev = torch.device("cuda", local)
+    self.stream = torch.cuda.current_stream()
+    self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)  # > L2
+
+  def timed(self, fn, steps, flush=True):
+    """Per-call CUDA-event times (ms) of `steps` calls on the launching stream, the L2 flushed
+    (256 MB memset) before each one."""
+    torch = self.torch
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for i in range(steps):
+      if flush:
+        self.flush.zero_()
+      starts[i].record(self.stream); fn(); stops[i].record(self.stream)
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
+
+
+def logprob_kernel_name(cfg, team_w=4):
+  if cfg["model"] == 1:
+    return "k_logpost_llt<float>"
+  nb = -(-cfg["T"] // 256)
+  if os.environ.get("CI_B200_TEAM", "1") != "0" and nb <= 8:
+    return "k_logpost_team<float>"
+  if os.environ.get("CI_B200_TEAM", "1") != "0" and os.environ.get("CI_B200_TSTREAM", "1") != "0":
+    return "k_logpost_tstream<float>"
+  return "k_logpost_scan<float>"
+
+
+def bench_logprob_config(gpu, cib, _engine, cfg, local, steps, warmup, rank=0, world=1,
+                         with_cpu=True, cpu_seconds=3.0, eng=None):
+  """Device-timed evals/s, kernel time, roofline, host-buffer e2e (and the CPU baseline) of one
+  log-prob config.  Returns (block, engine, per-step ms array, launches)."""
+  torch = gpu.torch
+  C = cfg["chains"]
+  y, X, th_all = make_inputs(cfg, chains=C * world)
+  th_np = np.ascontiguousarray(th_all[rank * C:(rank + 1) * C], dtype=np.float32)
+  spec = cib.build_problem(y, X, model=cfg["model"])
+  own = eng is None
+  if own:
+    eng = cib.Engine(local)
+  eng.set_data(spec)
+  dim, p = spec.dim, spec.p
+  theta = torch.from_numpy(th_np).to(gpu.dev)
+  value = torch.empty(C, dtype=torch.float32, device=gpu.dev)
+  grad = torch.empty(C, dim, dtype=torch.float32, device=gpu.dev)
+
+  def step():
+    eng.logprob_grad_ptr(theta.data_ptr(), C, value.data_ptr(), grad.data_ptr(),
+                         _engine.VARIANT_SCAN, _engine.WITH_PRIOR, gpu.stream.cuda_stream)
+
+  for _ in range(warmup):
+    gpu.flush.zero_(); step()
+  torch.cuda.synchronize()
+  l0 = eng.launch_count
+  ms = gpu.timed(step, steps)
+  launches = eng.launch_count - l0
+  # hot-L2 back-to-back (no flush) for reference
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(gpu.stream)
+  for _ in range(steps):
+    step()
+  e1.record(gpu.stream)
+  torch.cuda.synchronize()
+  t_hot = float(e0.elapsed_time(e1)) / steps
+  if not np.all(np.isfinite(value.cpu().numpy())):
+    raise SystemExit(f"non-finite log-prob in bench ({cfg['key']})")
+
+  # ---- end to end through the host-pointer C ABI, pinned host buffers ----
+  th_pin = torch.from_numpy(th_np).pin_memory()
+  val_pin = torch.empty(C, dtype=torch.float32).pin_memory()
+  grad_pin = torch.empty(C, dim, dtype=torch.float32).pin_memory()
+
+  def step_e2e():
+    eng.logprob_grad_ptr(th_pin.data_ptr(), C, val_pin.data_ptr(), grad_pin.data_ptr(),
+                         _engine.VARIANT_SCAN, _engine.WITH_PRIOR, host=True)
+
+  for _ in range(warmup):
+    step_e2e()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    step_e2e()
+  torch.cuda.synchronize()
+  t_e2e = (time.perf_counter() - t0) * 1e3 / steps
+  if not np.all(np.isfinite(val_pin.numpy())):
+    raise SystemExit(f"non-finite log-prob in e2e bench ({cfg['key']})")
+
+  kern_ms = float(ms.mean())
+  B = bytes_per_eval(cfg["T"], p, spec.d)
+  peak, peak_src = measured_peak_hbm()
+  achieved = C * B / (kern_ms * 1e-3) / 1e9
+  kname = logprob_kernel_name(cfg)
+  block = {
+      "config": cfg["key"], "workload": cfg["workload"], "metric": METRIC, "unit": UNIT,
+      "value": C / (kern_ms * 1e-3), "kernel_ms": kern_ms, "kernel_ms_hot_l2": t_hot,
+      "steps": steps, "chains": C, "T": cfg["T"], "p": p, "dtype": "f32",
+      "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                   "frac": achieved / peak, "traffic": kernel_traffic(kname), "kernel": kname,
+                   "peak_source": peak_src, "algorithmic_bytes_per_launch": C * B,
+                   "algorithmic_bytes_per_eval": B, "kernel_ms": kern_ms},
+      "e2e": {"value": C / (t_e2e * 1e-3), "unit": UNIT, "ms_per_step": t_e2e,
+              "h2d_bytes_per_step": int(th_np.nbytes),
+              "d2h_bytes_per_step": int(C * 4 + C * dim * 4),
+              "note": "ci_logprob_grad with pinned host buffers (zero-copy reads / writes over PCIe)"},
+  }
+  if with_cpu:
+    v, cores, sample = cpu_logprob_rate(cfg, seconds=cpu_seconds,
+                                        max_chains=None if cfg["idx"] == 1 else 64)
+    block["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample}
+  if own:
+    return block, eng, ms, launches
+  return block, eng, ms, launches
+
+
+def bench_forecast_config(gpu, cib, _engine, cfg, local, rank=0, world=1, with_cpu=True, reps=10):
+  """configs[4]: posterior draws/s.  One unit = one simulation-smoother level path + one
+  predictive trajectory + its share of the predictive mean and of the impact stage (three
+  per-time quantile families + summary).  Under N ranks the draws are SHARDED (rank r takes the
+  global draw ids r S/N ..), the per-draw rows are all-gathered (NCCL, on the device) and the
+  impact stage runs on the gathered draws: the gather is inside the timed region."""
+  torch = gpu.torch
+  import torch.distributed as dist
+  T, S = cfg["T"], cfg["draws"]
+  y, X, th_all = make_inputs(cfg)
+  spec = cib.build_problem(y, X)
+  eng = cib.Engine(local)
+  eng.set_data(spec)
+  p = spec.p
+  lib, ctx = eng._lib, eng._ctx
+  s0, s_local = cib.shard.split_range(S, world, rank)
+  th_np = np.ascontiguousarray(th_all[s0:s0 + s_local], dtype=np.float32)
+  th = torch.from_numpy(th_np).to(gpu.dev)
+  lvl = torch.empty(s_local, T, dtype=torch.float32, device=gpu.dev)
+  trj = torch.empty_like(lvl)
+  t_pre = int(round(0.7 * T))
+  per = np.zeros(T, np.uint8); per[t_pre:] = 1
+  obs = np.random.Generator(np.random.PCG64(6)).normal(size=T)
+  out_d = torch.empty(T * 9 + 20, dtype=torch.float64, device=gpu.dev)
+  iargs = _engine.CiImpactArgs(S=S, T=T, dtype=0, reserved=0, scale=2.0, offset=100.0, q_lo=0.025,
+                               q_hi=0.975, obs_sum=float(obs[t_pre:].sum()))
+  st = gpu.stream.cuda_stream
+  ev = lambda: torch.cuda.Event(enable_timing=True)
+  marks = [ev() for _ in range(5)]
+  mean_full = torch.empty(T, dtype=torch.float32, device=gpu.dev)
+  if world > 1:
+    cap = max(cib.shard.split_range(S, world, r)[1] for r in range(world))
+    send = torch.zeros(cap, 2 * T + spec.dim, dtype=torch.float32, device=gpu.dev)
+    recv = torch.empty(world * cap, 2 * T + spec.dim, dtype=torch.float32, device=gpu.dev)
+
+  def forecast(record=False):
+    if record: marks[0].record(gpu.stream)
+    rc = lib.ci_posterior_predict_d(ctx, th.data_ptr(), s_local, 11, s0, lvl.data_ptr(),
+                                    trj.data_ptr(), None, st)
+    assert rc == 0, lib.ci_last_error()
+    if record: marks[1].record(gpu.stream)
+    if world > 1:
+      # the ONE exchange: rows [theta | level | traj] of every rank's draws
+      send[:s_local, :spec.dim] = th; send[:s_local, spec.dim:spec.dim + T] = lvl
+      send[:s_local, spec.dim + T:] = trj
+      dist.all_gather_into_tensor(recv, send)
+      rows = recv.view(world, cap, -1)
+      if S % world:
+        rows = torch.cat([rows[r, :cib.shard.split_range(S, world, r)[1]] for r in range(world)])
+      else:
+        rows = rows.reshape(S, -1)
+      th_g = rows[:, :spec.dim].contiguous()
+      lvl_g = rows[:, spec.dim:spec.dim + T].contiguous()
+      trj_g = rows[:, spec.dim + T:].contiguous()
+    else:
+      th_g, lvl_g, trj_g = th, lvl, trj
+    if record: marks[2].record(gpu.stream)
+    rc = lib.ci_predictive_mean_d(ctx, th_g.data_ptr(), lvl_g.data_ptr(), S, mean_full.data_ptr(), st)
+    assert rc == 0, lib.ci_last_error()
+    rc = lib.ci_impact_d(ctx, ctypes.byref(iargs), trj_g.data_ptr(), mean_full.data_ptr(),
+                         obs.ctypes.data_as(ctypes.c_void_p), per.ctypes.data_as(ctypes.c_void_p),
+                         out_d.data_ptr(), out_d.data_ptr() + 8 * T * 9, st)
+    assert rc == 0, lib.ci_last_error()
+    if record: marks[3].record(gpu.stream)
+    return out_d
+
+  for _ in range(3):
+    forecast()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  l0 = eng.launch_count
+  splits = []
+  for _ in range(reps):
+    gpu.flush.zero_()
+    forecast(record=True)
+    torch.cuda.synchronize()
+    splits.append([marks[i].elapsed_time(marks[i + 1]) for i in range(3)])
+  launches = (eng.launch_count - l0) // reps
+  sp = np.array(splits).mean(0)
+  t_dev = float(sp.sum())
+  # wall clock incl. the D2H of series + summary (what a caller of the pipeline waits for)
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  tq = time.perf_counter()
+  for _ in range(reps):
+    res = forecast().cpu()
+  t_wall = (time.perf_counter() - tq) / reps * 1e3
+  assert np.isfinite(res.numpy()[:T * 9].reshape(T, 9)[:, 0]).all()
+  if world > 1:
+    tt = torch.tensor([t_dev, t_wall] + sp.tolist(), dtype=torch.float64, device=gpu.dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_wall = float(tt[0]), float(tt[1]); sp = tt[2:].cpu().numpy()
+
+  # ---- e2e through the host-pointer ABI (rank-local draws): H2D theta, D2H level + traj + mean
+  S_e = s_local
+  th_h = torch.from_numpy(th_np).pin_memory()
+  lv_h = torch.empty(S_e, T, dtype=torch.float32).pin_memory()
+  tr_h = torch.empty(S_e, T, dtype=torch.float32).pin_memory()
+  mu_h = torch.empty(T, dtype=torch.float32).pin_memory()
+  def e2e():
+    rc = lib.ci_posterior_predict(ctx, th_h.data_ptr(), S_e, 11, s0, lv_h.data_ptr(), tr_h.data_ptr(),
+                                  mu_h.data_ptr())
+    assert rc == 0, lib.ci_last_error()
+  e2e(); e2e()
+  tq = time.perf_counter()
+  for _ in range(5):
+    e2e()
+  t_e2e = (time.perf_counter() - tq) / 5 * 1e3
+  if world > 1:
+    tt = torch.tensor([t_e2e], dtype=torch.float64, device=gpu.dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_e2e = float(tt[0])
+  eng.close()
+  Bd = bytes_per_draw(T, p, T - t_pre)
+  peak, peak_src = measured_peak_hbm()
+  achieved = S * Bd / (t_dev * 1e-3) / 1e9 / world
+  block = {
+      "config": cfg["key"], "workload": cfg["workload"], "metric": "posterior_draws_per_sec",
+      "unit": "draws/s", "value": S / (t_dev * 1e-3), "kernel_ms": t_dev,
+      "draws": S, "draws_per_gpu": s_local, "T": T, "p": p, "dtype": "f32", "n_gpus": world,
+      "scaling": "strong" if world > 1 else None, "gpu_launches_per_step": int(launches),
+      "split_ms": {"smoother_predictive": float(sp[0]), "all_gather": float(sp[1]),
+                   "mean_and_impact": float(sp[2])},
+      "wall_ms_incl_d2h_of_series": t_wall, "value_wall": S / (t_wall * 1e-3),
+      "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                   "frac": achieved / peak, "traffic": kernel_traffic("k_predict<float>"),
+                   "kernel": "k_predict<float> (+ k_predict_mean, k_impact_rows, k_impact_jobs)",
+                   "peak_source": peak_src, "algorithmic_bytes_per_launch": S * Bd,
+                   "algorithmic_bytes_per_draw": Bd, "kernel_ms": t_dev,
+                   "note": "per GPU: S B_draw / (device time of the pipeline) / n_gpus; traffic is "
+                           "k_predict's alone"},
+      "e2e": {"value": S_e * world / (t_e2e * 1e-3), "unit": "draws/s", "ms_per_step": t_e2e,
+              "h2d_bytes_per_step": int(th_np.nbytes),
+              "d2h_bytes_per_step": int(2 * S_e * T * 4 + T * 4),
+              "note": "ci_posterior_predict with pinned host buffers: theta in, level + traj + mean "
+                      "out (the [S,T] arrays cross PCIe; the product path leaves them in HBM)"},
+  }
+  if with_cpu:
+    v, cores, sample = cpu_forecast_rate(cfg)
+    block["cpu_baseline"] = {"value": v, "unit": "draws/s", "cores": cores, "kind": "port",
+                             "sample": sample}
+  return block
+
+
+def bench_saturation(gpu, cib, _engine, eng, cfg, counts=(256, 512, 1024, 2048, 4096, 8192, 16384)):
+  """Chains-per-launch curve of the configs[1] kernel: where the launch stops being latency-bound
+  (time flat in the chain count) and becomes throughput-bound (time linear in it)."""
+  torch = gpu.torch
+  y, X, th = make_inputs(cfg, chains=max(counts))
+  p = X.shape[1]
+  B = bytes_per_eval(cfg["T"], p)
+  out = []
+  for C in counts:
+    theta = torch.from_numpy(np.ascontiguousarray(th[:C], dtype=np.float32)).to(gpu.dev)
+    value = torch.empty(C, dtype=torch.float32, device=gpu.dev)
+    grad = torch.empty(C, p + 2, dtype=torch.float32, device=gpu.dev)
+    fn = lambda: eng.logprob_grad_ptr(theta.data_ptr(), C, value.data_ptr(), grad.data_ptr(),
+                                      _engine.VARIANT_SCAN, _engine.WITH_PRIOR, gpu.stream.cuda_stream)
+    for _ in range(3):
+      fn()
+    ms = float(gpu.timed(fn, 20).mean())
+    out.append({"chains": C, "kernel_us": ms * 1e3, "evals_per_sec": C / (ms * 1e-3),
+                "algorithmic_GBps": C * B / (ms * 1e-3) / 1e9})
+  return out
+
+
+def bench_sharded_fit(gpu, cib, local, rank, world):
+  """The product call with its chains SHARDED over the ranks (strong scaling): fit_causalimpact at
+  the BASELINE configs[4] scale -- T=2000, 10 covariates, 10 000 draws from 256 chains (the
+  reference's sampler: spike-and-slab Gibbs), sampler -> predictive draws -> the ONE all-gather ->
+  predictive mean + impact -> result frames.  Wall clock of the whole call (max over ranks) and
+  its phases."""
+  torch = gpu.torch
+  import pandas as pd
+  import torch.distributed as dist
+  rs = np.random.Generator(np.random.PCG64(20245))
+  T, k = 2000, 10
+  xs = 100 + np.cumsum(rs.normal(size=(T, k)), axis=0) * 0.3
+  yv = xs[:, :3] @ np.array([1.2, 0.6, -0.4]) + rs.normal(size=T)
+  yv[1400:] += 10
+  df = pd.DataFrame(np.column_stack([yv, xs]), columns=["y"] + [f"x{i}" for i in range(k)])
+  kw = dict(seed=3, inference_options=cib.InferenceOptions(num_results=10000, num_warmup_steps=100),
+            engine_options=cib.EngineOptions(num_chains=256, device=local, profile=True))
+  res = None
+  walls = []
+  for i in range(3):
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    tq = time.perf_counter()
+    res = cib.fit_causalimpact(df, (0, 1399), (1400, 1999), **kw)
+    walls.append((time.perf_counter() - tq) * 1e3)
+  wall = float(np.min(walls[1:]))
+  phases = dict(res.diagnostics.get("phases_ms", {}))
+  if world > 1:
+    keys = sorted(phases)
+    tt = torch.tensor([wall] + [phases[k2] for k2 in keys], dtype=torch.float64, device=gpu.dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall = float(tt[0]); phases = {k2: float(v) for k2, v in zip(keys, tt[1:].tolist())}
+  return {"workload": "fit_causalimpact, T=2000, 10 covariates, 10000 draws from 256 chains "
+                      "(BASELINE configs[4] scale), chains sharded over the ranks, one all-gather",
+          "n_gpus": world, "scaling": "strong", "wall_ms": wall, "phases_ms": phases,
+          "abs_effect": float(res.summary.loc["average", "abs_effect"]),
+          "note": "wall = max over ranks of the 2nd/3rd call; phases are host-timed with a device "
+                  "synchronise at each boundary (EngineOptions.profile)"}
 
 
 def main():
@@ -210,6 +629,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=20)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--cpu-seconds", type=float, default=10.0)
+  ap.add_argument("--quick", action="store_true", help="headline only (skip the extra blocks)")
   args = ap.parse_args()
   if args.impl == "reference":
     return run_reference(args)
@@ -229,314 +649,170 @@ def main():
   torch.cuda.set_device(local)
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-  dev = torch.device("cuda", local)
-
-  cfg = dict(WORKLOAD)
-  # weak scaling: every rank evaluates its own 256 chains (global chain ids
-  # rank*256 .. rank*256+255); the series is replicated.
-  y, X, th_all = make_inputs(dict(cfg, chains=cfg["chains"] * world))
-  C = cfg["chains"]
-  th_np = np.ascontiguousarray(th_all[rank * C:(rank + 1) * C], dtype=np.float32)
-  spec = cib.build_problem(y, X)
-  eng = cib.Engine(local)
-  eng.set_data(spec)
-  dim, p = spec.dim, spec.p
-
-  theta = torch.from_numpy(th_np).to(dev)
-  value = torch.empty(C, dtype=torch.float32, device=dev)
-  grad = torch.empty(C, dim, dtype=torch.float32, device=dev)
-  flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > L2
-  stream = torch.cuda.current_stream()
-
-  def step():
-    eng.logprob_grad_ptr(theta.data_ptr(), C, value.data_ptr(), grad.data_ptr(),
-                         _engine.VARIANT_SCAN, _engine.WITH_PRIOR, stream.cuda_stream)
+  gpu = Gpu(local)
 
   def sync_all():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
-  for _ in range(args.warmup):
-    flush.zero_(); step()
-  sync_all()
-  l0 = eng.launch_count
-
-  # ---- device-resident throughput: per-step CUDA events, L2 flushed between ----
-  starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-  stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+  extra = {}
   with ClockSampler(local) as clk:
+    # ---- headline: configs[1], weak scaling (every rank its own 256 chains, global chain ids
+    # rank*256 ..; the series is replicated, no data-path collective: SURVEY section 8e) ----
     sync_all()
-    for i in range(args.steps):
-      flush.zero_()
-      starts[i].record(stream); step(); stops[i].record(stream)
+    head, eng, ms, launches = bench_logprob_config(
+        gpu, cib, _engine, WORKLOAD, local, args.steps, args.warmup, rank, world, with_cpu=False)
     sync_all()
-    # hot-L2 back-to-back (no flush) for reference
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-      step()
-    e1.record(stream)
-    sync_all()
-  launches = eng.launch_count - l0
-  ms = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
-  t_step = float(ms.sum())                      # ms over K steps, kernel only
-  t_hot = float(e0.elapsed_time(e1))
+    t_step = float(ms.sum())
+    t_e2e = head["e2e"]["ms_per_step"] * args.steps
+    t_hot = head["kernel_ms_hot_l2"] * args.steps
+    C = WORKLOAD["chains"]
 
-  # ---- end to end through the host-pointer C ABI, pinned host buffers ----
-  th_pin = torch.from_numpy(th_np).pin_memory()
-  val_pin = torch.empty(C, dtype=torch.float32).pin_memory()
-  grad_pin = torch.empty(C, dim, dtype=torch.float32).pin_memory()
-
-  def step_e2e():
-    eng.logprob_grad_ptr(th_pin.data_ptr(), C, val_pin.data_ptr(), grad_pin.data_ptr(),
-                         _engine.VARIANT_SCAN, _engine.WITH_PRIOR, host=True)
-
-  for _ in range(args.warmup):
-    step_e2e()
-  sync_all()
-  t0 = time.perf_counter()
-  for _ in range(args.steps):
-    step_e2e()
-  torch.cuda.synchronize()
-  t_e2e = (time.perf_counter() - t0) * 1e3
-  # parity guard on the numbers just produced
-  if not np.all(np.isfinite(val_pin.numpy())):
-    raise SystemExit("non-finite log-prob in bench")
-
-  # ---- secondary metrics (BASELINE.json names both): HMC leapfrog evals/s inside the
-  # persistent kernel, and posterior draws/s (simulation smoother + predictive) ----
-  hmc_kw = dict(n_warmup=40, n_results=20, seed=20242, max_leapfrog=8, init_step=0.02)
-  th0 = th_np.astype(np.float64)
-  eng.hmc_run(th0, chain_id0=rank * C, **dict(hmc_kw, n_warmup=5, n_results=2))     # warm
-  sync_all()
-  t0 = time.perf_counter()
-  _, hstats = eng.hmc_run(th0, chain_id0=rank * C, **hmc_kw)
-  t_hmc = (time.perf_counter() - t0) * 1e3
-  hmc_evals = int(hstats["n_leapfrog"].sum())
-  S_pred = 4096
-  thp = torch.from_numpy(np.ascontiguousarray(np.tile(th_np, (S_pred // C + 1, 1))[:S_pred])).to(dev)
-  lvl = torch.empty(S_pred, cfg["T"], dtype=torch.float32, device=dev)
-  trj = torch.empty_like(lvl)
-  mean_d = torch.empty(cfg["T"], dtype=torch.float32, device=dev)
-  lib, ctx = eng._lib, eng._ctx                       # raw _d entry for device-resident timing
-  def predict():
-    rc = lib.ci_posterior_predict_d(ctx, thp.data_ptr(), S_pred, 7, rank * S_pred, lvl.data_ptr(),
-                                    trj.data_ptr(), mean_d.data_ptr(), stream.cuda_stream)
-    assert rc == 0, lib.ci_last_error()
-  for _ in range(3):
-    predict()
-  sync_all()
-  p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  p0.record(stream)
-  for _ in range(10):
-    predict()
-  p1.record(stream)
-  sync_all()
-  t_pred = float(p0.elapsed_time(p1)) / 10.0
-
-  # ---- impact series + summary on the device (ci_impact_d) on those draws ----
-  import types
-  Tn = cfg["T"]
-  t_pre = int(0.7 * Tn)
-  per = np.zeros(Tn, np.uint8); per[t_pre:] = 1
-  obs = np.random.Generator(np.random.PCG64(5)).normal(size=Tn)
-  meta = types.SimpleNamespace(observed=obs, period=per, scale=2.0, offset=100.0, q_lo=0.025,
-                               q_hi=0.975, obs_sum=float(obs[t_pre:].sum()))
-  out_d = torch.empty(Tn * 9 + 20, dtype=torch.float64, device=dev)
-  iargs = _engine.CiImpactArgs(S=S_pred, T=Tn, dtype=0, reserved=0, scale=2.0, offset=100.0,
-                               q_lo=0.025, q_hi=0.975, obs_sum=meta.obs_sum)
-  import ctypes
-  def impact_step():
-    rc = lib.ci_impact_d(ctx, ctypes.byref(iargs), trj.data_ptr(), mean_d.data_ptr(),
-                         obs.ctypes.data_as(ctypes.c_void_p), per.ctypes.data_as(ctypes.c_void_p),
-                         out_d.data_ptr(), out_d.data_ptr() + 8 * Tn * 9, stream.cuda_stream)
-    assert rc == 0, lib.ci_last_error()
-  for _ in range(3):
-    impact_step()
-  sync_all()
-  p0.record(stream)
-  for _ in range(10):
-    impact_step()
-  p1.record(stream)
-  sync_all()
-  t_impact = float(p0.elapsed_time(p1)) / 10.0
-
-  # ---- BASELINE configs[4] shape on this GPU: 10 000-draw posterior forecast, T = 2000, 10
-  # covariates -- simulation smoother + predictive draws + mean + the whole impact stage,
-  # device resident (the second headline quantity: posterior draws/s) ----
-  from conftest import make_series as _mk
-  y5, X5, _ = _mk(2000, 10, 20245)
-  eng5 = cib.Engine(local)
-  eng5.set_data(cib.build_problem(y5, X5))
-  S5 = 10000
-  th5 = torch.from_numpy(np.ascontiguousarray(np.tile(th_np, (S5 // C + 1, 1))[:S5])).to(dev)
-  per5 = np.zeros(2000, np.uint8); per5[1400:] = 1
-  obs5 = np.random.Generator(np.random.PCG64(6)).normal(size=2000)
-  meta5 = types.SimpleNamespace(observed=obs5, period=per5, scale=2.0, offset=100.0, q_lo=0.025,
-                                q_hi=0.975, obs_sum=float(obs5[1400:].sum()))
-  def forecast():
-    lv5, tr5 = eng5.posterior_predict_t(th5, seed=11, draw_id0=rank * S5)
-    mu5 = eng5.predictive_mean_t(th5, lv5)
-    return eng5.impact(tr5, mu5, meta5)          # ends with the D2H of series + summary
-  for _ in range(3):
-    forecast()
-  sync_all()
-  tq = time.perf_counter()
-  for _ in range(5):
-    forecast()
-  sync_all()
-  t_fc = (time.perf_counter() - tq) / 5 * 1e3
-  eng5.close()
-
-  # ---- batch of independent series: one launch, grid.y = series ----
-  specs_b = []
-  for sb in range(128):
-    yb, Xb, _ = _mk(300, 2, 3000 + sb)
-    specs_b.append(cib.build_problem(yb, Xb))
-  engb = cib.Engine(local)
-  engb.set_data_batch(specs_b)
-  engb.gibbs_run_batch_t(8, n_warmup=2, n_results=2, seed=1)
-  sync_all()
-  tq = time.perf_counter()
-  engb.gibbs_run_batch_t(8, n_warmup=100, n_results=50, seed=1)
-  sync_all()
-  t_batch = (time.perf_counter() - tq) * 1e3
-  engb.close()
-
-  # ---- the whole product call for a panel of series (fit_causalimpact_panel): vectorised data
-  # prep + batched sampler + queued mean / impact + one read-back; every rank fits its own panel
-  # (series are independent: no collective) ----
-  rp = np.random.Generator(np.random.PCG64(77 + rank))
-  Np, Tp = 128, 300
-  xs_p = 100 + np.cumsum(rp.normal(size=(Np, Tp, 2)), axis=1) * 0.3
-  y_p = xs_p[:, :, 0] + rp.normal(size=(Np, Tp)); y_p[:, 210:] += 3.0
-  vals_p = np.concatenate([y_p[:, :, None], xs_p], axis=2)
-  kw_p = dict(seed=1, inference_options=cib.InferenceOptions(num_results=400),
-              engine_options=cib.EngineOptions(num_chains=8, device=local))
-  # (fit_causalimpact_panel shards over an initialised group; here every rank times its OWN
-  # full panel, so run it with the group hidden)
-  _w = cib.shard.world
-  cib.shard.world = lambda: (0, 1)
-  try:
-    cib.fit_causalimpact_panel(vals_p[:4], np.arange(Tp), (0, 209), (210, Tp - 1), **kw_p)
-    sync_all()
-    tq = time.perf_counter()
-    cib.fit_causalimpact_panel(vals_p, np.arange(Tp), (0, 209), (210, Tp - 1), **kw_p)
-    t_panel = (time.perf_counter() - tq) * 1e3
-  finally:
-    cib.shard.world = _w
-
-  # ---- the reference's own sampler on the GPU: Gibbs sweeps/s (spike-and-slab, 256 chains)
-  eng.gibbs_run(C, n_warmup=2, n_results=2, seed=1, chain_id0=rank * C, want_level=False,
-                want_traj=False)
-  sync_all()
-  t0 = time.perf_counter()
-  eng.gibbs_run(C, n_warmup=30, n_results=30, seed=1, chain_id0=rank * C, want_level=False,
-                want_traj=False)
-  t_gibbs = (time.perf_counter() - t0) * 1e3
-
-  # ---- the product call itself: fit_causalimpact on the quickstart shape (configs[0]:
-  # T=100, 1 covariate, defaults = 900 draws).  The reference's only published number is
-  # 5.17 s wall for this call on an unspecified notebook CPU (docs/quickstart.ipynb:361-362).
-  # (every rank calls it: with a process group the fit shards its chains over the ranks
-  # and ends with one all-gather, so a rank-0-only call would wait forever)
-  import pandas as pd
-  rs = np.random.Generator(np.random.PCG64(20241))
-  xq = 100 + np.cumsum(rs.normal(size=100)) * 0.3
-  yq = 1.2 * xq + rs.normal(size=100)
-  yq[71:] += 10
-  dfq = pd.DataFrame({"y": yq, "x": xq})
-  t_fit = None
-  for _ in range(2):
-    sync_all()
-    tq = time.perf_counter()
-    cib.fit_causalimpact(dfq, (0, 70), (71, 99), seed=1,
-                         engine_options=cib.EngineOptions(device=local))
-    t_fit = (time.perf_counter() - tq) * 1e3
+    if not args.quick:
+      # ---- throughput step: the same kernel with enough chains to fill the GPU ----
+      extra["saturation"] = bench_saturation(gpu, cib, _engine, eng, WORKLOAD) if rank == 0 else None
+      sync_all()
+      # ---- HMC leapfrog evals/s inside the persistent kernel, Gibbs sweeps/s ----
+      y, X, th_all = make_inputs(WORKLOAD, chains=C * world)
+      th0 = np.ascontiguousarray(th_all[rank * C:(rank + 1) * C], dtype=np.float64)
+      hmc_kw = dict(n_warmup=40, n_results=20, seed=20242, max_leapfrog=8, init_step=0.02)
+      eng.hmc_run(th0, chain_id0=rank * C, **dict(hmc_kw, n_warmup=5, n_results=2))     # warm
+      sync_all()
+      t0 = time.perf_counter()
+      _, hstats = eng.hmc_run(th0, chain_id0=rank * C, **hmc_kw)
+      t_hmc = (time.perf_counter() - t0) * 1e3
+      hmc_evals = int(hstats["n_leapfrog"].sum())
+      eng.gibbs_run_t(C, n_warmup=2, n_results=2, seed=1, chain_id0=rank * C)
+      sync_all()
+      g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      g0.record(gpu.stream)
+      eng.gibbs_run_t(C, n_warmup=90, n_results=10, seed=1, chain_id0=rank * C)
+      g1.record(gpu.stream)
+      torch.cuda.synchronize()
+      t_gibbs = float(g0.elapsed_time(g1))
+      # ---- the other BASELINE configs (rank 0; configs[4] runs on every rank, sharded) ----
+      cfg_blocks = []
+      if rank == 0:
+        cfg_blocks.append(dict(head))
+        for cfg in CONFIGS[1:3]:
+          blk, e2, _, _ = bench_logprob_config(gpu, cib, _engine, cfg, local, 20, 3,
+                                               with_cpu=False)
+          e2.close()
+          cfg_blocks.append(blk)
+      sync_all()
+      fc = bench_forecast_config(gpu, cib, _engine, CONFIGS[3], local, rank, world, with_cpu=False)
+      sync_all()
+      # ---- panel of independent series: the whole product call ----
+      rp = np.random.Generator(np.random.PCG64(77 + rank))
+      Np, Tp = 128, 300
+      xs_p = 100 + np.cumsum(rp.normal(size=(Np, Tp, 2)), axis=1) * 0.3
+      y_p = xs_p[:, :, 0] + rp.normal(size=(Np, Tp)); y_p[:, 210:] += 3.0
+      vals_p = np.concatenate([y_p[:, :, None], xs_p], axis=2)
+      kw_p = dict(seed=1, inference_options=cib.InferenceOptions(num_results=400),
+                  engine_options=cib.EngineOptions(num_chains=8, device=local))
+      _w = cib.shard.world
+      cib.shard.world = lambda: (0, 1)      # every rank times its OWN full panel (no sharding here)
+      try:
+        cib.fit_causalimpact_panel(vals_p[:4], np.arange(Tp), (0, 209), (210, Tp - 1), **kw_p)
+        sync_all()
+        tq = time.perf_counter()
+        cib.fit_causalimpact_panel(vals_p, np.arange(Tp), (0, 209), (210, Tp - 1), **kw_p)
+        t_panel = (time.perf_counter() - tq) * 1e3
+      finally:
+        cib.shard.world = _w
+      # ---- the product call, quickstart shape (configs[0]) and sharded at the configs[4] scale
+      import pandas as pd
+      rs = np.random.Generator(np.random.PCG64(20241))
+      xq = 100 + np.cumsum(rs.normal(size=100)) * 0.3
+      yq = 1.2 * xq + rs.normal(size=100)
+      yq[71:] += 10
+      dfq = pd.DataFrame({"y": yq, "x": xq})
+      t_fit = None
+      for _ in range(2):
+        sync_all()
+        tq = time.perf_counter()
+        cib.fit_causalimpact(dfq, (0, 70), (71, 99), seed=1,
+                             engine_options=cib.EngineOptions(device=local))
+        t_fit = (time.perf_counter() - tq) * 1e3
+      sync_all()
+      sharded = bench_sharded_fit(gpu, cib, local, rank, world)
+      sync_all()
+  eng.close()
 
   if world > 1:
-    t = torch.tensor([t_step, t_e2e, t_hot, t_hmc, t_pred, t_gibbs], dtype=torch.float64,
-                     device=dev)
+    t = torch.tensor([t_step, t_e2e, t_hot], dtype=torch.float64, device=gpu.dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_step, t_e2e, t_hot, t_hmc, t_pred, t_gibbs = (float(x) for x in t.tolist())
-    he = torch.tensor([hmc_evals], dtype=torch.float64, device=dev)
-    dist.all_reduce(he, op=dist.ReduceOp.SUM)
-    hmc_evals = int(he.item())
+    t_step, t_e2e, t_hot = (float(x) for x in t.tolist())
+    if not args.quick:
+      t = torch.tensor([t_hmc, t_gibbs, t_panel], dtype=torch.float64, device=gpu.dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      t_hmc, t_gibbs, t_panel = (float(x) for x in t.tolist())
+      he = torch.tensor([hmc_evals], dtype=torch.float64, device=gpu.dev)
+      dist.all_reduce(he, op=dist.ReduceOp.SUM)
+      hmc_evals = int(he.item())
 
-  team = os.environ.get("CI_B200_TEAM", "1") != "0" and 2 <= -(-cfg["T"] // 256) <= 8
   if rank == 0:
     total = C * world * args.steps
     val = total / (t_step * 1e-3)
-    B = bytes_per_eval(cfg["T"], p)
-    peak, peak_src = measured_peak_hbm()
     kern_ms = float(ms.mean())
-    achieved = C * B / (kern_ms * 1e-3) / 1e9
-    cpu_val, cores, sample = cpu_port_rate(cfg, seconds=args.cpu_seconds)
+    roof = dict(head["roofline"])
+    # CPU baselines after the GPU work (the clock sampler must not see a busy host as GPU load)
+    cpu_val, cores, sample = cpu_logprob_rate(WORKLOAD, seconds=args.cpu_seconds)
     out = {
         "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "local-level + 10 covariates, T=1000, 256 chains per GPU "
-                               "(BASELINE.json configs[1]); value+gradient, prior included",
-                   "variant": ("associative scan, TEAM mode: warp-shuffle scan per 256-step tile, one "
-                               "warp per tile (4 warps per chain), tile aggregates exchanged via smem")
-                              if team else "associative scan, one warp per chain (CI_B200_TEAM=0)",
+        "config": {"workload": WORKLOAD["workload"],
+                   "variant": "associative scan, TEAM mode: warp-shuffle scan per 256-step tile, one "
+                              "warp per tile (4 warps per chain), tile aggregates exchanged via smem"
+                              if roof["kernel"].startswith("k_logpost_team") else roof["kernel"],
                    "l2": "flushed (256 MB memset) between timed steps",
                    "timing": "CUDA events per step on the launching stream"},
         "e2e": {"value": total / (t_e2e * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": int(th_np.nbytes),
-                "d2h_bytes_per_step": int(C * 4 + C * dim * 4)},
+                "h2d_bytes_per_step": head["e2e"]["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": head["e2e"]["d2h_bytes_per_step"]},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
-                     # dram__bytes_read+write per launch, ncu --set full (profiles/r01_k_logpost_*_ncu.md, run 33)
-                     "traffic": 140288 if team else 133888,
-                     "kernel": "k_logpost_team<float>" if team else "k_logpost_scan<float>",
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": C * B,
-                     "kernel_ms": kern_ms},
+        "roofline": roof,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "clocks": clk.summary(),
-        "extra": {"value_hot_l2": total / (t_hot * 1e-3),
-                  "ms_per_step_hot_l2": t_hot / args.steps,
-                  "hmc_leapfrog_evals_per_sec": hmc_evals / (t_hmc * 1e-3),
-                  "hmc_run": {"chains_per_gpu": C, "iterations": 60, "wall_ms": t_hmc,
-                              "note": "host-pointer ci_hmc_run incl. copies + sync"},
-                  "gibbs_sweeps_per_sec": C * world * 60 / (t_gibbs * 1e-3),
-                  "gibbs_run": {"chains_per_gpu": C, "sweeps": 60, "wall_ms": t_gibbs,
-                                "note": "ci_gibbs_run, spike-and-slab (inclusion prob 3/11), "
-                                        "one sweep = SSVS + FFBS + 2 InvGamma draws; the reference "
-                                        "publishes <= 5.2 ms per sweep (1 chain, T=100)"},
-                  "fit_causalimpact_quickstart_ms": t_fit,
-                  "fit_note": "T=100, 1 covariate, 900 draws, 64 chains, 2nd call; reference "
-                              "publishes 5170 ms for this call (other hardware, incl. tracing)",
-                  "forecast_10000_draws_T2000_ms": t_fc,
-                  "forecast_draws_per_sec": S5 * world / (t_fc * 1e-3),
-                  "forecast_note": "BASELINE configs[4] shape per GPU: ci_posterior_predict_d + "
-                                   "ci_predictive_mean_d + ci_impact_d for 10 000 draws, T=2000, 10 "
-                                   "covariates, wall clock incl. the D2H of series + summary",
-                  "batch_gibbs": {"series": 128, "T": 300, "chains_per_series": 8, "sweeps": 150,
-                                  "wall_ms": t_batch,
-                                  "sweeps_per_sec": 128 * 8 * 150 * world / (t_batch * 1e-3),
-                                  "note": "ci_gibbs_run_batch_d: every chain of every series in "
-                                          "one launch (rank 0's time)"},
-                  "panel_fit": {"series": Np, "T": Tp, "covariates": 2, "chains_per_series": 8,
-                                "draws": 400, "wall_ms": t_panel,
-                                "series_per_sec": Np * world / (t_panel * 1e-3),
-                                "note": "fit_causalimpact_panel: the whole call (data prep, sampler, "
-                                        "predictive mean, impact, result arrays) for a panel of "
-                                        "independent series; the reference takes ~5 s per series"},
-                  "impact_ms": t_impact,
-                  "impact_note": f"ci_impact_d on {S_pred} draws x T={cfg['T']}: effect paths, 3 per-time "
-                                 "quantile families, post-period summary; device resident "
-                                 "(rank 0's time)",
-                  "posterior_draws_per_sec": S_pred * world / (t_pred * 1e-3),
-                  "posterior_draws": {"draws_per_gpu": S_pred, "T": cfg["T"], "ms": t_pred,
-                                      "note": "ci_posterior_predict_d: level + trajectory + mean, "
-                                              "device resident, CUDA events"}},
+        "extra": {"value_hot_l2": total / (t_hot * 1e-3), "ms_per_step_hot_l2": t_hot / args.steps},
     }
+    if not args.quick:
+      cfg_blocks[0]["cpu_baseline"] = dict(out["cpu_baseline"])
+      for blk, cfg in zip(cfg_blocks[1:], CONFIGS[1:3]):
+        v, cr, smp = cpu_logprob_rate(cfg, seconds=3.0, max_chains=64)
+        blk["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cr, "kind": "port", "sample": smp}
+      v, cr, smp = cpu_forecast_rate(CONFIGS[3])
+      fc["cpu_baseline"] = {"value": v, "unit": "draws/s", "cores": cr, "kind": "port", "sample": smp}
+      cfg_blocks.append(fc)
+      out["extra"].update({
+          "configs": cfg_blocks,
+          "posterior_draws": {k2: fc[k2] for k2 in ("metric", "unit", "value", "kernel_ms", "draws",
+                                                    "n_gpus", "split_ms", "roofline", "e2e",
+                                                    "cpu_baseline", "value_wall")},
+          "saturation": extra["saturation"],
+          "saturation_note": "configs[1] kernel vs chains per launch: flat time = latency-bound, "
+                             "linear = throughput-bound",
+          "hmc_leapfrog_evals_per_sec": hmc_evals / (t_hmc * 1e-3),
+          "hmc_run": {"chains_per_gpu": C, "iterations": 60, "wall_ms": t_hmc,
+                      "note": "host-pointer ci_hmc_run incl. copies + sync"},
+          "gibbs_sweeps_per_sec": C * world * 100 / (t_gibbs * 1e-3),
+          "gibbs_run": {"chains_per_gpu": C, "sweeps": 100, "device_ms": t_gibbs,
+                        "us_per_sweep": t_gibbs * 10.0,
+                        "note": "ci_gibbs_run_d (team kernel), spike-and-slab (inclusion prob 3/11), one "
+                                "sweep = SSVS + FFBS + 2 InvGamma draws; the reference publishes <= 5.2 "
+                                "ms per sweep (1 chain, T=100)"},
+          "panel_fit": {"series": Np, "T": Tp, "covariates": 2, "chains_per_series": 8, "draws": 400,
+                        "wall_ms": t_panel, "series_per_sec": Np * world / (t_panel * 1e-3),
+                        "note": "fit_causalimpact_panel: the whole call for a panel of independent "
+                                "series (every rank its own panel); the reference takes ~5 s per series"},
+          "fit_causalimpact_quickstart_ms": t_fit,
+          "fit_note": "T=100, 1 covariate, 900 draws, 64 chains, 2nd call; reference publishes 5170 "
+                      "ms for this call (other hardware, incl. tracing)",
+          "sharded_fit": sharded,
+      })
     print(json.dumps(out))
   if world > 1:
     dist.destroy_process_group()

@@ -525,6 +525,11 @@ class Engine:
     import torch
     return torch, torch.device("cuda", self.device)
 
+  def synchronize(self):
+    """Wait for everything queued on this engine's device."""
+    import torch
+    torch.cuda.synchronize(self.device)
+
   def torch_device(self):
     """torch.device of this engine's GPU."""
     return self._torch_dev()[1]

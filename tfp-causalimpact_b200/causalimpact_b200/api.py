@@ -118,6 +118,11 @@ class EngineOptions:
     global chain ids ``i * num_chains + c``, so the Monte-Carlo errors of different series are
     independent and panel aggregates average them out.  False: every series consumes the same
     streams and result i is bit-identical to ``fit_causalimpact(datas[i], sampler="gibbs")``.
+  return_level: False leaves ``posterior_samples.level`` (and ``seasonal_levels``) as None: the
+    [S, T] level paths are then neither all-gathered across ranks nor copied to the host (they
+    are the largest part of both); series and summary are unaffected.
+  profile: record the wall time of every phase of the fit in ``diagnostics["phases_ms"]`` (the
+    device is synchronised at each phase boundary, so the phases do not overlap).
   """
   num_chains: int = 64
   sampler: str = "auto"
@@ -131,9 +136,30 @@ class EngineOptions:
   upper_bound_on: str = "variance"
   ssvs_order: str = "random"
   decorrelate_series: bool = True
+  return_level: bool = True
+  profile: bool = False
 
 
 _ENGINES = {}
+
+
+class _Phases:
+  """Wall time per phase of a fit (EngineOptions.profile); a no-op when off."""
+
+  def __init__(self, on: bool, eng=None):
+    import time
+    self.on, self.t, self._eng, self._clock = on, {}, eng, time.perf_counter
+    self._last = self._clock()
+
+  def mark(self, name: str):
+    if not self.on:
+      return
+    sync = getattr(self._eng, "synchronize", None)
+    if sync is not None:
+      sync()
+    now = self._clock()
+    self.t[name] = self.t.get(name, 0.0) + (now - self._last) * 1e3
+    self._last = now
 
 
 def _engine_for(device: int) -> Engine:
@@ -217,6 +243,7 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
 
   rank, ws = _shard.world()
   eng = _resolve_engine(opts)
+  ph = _Phases(opts.profile, eng)
   if seed is None and ws > 1:          # fresh entropy: every rank must use rank 0's
     seed64 = _shard.broadcast_u64(seed64, getattr(eng, "torch_device", lambda: None)())
 
@@ -238,6 +265,7 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   if sched is not None:
     eng.set_seasonal(sched)
   K = 0 if sched is None else sched.K
+  ph.mark("prepare_upload")
 
   # ---- chains: global ids 0..C-1, contiguous shard per rank ----
   # Everything below stays in the engine's HBM (tensors on eng's device; torch is the
@@ -290,6 +318,7 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
                                   target_accept=opts.target_accept)
     # chain-major draw ids: g = chain * n_per + iteration  (contiguous per rank)
     theta_l = draws.permute(1, 0, 2).reshape(-1, spec.dim).contiguous()
+    ph.mark("sampler")
     level_l, traj_l = eng.posterior_predict_t(theta_l, seed=seed64 ^ 0x9E3779B97F4A7C15,
                                               draw_id0=lo * n_per)
     hstats = hstats[:c_local]
@@ -297,6 +326,7 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
              "step_size": np.asarray(hstats["step_size"]),
              "n_divergent": np.asarray(hstats["n_divergent"]),
              "n_leapfrog": np.asarray(hstats["n_leapfrog"])}
+  ph.mark("predictive" if stats.get("sampler") == "hmc" else "sampler")
   n_local = c_local * n_per
   parts = [theta_l, level_l, traj_l] + extra_l
   if ws == 1:
@@ -309,13 +339,17 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
     rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
     parts = [t.contiguous() for t in torch.split(rows, widths, dim=1)]
   theta_t, level_t, traj_t = parts[:3]
+  ph.mark("all_gather")
   # mean of the predictive mixture = average of level (+ seasonal) + X.w over the draws
   # (causalimpact_lib.py:627); fixed summation order over the gathered draws => the same
   # for any GPU count
   mean_t = eng.predictive_mean_t(theta_t, parts[3] if sched is not None else level_t)
+  ph.mark("predictive_mean")
 
-  samples = _package_samples(eng, theta_t, level_t, p, T, np_dt, wh,
-                             (parts[4], parts[5], K) if sched is not None else None)
+  samples = _package_samples(eng, theta_t, level_t if opts.return_level else None, p, T, np_dt, wh,
+                             (parts[4] if opts.return_level else None, parts[5], K)
+                             if sched is not None else None)
+  ph.mark("package_samples")
   if stats is not None:
     # convergence across the parallel chains: split-R-hat of (log sigma_obs^2, log sigma_level^2)
     # over the complete chains among the kept draws (rows are chain-major)
@@ -324,6 +358,7 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
       th = eng.to_host(theta_t[:full, p:p + 2]).reshape(full // n_per, n_per, 2)
       stats["rhat_log_variances"] = split_rhat(th)
   samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
+  samples.phases = ph                  # pylint: disable=attribute-defined-outside-init
   return samples, DeviceArray(mean_t), DeviceArray(traj_t)
 
 
@@ -346,7 +381,7 @@ def split_rhat(x: np.ndarray) -> np.ndarray:
 def _package_samples(eng, theta_t, level_t, p, T, np_dt, wh=None, seasonal=None):
   """Device draws -> the reference's posterior-sample record (host arrays)."""
   theta = eng.to_host(theta_t).astype(np.float64)
-  level = eng.to_host(level_t)
+  level = None if level_t is None else eng.to_host(level_t)
   z = theta[:, :p]
   weights = wh.to_weights(z) if wh is not None else z
   S = theta.shape[0]
@@ -354,17 +389,18 @@ def _package_samples(eng, theta_t, level_t, p, T, np_dt, wh=None, seasonal=None)
     # each component's contribution at every step: what the reference extracts as the
     # 0-th element of the component's latent (lib.py:299-317), [S, T, K]
     seas_t, drift_t, K = seasonal
-    seas_levels = eng.to_host(seas_t).reshape(S, T, K).astype(np_dt, copy=False)
+    seas_levels = None if seas_t is None else \
+        eng.to_host(seas_t).reshape(S, T, K).astype(np_dt, copy=False)
     drift_scales = np.exp(0.5 * eng.to_host(drift_t).astype(np.float64)).astype(np_dt)
   else:
     seas_levels, drift_scales = np.zeros((S, T, 0), np_dt), np.zeros((S, 0), np_dt)
   return CausalImpactPosteriorSamples(
       observation_noise_scale=Samples(np.exp(0.5 * theta[:, p]).astype(np_dt)),
       level_scale=Samples(np.exp(0.5 * theta[:, p + 1]).astype(np_dt)),
-      level=Samples(level.astype(np_dt, copy=False)),
+      level=None if level is None else Samples(level.astype(np_dt, copy=False)),
       weights=Samples(weights.astype(np_dt)) if p else Samples(np.zeros((S, 0), np_dt)),
       seasonal_drift_scales=Samples(drift_scales),
-      seasonal_levels=Samples(seas_levels))
+      seasonal_levels=None if seas_levels is None else Samples(seas_levels))
 
 
 def fit_causalimpact(data: pd.DataFrame,
@@ -404,6 +440,10 @@ def fit_causalimpact(data: pd.DataFrame,
       experimental_tf_function_cache_key_addition=cache_key, engine_options=engine_options)
   eng = _resolve_engine(engine_options)
   series, summary = _impact.compute_impact(means, trajectories, ci_data, alpha, eng.impact)
+  ph = getattr(samples, "phases", None)
+  if ph is not None and ph.on:
+    ph.mark("impact_and_frames")
+    samples.hmc_stats["phases_ms"] = dict(ph.t)
   return _analysis(series, summary, samples)
 
 
