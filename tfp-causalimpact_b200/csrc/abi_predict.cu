@@ -14,13 +14,28 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
   const ProbDev<R> prt = make_probdev<R>(c);
   int GT = 0;
   // The kernel choice must NOT depend on S: a draw has to come out bit-identical however
-  // the batch is split over calls / GPUs.  The one-warp kernel is the default (better
-  // occupancy at thousands of draws: 21.5 vs 20.0 M draws/s at S=4096, run 8); the team
-  // kernel (lower latency for a handful of draws) is opt-in via CI_B200_PREDICT_TEAM=1.
-  if (c->predict_team && plan_team<R>(c, S, &GT, &cfg)) {
+  // the batch is split over calls / GPUs.
+  // Team kernel (one warp per tile of a draw) whenever the series is resident: the choice
+  // depends on the SHAPE only; the number of teams per CTA may follow S (it does not change a
+  // draw's arithmetic).
+  bool team_ok = false;
+  if (c->predict_team && c->team_mode && c->NB >= 1 && c->NB <= MAXW &&
+      c->prob.model == CI_MODEL_LOCAL_LEVEL) {
+    const int W = c->NB;
+    int gt = c->force_G > 0 ? c->force_G : (S + c->sm_count - 1) / c->sm_count;
+    if (gt < 1) gt = 1;
+    if (gt * W > PT_MAXWARPS) gt = PT_MAXWARPS / W;
+    std::string keep = cih_err();
+    for (; gt >= 1 && !team_ok; --gt) {
+      const uint32_t tail = (uint32_t)gt * (uint32_t)sizeof(TeamShared<R>) + 16u;
+      if (plan_smem(c, gt * W, 0, &cfg, tail, 0) == CI_OK && cfg.resident) { team_ok = true; GT = gt; }
+    }
+    cih_err() = keep;
+  }
+  if (team_ok) {
     auto tk = k_predict_team<R>;
     CU_TRY(set_smem(tk, (uint32_t)cfg.total_bytes));
-    tk<<<(S + GT - 1) / GT, 32 * (GT * c->NB + 1), cfg.total_bytes, st>>>(
+    tk<<<(S + GT - 1) / GT, 32 * GT * c->NB, cfg.total_bytes, st>>>(
         prt, cfg, c->NB, static_cast<const R*>(theta_d), S, seed, draw_id0,
         static_cast<R*>(level_d), static_cast<R*>(traj_d));
     CU_TRY(cudaGetLastError());

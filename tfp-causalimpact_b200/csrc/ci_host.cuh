@@ -110,7 +110,7 @@ struct ci_ctx {
   }
   int force_G = 0;                   // CI_B200_G env override (tuning)
   int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
-  int predict_team = 0;              // CI_B200_PREDICT_TEAM=1: team kernel for ci_posterior_predict
+  int predict_team = 1;              // CI_B200_PREDICT_TEAM=0: one warp per draw in ci_posterior_predict
   int gibbs_team = 1;                // CI_B200_GIBBS_TEAM=0: one warp per chain in the Gibbs kernel
   int tstream_mode = 1;              // CI_B200_TSTREAM=0 disables the long-series team kernels
   int tstream_W = 0;                 // CI_B200_TSW: warps per chain of the long-series team kernels (tuning)

@@ -182,18 +182,30 @@ k_hmc_team(ProbDev<R> pr, SmemCfg cfg, int W, HmcPlan plan, uint64_t seed, uint6
                c, C, draws, stats);
 }
 
+// CTA = GT teams x W warps, NO producer warp (thread 0 starts the resident tile copies): up to
+// PT_MAXWARPS warps share one resident copy of the series -- at BASELINE configs[4] (T = 2000:
+// 106 KB of tiles per CTA) the one-warp kernel fits a single 8-warp CTA per SM (ncu r2_09:
+// 10.8 % warps active); 16 warps per CTA double that with ~45 % fewer instructions per draw.
+constexpr int PT_MAXWARPS = 16;
+
 template <typename R>
-__global__ void __launch_bounds__(32 * (MAXW + 1), 1)
+__global__ void __launch_bounds__(32 * PT_MAXWARPS, 1)
 k_predict_team(ProbDev<R> pr, SmemCfg cfg, int W, const R* __restrict__ theta, int S,
                uint64_t seed, uint64_t draw_id0, R* __restrict__ level, R* __restrict__ traj) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int lane = threadIdx.x & 31;
-  const int n_warps = (blockDim.x >> 5) - 1;
-  CtaShared<R> cs; int team, wt, s;
-  if (!team_prologue(smem, cfg, pr, W, S, cs, team, wt, s)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+  const int GT = n_warps / W;
+  const CtaShared<R> cs = cta_prologue(smem, cfg, pr, 1);
+  if (threadIdx.x == 0)
+    tile_producer(pr.tiles, cs.stage0, cs.full, cs.empty, cfg.stage_elems, cfg.nstage, pr.NB, true,
+                  0LL, [](long long) { return true; });
+  const int team = warp / W, wt = warp - team * W;
+  const int s = blockIdx.x * GT + team;
+  if (s >= S) return;
   const int p = pr.p, dim = pr.dim;
   const R* th = theta + (size_t)s * dim;
-  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, threadIdx.x >> 5);
+  const WarpScratch<R> ws = warp_scratch<R>(smem, cfg, warp);
   for (int j = lane; j < dim; j += 32) ws.w[j] = th[j];
   __syncwarp();
   const R s_e = Num<R>::exp(ws.w[p]), s_h = Num<R>::exp(ws.w[p + 1]);
