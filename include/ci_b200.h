@@ -336,6 +336,27 @@ int ci_impact_d(ci_ctx* ctx, const ci_impact_args* args, const void* traj_d,
                 const void* mean_d, const double* observed, const uint8_t* period,
                 double* series_d, double* summary_d, void* stream);
 
+/* ---- the one collective of the path -----------------------------------------
+ * Chains and posterior draws are sharded over GPUs by GLOBAL id (chain_id0 / draw_id0 above), one
+ * process per GPU; the only exchange is an all-gather of the per-draw result rows at the end of a
+ * fit.  ci_comm wraps an NCCL communicator (resolved at run time with dlopen("libnccl.so.2"); no
+ * link-time dependency, shared with a torch-loaded NCCL when there is one).  The reference has no
+ * counterpart: it is single process, single device (lib.py:342-345).
+ *   ci_comm_get_unique_id   rank 0 creates the 128-byte ncclUniqueId and hands it to the other
+ *                           ranks out of band (file, socket, MPI, torch.distributed store, ...)
+ *   ci_comm_create          every rank, with the same id; collective (returns when all joined)
+ *   ci_allgather            recv_d [nranks * bytes_per_rank] <- every rank's send_d
+ *                           [bytes_per_rank], in rank order; enqueued on `stream`, no host sync
+ */
+#define CI_COMM_ID_BYTES 128
+typedef struct ci_comm ci_comm;
+int ci_comm_get_unique_id(uint8_t* id /* [CI_COMM_ID_BYTES] out */);
+int ci_comm_create(ci_ctx* ctx, const uint8_t* id /* [CI_COMM_ID_BYTES] */, int rank, int nranks,
+                   ci_comm** out);
+int ci_allgather(ci_comm* comm, const void* send_d, void* recv_d, size_t bytes_per_rank,
+                 void* stream);
+int ci_comm_destroy(ci_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ Drop-in surface (reference causalimpact/__init__.py:29-37):
 """
 __version__ = "0.1.0"
 
-from ._engine import DeviceArray, Engine, EngineError, ProblemSpec  # noqa: F401
+from ._engine import Comm, DeviceArray, Engine, EngineError, ProblemSpec, comm_unique_id  # noqa: F401
 from .api import (CausalImpactAnalysis, CausalImpactPosteriorSamples, DataOptions,  # noqa: F401
                   EngineOptions, InferenceOptions, ModelOptions, Seasons, fit_causalimpact,
                   fit_causalimpact_many)

@@ -81,6 +81,7 @@ EXPORTS = (
     "ci_set_seasonal", "ci_gibbs_seasonal_run", "ci_gibbs_seasonal_run_d",
     "ci_set_data_batch", "ci_batch_select", "ci_gibbs_run_batch_d", "ci_set_seasonal_batch",
     "ci_gibbs_seasonal_run_batch_d",
+    "ci_comm_get_unique_id", "ci_comm_create", "ci_allgather", "ci_comm_destroy",
 )
 
 _lib = None
@@ -132,6 +133,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
   lib.ci_set_data_batch.argtypes = [vp, C.POINTER(CiProblem), i32, vp, vp, vp]
   lib.ci_batch_select.argtypes = [vp, i32]
   lib.ci_gibbs_run_batch_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp, vp]
+  lib.ci_comm_get_unique_id.argtypes = [vp]
+  lib.ci_comm_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+  lib.ci_allgather.argtypes = [vp, vp, vp, C.c_size_t, vp]
+  lib.ci_comm_destroy.argtypes = [vp]
   _lib = lib
   return lib
 
@@ -216,6 +221,46 @@ class DeviceArray:
   def __array__(self, dtype=None, copy=None):
     a = self.numpy()
     return a if dtype is None else a.astype(dtype, copy=False)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+  """ci_comm_get_unique_id: the 128-byte NCCL id rank 0 hands to the other ranks."""
+  lib = load_library()
+  buf = C.create_string_buffer(COMM_ID_BYTES)
+  rc = lib.ci_comm_get_unique_id(buf)
+  if rc != 0:
+    raise EngineError(f"ci_b200 error {rc}: {lib.ci_last_error().decode()}")
+  return buf.raw
+
+
+class Comm:
+  """``ci_comm``: the path's one collective without torch.distributed (NCCL under the C ABI)."""
+
+  def __init__(self, engine: "Engine", unique_id: bytes, rank: int, nranks: int):
+    if len(unique_id) != COMM_ID_BYTES:
+      raise ValueError(f"unique_id must be {COMM_ID_BYTES} bytes")
+    self._eng, self.rank, self.nranks = engine, rank, nranks
+    self._h = C.c_void_p()
+    engine._check(engine._lib.ci_comm_create(engine._ctx, unique_id, rank, nranks, C.byref(self._h)))
+
+  def allgather_rows(self, local):
+    """[rows, width] device tensor of every rank (same shape) -> [nranks * rows, width]."""
+    torch, dev = self._eng._torch_dev()
+    local = local.contiguous()
+    out = torch.empty((self.nranks * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                      device=dev)
+    self._eng._check(self._eng._lib.ci_allgather(
+        self._h, local.data_ptr(), out.data_ptr(), local.numel() * local.element_size(),
+        self._eng._stream(torch)))
+    return out
+
+  def close(self):
+    if self._h:
+      self._eng._lib.ci_comm_destroy(self._h)
+      self._h = C.c_void_p()
 
 
 class Engine:
