@@ -194,7 +194,9 @@ int ci_gibbs_run_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64_t seed,
  *   level [S,T] out  (may be NULL) posterior sample of the level path
  *   traj  [S,T] out  level + X.w + sigma_obs * N(0,1)      (lib.py:629-631)
  *   mean  [T]   out  average over draws of level + X.w     (lib.py:627)
- * RNG keyed by (seed, draw_id0 + s).
+ * RNG keyed by (seed, draw_id0 + s).  With model = CI_MODEL_LOCAL_LINEAR_TREND (extension,
+ * BASELINE configs[2]) the state is (level, slope): the d = 2 simulation smoother runs, `level`
+ * receives the level component, theta rows have p + 3 entries.
  */
 int ci_posterior_predict(ci_ctx* ctx, const void* theta_draws, int S,
                          uint64_t seed, uint64_t draw_id0, void* level,
@@ -286,6 +288,32 @@ int ci_gibbs_seasonal_run_batch_d(ci_ctx* ctx, const ci_gibbs_opts* opts, uint64
                                   void* level_d, void* traj_d, float* incl_d, void* latent_d,
                                   void* seasonal_d, void* drift_d, void* stream);
 
+/* ---- panel data preparation on the device ----------------------------------
+ * Replaces, for N series at once, the per-series pandas work of CausalImpactData (data.py:77-137:
+ * split into pre / after-pre rows, nan-aware standardisation with the pre-period statistics of
+ * standardize.py:42-64, intercept column, masked outcome), the priors / initial state of
+ * lib.py:398-500, 563-572 and the host half of ci_set_data_batch (tiles, X'X / X'y over observed
+ * rows, slab precision over the full design): ONE kernel, one CTA per series, float64 arithmetic.
+ *   values [N, T_total, n_cols]  HOST float64, column 0 = outcome (NaN = missing), the others are
+ *                                covariates (no NaN); rows [row0, row0 + n_pre) are the
+ *                                pre-period, rows [row0, T_total) the modelled span
+ *   stats  [N, CI_PANEL_STATS]   HOST out: y_scale, y_offset (original = standardized * scale +
+ *                                offset), outcome_sd, n_obs, y'y, m0, error code, reserved
+ * Afterwards the context holds the batch exactly as after ci_set_data_batch (T = T_total - row0,
+ * p = n_cols if n_cols > 1 else 0): every batched and -- through ci_batch_select -- every
+ * single-series entry point works on it.  Errors carry the reference's messages (data.py:140-190).
+ */
+#define CI_PANEL_STATS 8
+typedef struct {
+  int32_t n_series, T_total, n_cols;
+  int32_t row0, n_pre;
+  int32_t standardize;    /* DataOptions.standardize_data                                   */
+  int32_t dtype;          /* element type of the ENGINE buffers (tiles, draws): CI_F32 / F64 */
+  int32_t ub_on_scale;    /* see ci_problem                                                  */
+  double prior_level_sd;  /* ModelOptions.prior_level_sd (lib.py:202)                        */
+} ci_panel_args;
+int ci_set_panel(ci_ctx* ctx, const ci_panel_args* args, const double* values, double* stats);
+
 /* Mean of the predictive mixture alone (lib.py:627): mean_t = avg_s level[s,t] + x_t . avg_s w_s,
  * for draws whose level paths are already on the device (the Gibbs kernel's output).
  * Deterministic: fixed summation order, float64 accumulation. */
@@ -335,6 +363,18 @@ int ci_impact(ci_ctx* ctx, const ci_impact_args* args, const void* traj, const v
 int ci_impact_d(ci_ctx* ctx, const ci_impact_args* args, const void* traj_d,
                 const void* mean_d, const double* observed, const uint8_t* period,
                 double* series_d, double* summary_d, void* stream);
+
+/* Batched (grid.y = series) versions of ci_predictive_mean_d and ci_impact_d for the batch in the
+ * context: theta [N,S,dim], level [N,S,T] -> mean [N,T];
+ * traj [N,S,T], mean [N,T], observed HOST [N,T], period HOST [T] (shared), per-series scale /
+ * offset / obs_sum HOST [N] (args->scale / offset / obs_sum are ignored)
+ * -> series [N,T,9], summary [N,CI_IMPACT_SUMMARY_LEN].  Two launches for the whole panel. */
+int ci_predictive_mean_batch_d(ci_ctx* ctx, const void* theta_d, const void* level_d, int S,
+                               void* mean_d, void* stream);
+int ci_impact_batch_d(ci_ctx* ctx, const ci_impact_args* args, int n_series, const double* scale,
+                      const double* offset, const double* obs_sum, const void* traj_d,
+                      const void* mean_d, const double* observed, const uint8_t* period,
+                      double* series_d, double* summary_d, void* stream);
 
 /* ---- the one collective of the path -----------------------------------------
  * Chains and posterior draws are sharded over GPUs by GLOBAL id (chain_id0 / draw_id0 above), one

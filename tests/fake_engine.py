@@ -146,6 +146,42 @@ class FakeEngine:
     return (torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]),
             torch.stack([o[2] for o in outs]), np.stack([o[3] for o in outs]))
 
+  # ---- panel prep + batched mean / impact (ci_set_panel, ci_*_batch_d): the host restatement ----
+  def set_panel(self, values, *, row0, n_pre, standardize=True, dtype=np.float32,
+                prior_level_sd=0.01, ub_on_scale=False):
+    import causalimpact_b200 as cib
+    from causalimpact_b200 import panel
+    values = np.asarray(values, dtype=np.float64)
+    N, T, _ = values.shape
+    prep = panel.prepare_panel(values, np.arange(T), (row0, row0 + n_pre - 1),
+                               (row0 + n_pre, T - 1), standardize, dtype)
+    specs = [cib.build_problem(prep["y_ext"][i], None if prep["design"] is None else prep["design"][i],
+                               prior_level_sd=prior_level_sd, outcome_sd=float(prep["outcome_sd"][i]),
+                               dtype=dtype, ub_on_scale=ub_on_scale) for i in range(N)]
+    self.set_data_batch(specs)
+    stats = np.zeros((N, 8))
+    stats[:, 0], stats[:, 1], stats[:, 2] = prep["y_scale"], prep["y_offset"], prep["outcome_sd"]
+    return stats
+
+  def predictive_mean_batch_t(self, theta, level):
+    import torch
+    out = []
+    for i in range(theta.shape[0]):
+      self.batch_select(i)
+      out.append(self.predictive_mean_t(theta[i], level[i]))
+    self.batch_select(0)
+    return torch.stack(out)
+
+  def impact_batch_t(self, traj, mean, *, scale, offset, obs_sum, observed, period, q_lo, q_hi):
+    import torch
+    ser, summ = [], []
+    for i in range(traj.shape[0]):
+      s9, sm = impact_np.impact_arrays(np.asarray(traj[i]), np.asarray(mean[i]), observed[i], period,
+                                       float(scale[i]), float(offset[i]), q_lo, q_hi,
+                                       float(obs_sum[i]))
+      ser.append(s9.reshape(-1)); summ.append(sm)
+    return torch.from_numpy(np.stack(ser)), torch.from_numpy(np.stack(summ))
+
   def to_host(self, t):
     return t.detach().cpu().numpy()
 

@@ -168,3 +168,54 @@ def test_seasonal_panel_and_many_equal_single_seasonal_fits():
     # the weekly pattern is found in every series
     contrib = one.posterior_samples.seasonal_levels.numpy()[:, :98, 0].mean(0).reshape(14, 7).mean(0)
     assert np.corrcoef(contrib, pat)[0, 1] > 0.95
+
+
+def test_device_panel_prep_matches_the_host_restatement(engine):
+  """ci_set_panel (data.py:77-137 + priors + tiles + Gram matrices for N series in ONE kernel) vs the
+  host path (panel.prepare_panel + build_problem + ci_set_data_batch): the per-series statistics
+  agree to float64 rounding, and every single-series entry point sees the same problem
+  (log-posterior and gradient of series i through ci_batch_select agree to float32 rounding: a
+  standardized value can differ by one float32 ulp where the two summation orders of the
+  pre-period mean / sd differ in the last float64 bit)."""
+  from causalimpact_b200 import panel as pn
+  rng = np.random.default_rng(12)
+  N, T, k = 6, 150, 3
+  xs = 100 + np.cumsum(rng.normal(size=(N, T, k)), axis=1) * 0.3
+  y = xs[:, :, 0] * 1.1 - 0.4 * xs[:, :, 1] + rng.normal(size=(N, T))
+  y[:, 100:] += 2.0
+  y[1, 7] = np.nan; y[4, 0] = np.nan; y[4, 33] = np.nan            # missing pre-period points
+  vals = np.concatenate([y[:, :, None], xs], axis=2)
+  row0, n_pre = 5, 95                                               # rows before the pre-period are ignored
+  for std in (True, False):
+    stats = engine.set_panel(vals, row0=row0, n_pre=n_pre, standardize=std, prior_level_sd=0.02)
+    prep = pn.prepare_panel(vals, np.arange(T), (row0, row0 + n_pre - 1), (row0 + n_pre, T - 1), std,
+                            np.float32)
+    np.testing.assert_allclose(stats[:, 0], prep["y_scale"], rtol=1e-12)
+    np.testing.assert_allclose(stats[:, 1], prep["y_offset"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(stats[:, 2], prep["outcome_sd"], rtol=2e-6)
+    assert np.array_equal(stats[:, 3], np.sum(~np.isnan(prep["y_ext"]), axis=1))
+    specs = [ci.build_problem(prep["y_ext"][i], prep["design"][i], prior_level_sd=0.02,
+                              outcome_sd=float(prep["outcome_sd"][i])) for i in range(N)]
+    rng2 = np.random.default_rng(1)
+    th = np.tile(ci.initial_theta(specs[0], 0.02), (5, 1)) + 0.05 * rng2.normal(size=(5, specs[0].dim))
+    got = []
+    for i in range(N):
+      engine.batch_select(i)
+      got.append(engine.logprob_grad(th, with_prior=True))
+    for i in range(N):
+      engine.set_data(specs[i])
+      v, g = engine.logprob_grad(th, with_prior=True)
+      np.testing.assert_allclose(got[i][0], v, rtol=1e-4, atol=1e-2)
+      np.testing.assert_allclose(got[i][1], g, rtol=2e-3, atol=5e-2)
+  # the reference's input errors (data.py:140-190), raised from the device-side validation
+  bad = vals.copy(); bad[2, :, 0] = 3.0
+  with pytest.raises(ValueError, match="constant"):
+    engine.set_panel(bad, row0=row0, n_pre=n_pre)
+  bad = vals.copy(); bad[3, 40, 2] = np.nan
+  with pytest.raises(ValueError, match="missing values"):
+    engine.set_panel(bad, row0=row0, n_pre=n_pre)
+  # no covariates
+  stats = engine.set_panel(vals[:, :, :1], row0=0, n_pre=100)
+  assert engine.spec.p == 0 and np.all(stats[:, 3] >= 98)
+  d, l, t, inc = engine.gibbs_run_batch_t(3, n_warmup=5, n_results=3, seed=1)
+  assert bool(d.isfinite().all()) and tuple(d.shape) == (N, 9, 2)

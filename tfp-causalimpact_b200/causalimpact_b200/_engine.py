@@ -54,6 +54,13 @@ class CiImpactArgs(C.Structure):
               ("q_hi", C.c_double), ("obs_sum", C.c_double)]
 
 
+class CiPanelArgs(C.Structure):
+  _fields_ = [("n_series", C.c_int32), ("T_total", C.c_int32), ("n_cols", C.c_int32),
+              ("row0", C.c_int32), ("n_pre", C.c_int32), ("standardize", C.c_int32),
+              ("dtype", C.c_int32), ("ub_on_scale", C.c_int32), ("prior_level_sd", C.c_double)]
+
+
+PANEL_STATS = 8
 IMPACT_SERIES_COLS, IMPACT_SUMMARY_LEN = 9, 20
 MAX_SEASONAL = 7
 
@@ -82,6 +89,7 @@ EXPORTS = (
     "ci_set_data_batch", "ci_batch_select", "ci_gibbs_run_batch_d", "ci_set_seasonal_batch",
     "ci_gibbs_seasonal_run_batch_d",
     "ci_comm_get_unique_id", "ci_comm_create", "ci_allgather", "ci_comm_destroy",
+    "ci_set_panel", "ci_predictive_mean_batch_d", "ci_impact_batch_d",
 )
 
 _lib = None
@@ -133,6 +141,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
   lib.ci_set_data_batch.argtypes = [vp, C.POINTER(CiProblem), i32, vp, vp, vp]
   lib.ci_batch_select.argtypes = [vp, i32]
   lib.ci_gibbs_run_batch_d.argtypes = [vp, C.POINTER(CiGibbsOpts), u64, u64, i32, vp, vp, vp, vp, vp]
+  lib.ci_set_panel.argtypes = [vp, C.POINTER(CiPanelArgs), vp, vp]
+  lib.ci_predictive_mean_batch_d.argtypes = [vp, vp, vp, i32, vp, vp]
+  lib.ci_impact_batch_d.argtypes = [vp, C.POINTER(CiImpactArgs), i32, vp, vp, vp, vp, vp, vp, vp, vp,
+                                    vp, vp]
   lib.ci_comm_get_unique_id.argtypes = [vp]
   lib.ci_comm_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
   lib.ci_allgather.argtypes = [vp, vp, vp, C.c_size_t, vp]
@@ -342,6 +354,71 @@ class Engine:
     self.spec, self.seasonal, self.batch_specs = s0, None, specs
     self._check(self._lib.ci_set_data_batch(self._ctx, probs, len(specs), _ptr(y), _ptr(X), _ptr(Om)))
 
+  def set_panel(self, values, *, row0: int, n_pre: int, standardize: bool = True, dtype=np.float32,
+                prior_level_sd: float = 0.01, ub_on_scale: bool = False) -> np.ndarray:
+    """ci_set_panel: data prep of a whole panel ON THE DEVICE.  values [N, T_total, 1 + k]
+    float64 (column 0 = outcome); rows [row0, row0 + n_pre) are the pre-period, rows from row0
+    on the modelled span.  Returns stats [N, 8]: y_scale, y_offset, outcome_sd, n_obs, y'y, m0,
+    error code, reserved.  Afterwards the engine holds the batch (as after set_data_batch)."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if values.ndim != 3:
+      raise ValueError("values must be [n_series, T, 1 + n_covariates]")
+    N, T_total, ncol = values.shape
+    np_dt = np.dtype(dtype)
+    args = CiPanelArgs(n_series=N, T_total=T_total, n_cols=ncol, row0=int(row0), n_pre=int(n_pre),
+                       standardize=int(bool(standardize)), dtype=F64 if np_dt == np.float64 else F32,
+                       ub_on_scale=int(bool(ub_on_scale)), prior_level_sd=float(prior_level_sd))
+    stats = np.empty((N, PANEL_STATS), dtype=np.float64)
+    rc = self._lib.ci_set_panel(self._ctx, C.byref(args), _ptr(values), _ptr(stats))
+    if rc != 0:
+      msg = self._lib.ci_last_error().decode()
+      # the reference's own input errors are ValueErrors (data.py:140-190)
+      if rc == -1 and ("Input " in msg or "observed" in msg):
+        raise ValueError(msg)
+      raise EngineError(f"ci_b200 error {rc}: {msg}")
+    Tm, p = T_total - int(row0), (ncol if ncol > 1 else 0)
+    # a shape-only spec: the batched entry points need T / p / dim / dtype, not the arrays
+    self.spec = ProblemSpec(model=MODEL_LOCAL_LEVEL, dtype=args.dtype, y=np.empty(Tm),
+                            X=np.empty((Tm, p)) if p else None, Omega=None, m0=0.0, P0=1.0,
+                            obs_conc=0.0, obs_scale=0.0, obs_ub=0.0, lvl_conc=0.0, lvl_scale=0.0,
+                            lvl_ub=0.0, ub_on_scale=bool(ub_on_scale))
+    self.seasonal = None
+    self.batch_specs = [self.spec] * N
+    return stats
+
+  def predictive_mean_batch_t(self, theta, level):
+    """ci_predictive_mean_batch_d: theta [N,S,dim], level [N,S,T] device tensors -> mean [N,T]."""
+    torch, dev = self._torch_dev()
+    th, lv = theta.contiguous(), level.contiguous()
+    N, S = th.shape[0], th.shape[1]
+    mean = torch.empty((N, self.spec.T), dtype=th.dtype, device=dev)
+    self._check(self._lib.ci_predictive_mean_batch_d(self._ctx, th.data_ptr(), lv.data_ptr(), S,
+                                                     mean.data_ptr(), self._stream(torch)))
+    return mean
+
+  def impact_batch_t(self, traj, mean, *, scale, offset, obs_sum, observed, period, q_lo, q_hi):
+    """ci_impact_batch_d: traj [N,S,T], mean [N,T] device tensors; scale / offset / obs_sum [N],
+    observed [N,T], period [T] host arrays.  Returns ONE float64 device tensor [N, T*9 + 20]
+    (series then summary per series); nothing is synchronised."""
+    torch, dev = self._torch_dev()
+    traj, mean = traj.contiguous(), mean.contiguous()
+    N, S, T = traj.shape
+    dt = F64 if traj.dtype == torch.float64 else F32
+    args = CiImpactArgs(S=S, T=T, dtype=dt, reserved=0, scale=1.0, offset=0.0, q_lo=q_lo, q_hi=q_hi,
+                        obs_sum=0.0)
+    sc = np.ascontiguousarray(scale, dtype=np.float64); of = np.ascontiguousarray(offset, dtype=np.float64)
+    os_ = np.ascontiguousarray(obs_sum, dtype=np.float64)
+    obs = np.ascontiguousarray(observed, dtype=np.float64)
+    per = np.ascontiguousarray(period, dtype=np.uint8)
+    if obs.shape != (N, T) or per.shape != (T,) or sc.shape != (N,):
+      raise ValueError("observed must be [N,T], period [T], scale / offset / obs_sum [N]")
+    series = torch.empty((N, T * IMPACT_SERIES_COLS), dtype=torch.float64, device=dev)
+    summ = torch.empty((N, IMPACT_SUMMARY_LEN), dtype=torch.float64, device=dev)
+    self._check(self._lib.ci_impact_batch_d(
+        self._ctx, C.byref(args), N, _ptr(sc), _ptr(of), _ptr(os_), traj.data_ptr(), mean.data_ptr(),
+        _ptr(obs), _ptr(per), series.data_ptr(), summ.data_ptr(), self._stream(torch)))
+    return series, summ
+
   def batch_select(self, i: int, spec: Optional[ProblemSpec] = None):
     """ci_batch_select: series i of the batch becomes the current problem."""
     self._check(self._lib.ci_batch_select(self._ctx, int(i)))
@@ -370,11 +447,17 @@ class Engine:
         level.data_ptr(), traj.data_ptr(), incl.data_ptr(), self._stream(torch)))
     return draws, level, traj, incl.cpu().numpy()[:, :, :sp.p]
 
-  def set_seasonal_batch(self, scheds):
-    """ci_set_seasonal_batch: one model.SeasonalSchedule per series of the batch (same calendar,
-    per-series prior scales)."""
-    scheds = list(scheds)
-    s0 = scheds[0]
+  def set_seasonal_batch(self, scheds, init_sd=None, drift_scale=None, drift_ub=None):
+    """ci_set_seasonal_batch: one season calendar for the panel + per-series prior scales.
+    ``scheds``: a list of model.SeasonalSchedule (one per series), or ONE schedule together with
+    the per-series arrays init_sd / drift_scale / drift_ub [N]."""
+    if isinstance(scheds, (list, tuple)):
+      s0 = scheds[0]
+      init_sd = [sc.init_sd for sc in scheds]
+      drift_scale = [sc.drift_scale for sc in scheds]
+      drift_ub = [sc.drift_ub for sc in scheds]
+    else:
+      s0 = scheds
     act = np.ascontiguousarray(s0.active, dtype=np.uint8)
     ends = np.ascontiguousarray(s0.ends, dtype=np.uint8)
     cs = CiSeasonal(n_components=s0.K, active=act.ctypes.data, ends=ends.ctypes.data,
@@ -382,9 +465,9 @@ class Engine:
                     drift_ub=s0.drift_ub)
     for k, n in enumerate(s0.num_seasons):
       cs.num_seasons[k] = int(n)
-    a = np.ascontiguousarray([sc.init_sd for sc in scheds], dtype=np.float64)
-    b = np.ascontiguousarray([sc.drift_scale for sc in scheds], dtype=np.float64)
-    u = np.ascontiguousarray([sc.drift_ub for sc in scheds], dtype=np.float64)
+    a = np.ascontiguousarray(init_sd, dtype=np.float64)
+    b = np.ascontiguousarray(drift_scale, dtype=np.float64)
+    u = np.ascontiguousarray(drift_ub, dtype=np.float64)
     self._check(self._lib.ci_set_seasonal_batch(self._ctx, C.byref(cs), _ptr(a), _ptr(b), _ptr(u)))
     self.seasonal = s0
 

@@ -45,6 +45,7 @@ class CausalImpactPosteriorSamples:
   weights: Optional[Samples]                  # [S, covariates + 1 intercept] or None
   seasonal_drift_scales: Optional[Samples]    # None (no seasonal components)
   seasonal_levels: Optional[Samples]          # [S, T, 0]
+  slope_scale: Optional[Samples] = None       # [S]; extension: EngineOptions.local_linear_trend
 
 
 @dataclasses.dataclass
@@ -121,6 +122,11 @@ class EngineOptions:
   return_level: False leaves ``posterior_samples.level`` (and ``seasonal_levels``) as None: the
     [S, T] level paths are then neither all-gathered across ranks nor copied to the host (they
     are the largest part of both); series and summary are unaffected.
+  local_linear_trend: EXTENSION (the reference's model has no slope, lib.py:496; BASELINE.json
+    configs[2] asks for it): the level follows a local linear trend -- state (level, slope),
+    slope variance ~ InverseGamma like the level's -- sampled by batched-chain HMC over the d = 2
+    scan filter (csrc/ci_llt.cuh) with the d = 2 simulation smoother for the predictive draws
+    (csrc/ci_llt_predict.cuh).  ``posterior_samples.slope_scale`` holds the extra draws.
   profile: record the wall time of every phase of the fit in ``diagnostics["phases_ms"]`` (the
     device is synchronised at each phase boundary, so the phases do not overlap).
   """
@@ -138,6 +144,7 @@ class EngineOptions:
   decorrelate_series: bool = True
   return_level: bool = True
   profile: bool = False
+  local_linear_trend: bool = False
 
 
 _ENGINES = {}
@@ -250,12 +257,17 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   y_ext, design, outcome_sd = ci_data.engine_inputs(np_dt)
   if opts.upper_bound_on not in ("variance", "scale"):
     raise ValueError(f"EngineOptions.upper_bound_on must be variance|scale, got {opts.upper_bound_on!r}")
+  if opts.local_linear_trend and (seasons or opts.sampler == "gibbs"):
+    raise NotImplementedError("local_linear_trend is sampled by HMC and has no seasonal components")
+  from ._engine import MODEL_LOCAL_LEVEL, MODEL_LOCAL_LINEAR_TREND
   spec = build_problem(y_ext, design, prior_level_sd=prior_level_sd, outcome_sd=outcome_sd,
-                       dtype=np_dt, ub_on_scale=opts.upper_bound_on == "scale")
+                       dtype=np_dt, ub_on_scale=opts.upper_bound_on == "scale",
+                       model=MODEL_LOCAL_LINEAR_TREND if opts.local_linear_trend else MODEL_LOCAL_LEVEL)
   p, T = spec.p, spec.T
   if opts.sampler not in ("auto", "hmc", "gibbs"):
     raise ValueError(f"EngineOptions.sampler must be auto|hmc|gibbs, got {opts.sampler!r}")
-  use_gibbs = opts.sampler == "gibbs" or (opts.sampler == "auto" and p > 3) or bool(seasons)
+  use_gibbs = (opts.sampler == "gibbs" or (opts.sampler == "auto" and p > 3) or bool(seasons)) \
+      and not opts.local_linear_trend
   wh = None
   if p and opts.whiten and not use_gibbs:
     wh = _Whitening.build(design, ~np.isnan(y_ext), spec.Omega)
@@ -308,6 +320,8 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
     # a chain that starts at log-density -inf could never move
     theta0[:, p] = np.minimum(theta0[:, p], np.log(0.8 * spec.ub_variance(spec.obs_ub)))
     theta0[:, p + 1] = np.minimum(theta0[:, p + 1], np.log(0.8 * spec.ub_variance(spec.lvl_ub)))
+    if spec.d == 2:
+      theta0[:, p + 2] = np.minimum(theta0[:, p + 2], np.log(0.8 * spec.ub_variance(spec.slope_ub)))
     n_warm = max(int(num_warmup_steps), int(opts.min_warmup))
     # a rank without chains (more ranks than chains) still runs one throw-away chain so
     # that every rank holds tensors of the right width for the all-gather
@@ -400,7 +414,9 @@ def _package_samples(eng, theta_t, level_t, p, T, np_dt, wh=None, seasonal=None)
       level=None if level is None else Samples(level.astype(np_dt, copy=False)),
       weights=Samples(weights.astype(np_dt)) if p else Samples(np.zeros((S, 0), np_dt)),
       seasonal_drift_scales=Samples(drift_scales),
-      seasonal_levels=None if seas_levels is None else Samples(seas_levels))
+      seasonal_levels=None if seas_levels is None else Samples(seas_levels),
+      slope_scale=(Samples(np.exp(0.5 * theta[:, p + 2]).astype(np_dt))
+                   if theta.shape[1] == p + 3 else None))
 
 
 def fit_causalimpact(data: pd.DataFrame,
@@ -455,7 +471,7 @@ def _analysis(series, summary, samples) -> CausalImpactAnalysis:
       weights=samples.weights if samples.weights.shape[1] > 0 else None,    # :330-331
       seasonal_drift_scales=(samples.seasonal_drift_scales
                              if samples.seasonal_drift_scales.shape[-1] > 0 else None),   # :332-334
-      seasonal_levels=samples.seasonal_levels)
+      seasonal_levels=samples.seasonal_levels, slope_scale=samples.slope_scale)
   return CausalImpactAnalysis(series, summary, result_samples, stats)
 
 
@@ -529,15 +545,24 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
   else:
     theta, level, traj, incl = eng.gibbs_run_batch_t(C, **bkw)
     latent = level
+  # predictive mean and impact of EVERY series: one batched launch each (grid.y = series), one
+  # read-back; the frames are O(T) host packaging per series
+  S = min(num_results, C * n_per)
+  metas = [_impact.prepare(cid, alpha) for cid in cids]
+  mean_all = eng.predictive_mean_batch_t(theta[:, :S], latent[:, :S])
+  ser_d, sum_d = eng.impact_batch_t(
+      traj[:, :S], mean_all, scale=[m.scale for m in metas], offset=[m.offset for m in metas],
+      obs_sum=[m.obs_sum for m in metas], observed=np.stack([m.observed for m in metas]),
+      period=metas[0].period, q_lo=metas[0].q_lo, q_hi=metas[0].q_hi)
+  series9 = eng.to_host(ser_d).reshape(len(cids), T, 9)
+  summ = eng.to_host(sum_d)
   for i, cid in enumerate(cids):
-    eng.batch_select(i, specs[i])
-    th_i, lv_i, tr_i, la_i = (t[i][:num_results] for t in (theta, level, traj, latent))
-    mean_i = eng.predictive_mean_t(th_i, la_i)
+    if not np.array_equal(metas[i].period, metas[0].period):
+      raise ValueError("the series of a batch must share their index and periods")
     samples = _package_samples(
-        eng, th_i, lv_i, p, T, np_dt,
-        seasonal=(seas[i][:num_results], drift[i][:num_results], K) if seasons else None)
+        eng, theta[i, :S], level[i, :S], p, T, np_dt,
+        seasonal=(seas[i, :S], drift[i, :S], K) if seasons else None)
     samples.hmc_stats = {"sampler": "gibbs", "inclusion": incl[i]}
-    series, summary = _impact.compute_impact(DeviceArray(mean_i), DeviceArray(tr_i), cid, alpha,
-                                             eng.impact)
+    series, summary = _impact.package(series9[i], summ[i], S, metas[i], cid, alpha)
     out[s0 + i] = _analysis(series, summary, samples)
   return out

@@ -5,9 +5,10 @@ shared index and shared periods -- the "thousands of geographies" shape -- and r
 Everything the reference does per series in pandas (data.py:77-137: split, nan-aware
 standardisation with the pre-period statistics, intercept column, masked outcome; then
 causalimpact_lib.py:892-931 / :1021-1091: series and summary frames) is done once for the whole
-panel with vectorised numpy; sampling is one batched launch (``ci_gibbs_run_batch_d``), predictive
-mean and impact are queued per series on the device and read back with a single copy.  Frames
-are built only on demand (``PanelResult.analysis(i)``).
+panel ON THE DEVICE by one kernel (``ci_set_panel``: standardisation, intercept, masks, tiles, Gram
+matrices, priors); sampling is one batched launch (``ci_gibbs_run_batch_d``), predictive mean and
+impact are one batched launch each (grid.y = series) and everything is read back with a single
+copy.  Frames are built only on demand (``PanelResult.frames(i)``).
 
 The arithmetic per series is the one of ``fit_causalimpact``; only the summation order inside the
 pre-period mean / sd can differ from pandas' (1 ulp in float64 before the cast to the engine
@@ -62,8 +63,25 @@ class PanelResult:
     return ser, summ
 
 
+def panel_layout(index, pre_period, post_period):
+  """The O(T) row layout every series of a panel shares: validated periods, the modelled span
+  (rows of the pre-period and everything after it: contiguous, ``row0`` .. end) and the number of
+  pre-period rows."""
+  index = pd.Index(index)
+  probe = pd.DataFrame({"y": np.zeros(len(index))}, index=index)
+  pre, post = _frame.parse_and_validate_date_data(probe, pre_period, post_period)
+  in_pre = np.asarray((index >= pre[0]) & (index <= pre[1]))
+  after = np.asarray(index > pre[1])
+  rows = np.flatnonzero(in_pre | after)
+  if rows.size == 0 or not np.array_equal(rows, np.arange(rows[0], len(index))):
+    raise ValueError("the panel's index must be sorted: the modelled span has to be one block of rows")
+  return dict(index=index, pre=pre, post=post, rows=rows, row0=int(rows[0]), n_pre=int(in_pre.sum()))
+
+
 def prepare_panel(values, index, pre_period, post_period, standardize_data=True, dtype=np.float32):
-  """Vectorised data.py:77-137 for N series at once.
+  """Vectorised data.py:77-137 for N series at once -- the HOST restatement of what
+  ``ci_set_panel`` (csrc/abi_panel.cu) does on the device; the product path does not call it (the
+  CPU test double, tests/fake_engine.py, and the parity tests do).
 
   Returns dict: y_ext [N, Tm] (float64 view of the dtype-rounded standardized outcome, NaN where
   masked), design [N, Tm, k+1] or None, outcome_sd [N], y_scale / y_offset [N], model rows
@@ -154,15 +172,21 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
     seed64 = _shard.broadcast_u64(seed64, getattr(eng, "torch_device", lambda: None)())
   if n_local == 0:                     # more ranks than series: nothing to fit on this one
     return _empty_result(values, index, pre_period, post_period, np_dt, bool(seasons), keep_level)
-  prep = prepare_panel(values[s0:s0 + n_local], index, pre_period, post_period,
-                       data_options.standardize_data, np_dt)
-  N, Tm = prep["y_ext"].shape
-  specs = [build_problem(prep["y_ext"][i], None if prep["design"] is None else prep["design"][i],
-                         prior_level_sd=model_options.prior_level_sd,
-                         outcome_sd=float(prep["outcome_sd"][i]), dtype=np_dt,
-                         ub_on_scale=opts.upper_bound_on == "scale") for i in range(N)]
-  p = specs[0].p
-  eng.set_data_batch(specs)
+  # ---- O(T) layout shared by every series (host) ----
+  lay = panel_layout(index, pre_period, post_period)
+  vals_local = np.ascontiguousarray(values[s0:s0 + n_local], dtype=np.float64)
+  if vals_local.ndim != 3 or vals_local.shape[2] < 1:
+    raise ValueError("values must be [n_series, T, 1 + n_covariates]")
+  if vals_local.shape[1] != len(lay["index"]):
+    raise ValueError("index length differs from values.shape[1]")
+  # ---- data.py:77-137 + priors + tiles for the whole panel: ONE kernel (ci_set_panel) ----
+  stats = eng.set_panel(vals_local, row0=lay["row0"], n_pre=lay["n_pre"],
+                        standardize=data_options.standardize_data, dtype=np_dt,
+                        prior_level_sd=model_options.prior_level_sd,
+                        ub_on_scale=opts.upper_bound_on == "scale")
+  y_scale, y_offset, outcome_sd = stats[:, 0], stats[:, 1], stats[:, 2]
+  N, Tm = vals_local.shape[0], len(lay["rows"])
+  p = vals_local.shape[2] if vals_local.shape[2] > 1 else 0
   S = inference_options.num_results
   C = max(int(opts.num_chains), 1)
   n_per = max(1, math.ceil(S / C))
@@ -172,8 +196,10 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
   bkw = dict(n_warmup=n_warm, n_results=n_per, seed=seed64, chain_id0=s0 * stride, sparse=True,
              ssvs_order=opts.ssvs_order, series_stride=stride)
   if seasons:
-    eng.set_seasonal_batch([build_seasonal(seasons, Tm, float(prep["outcome_sd"][i]))
-                            for i in range(N)])
+    # one calendar for the panel; the priors scale with every series' own outcome sd (lib.py:472-489)
+    sched = build_seasonal(seasons, Tm, 1.0)
+    eng.set_seasonal_batch(sched, init_sd=outcome_sd, drift_scale=5e-7 * outcome_sd ** 2,
+                           drift_ub=outcome_sd)
     theta, level, latent, traj, seas, drift, incl = eng.gibbs_seasonal_run_batch_t(C, **bkw)
   else:
     theta, level, traj, incl = eng.gibbs_run_batch_t(C, **bkw)
@@ -181,37 +207,31 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
   S = min(S, C * n_per)
 
   # ---- O(T) metadata of the impact stage, shared / vectorised (impact.prepare per series) ----
-  mi = prep["index"][prep["rows"]]
-  pre, post = prep["pre"], prep["post"]
+  mi = lay["index"][lay["rows"]]
+  pre, post = lay["pre"], lay["post"]
   in_pre = np.asarray(mi <= pre[1])
   in_post = np.asarray((mi >= post[0]) & (mi <= post[1]))
   period = np.where(np.asarray(mi < post[0]), 0, np.where(in_post, 1, 2)).astype(np.uint8)
-  observed = np.where((in_pre | in_post)[None, :], prep["y_model"], np.nan)      # [N, Tm]
+  y_model = vals_local[:, lay["row0"]:, 0]
+  observed = np.where((in_pre | in_post)[None, :], y_model, np.nan)              # [N, Tm]
   hide = np.asarray(((mi > pre[1]) & (mi < post[0])) | (mi > post[1]))[None, :] | np.isnan(observed)
   y_post = observed[:, in_post]
   obs_mean, obs_sum = np.nanmean(y_post, axis=1), np.nansum(y_post, axis=1)
   q_lo, q_hi = _impact._percentile_q(alpha / 2.0), _impact._percentile_q(1.0 - alpha / 2.0)
 
-  import torch
-  out = torch.empty((N, Tm * 9 + 20), dtype=torch.float64, device=theta.device)
-  for i in range(N):
-    eng.batch_select(i, specs[i])
-    th_i, tr_i = theta[i, :S], traj[i, :S]
-    mean_i = eng.predictive_mean_t(th_i, latent[i, :S])
-    meta = _impact.ImpactMeta(index=mi, observed=observed[i], period=period, hide=hide[i],
-                              scale=float(prep["y_scale"][i]), offset=float(prep["y_offset"][i]),
-                              q_lo=q_lo, q_hi=q_hi, obs_mean=float(obs_mean[i]),
-                              obs_sum=float(obs_sum[i]))
-    eng.impact(tr_i, mean_i, meta, out=out[i])
-  res = eng.to_host(out)                                             # ONE read-back
-  series9 = res[:, :Tm * 9].reshape(N, Tm, 9)
-  summ = res[:, Tm * 9:]
+  # ---- predictive mean + impact of EVERY series: three launches, one read-back ----
+  mean_all = eng.predictive_mean_batch_t(theta[:, :S], latent[:, :S])
+  ser_d, sum_d = eng.impact_batch_t(traj[:, :S], mean_all, scale=y_scale, offset=y_offset,
+                                    obs_sum=obs_sum, observed=observed, period=period,
+                                    q_lo=q_lo, q_hi=q_hi)
+  series9 = eng.to_host(ser_d).reshape(N, Tm, 9)
+  summ = eng.to_host(sum_d)
 
   # ---- lib.py:892-931 for all series: NaN rules, re-index to the caller's index ----
   cols = np.concatenate([observed[:, :, None], series9], axis=2)     # [N, Tm, 10]
   cols[:, :, 4:][hide] = np.nan
-  full = np.full((N, len(prep["index"]), 10), np.nan)
-  full[:, prep["rows"], :] = cols
+  full = np.full((N, len(lay["index"]), 10), np.nan)
+  full[:, lay["rows"], :] = cols
   full[:, :, 0] = values[s0:s0 + n_local, :, 0]                      # `observed` = the input column
   # ---- lib.py:1021-1091 for all series ----
   qd = summ[:, 0:10].reshape(N, 5, 2); sd = summ[:, 10:15]
@@ -228,7 +248,7 @@ def fit_causalimpact_panel(values, index, pre_period, post_period, alpha: float 
     table[:, r, 14] = alpha
   th = eng.to_host(theta[:, :S]).astype(np.float64)
   return PanelResult(
-      index=prep["index"], series_ids=np.arange(s0, s0 + n_local), series=full, summary=table,
+      index=lay["index"], series_ids=np.arange(s0, s0 + n_local), series=full, summary=table,
       observation_noise_scale=np.exp(0.5 * th[:, :, p]).astype(np_dt),
       level_scale=np.exp(0.5 * th[:, :, p + 1]).astype(np_dt),
       weights=th[:, :, :p].astype(np_dt) if p else None,

@@ -28,7 +28,7 @@ int launch_impact(ci_ctx* c, const ImpactDev& a, const void* traj_d, const void*
   int nt = 1024;
   while (nt > 64 && nt / 2 >= S) nt >>= 1;
   kern<<<Tc + IMP_STATS + T + 1, nt, bytes, st>>>(trT, cumT, statsT, obs_d, a, series_d, summ_d,
-                                                   in_smem);
+                                                   in_smem, nullptr);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;

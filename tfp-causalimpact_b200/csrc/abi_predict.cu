@@ -1,6 +1,7 @@
 // abi_predict.cu -- K4 / K5 entry points: simulation smoother, predictive mean, per-time quantiles.
 #include "ci_host.cuh"
 #include "ci_predict.cuh"
+#include "ci_llt_predict.cuh"
 #include "ci_team_kernels.cuh"
 
 namespace {
@@ -13,6 +14,27 @@ int launch_predict(ci_ctx* c, const void* theta_d, int S, uint64_t seed, uint64_
   SmemCfg cfg;
   const ProbDev<R> prt = make_probdev<R>(c);
   int GT = 0;
+  if (c->prob.model == CI_MODEL_LOCAL_LINEAR_TREND) {
+    // d = 2 simulation smoother (ci_llt_predict.cuh): one warp per draw, any T
+    const int G = pick_G(c, S);
+    int rc = plan_smem(c, G, 0, &cfg);
+    if (rc) return rc;
+    auto lk = k_predict_llt<R>;
+    CU_TRY(set_smem(lk, (uint32_t)cfg.total_bytes));
+    lk<<<(S + G - 1) / G, 32 * (G + 1), cfg.total_bytes, st>>>(
+        prt, make_lltdev<R>(c), cfg, static_cast<const R*>(theta_d), S, seed, draw_id0,
+        static_cast<R*>(level_d), nullptr, static_cast<R*>(traj_d));
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    if (mean_d) {
+      k_predict_mean<R><<<(c->prob.T + MEAN_COLS - 1) / MEAN_COLS, dim3(MEAN_COLS, MEAN_ROWS), 0, st>>>(
+          prt, static_cast<const R*>(theta_d), static_cast<const R*>(level_d), S,
+          static_cast<R*>(mean_d));
+      CU_TRY(cudaGetLastError());
+      c->launches++;
+    }
+    return CI_OK;
+  }
   // The kernel choice must NOT depend on S: a draw has to come out bit-identical however
   // the batch is split over calls / GPUs.
   // Team kernel (one warp per tile of a draw) whenever the series is resident: the choice
@@ -102,9 +124,6 @@ int ci_posterior_predict_d(ci_ctx* c, const void* theta_d, int S, uint64_t seed,
   if (!c || !theta_d || !traj_d) return fail(CI_ERR_INVALID, "null argument");
   if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
   if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
-  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
-    return fail(CI_ERR_UNSUPPORTED, "ci_posterior_predict: local level only (the reference has "
-                "no slope component, causalimpact_lib.py:496)");
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!level_d && mean_d) {   // the mean needs the level paths: use the workspace
@@ -176,8 +195,6 @@ int ci_predictive_mean_d(ci_ctx* c, const void* theta_d, const void* level_d, in
   if (!c || !theta_d || !level_d || !mean_d) return fail(CI_ERR_INVALID, "null argument");
   if (!c->has_data) return fail(CI_ERR_STATE, "ci_set_data has not been called");
   if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
-  if (c->prob.model != CI_MODEL_LOCAL_LEVEL)
-    return fail(CI_ERR_UNSUPPORTED, "ci_predictive_mean: local level only");
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 blk(ci::MEAN_COLS, ci::MEAN_ROWS);

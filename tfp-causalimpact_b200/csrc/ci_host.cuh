@@ -81,6 +81,7 @@ struct ci_ctx {
   DevBuf gram, xty0;                 // X'X, X'y over observed rows (Gibbs regression step)
   DevBuf i_cum, i_stats, i_meta, i_series, i_summ, i_trT;   // ci_impact workspaces
   DevBuf s_sched, s_scratch, s_series, w_latent, w_seas, w_drift;   // seasonal components
+  DevBuf w_raw, w_pstats;            // ci_set_panel: the raw panel and the per-series statistics
   ci::SeasDev seas{};                // seas.K == 0: no seasonal components
   // views of the CURRENT series: the context's own buffers after ci_set_data, a slice of the
   // batch buffers after ci_batch_select
@@ -101,7 +102,7 @@ struct ci_ctx {
     return {&tiles, &omega, &w_theta, &w_value, &w_grad, &w_level, &w_traj, &w_mean, &w_q, &w_draws,
             &w_stats, &w_incl, &gram, &xty0, &i_cum, &i_stats, &i_meta, &i_series, &i_summ, &i_trT,
             &s_sched, &s_scratch, &s_series, &w_latent, &w_seas, &w_drift, &b_tiles, &b_omega,
-            &b_gram, &b_xty, &b_dev};
+            &b_gram, &b_xty, &b_dev, &w_raw, &w_pstats};
   }
   // only from entry points that synchronise anyway (ci_set_data*, ci_ctx_destroy, host-pointer calls)
   void free_retired() {

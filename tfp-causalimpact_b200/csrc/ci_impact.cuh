@@ -39,6 +39,8 @@ struct ImpactDev {
   int S, T, t_c0, n_post;            // t_c0: first step that is not before the post-period
   double scale, offset, q_lo, q_hi, obs_sum;
 };
+// per-series part of ImpactDev for batched launches (grid.y = series)
+struct ImpactSeries { double scale, offset, obs_sum; };
 
 // standardize.py:60-64: (x * stddev) + mean, two roundings like numpy (no FMA contraction)
 __device__ __forceinline__ double imp_unscale(double x, double scale, double offset) {
@@ -57,7 +59,16 @@ __global__ void __launch_bounds__(32 * IMP_TILE)
 k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
               const double* __restrict__ obs, const uint8_t* __restrict__ period, ImpactDev a,
               R* __restrict__ trT, double* __restrict__ cumT, double* __restrict__ statsT,
-              double* __restrict__ series, double* __restrict__ summ) {
+              double* __restrict__ series, double* __restrict__ summ,
+              const ImpactSeries* __restrict__ per = nullptr) {
+  if (per) {      // batched: this CTA row works on series blockIdx.y (obs is [N,T], period shared)
+    const size_t sidx = blockIdx.y;
+    a.scale = per[sidx].scale; a.offset = per[sidx].offset; a.obs_sum = per[sidx].obs_sum;
+    traj += sidx * (size_t)a.S * a.T; mean += sidx * (size_t)a.T; obs += sidx * (size_t)a.T;
+    trT += sidx * (size_t)a.S * a.T; cumT += sidx * (size_t)a.S * (a.T - a.t_c0);
+    statsT += sidx * (size_t)a.S * IMP_STATS;
+    series += sidx * (size_t)a.T * IMP_SERIES_COLS; summ += sidx * (size_t)IMP_SUMMARY_LEN;
+  }
   __shared__ R tile_raw[IMP_TILE][IMP_CH * IMP_TILE + 1];
   __shared__ double tile_cum[IMP_TILE][IMP_CH * IMP_TILE + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -279,7 +290,15 @@ __global__ void __launch_bounds__(1024)
 k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
                               const double* __restrict__ statsT, const double* __restrict__ obs,
                               ImpactDev a, double* __restrict__ series, double* __restrict__ summ,
-                              int in_smem) {
+                              int in_smem, const ImpactSeries* __restrict__ per = nullptr) {
+  if (per) {
+    const size_t sidx = blockIdx.y;
+    a.scale = per[sidx].scale; a.offset = per[sidx].offset; a.obs_sum = per[sidx].obs_sum;
+    obs += sidx * (size_t)a.T;
+    trT += sidx * (size_t)a.S * a.T; cumT += sidx * (size_t)a.S * (a.T - a.t_c0);
+    statsT += sidx * (size_t)a.S * IMP_STATS;
+    series += sidx * (size_t)a.T * IMP_SERIES_COLS; summ += sidx * (size_t)IMP_SUMMARY_LEN;
+  }
   extern __shared__ __align__(16) unsigned char key_mem[];
   __shared__ __align__(16) unsigned char sel_raw[sizeof(SelectShared<double>)];
   __shared__ int ibuf[10];

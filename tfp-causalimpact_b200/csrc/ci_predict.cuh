@@ -121,10 +121,17 @@ affine_scan_down(m, c, lane);
 // 32-byte sector, so T/8 CTAs spread over the whole GPU while every load stays sector-exact.
 constexpr int MEAN_COLS = 8, MEAN_ROWS = 128;
 
+// Batched launch (grid.y = series): series_tiles / tile_stride give every series'
+// tiles; theta [N,S,dim], level [N,S,T], mean [N,T].
 template <typename R>
 __global__ void __launch_bounds__(MEAN_COLS * MEAN_ROWS)
 k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta, const R* __restrict__ level, int S,
-               R* __restrict__ mean) {
+               R* __restrict__ mean, size_t tile_stride_elems = 0) {
+  if (gridDim.y > 1 || tile_stride_elems) {
+    const size_t sidx = blockIdx.y;
+    pr.tiles += sidx * tile_stride_elems;
+    theta += sidx * (size_t)S * pr.dim; level += sidx * (size_t)S * pr.T; mean += sidx * (size_t)pr.T;
+  }
   __shared__ double part[MEAN_ROWS][MEAN_COLS + 1];
   __shared__ double wpart[32][8];
   __shared__ double wbar[MAX_DIM];
