@@ -184,3 +184,44 @@ def test_fit_keeps_trajectories_on_device():
   _, design, _ = cid.engine_inputs(np.float32)
   np.testing.assert_allclose(np.asarray(means), lvl.mean(0) + design @ w.mean(0), rtol=2e-5,
                              atol=2e-5)
+
+
+def test_device_entry_point_does_not_synchronise_when_workspaces_grow(engine):
+  """`_d` calls promise not to synchronise (include/ci_b200.h).  With a long kernel keeping the
+  stream busy, ci_impact_d is called with draws that outgrow every workspace of the previous call
+  (a growing workspace used to cudaFree = a device-wide synchronisation) and with pageable host
+  arrays (which cudaMemcpyAsync would wait for the stream on): both calls must RETURN while the
+  stream is still busy, and the results must be the ones of an unloaded run."""
+  import time
+  import types
+  import torch
+  rng = np.random.default_rng(5)
+  T = 120
+  per = np.zeros(T, np.uint8); per[80:] = 1
+  obs = rng.normal(size=T)
+  meta = types.SimpleNamespace(observed=obs, period=per, scale=1.5, offset=3.0, q_lo=0.05, q_hi=0.95,
+                               obs_sum=float(obs[80:].sum()))
+  dev = torch.device("cuda", 0)
+  small = torch.randn(64, T, device=dev)
+  big = torch.randn(4096, T, device=dev)
+  want_small = engine.impact(small, small.mean(0), meta)
+  torch.cuda.synchronize()
+  eng2 = cib.Engine(0)                       # fresh context: every workspace still has to grow
+  out_s = torch.empty(T * 9 + 20, dtype=torch.float64, device=dev)
+  out_b = torch.empty(T * 9 + 20, dtype=torch.float64, device=dev)
+  m_s, m_b = small.mean(0), big.mean(0)
+  torch.cuda.synchronize()
+  torch.cuda._sleep(int(4e8))                # ~0.2 s of busy stream
+  t0 = time.perf_counter()
+  eng2.impact(small, m_s, meta, out=out_s)   # allocates the workspaces
+  eng2.impact(big, m_b, meta, out=out_b)     # outgrows all of them
+  dt = time.perf_counter() - t0
+  busy = not torch.cuda.current_stream().query()
+  torch.cuda.synchronize()
+  assert busy and dt < 0.1, (busy, dt)
+  got = out_s.cpu().numpy()
+  np.testing.assert_array_equal(got[:T * 9].reshape(T, 9), want_small[0])
+  np.testing.assert_array_equal(got[T * 9:], want_small[1])
+  want_big = engine.impact(big, m_b, meta)
+  np.testing.assert_array_equal(out_b.cpu().numpy()[:T * 9].reshape(T, 9), want_big[0])
+  eng2.close()

@@ -143,6 +143,8 @@ int ci_ctx_create(int device, ci_ctx** out) {
   if (const char* g = getenv("CI_B200_PREDICT_TEAM")) c->predict_team = atoi(g);
   if (const char* g = getenv("CI_B200_TSTREAM")) c->tstream_mode = atoi(g);
   if (const char* g = getenv("CI_B200_GIBBS_TEAM")) c->gibbs_team = atoi(g);
+  if (const char* g = getenv("CI_B200_SEL_NT")) c->sel_nt = atoi(g);
+  if (const char* g = getenv("CI_B200_SEL_SMEM")) c->sel_smem = atoi(g);
   if (const char* g = getenv("CI_B200_TSW")) c->tstream_W = atoi(g);
   *out = c;
   return CI_OK;
@@ -154,6 +156,7 @@ int ci_ctx_destroy(ci_ctx* c) {
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   for (DevBuf* b : c->bufs()) b->release();
   c->free_retired();
+  c->ring.release();
   delete c;
   return CI_OK;
 }

@@ -20,13 +20,10 @@ int launch_impact(ci_ctx* c, const ImpactDev& a, const void* traj_d, const void*
       statsT, series_d, summ_d);
   CU_TRY(cudaGetLastError());
   c->launches++;
-  size_t bytes = (((size_t)S * sizeof(double)) + 15) & ~(size_t)15;   // float64 jobs
-  const int in_smem = bytes + QSTATIC <= (size_t)c->smem_optin;       // else: select from global memory
-  if (!in_smem) bytes = 0;
+  size_t bytes; int in_smem, nt;                                      // float64 jobs size the staging
+  select_launch_cfg(c, S, sizeof(double), &nt, &bytes, &in_smem);
   auto kern = k_impact_jobs<R>;
   CU_TRY(set_smem(kern, (uint32_t)bytes));
-  int nt = 1024;
-  while (nt > 64 && nt / 2 >= S) nt >>= 1;
   kern<<<Tc + IMP_STATS + T + 1, nt, bytes, st>>>(trT, cumT, statsT, obs_d, a, series_d, summ_d,
                                                    in_smem, nullptr);
   CU_TRY(cudaGetLastError());
@@ -68,9 +65,11 @@ int ci_impact_d(ci_ctx* c, const ci_impact_args* a, const void* traj_d, const vo
   CU_TRY(c->i_trT.reserve((size_t)S * T * (a->dtype == CI_F64 ? 8 : 4)));
   const size_t ob = (size_t)T * sizeof(double);
   CU_TRY(c->i_meta.reserve(ob + (size_t)T));
-  CU_TRY(cudaMemcpyAsync(c->i_meta.p, observed, ob, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(static_cast<char*>(c->i_meta.p) + ob, period, (size_t)T,
-                         cudaMemcpyHostToDevice, st));
+  {  // one asynchronous copy through the pinned ring (pageable sources would wait for the stream)
+    const void* srcs[2] = {observed, period};
+    const size_t sizes[2] = {ob, (size_t)T}, offs[2] = {0, ob};
+    CU_TRY(c->ring.upload(c->i_meta.p, srcs, sizes, offs, 2, ob + (size_t)T, st));
+  }
   const double* obs_d = static_cast<const double*>(c->i_meta.p);
   const uint8_t* per_d = reinterpret_cast<const uint8_t*>(static_cast<char*>(c->i_meta.p) + ob);
   if (a->dtype == CI_F64)

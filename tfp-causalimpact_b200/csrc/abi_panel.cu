@@ -389,21 +389,17 @@ int ci_impact_batch_d(ci_ctx* c, const ci_impact_args* a, int n_series, const do
   const size_t sb = (size_t)N * sizeof(ci::ImpactSeries);
   CU_TRY(c->i_meta.reserve(ob + pb + sb));
   char* meta = static_cast<char*>(c->i_meta.p);
-  CU_TRY(cudaMemcpyAsync(meta, observed, ob, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(meta + ob, period, (size_t)T, cudaMemcpyHostToDevice, st));
-  // (pageable source: cudaMemcpyAsync returns once the bytes sit in the driver's staging buffer,
-  // so the vector may die with this call -- the same contract ci_impact_d relies on for the
-  // caller's observed / period arrays)
-  CU_TRY(cudaMemcpyAsync(meta + ob + pb, per.data(), sb, cudaMemcpyHostToDevice, st));
+  {  // one asynchronous copy through the pinned ring (pageable sources would wait for the stream)
+    const void* srcs[3] = {observed, period, per.data()};
+    const size_t sizes[3] = {ob, (size_t)T, sb}, offs[3] = {0, ob, ob + pb};
+    CU_TRY(c->ring.upload(meta, srcs, sizes, offs, 3, ob + pb + sb, st));
+  }
   const double* obs_d = reinterpret_cast<const double*>(meta);
   const uint8_t* per_d = reinterpret_cast<const uint8_t*>(meta + ob);
   const ci::ImpactSeries* ps_d = reinterpret_cast<const ci::ImpactSeries*>(meta + ob + pb);
   const int row_ctas = (S + ci::IMP_TILE - 1) / ci::IMP_TILE + 1;
-  size_t bytes = (((size_t)S * sizeof(double)) + 15) & ~(size_t)15;
-  const int in_smem = bytes + QSTATIC <= (size_t)c->smem_optin;
-  if (!in_smem) bytes = 0;
-  int nt = 1024;
-  while (nt > 64 && nt / 2 >= S) nt >>= 1;
+  size_t bytes; int in_smem, nt;
+  select_launch_cfg(c, S, sizeof(double), &nt, &bytes, &in_smem);
   if (a->dtype == CI_F64) {
     ci::k_impact_rows<double><<<dim3(row_ctas, N), 32 * ci::IMP_TILE, 0, st>>>(
         static_cast<const double*>(traj_d), static_cast<const double*>(mean_d), obs_d, per_d, d,

@@ -98,16 +98,13 @@ int launch_quantiles(ci_ctx* c, const void* a_d, int S, int T, const double* q, 
                      void* out_d, cudaStream_t st, int out_ld = 0) {
   // the whole column lives in shared memory as integer keys when it fits; longer columns are
   // selected straight from global memory (every sweep re-reads them through L2)
-  size_t bytes = (((size_t)S * sizeof(R)) + 15) & ~(size_t)15;
-  const int in_smem = bytes + QSTATIC <= (size_t)c->smem_optin;
-  if (!in_smem) bytes = 0;
+  size_t bytes; int in_smem, nt;
+  select_launch_cfg(c, S, sizeof(R), &nt, &bytes, &in_smem);
   QuantArgs qa;
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q[i];
   auto kern = k_row_quantiles<R>;
   CU_TRY(set_smem(kern, (uint32_t)bytes));
-  int nt = 1024;
-  while (nt > 64 && nt / 2 >= S) nt >>= 1;
   kern<<<T, nt, bytes, st>>>(static_cast<const R*>(a_d), S, T, qa, static_cast<R*>(out_d),
                              out_ld > 0 ? out_ld : nq, in_smem);
   CU_TRY(cudaGetLastError());

@@ -64,6 +64,45 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Host -> device staging for the small per-call arrays of the _d entry points (observed / period of
+// ci_impact_d).  cudaMemcpyAsync from PAGEABLE memory first waits for the stream's earlier work;
+// copying through a ring of pinned slots keeps the call asynchronous: a slot is reused only after
+// the copy that read it has completed (its event), which blocks only when RING calls are in flight.
+struct PinnedRing {
+  static constexpr int RING = 8;
+  struct Slot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
+  Slot slots[RING];
+  int next = 0;
+  cudaError_t upload(void* dst_d, const void* const* srcs, const size_t* sizes, const size_t* offs,
+                     int n, size_t total, cudaStream_t st) {
+    Slot& s = slots[next];
+    next = (next + 1) % RING;
+    cudaError_t e;
+    if (s.used) { e = cudaEventSynchronize(s.ev); if (e != cudaSuccess) return e; }
+    if (s.cap < total) {
+      if (s.p) cudaFreeHost(s.p);
+      s.p = nullptr; s.cap = 0;
+      size_t want = total < 4096 ? 4096 : total + total / 2;
+      e = cudaHostAlloc(&s.p, want, cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+      s.cap = want;
+    }
+    if (!s.ev) { e = cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    for (int i = 0; i < n; ++i) memcpy(static_cast<char*>(s.p) + offs[i], srcs[i], sizes[i]);
+    e = cudaMemcpyAsync(dst_d, s.p, total, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    s.used = true;
+    return cudaEventRecord(s.ev, st);
+  }
+  void release() {
+    for (Slot& s : slots) {
+      if (s.ev) { cudaEventSynchronize(s.ev); cudaEventDestroy(s.ev); }
+      if (s.p) cudaFreeHost(s.p);
+      s = Slot{};
+    }
+  }
+};
+
 }  // namespace
 
 struct ci_ctx {
@@ -97,6 +136,7 @@ struct ci_ctx {
   double yty0 = 0.0;
   int n_obs = 0;
   int64_t launches = 0;
+  PinnedRing ring;                   // pinned staging of the _d entry points' small host arrays
   std::vector<void*> retired;        // outgrown workspaces, freed by the next synchronising call
   std::vector<DevBuf*> bufs() {
     return {&tiles, &omega, &w_theta, &w_value, &w_grad, &w_level, &w_traj, &w_mean, &w_q, &w_draws,
@@ -112,6 +152,7 @@ struct ci_ctx {
   int force_G = 0;                   // CI_B200_G env override (tuning)
   int team_mode = 1;                 // CI_B200_TEAM=0 disables the warp-team kernels
   int predict_team = 1;              // CI_B200_PREDICT_TEAM=0: one warp per draw in ci_posterior_predict
+  int sel_nt = 0, sel_smem = -1;     // CI_B200_SEL_NT / CI_B200_SEL_SMEM: select-kernel launch shape (tuning)
   int gibbs_team = 1;                // CI_B200_GIBBS_TEAM=0: one warp per chain in the Gibbs kernel
   int tstream_mode = 1;              // CI_B200_TSTREAM=0 disables the long-series team kernels
   int tstream_W = 0;                 // CI_B200_TSW: warps per chain of the long-series team kernels (tuning)
@@ -223,6 +264,22 @@ int plan_smem(const ci_ctx* c, int G, uint32_t extra_elems, SmemCfg* out,
   cfg.total_bytes = off;
   *out = cfg;
   return CI_OK;
+}
+
+// Launch shape of the per-column select kernels (k_row_quantiles, k_impact_jobs): threads per
+// column CTA and whether the column's keys are staged in shared memory (else every sweep reads
+// them through L2).  elem_bytes = size of one staged key.  CI_B200_SEL_NT / CI_B200_SEL_SMEM
+// override (tuning).
+inline void select_launch_cfg(const ci_ctx* c, int S, size_t elem_bytes, int* nt, size_t* bytes,
+                              int* in_smem) {
+  size_t b = (((size_t)S * elem_bytes) + 15) & ~(size_t)15;
+  int sm = b + QSTATIC <= (size_t)c->smem_optin;
+  if (c->sel_smem >= 0 && !c->sel_smem) sm = 0;
+  if (!sm) b = 0;
+  int n = 1024;
+  while (n > 64 && n / 2 >= S) n >>= 1;
+  if (c->sel_nt > 0) n = c->sel_nt;
+  *nt = n; *bytes = b; *in_smem = sm;
 }
 
 int pick_G(const ci_ctx* c, int C) {
