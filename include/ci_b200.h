@@ -226,8 +226,9 @@ int ci_row_quantiles_d(ci_ctx* ctx, const void* a_d, int S, int T, int dtype,
  *   active [K][T] uint8 HOST: season index (0 .. num_seasons-1) active at step t
  *   ends   [K][T] uint8 HOST: 1 when that season is over after step t
  * (the host derives both from Seasons.num_steps_per_season, lib.py:162-180).
- * Limits: K <= CI_MAX_SEASONAL, 1 + sum(num_seasons) <= 32 (one warp lane per state
- * element); beyond that CI_ERR_UNSUPPORTED.  Call after ci_set_data; n_components = 0
+ * Limits: K <= CI_MAX_SEASONAL, 1 + sum(num_seasons) <= 192 (up to six state elements per warp
+ * lane: week-of-year and hour-of-week calendars fit) and the d x d state covariance of a chain must
+ * fit in shared memory (float64 stops near d = 160); beyond that CI_ERR_UNSUPPORTED.  Call after ci_set_data; n_components = 0
  * (or seas == NULL) removes the components; ci_set_data also removes them.
  */
 #define CI_MAX_SEASONAL 7

@@ -52,9 +52,9 @@ def test_unexpected_kwargs_raise():                    # lib_test.py:231-240
 
 def test_unsupported_model_options_fail_loudly():
   data, pre, post = csv_data()
-  with pytest.raises(ValueError, match="state dimension"):           # 1 + 52 > one warp
+  with pytest.raises(ValueError, match="state dimension"):           # 1 + 200 > 192
     ci.fit_causalimpact(data, pre, post, seed=1,
-                        model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=52)]))
+                        model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=200)]))
   with pytest.raises(NotImplementedError):
     ci.fit_causalimpact(data, pre, post, seed=1, experimental_model=object())
   # seasons themselves are supported (csrc/ci_seasonal.cuh): data.csv with a weekly component

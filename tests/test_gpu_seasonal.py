@@ -37,25 +37,29 @@ def pinned_spec(y_ext, s_e, s_h, dtype, m0=0.3, P0=1.4):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_joint_smoother_matches_dense_gaussian_conditional(engine, dtype):
+@pytest.mark.parametrize("case", ["two_components_d12", "week_of_year_d53", "wide_d131"])
+def test_joint_smoother_matches_dense_gaussian_conditional(engine, dtype, case):
+  """d = 12: one state element per lane; d = 53 (52 weeks): two per lane; d = 131: six per lane
+  (the hour-of-week instantiation)."""
   rng = np.random.default_rng(0)
-  T = 60
-  ss = seasons((4, (2, 1, 1, 1)), (7, 1))
+  ss, T = {"two_components_d12": (seasons((4, (2, 1, 1, 1)), (7, 1)), 60),
+           "week_of_year_d53": (seasons((52, 1)), 130),
+           "wide_d131": (seasons((100, 1), (30, 2)), 150)}[case]
+  Kc = len(ss)
   y = 0.5 + rng.normal(size=T)
-  y[[3, 11]] = np.nan; y[45:] = np.nan
+  y[[3, 11]] = np.nan; y[int(0.75 * T):] = np.nan
   mask = np.isnan(y)
-  s_e, s_h, s_d = 0.2, 0.01, [0.03, 0.004]
+  s_e, s_h, s_d = 0.2, 0.01, [0.03] * Kc
   spec = pinned_spec(y, s_e, s_h, dtype)
   engine.set_data(spec)
   sched = model.build_seasonal(ss, T, 1.1)
-  # pin the drift variances too
+  # pin the drift variances too (one drift prior for all components in the ABI)
   sched = dataclasses.replace(sched, drift_conc=1e9, drift_scale=1e9 * s_d[0], drift_ub=1e3)
-  # (one drift prior for all components in the ABI: use equal drift for the exact test)
-  s_d = [s_d[0], s_d[0]]
   engine.set_seasonal(sched)
-  out = engine.gibbs_seasonal_run(64, n_warmup=2, n_results=60, seed=7, sparse=False)
+  n_chains, n_res = (64, 60) if case == "two_components_d12" else (48, 40)
+  out = engine.gibbs_seasonal_run(n_chains, n_warmup=2, n_results=n_res, seed=7, sparse=False)
   lvl = out["level"].reshape(-1, T).astype(np.float64)
-  sea = out["seasonal"].reshape(-1, T, 2).astype(np.float64)
+  sea = out["seasonal"].reshape(-1, T, Kc).astype(np.float64)
   lat = out["latent"].reshape(-1, T).astype(np.float64)
   n = lvl.shape[0]
   np.testing.assert_allclose(lat, lvl + sea.sum(-1), atol=2e-5)
@@ -67,14 +71,14 @@ def test_joint_smoother_matches_dense_gaussian_conditional(engine, dtype):
   mu, Syy, Sxy, covs = S.dense_moments(sp, T, s_e, s_h, s_d, spec.m0, spec.P0)
   o = ~mask
   Sinv_r = np.linalg.solve(Syy[np.ix_(o, o)], (y - mu)[o])
-  for t in range(T):
+  for t in range(0, T, 1 if T <= 60 else 3):
     G = Sxy[t][:, o]
     cmean = np.r_[spec.m0, np.zeros(sp.d - 1)] + G @ Sinv_r
     ccov = covs[t] - G @ np.linalg.solve(Syy[np.ix_(o, o)], G.T)
     cols = S.obs_cols(sp, t)
     # level, each contribution, and their sum: mean within 5 MC standard errors (+ float32 slack)
-    for got, idx in ((lvl[:, t], [0]), (sea[:, t, 0], [cols[1]]), (sea[:, t, 1], [cols[2]]),
-                     (lat[:, t], cols)):
+    checks = [(lvl[:, t], [0]), (lat[:, t], cols)] + [(sea[:, t, k], [cols[1 + k]]) for k in range(Kc)]
+    for got, idx in checks:
       m_ref = cmean[idx].sum()
       v_ref = ccov[np.ix_(idx, idx)].sum()
       assert abs(got.mean() - m_ref) < 5 * np.sqrt(v_ref / n) + 2e-4, (t, idx)
@@ -82,6 +86,28 @@ def test_joint_smoother_matches_dense_gaussian_conditional(engine, dtype):
   # predictive draw: traj = latent + sigma_obs * N(0,1)
   e = (out["traj"] - out["latent"]).reshape(-1).astype(np.float64)
   assert abs(e.std() - np.sqrt(s_e)) < 0.01 and abs(e.mean()) < 0.01
+
+
+def test_week_of_year_through_fit_causalimpact():
+  """Seasons(num_seasons=52) -- rejected in round 1 (state wider than one warp) -- through the
+  reference's entry point: weekly data over three years with a yearly pattern."""
+  rng = np.random.default_rng(8)
+  n = 52 * 3 + 20
+  pat = 2.0 * np.sin(2 * np.pi * np.arange(52) / 52.0)
+  x = 100 + np.cumsum(rng.normal(size=n)) * 0.2
+  y = 0.9 * x + pat[np.arange(n) % 52] + 0.3 * rng.normal(size=n)
+  y[156:] += 1.5
+  df = pd.DataFrame({"y": y, "x": x}, index=pd.date_range("2019-01-07", periods=n, freq="W-MON"))
+  res = ci.fit_causalimpact(df, (df.index[0], df.index[155]), (df.index[156], df.index[-1]), seed=2,
+                            model_options=ci.ModelOptions(seasons=[ci.Seasons(num_seasons=52)]),
+                            inference_options=ci.InferenceOptions(num_results=200),
+                            engine_options=ci.EngineOptions(num_chains=32))
+  assert res.posterior_samples.seasonal_levels.shape == (200, n, 1)
+  lo, hi = res.summary.loc["average", "abs_effect_lower"], res.summary.loc["average", "abs_effect_upper"]
+  assert lo < 1.5 < hi and hi - lo < 3.0, (lo, hi)
+  contrib = res.posterior_samples.seasonal_levels.numpy()[:, :156, 0].mean(0).reshape(3, 52).mean(0)
+  sd_y = float(np.std(y[:156], ddof=1))
+  assert np.corrcoef(contrib, pat)[0, 1] > 0.8, np.corrcoef(contrib, pat)[0, 1]
 
 
 def test_full_sweep_matches_restated_sampler(engine):
@@ -168,7 +194,7 @@ def test_limits_and_errors(engine):
   y = rng.normal(size=80); y[60:] = np.nan
   engine.set_data(ci.build_problem(y, None, outcome_sd=1.0))
   with pytest.raises(ValueError, match="state dimension"):       # checked on the host, loudly
-    model.build_seasonal(seasons((24, 1), (12, 2)), 80, 1.0)
+    model.build_seasonal(seasons((150, 1), (60, 2)), 80, 1.0)
   engine.set_seasonal(None)
   with pytest.raises(EngineError, match="ci_set_seasonal"):
     engine.seasonal = model.build_seasonal(seasons((7, 1)), 80, 1.0)

@@ -74,7 +74,8 @@ class Seasons:
   """reference :162-180.  One seasonal effect (e.g. day of week): ``num_seasons`` effects,
   each lasting ``num_steps_per_season`` steps (int, per-season tuple, or per-cycle tuple of
   tuples).  Sampled by the seasonal Gibbs kernel (csrc/ci_seasonal.cuh); the sum of
-  num_seasons over all components is limited to 31."""
+  num_seasons over all components is limited to 191 (week-of-year and hour-of-week fit), at most 7
+  components."""
   num_seasons: int
   num_steps_per_season: Union[int, Tuple[int], Tuple[Tuple[int]]] = 1
 

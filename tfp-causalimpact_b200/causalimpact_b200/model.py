@@ -89,7 +89,7 @@ def initial_theta(spec: ProblemSpec, prior_level_sd: float = 0.01) -> np.ndarray
 # seasonal components (ModelOptions.seasons; causalimpact_lib.py:162-180, 471-489)
 # ---------------------------------------------------------------------------
 MAX_SEASONAL_COMPONENTS = 7     # csrc/ci_device.cuh: MAX_SEAS
-MAX_SEASONAL_STATE = 32         # csrc/ci_device.cuh: SEAS_MAXD (level + every seasonal effect)
+MAX_SEASONAL_STATE = 192        # csrc/ci_device.cuh: SEAS_MAXD (level + every seasonal effect)
 
 
 @dataclasses.dataclass
@@ -140,7 +140,7 @@ def build_seasonal(seasons: Sequence, T: int, outcome_sd: float) -> Optional[Sea
   if total > MAX_SEASONAL_STATE:
     raise ValueError(
         f"1 + sum(num_seasons) = {total} exceeds the seasonal state dimension the engine "
-        f"supports ({MAX_SEASONAL_STATE}): e.g. Seasons(num_seasons=52) is not available")
+        f"supports ({MAX_SEASONAL_STATE})")
   active = np.zeros((K, T), np.uint8)
   ends = np.zeros((K, T), np.uint8)
   ns = []

@@ -62,7 +62,8 @@ int launch_gibbs_seasonal(ci_ctx* c, const ci_gibbs_opts* o, uint64_t seed, uint
     CU_TRY(c->s_scratch.reserve((size_t)C * (batch ? c->batch_n : 1) * c->prob.T * (d + 1) * sizeof(R)));
     sz.scratch = c->s_scratch.p;
   }
-  auto kern = k_gibbs_seasonal<R>;
+  // state elements per lane: 1 (d <= 32), 2 (d <= 64: week-of-year), 6 (d <= 192: hour-of-week)
+  auto kern = d <= 32 ? k_gibbs_seasonal<R, 1> : (d <= 64 ? k_gibbs_seasonal<R, 2> : k_gibbs_seasonal<R, 6>);
   CU_TRY(set_smem(kern, (uint32_t)cfg.total_bytes));
   const dim3 grid((C + G - 1) / G, batch ? c->batch_n : 1);
   kern<<<grid, 32 * (G + 1), cfg.total_bytes, st>>>(

@@ -20,7 +20,7 @@ template <typename R> struct ProbDev {
 
 // Seasonal components as the kernels see them (ci_set_seasonal; kernel in ci_seasonal.cuh).
 constexpr int MAX_SEAS = 7;     // components (the "season ends" flags of a step are one byte)
-constexpr int SEAS_MAXD = 32;   // 1 + sum of num_seasons
+constexpr int SEAS_MAXD = 192;  // 1 + sum of num_seasons: up to 6 state elements per lane (hour-of-week = 169)
 
 struct SeasDev {
   int K, d;

@@ -44,7 +44,23 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
-template <typename R>
+// value of element `idx` (uniform or per-lane) of a vector distributed as element i <-> lane i % 32,
+// slot i / 32
+template <typename R, int E>
+__device__ __forceinline__ R seas_pick(const R (&v)[E], int idx) {
+  R r = __shfl_sync(FULL, v[0], idx & 31);
+#pragma unroll
+  for (int e = 1; e < E; ++e) {
+    const R t = __shfl_sync(FULL, v[e], idx & 31);
+    r = (idx >> 5) == e ? t : r;
+  }
+  return r;
+}
+
+// E = state elements per lane: the state x = (level, effects of every component) has d <= 32 E
+// elements, element i lives in lane i % 32, slot i / 32 (E = 1: day-of-week and the like; E = 2:
+// week-of-year, d = 53; E = 6: hour-of-week, d = 169).
+template <typename R, int E>
 __global__ void __launch_bounds__(32 * (MAXG + 1), 1)
 k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPlan plan,
                  uint64_t seed, uint64_t chain_id0, int C, R* __restrict__ draws,
@@ -89,9 +105,8 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   gs.bvec = ws.extra; gs.La = gs.bvec + p; gs.Lo = gs.La + (p + 1) * (p + 1);
   gs.idx = gs.Lo + p * p; gs.vec = gs.idx + p; gs.perm = gs.vec + (p + 1);
   const int d = sz.d, K = sz.K, LDP = d | 1;
-  R* Ps = gs.perm + p;                  // [d][LDP] state covariance, row i <-> lane i
+  R* Ps = gs.perm + p;                  // [d][LDP] state covariance, row i <-> element i
   R* phs = Ps + d * LDP;                // [d]      P h of the current step
-  R* Prow = Ps + (lane < d ? lane : 0) * LDP;
   R* st_a = phs + d;                    // [TB] x3: per-step staging of the current tile
   R* st_b = st_a + TB;
   R* st_c = st_b + TB;
@@ -103,11 +118,19 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   const uint64_t gid = chain_id0 + (uint64_t)c + (batch ? (uint64_t)blockIdx.y * plan.series_stride : 0ull);
   const uint32_t id_lo = (uint32_t)gid, id_hi8 = (uint32_t)(gid >> 32) << 8;
 
-  // which block element `lane` belongs to: -1 level, k component, -2 unused lane
-  int comp = lane == 0 ? -1 : -2, my_n = 1, my_off = 0;
-  for (int k = 0; k < K; ++k)
-    if (lane >= sz.off[k] && lane < sz.off[k] + sz.n[k]) { comp = k; my_n = sz.n[k]; my_off = sz.off[k]; }
-  const R inv_n = (R)1 / (R)my_n;
+  // which block each of the lane's elements belongs to: -1 level, k component, -2 unused slot
+  int comp[E], my_n[E], my_off[E], el[E];
+  R inv_n[E];
+  R* Prow[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    el[e] = lane + 32 * e;
+    comp[e] = el[e] == 0 ? -1 : -2; my_n[e] = 1; my_off[e] = 0;
+    for (int k = 0; k < K; ++k)
+      if (el[e] >= sz.off[k] && el[e] < sz.off[k] + sz.n[k]) { comp[e] = k; my_n[e] = sz.n[k]; my_off[e] = sz.off[k]; }
+    inv_n[e] = (R)1 / (R)my_n[e];
+    Prow[e] = Ps + (el[e] < d ? el[e] : 0) * LDP;
+  }
   const int my_coff = (lane >= 1 && lane <= K) ? sz.off[lane - 1] : 0;   // lane l in 1..K <-> component l-1
 
   // ---- initial state: the reference's (lib.py:566-581) ----
@@ -125,37 +148,46 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
   const GibbsReg<R> reg{pr, gs, gram_s, om_s, p, lane, conc_e, seed, id_lo, id_hi8};
   const R sd0 = Num<R>::sqrt(pr.P0), sdi = (R)sqrt(sz.init_var);
 
-  // mean over component k's block of the lane-distributed vector v (0 outside blocks)
-  auto block_centered = [&](R v) -> R {
-    R out = 0;
+  // v minus the mean of v over its component's block (0 outside blocks)
+  auto block_centered = [&](const R (&v)[E], R (&out)[E]) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) out[e] = 0;
     for (int k = 0; k < K; ++k) {
-      const R s = warp_sum(comp == k ? v : (R)0);
-      if (comp == k) out = v - s * inv_n;
+      R part = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) part += comp[e] == k ? v[e] : (R)0;
+      const R s = warp_sum(part);
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (comp[e] == k) out[e] = v[e] - s * inv_n[e];
     }
-    return out;
   };
   // the step's schedule: cols[k] (uniform) = state index of the k-th observed column
-  // (k = 0: the level, k >= 1: component k-1's active season), mask of those columns, ends flags
-  auto step_sched = [&](int t, int (&cols)[MAX_SEAS + 1], unsigned& cmask, int& em) -> int {
+  // (k = 0: the level, k >= 1: component k-1's active season), per-slot masks of those columns,
+  // ends flags
+  auto step_sched = [&](int t, int (&cols)[MAX_SEAS + 1], unsigned (&cmask)[E], int& em) -> int {
     const uint8_t* sc = sz.sched + (size_t)t * (K + 1);
     em = sc[K];
     const int src = (lane >= 1 && lane <= K) ? my_coff + (int)sc[lane - 1] : 0;
-    cmask = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) cmask[e] = 0u;
 #pragma unroll
     for (int k = 0; k <= MAX_SEAS; ++k) {
       cols[k] = 0;
       if (k <= K) {                                   // K is uniform: no divergence
         cols[k] = __shfl_sync(FULL, src, k);
-        cmask |= 1u << cols[k];
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if ((cols[k] >> 5) == e) cmask[e] |= 1u << (cols[k] & 31);
       }
     }
     return src;      // lane l in 1..K: state index of component l-1's active season
   };
-  auto gather = [&](R v, const int (&cols)[MAX_SEAS + 1]) -> R {      // h' v
+  auto gather = [&](const R (&v)[E], const int (&cols)[MAX_SEAS + 1]) -> R {      // h' v
     R acc = 0;
 #pragma unroll
     for (int k = 0; k <= MAX_SEAS; ++k)
-      if (k <= K) acc += __shfl_sync(FULL, v, cols[k]);
+      if (k <= K) acc += seas_pick<R, E>(v, cols[k]);
     return acc;
   };
   // All normals of step t: level noise, observation noise of y+, predictive noise, and one
@@ -179,12 +211,18 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       }
     }
   };
-  auto init_xplus = [&](int it) -> R {
-    const uint4 x = Philox::gen(seed, id_lo, RNG_S_INIT | id_hi8, (uint32_t)lane, (uint32_t)it);
-    R z0, z1;
-    box_muller<R>(x.x, x.y, z0, z1);
-    const R zc = block_centered(z0);
-    return lane == 0 ? fma(sd0, z0, pr.m0) : (comp >= 0 ? sdi * zc : (R)0);
+  auto init_xplus = [&](int it, R (&out)[E]) {
+    R z[E], zc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const uint4 x = Philox::gen(seed, id_lo, RNG_S_INIT | id_hi8, (uint32_t)el[e], (uint32_t)it);
+      R z1;
+      box_muller<R>(x.x, x.y, z[e], z1);
+    }
+    block_centered(z, zc);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      out[e] = el[e] == 0 ? fma(sd0, z[e], pr.m0) : (comp[e] >= 0 ? sdi * zc[e] : (R)0);
   };
 
   for (int it = 0; it < n_iter; ++it) {
@@ -201,15 +239,21 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       inv_nk[k] = k < K ? (R)1 / (R)sz.n[k] : (R)0;
     }
     // ---- pass A ----
-    if (lane < d) {
-      for (int j = 0; j < d; ++j) Prow[j] = 0;
-      if (lane == 0) Prow[0] = pr.P0;
-      if (comp >= 0)
-        for (int j = 0; j < my_n; ++j)
-          Prow[my_off + j] = (R)sz.init_var * ((my_off + j == lane ? (R)1 : (R)0) - inv_n);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (el[e] < d) {
+        for (int j = 0; j < d; ++j) Prow[e][j] = 0;
+        if (el[e] == 0) Prow[e][0] = pr.P0;
+        if (comp[e] >= 0)
+          for (int j = 0; j < my_n[e]; ++j)
+            Prow[e][my_off[e] + j] = (R)sz.init_var * ((my_off[e] + j == el[e] ? (R)1 : (R)0) - inv_n[e]);
+      }
     }
     __syncwarp();
-    R xp = init_xplus(it), a = 0;
+    R xp[E], a[E];
+    init_xplus(it, xp);
+#pragma unroll
+    for (int e = 0; e < E; ++e) a[e] = 0;
     for (int b = 0; b < NB; ++b) {
       const R* tile = pipe.acquire(b);
       Blk<R> B;
@@ -236,49 +280,79 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       for (int tl = 0; tl < nstep; ++tl) {
         const int t = b * TB + tl;
         const R r_t = st_a[tl], eta = st_b[tl], eps = st_c[tl];
-        int cols[MAX_SEAS + 1], em; unsigned cmask;
+        int cols[MAX_SEAS + 1], em; unsigned cmask[E];
         step_sched(t, cols, cmask, em);
-        R Kg = 0, e = 0;
-        if (r_t == r_t) {                                       // observed step
-          const R hxa = gather(xp + a, cols);
-          R Ph = 0;
-          if (lane < d) {
+        R Kg[E], ee = 0;
 #pragma unroll
-            for (int k = 0; k <= MAX_SEAS; ++k)
-              if (k <= K) Ph += Prow[cols[k]];
+        for (int e = 0; e < E; ++e) Kg[e] = 0;
+        if (r_t == r_t) {                                       // observed step
+          R xa[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) xa[e] = xp[e] + a[e];
+          const R hxa = gather(xa, cols);
+          R Ph[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            Ph[e] = 0;
+            if (el[e] < d) {
+#pragma unroll
+              for (int k = 0; k <= MAX_SEAS; ++k)
+                if (k <= K) Ph[e] += Prow[e][cols[k]];
+            }
           }
           const R rF = Num<R>::rcp(gather(Ph, cols) + se);
           const R v = (r_t - sig_e * eps) - hxa;
-          e = v * rF; Kg = Ph * rF;
-          a = fma(Kg, v, a);
-          // P -= (P h)(P h)' / F: row i in lane i, (P h)_j by shuffle (symmetric in fp: the
-          // product Ph_i Ph_j commutes)
+          ee = v * rF;
+#pragma unroll
+          for (int e = 0; e < E; ++e) { Kg[e] = Ph[e] * rF; a[e] = fma(Kg[e], v, a[e]); }
+          // P -= (P h)(P h)' / F: row i in the lane owning element i; (P h)_j is broadcast
+          // by shuffle for one slot per lane (symmetric in fp: the product Ph_i Ph_j commutes),
+          // through shared memory for wider states
+          if (E == 1) {
 #pragma unroll 4
-          for (int j = 0; j < d; ++j) {
-            const R pj = __shfl_sync(FULL, Ph, j);
-            if (lane < d) Prow[j] = fma(-(Ph * pj), rF, Prow[j]);
+            for (int j = 0; j < d; ++j) {
+              const R pj = __shfl_sync(FULL, Ph[0], j);
+              if (lane < d) Prow[0][j] = fma(-(Ph[0] * pj), rF, Prow[0][j]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+              if (el[e] < d) phs[el[e]] = Ph[e];
+            __syncwarp();
+#pragma unroll 2
+            for (int j = 0; j < d; ++j) {
+              const R pj = phs[j];
+#pragma unroll
+              for (int e = 0; e < E; ++e)
+                if (el[e] < d) Prow[e][j] = fma(-(Ph[e] * pj), rF, Prow[e][j]);
+            }
           }
           __syncwarp();
         }
         R* srow = scr + (size_t)t * (d + 1);
-        if (lane < d) srow[lane] = Kg;
-        if (lane == 0) srow[d] = e;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (el[e] < d) srow[el[e]] = Kg[e];
+        if (lane == 0) srow[d] = ee;
         // x_{t+1} = x_t + noise_t
-        if (lane == 0) { Prow[0] += sh; xp = fma(sig_h, eta, xp); }
+        if (lane == 0) { Prow[0][0] += sh; xp[0] = fma(sig_h, eta, xp[0]); }
         if (em) {
 #pragma unroll
           for (int k = 0; k < MAX_SEAS; ++k) {
             if (k >= K || !((em >> k) & 1)) continue;
             const int jk = cols[k + 1];
             const R sdk = __shfl_sync(FULL, sdv, k);
-            const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
-            if (comp == k) {
-              // P_block += sdk c c',  c = e_jk - 1/n:  row i gets  sdk c_i (e_jk - 1/n)'
-              const R f = sdk * ci, g0 = -f * inv_n;
-              for (int j = 0; j < my_n; ++j) Prow[my_off + j] += g0;
-              Prow[jk] += f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const R ci = comp[e] == k ? ((el[e] == jk ? (R)1 : (R)0) - inv_n[e]) : (R)0;
+              if (comp[e] == k) {
+                // P_block += sdk c c',  c = e_jk - 1/n:  row i gets  sdk c_i (e_jk - 1/n)'
+                const R f = sdk * ci, g0 = -f * inv_n[e];
+                for (int j = 0; j < my_n[e]; ++j) Prow[e][my_off[e] + j] += g0;
+                Prow[e][jk] += f;
+              }
+              xp[e] = fma(sig_d[k] * st_d[k * TB + tl], ci, xp[e]);
             }
-            xp = fma(sig_d[k] * st_d[k * TB + tl], ci, xp);
           }
           __syncwarp();
         }
@@ -288,18 +362,27 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
     }
     __syncwarp();
     // ---- pass B ----
-    R rr = 0;
+    R rr[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) rr[e] = 0;
 #pragma unroll 1
     for (int t = T - 1; t >= 0; --t) {
-      int cols[MAX_SEAS + 1], em; unsigned cmask;
+      int cols[MAX_SEAS + 1], em; unsigned cmask[E];
       step_sched(t, cols, cmask, em);
       R* srow = scr + (size_t)t * (d + 1);
       if (!scr_smem && t >= 4 && lane == 0) prefetch_l1(srow - 4 * (d + 1));
-      const R Kg = lane < d ? srow[lane] : (R)0;
-      const R e = srow[d];
-      if (lane < d) srow[lane] = rr;                       // r_t, read back by pass C
-      const R dot = warp_sum(Kg * rr);
-      if ((cmask >> lane) & 1u) rr += e - dot;
+      const R ee = srow[d];
+      R part = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const R Kg = el[e] < d ? srow[el[e]] : (R)0;
+        if (el[e] < d) srow[el[e]] = rr[e];                // r_t, read back by pass C
+        part = fma(Kg, rr[e], part);
+      }
+      const R dot = warp_sum(part);
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if ((cmask[e] >> lane) & 1u) rr[e] += ee - dot;
     }
     __syncwarp();
     // ---- pass C ----
@@ -307,10 +390,14 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
     const size_t out_row = !keep ? 0
         : series_row0 + (plan.chain_major ? ((size_t)c * plan.n_results + (size_t)(it - plan.n_warmup))
                                           : ((size_t)(it - plan.n_warmup) * C + c));
-    R xt = init_xplus(it);                                 // x = x+ + xhat, element `lane`
+    R xt[E];                                               // x = x+ + xhat
+    init_xplus(it, xt);
     {
-      const R rc = block_centered(rr);
-      xt += lane == 0 ? pr.P0 * rr : (comp >= 0 ? (R)sz.init_var * rc : (R)0);
+      R rc[E];
+      block_centered(rr, rc);
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        xt[e] += el[e] == 0 ? pr.P0 * rr[e] : (comp[e] >= 0 ? (R)sz.init_var * rc[e] : (R)0);
     }
     const XtMap xm = xt_map(p, lane);
     const bool small_p = p <= PSMALL;
@@ -344,32 +431,39 @@ k_gibbs_seasonal(ProbDev<R> pr, GibbsDev<R> gd, SeasDev sz, SmemCfg cfg, GibbsPl
       for (int tl = 0; tl < nstep; ++tl) {
         const int t = b * TB + tl;
         const R eta = st_a[tl];
-        int cols[MAX_SEAS + 1], em; unsigned cmask;
+        int cols[MAX_SEAS + 1], em; unsigned cmask[E];
         const int src = step_sched(t, cols, cmask, em);
         const R* srow = scr + (size_t)t * (d + 1);
         if (!scr_smem && t + 4 < T && lane == 0) prefetch_l1(srow + 4 * (d + 1));
-        const R level_t = __shfl_sync(FULL, xt, 0);
+        const R level_t = __shfl_sync(FULL, xt[0], 0);
         const R tot = gather(xt, cols);                     // level + all contributions
-        const R mine = __shfl_sync(FULL, xt, src);          // lane l in 1..K: component l-1's share
+        const R mine = seas_pick<R, E>(xt, src);            // lane l in 1..K: component l-1's share
         if (lane == 0) { st_b[tl] = level_t; st_c[tl] = tot - level_t; }
         if (keep && seas_out && lane >= 1 && lane <= K)
           seas_out[(out_row * T + t) * K + (lane - 1)] = mine;
         if (t > 0) { const double dl = (double)(level_t - prev_level); d2 += dl * dl; }
         prev_level = level_t;
         if (t < T - 1) {
-          const R rt = lane < d ? srow[lane] : (R)0;
-          if (lane == 0) xt += fma(sh, rt, sig_h * eta);
+          R rt[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) rt[e] = el[e] < d ? srow[el[e]] : (R)0;
+          if (lane == 0) xt[0] += fma(sh, rt[0], sig_h * eta);
           if (em) {
 #pragma unroll
             for (int k = 0; k < MAX_SEAS; ++k) {
               if (k >= K || !((em >> k) & 1)) continue;
               const int jk = cols[k + 1];
               const R sdk = __shfl_sync(FULL, sdv, k);
-              const R ci = comp == k ? ((lane == jk ? (R)1 : (R)0) - inv_n) : (R)0;
-              const R cr = __shfl_sync(FULL, rt, jk) -
-                           warp_sum(comp == k ? rt : (R)0) * inv_nk[k];
+              R part = 0;
+#pragma unroll
+              for (int e = 0; e < E; ++e) part += comp[e] == k ? rt[e] : (R)0;
+              const R cr = seas_pick<R, E>(rt, jk) - warp_sum(part) * inv_nk[k];
               const R u = fma(sdk, cr, sig_d[k] * st_d[k * TB + tl]);
-              xt = fma(u, ci, xt);
+#pragma unroll
+              for (int e = 0; e < E; ++e) {
+                const R ci = comp[e] == k ? ((el[e] == jk ? (R)1 : (R)0) - inv_n[e]) : (R)0;
+                xt[e] = fma(u, ci, xt[e]);
+              }
               if (lane == k) su2 += (double)u * (double)u;
             }
           }
