@@ -195,6 +195,7 @@ def test_device_entry_point_does_not_synchronise_when_workspaces_grow(engine):
   import time
   import types
   import torch
+  import causalimpact_b200 as cib
   rng = np.random.default_rng(5)
   T = 120
   per = np.zeros(T, np.uint8); per[80:] = 1
