@@ -479,34 +479,71 @@ def bench_forecast_config(gpu, cib, _engine, cfg, local, rank=0, world=1, with_c
     if record: marks[3].record(gpu.stream)
     return out_d
 
-  for _ in range(3):
-    forecast()
-  torch.cuda.synchronize()
-  if world > 1:
-    dist.barrier()
-  l0 = eng.launch_count
-  splits = []
-  for _ in range(reps):
-    gpu.flush.zero_()
-    forecast(record=True)
+  # N > 1, the time-sharded exchange (shard.impact_sharded): the trajectories are never gathered;
+  # the ranks swap time blocks of the transposed paths and select T/N steps each
+  from causalimpact_b200 import impact as _imp
+  meta = _imp.ImpactMeta(index=None, observed=obs, period=per, hide=None, scale=2.0, offset=100.0,
+                         q_lo=0.025, q_hi=0.975, obs_mean=float(obs[t_pre:].mean()),
+                         obs_sum=float(obs[t_pre:].sum()))
+  counts = cib.shard.even_counts(S, world)
+
+  def forecast_columns(record=False):
+    if record: marks[0].record(gpu.stream)
+    rc = lib.ci_posterior_predict_d(ctx, th.data_ptr(), s_local, 11, s0, lvl.data_ptr(),
+                                    trj.data_ptr(), None, st)
+    assert rc == 0, lib.ci_last_error()
+    if record: marks[1].record(gpu.stream)
+    mean_s = cib.shard.ShardedMean(eng, cib.shard.predictive_mean_part(eng, th, lvl, counts), counts)
+    if record: marks[2].record(gpu.stream)
+    out = cib.shard.impact_sharded(eng, trj, mean_s, meta, counts)      # ci_impact_sharded_d
+    if record: marks[3].record(gpu.stream)
+    return out
+
+  def timed(fn):
+    for _ in range(3):
+      fn()
     torch.cuda.synchronize()
-    splits.append([marks[i].elapsed_time(marks[i + 1]) for i in range(3)])
-  launches = (eng.launch_count - l0) // reps
-  sp = np.array(splits).mean(0)
-  t_dev = float(sp.sum())
-  # wall clock incl. the D2H of series + summary (what a caller of the pipeline waits for)
-  torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    l0 = eng.launch_count
+    splits = []
+    for _ in range(reps):
+      gpu.flush.zero_()
+      fn(record=True)
+      torch.cuda.synchronize()
+      splits.append([marks[i].elapsed_time(marks[i + 1]) for i in range(3)])
+    launches = (eng.launch_count - l0) // reps
+    sp = np.array(splits).mean(0)
+    t_dev = float(sp.sum())
+    # wall clock incl. the D2H of series + summary (what a caller of the pipeline waits for)
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    tq = time.perf_counter()
+    for _ in range(reps):
+      res = fn().cpu()
+    t_wall = (time.perf_counter() - tq) / reps * 1e3
+    assert np.isfinite(res.numpy()[:T * 9].reshape(T, 9)[:, 0]).all()
+    if world > 1:
+      tt = torch.tensor([t_dev, t_wall] + sp.tolist(), dtype=torch.float64, device=gpu.dev)
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      t_dev, t_wall = float(tt[0]), float(tt[1]); sp = tt[2:].cpu().numpy()
+    return t_dev, t_wall, sp, launches, res.numpy()
+
+  t_dev, t_wall, sp, launches, res_draws = timed(forecast)
+  by_draws = None
   if world > 1:
-    dist.barrier()
-  tq = time.perf_counter()
-  for _ in range(reps):
-    res = forecast().cpu()
-  t_wall = (time.perf_counter() - tq) / reps * 1e3
-  assert np.isfinite(res.numpy()[:T * 9].reshape(T, 9)[:, 0]).all()
-  if world > 1:
-    tt = torch.tensor([t_dev, t_wall] + sp.tolist(), dtype=torch.float64, device=gpu.dev)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_dev, t_wall = float(tt[0]), float(tt[1]); sp = tt[2:].cpu().numpy()
+    # both exchanges are measured; the block's value is the time-sharded one, the gather of all
+    # draws is kept beside it (and checked: the quantile columns must be identical)
+    by_draws = {"kernel_ms": t_dev, "value": S / (t_dev * 1e-3),
+                "split_ms": {"smoother_predictive": float(sp[0]), "all_gather": float(sp[1]),
+                             "mean_and_impact": float(sp[2])}}
+    t_dev, t_wall, sp, launches, res_cols = timed(forecast_columns)
+    a, b = res_draws[:T * 9].reshape(T, 9), res_cols[:T * 9].reshape(T, 9)
+    qc = [1, 2, 4, 5, 7, 8]
+    assert np.array_equal(a[:, qc], b[:, qc], equal_nan=True), "time-sharded quantiles differ"
+    assert np.allclose(a[:, [0, 3, 6]], b[:, [0, 3, 6]], rtol=1e-5, atol=1e-4)
+    assert np.allclose(res_draws[T * 9:], res_cols[T * 9:], rtol=1e-5, atol=1e-4)
 
   # ---- e2e through the host-pointer ABI (rank-local draws): H2D theta, D2H level + traj + mean
   S_e = s_local
@@ -536,8 +573,13 @@ def bench_forecast_config(gpu, cib, _engine, cfg, local, rank=0, world=1, with_c
       "unit": "draws/s", "value": S / (t_dev * 1e-3), "kernel_ms": t_dev,
       "draws": S, "draws_per_gpu": s_local, "T": T, "p": p, "dtype": "f32", "n_gpus": world,
       "scaling": "strong" if world > 1 else None, "gpu_launches_per_step": int(launches),
-      "split_ms": {"smoother_predictive": float(sp[0]), "all_gather": float(sp[1]),
-                   "mean_and_impact": float(sp[2])},
+      "split_ms": ({"smoother_predictive": float(sp[0]), "all_gather": float(sp[1]),
+                    "mean_and_impact": float(sp[2])} if world == 1 else
+                   {"smoother_predictive": float(sp[0]), "mean_over_own_draws": float(sp[1]),
+                    "rows_exchange_columns_allreduce": float(sp[2])}),
+      "exchange": "none" if world == 1 else "columns (ci_impact_sharded_d: time blocks of the "
+                  "transposed paths swapped in one grouped ncclSend/ncclRecv, one all-reduce)",
+      "exchange_draws": by_draws,
       "wall_ms_incl_d2h_of_series": t_wall, "value_wall": S / (t_wall * 1e-3),
       "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "traffic": kernel_traffic("k_predict<float>"),
@@ -596,30 +638,44 @@ def bench_sharded_fit(gpu, cib, local, rank, world):
   yv = xs[:, :3] @ np.array([1.2, 0.6, -0.4]) + rs.normal(size=T)
   yv[1400:] += 10
   df = pd.DataFrame(np.column_stack([yv, xs]), columns=["y"] + [f"x{i}" for i in range(k)])
-  kw = dict(seed=3, inference_options=cib.InferenceOptions(num_results=10000, num_warmup_steps=100),
-            engine_options=cib.EngineOptions(num_chains=256, device=local, profile=True))
-  res = None
-  walls = []
-  for i in range(3):
-    torch.cuda.synchronize()
+  def run(exchange, return_level):
+    kw = dict(seed=3, inference_options=cib.InferenceOptions(num_results=10000, num_warmup_steps=100),
+              engine_options=cib.EngineOptions(num_chains=256, device=local, profile=True,
+                                               exchange=exchange, return_level=return_level))
+    res = None
+    walls = []
+    for i in range(3):
+      torch.cuda.synchronize()
+      if world > 1:
+        dist.barrier()
+      tq = time.perf_counter()
+      res = cib.fit_causalimpact(df, (0, 1399), (1400, 1999), **kw)
+      walls.append((time.perf_counter() - tq) * 1e3)
+    wall = float(np.min(walls[1:]))
+    phases = dict(res.diagnostics.get("phases_ms", {}))
     if world > 1:
-      dist.barrier()
-    tq = time.perf_counter()
-    res = cib.fit_causalimpact(df, (0, 1399), (1400, 1999), **kw)
-    walls.append((time.perf_counter() - tq) * 1e3)
-  wall = float(np.min(walls[1:]))
-  phases = dict(res.diagnostics.get("phases_ms", {}))
+      keys = sorted(phases)
+      tt = torch.tensor([wall] + [phases[k2] for k2 in keys], dtype=torch.float64, device=gpu.dev)
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      wall = float(tt[0]); phases = {k2: float(v) for k2, v in zip(keys, tt[1:].tolist())}
+    return {"wall_ms": wall, "phases_ms": phases,
+            "abs_effect": float(res.summary.loc["average", "abs_effect"]),
+            "abs_effect_lower": float(res.summary.loc["average", "abs_effect_lower"])}
+
+  out = {"workload": "fit_causalimpact, T=2000, 10 covariates, 10000 draws from 256 chains "
+                     "(BASELINE configs[4] scale), chains sharded over the ranks",
+         "n_gpus": world, "scaling": "strong",
+         "note": "wall = max over ranks of the 2nd/3rd call; phases are host-timed with a device "
+                 "synchronise at each boundary (EngineOptions.profile)"}
+  out.update(run("draws", True))
+  out["exchange"] = "draws (one all-gather of every result row; the default)"
+  # the same fit without the level paths in the result object (they are most of the gather and of
+  # the D2H), and -- under N > 1 -- with the time-sharded impact stage
+  out["without_level_paths"] = run("draws", False)
   if world > 1:
-    keys = sorted(phases)
-    tt = torch.tensor([wall] + [phases[k2] for k2 in keys], dtype=torch.float64, device=gpu.dev)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    wall = float(tt[0]); phases = {k2: float(v) for k2, v in zip(keys, tt[1:].tolist())}
-  return {"workload": "fit_causalimpact, T=2000, 10 covariates, 10000 draws from 256 chains "
-                      "(BASELINE configs[4] scale), chains sharded over the ranks, one all-gather",
-          "n_gpus": world, "scaling": "strong", "wall_ms": wall, "phases_ms": phases,
-          "abs_effect": float(res.summary.loc["average", "abs_effect"]),
-          "note": "wall = max over ranks of the 2nd/3rd call; phases are host-timed with a device "
-                  "synchronise at each boundary (EngineOptions.profile)"}
+    out["exchange_columns"] = run("columns", True)
+    out["exchange_columns_without_level_paths"] = run("columns", False)
+  return out
 
 
 def main():

@@ -365,6 +365,31 @@ int ci_impact_d(ci_ctx* ctx, const ci_impact_args* args, const void* traj_d,
                 const void* mean_d, const double* observed, const uint8_t* period,
                 double* series_d, double* summary_d, void* stream);
 
+/* The two halves of ci_impact_d, for draws sharded over GPUs.  The quantile columns
+ * need ALL draws of a time step, so a sharded fit exchanges the TRANSPOSED paths by time block
+ * (an all-to-all of S*T/world elements per rank) instead of gathering every draw on every GPU:
+ *   1. ci_impact_rows_d on each rank's own draws (args->S = its draw count):
+ *        trT [T,S] (args.dtype), cumT [T - t_c0, S] float64, stats [5,S] float64 -- the paths and
+ *        the per-draw post-period statistics, draws contiguous per time step.  With mean_d (the
+ *        predictive mean over ALL draws; one rank passes it, the others NULL) the mean-derived
+ *        series columns 0, 3, 6 and summary[18..19] are written too.
+ *   2. the caller's collective moves rows [t_begin, t_begin + t_count) of every rank's trT (and
+ *        [c_begin, ...) of cumT) to the rank that owns that time block, and stats to one rank,
+ *        and lays the received blocks side by side as [t_count, S_total].
+ *   3. ci_impact_cols_d (args->S = S_total): the quantile columns of this rank's time block; with
+ *        stats_d (all draws, [5,S_total]) also summary[0..17].  Entries this call does not own
+ *        are left untouched: zero series / summary first and sum the buffers over ranks.
+ * t_c0 = the first step with period != 0.  Results equal ci_impact_d on the gathered draws bit
+ * for bit (the select is exact); reference: the same lines as ci_impact. */
+int ci_impact_rows_d(ci_ctx* ctx, const ci_impact_args* args, const void* traj_d,
+                     const void* mean_d, const double* observed, const uint8_t* period,
+                     void* trT_d, double* cumT_d, double* stats_d, double* series_d,
+                     double* summary_d, void* stream);
+int ci_impact_cols_d(ci_ctx* ctx, const ci_impact_args* args, const void* trT_d, int t_begin,
+                     int t_count, const double* cumT_d, int c_begin, int c_count,
+                     const double* stats_d, const double* observed, const uint8_t* period,
+                     double* series_d, double* summary_d, void* stream);
+
 /* Batched (grid.y = series) versions of ci_predictive_mean_d and ci_impact_d for the batch in the
  * context: theta [N,S,dim], level [N,S,T] -> mean [N,T];
  * traj [N,S,T], mean [N,T], observed HOST [N,T], period HOST [T] (shared), per-series scale /
@@ -397,6 +422,33 @@ int ci_comm_create(ci_ctx* ctx, const uint8_t* id /* [CI_COMM_ID_BYTES] */, int 
 int ci_allgather(ci_comm* comm, const void* send_d, void* recv_d, size_t bytes_per_rank,
                  void* stream);
 int ci_comm_destroy(ci_comm* comm);
+
+/* The impact stage of a fit whose draws are sharded over the ranks of `comm`, in ONE call: steps
+ * 1-3 of ci_impact_rows_d / ci_impact_cols_d above with the exchange inside.  Everything is
+ * enqueued on `stream` (kernels and NCCL alike; no host synchronisation):
+ *   k_impact_rows on the rank's own draws -> ONE grouped ncclSend/ncclRecv exchange (time block g
+ *   of the transposed float paths, and of the float64 cumulative paths with the per-draw
+ *   statistics riding to rank 0, go to rank g; every rank's predictive-mean part goes to
+ *   everyone) -> the received blocks side by side -> k_impact_jobs on T/nranks time steps over
+ *   all draws -> ncclAllReduce of the [T*9 + 20] result (each entry written by one rank).
+ * Time blocks: rank r owns steps start..start+count-1 with base = T / nranks, extra = T % nranks,
+ * start = r*base + min(r, extra), count = base + (r < extra); likewise for the T - t_c0
+ * cumulative columns.
+ *   args->S       this rank's draw count (may be 0 on ranks other than 0)
+ *   counts        [nranks] HOST int32: the draw count of every rank (global draw order = rank order)
+ *   traj_d        [args->S, T] this rank's predictive draws
+ *   mean_part_d   [T] the predictive mean over THIS rank's draws (ci_predictive_mean_d); ignored
+ *                 where counts[rank] == 0
+ *   mean_d        [T] out: the predictive mean over all draws (draw-count-weighted float64 sum of
+ *                 the parts in rank order)
+ *   out_d         [T*9 + CI_IMPACT_SUMMARY_LEN] float64 out, on every rank: series then summary of
+ *                 ci_impact; the quantile entries are bit-identical to ci_impact_d on the gathered
+ *                 draws, the mean-derived ones agree to the rounding of the parts to args->dtype.
+ * comm with nranks == 1 is allowed (the exchange is a self send/receive). */
+int ci_impact_sharded_d(ci_ctx* ctx, ci_comm* comm, const ci_impact_args* args,
+                        const int32_t* counts, const void* traj_d, const void* mean_part_d,
+                        const double* observed, const uint8_t* period, void* mean_d,
+                        double* out_d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -182,6 +182,58 @@ class FakeEngine:
       ser.append(s9.reshape(-1)); summ.append(sm)
     return torch.from_numpy(np.stack(ser)), torch.from_numpy(np.stack(summ))
 
+  # ---- the two halves of ci_impact_d for sharded draws (ci_impact_rows_d / ci_impact_cols_d) ----
+  def impact_rows_t(self, traj, mean, meta, out=None):
+    import torch
+    raw = np.asarray(traj)
+    S, T = raw.shape
+    per, obs = np.asarray(meta.period), np.asarray(meta.observed, dtype=np.float64)
+    t_c0 = int(np.argmax(per != 0)) if np.any(per != 0) else T
+    x = raw.astype(np.float64) * meta.scale + meta.offset
+    point = obs[None, :] - x
+    cum = impact_np._nan_cumsum(np.where((per == 0)[None, :], 0.0, point), axis=1)
+    in_post = per == 1
+    pred_sum = x[:, in_post].sum(axis=1)
+    with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
+      __import__("warnings").simplefilter("ignore")
+      eff_mean = np.nanmean(point[:, in_post], axis=1)
+    stats = np.stack([x[:, in_post].mean(axis=1), pred_sum, eff_mean,
+                      np.nansum(point[:, in_post], axis=1), meta.obs_sum / pred_sum - 1.0])
+    packed = torch.from_numpy(np.ascontiguousarray(np.concatenate([stats, cum[:, t_c0:].T])))
+    if mean is not None:
+      m = np.asarray(mean, dtype=np.float64).reshape(-1) * meta.scale + meta.offset
+      o = out.numpy()
+      ser = o[:T * 9].reshape(T, 9)
+      ser[:, 0], ser[:, 3] = m, obs - m
+      ser[:, 6] = impact_np._nan_cumsum(np.where(per == 0, 0.0, obs - m), axis=0)
+      o[T * 9 + 18], o[T * 9 + 19] = m[in_post].mean(), m[in_post].sum()
+    return torch.from_numpy(np.ascontiguousarray(raw.T)), packed[5:], packed[:5], packed
+
+  def impact_cols_t(self, trT, t_begin, cumT, c_begin, stats, meta, out):
+    from oracle import quantiles_np
+    per, obs = np.asarray(meta.period), np.asarray(meta.observed, dtype=np.float64)
+    T = obs.shape[0]
+    t_c0 = int(np.argmax(per != 0)) if np.any(per != 0) else T
+    q = np.array([meta.q_lo, meta.q_hi])
+    o = out.numpy()
+    ser, summ = o[:T * 9].reshape(T, 9), o[T * 9:]
+    nt, nc = trT.shape[0], cumT.shape[0]
+    if nt:
+      x = np.asarray(trT, dtype=np.float64).T * meta.scale + meta.offset       # [S, nt]
+      ser[t_begin:t_begin + nt, 1:3] = quantiles_np.row_quantiles(x, q)
+      ser[t_begin:t_begin + nt, 4:6] = quantiles_np.row_quantiles(obs[None, t_begin:t_begin + nt] - x, q)
+      early = np.arange(t_begin, t_begin + nt) < t_c0
+      ser[t_begin:t_begin + nt][early, 7:9] = 0.0
+    if nc:
+      ser[t_c0 + c_begin:t_c0 + c_begin + nc, 7:9] = quantiles_np.row_quantiles(np.asarray(cumT).T, q)
+    if stats is not None:
+      st = np.asarray(stats)                                                   # [5, S]
+      S = st.shape[1]
+      summ[0:10] = quantiles_np.row_quantiles(st.T, q).reshape(-1)
+      summ[10:15] = st.std(axis=1, ddof=1) if S > 1 else np.nan
+      summ[15] = st[4].mean()
+      summ[16], summ[17] = np.sum(meta.obs_sum <= st[1]), np.sum(meta.obs_sum >= st[1])
+
   def to_host(self, t):
     return t.detach().cpu().numpy()
 

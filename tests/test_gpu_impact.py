@@ -226,3 +226,53 @@ def test_device_entry_point_does_not_synchronise_when_workspaces_grow(engine):
   want_big = engine.impact(big, m_b, meta)
   np.testing.assert_array_equal(out_b.cpu().numpy()[:T * 9].reshape(T, 9), want_big[0])
   eng2.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("S,T,t_pre,t_post0,t_post1,shards", [
+    (1000, 517, 300, 310, 500, (400, 350, 250)), (97, 64, 40, 40, 64, (50, 47)),
+    (10, 33, 20, 22, 30, (4, 3, 2, 1)), (4096, 131, 100, 100, 131, (4096,)),
+    (5, 40, 37, 37, 40, (2, 0, 3))])
+def test_rows_and_column_halves_equal_the_one_call(engine, dtype, S, T, t_pre, t_post0, t_post1,
+                                                   shards):
+  """ci_impact_rows_d + ci_impact_cols_d, the pieces a sharded fit runs around its all-to-all
+  (shard.impact_sharded), with the exchange done locally: draws split into ragged shards, one rows
+  call per shard, the time axis split into len(shards) blocks, one column call per block over the
+  side-by-side shards, every result entry written by exactly one call.  Bit-identical to
+  ci_impact_d on all the draws (also when a shard is empty or a time block has no post steps)."""
+  import torch
+  from causalimpact_b200.shard import split_range
+  rng = np.random.default_rng(S + T)
+  m = make_meta(T, t_pre, t_post0, t_post1, rng, nan_obs=2 if t_pre > 8 else 0)
+  traj = rng.normal(size=(S, T)).astype(dtype)
+  traj[:, t_post0:] += 0.5
+  traj[::3] = np.round(traj[::3], 1)                                 # ties
+  mean = traj.mean(axis=0).astype(dtype)
+  traj_d, mean_d = torch.from_numpy(traj).cuda(), torch.from_numpy(mean).cuda()
+  want = engine.impact(traj_d, mean_d, m)
+  W = len(shards)
+  t_c0 = int(np.argmax(m.period != 0))
+  out = torch.zeros(T * 9 + 20, dtype=torch.float64, device="cuda")
+  pieces, s0 = [], 0
+  for r, n in enumerate(shards):
+    if n:
+      pieces.append(engine.impact_rows_t(traj_d[s0:s0 + n], mean_d if r == 0 else None, m, out))
+    s0 += n
+  tr_all = torch.cat([pc[0] for pc in pieces], dim=1)                # [T, S]
+  packed = torch.cat([pc[3] for pc in pieces], dim=1)                # [5 + Tc, S]
+  assert tr_all.shape == (T, S) and packed.shape == (5 + T - t_c0, S)
+  for r in range(W):
+    tb, tn = split_range(T, W, r)
+    cb, cn = split_range(T - t_c0, W, r)
+    part = torch.zeros_like(out)
+    if r == 0:
+      part.copy_(out)                                                # the mean-derived entries
+    engine.impact_cols_t(tr_all[tb:tb + tn], tb, packed[5 + cb:5 + cb + cn], cb,
+                         packed[:5] if r == 0 else None, m, part)
+    if r == 0:
+      out.copy_(part)
+    else:
+      out += part
+  got = out.cpu().numpy()
+  np.testing.assert_array_equal(got[:T * 9].reshape(T, 9), want[0])
+  np.testing.assert_array_equal(got[T * 9:], want[1])

@@ -31,7 +31,9 @@ api._resolve_engine = lambda opts: fake
 rng = np.random.default_rng(3)
 n = 60
 n_cov = int(sys.argv[3])
-seasonal = len(sys.argv) > 4 and sys.argv[4] == "seasonal"
+mode = sys.argv[4] if len(sys.argv) > 4 else ""
+seasonal = "seasonal" in mode
+exchange = "columns" if "columns" in mode else "draws"
 xs = 100 + np.cumsum(rng.normal(size=(n, n_cov)), axis=0); y = 1.2 * xs[:, 0] + rng.normal(size=n); y[40:] += 4
 df = pd.DataFrame(np.column_stack([y, xs]), columns=["y"] + [f"x{i}" for i in range(n_cov)],
                   index=pd.date_range("2021-01-01", periods=n))
@@ -40,7 +42,7 @@ mo = cib.ModelOptions(seasons=[cib.Seasons(num_seasons=4), cib.Seasons(num_seaso
 ci = cib.fit_causalimpact(df, (df.index[0], df.index[39]), (df.index[40], df.index[-1]), seed=(1, 2),
     model_options=mo, inference_options=cib.InferenceOptions(num_results=22),
     engine_options=cib.EngineOptions(num_chains=5, min_warmup=25, max_leapfrog=3,
-                                     gibbs_min_warmup=10))
+                                     gibbs_min_warmup=10, exchange=exchange))
 if int(os.environ.get("RANK", "0")) == 0:
   vals = [c for c in ci.series.columns if not c.endswith(("_start", "_end"))]
   pickle.dump(dict(series=ci.series[vals].values, summary=ci.summary.values,
@@ -101,6 +103,30 @@ def test_world2_gloo_equals_single_process_with_seasonal_components(tmp_path):
   for k in one:
     assert np.array_equal(one[k], two[k], equal_nan=True), k
   assert one["seasonal"].shape == (22, 60, 2) and one["drift"].shape == (22, 2)
+
+
+@pytest.mark.parametrize("n_cov,mode", [(1, "columns"), (4, "columns"), (1, "seasonal-columns")],
+                         ids=["hmc_path", "gibbs_path", "seasonal"])
+def test_world2_gloo_time_sharded_impact_equals_single_process(tmp_path, n_cov, mode):
+  """EngineOptions.exchange = "columns": the trajectories are never gathered; the ranks swap
+  time blocks of the transposed paths (two all-to-alls), select the quantiles of their half of
+  the time axis, and sum the disjoint results (shard.impact_sharded).  22 draws from 5 chains of
+  5 -> rank 0 holds 15 draws, rank 1 the remaining 7 (25 truncated to 22): ragged shards.
+  Latent draws and every quantile column equal the single-process fit exactly; the
+  mean-derived columns agree to the float32 rounding of the per-rank partial means."""
+  one = _run(1, str(tmp_path / "c1.pkl"), n_cov, mode.replace("columns", "").strip("-"))
+  two = _run(2, str(tmp_path / "c2.pkl"), n_cov, mode)
+  for k in ("level", "weights", "seasonal", "drift"):
+    if one[k] is not None:
+      assert np.array_equal(one[k], two[k], equal_nan=True), k
+  # series value columns: observed, posterior_{mean,lower,upper}, point_effects_*, cumulative_*
+  a, b = one["series"].astype(np.float64), two["series"].astype(np.float64)
+  mean_cols = [1, 4, 7]
+  quant_cols = [c for c in range(a.shape[1]) if c not in mean_cols]
+  assert np.array_equal(a[:, quant_cols], b[:, quant_cols], equal_nan=True)
+  np.testing.assert_allclose(a[:, mean_cols], b[:, mean_cols], rtol=1e-5, atol=1e-4)
+  np.testing.assert_allclose(one["summary"].astype(np.float64), two["summary"].astype(np.float64),
+                             rtol=1e-5, atol=1e-4)
 
 
 MANY_WORKER = r'''

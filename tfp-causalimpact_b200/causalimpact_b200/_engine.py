@@ -90,6 +90,7 @@ EXPORTS = (
     "ci_gibbs_seasonal_run_batch_d",
     "ci_comm_get_unique_id", "ci_comm_create", "ci_allgather", "ci_comm_destroy",
     "ci_set_panel", "ci_predictive_mean_batch_d", "ci_impact_batch_d",
+    "ci_impact_rows_d", "ci_impact_cols_d", "ci_impact_sharded_d",
 )
 
 _lib = None
@@ -145,6 +146,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
   lib.ci_predictive_mean_batch_d.argtypes = [vp, vp, vp, i32, vp, vp]
   lib.ci_impact_batch_d.argtypes = [vp, C.POINTER(CiImpactArgs), i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                     vp, vp]
+  lib.ci_impact_rows_d.argtypes = [vp, C.POINTER(CiImpactArgs), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+  lib.ci_impact_cols_d.argtypes = [vp, C.POINTER(CiImpactArgs), vp, i32, i32, vp, i32, i32, vp, vp,
+                                   vp, vp, vp, vp]
+  lib.ci_impact_sharded_d.argtypes = [vp, vp, C.POINTER(CiImpactArgs), vp, vp, vp, vp, vp, vp, vp, vp]
   lib.ci_comm_get_unique_id.argtypes = [vp]
   lib.ci_comm_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
   lib.ci_allgather.argtypes = [vp, vp, vp, C.c_size_t, vp]
@@ -268,6 +273,33 @@ class Comm:
         self._h, local.data_ptr(), out.data_ptr(), local.numel() * local.element_size(),
         self._eng._stream(torch)))
     return out
+
+  def impact_sharded_t(self, traj_local, mean_part, meta, counts):
+    """ci_impact_sharded_d: the impact stage over draws sharded ``counts[r]`` per rank, the
+    exchange inside (one grouped send/receive + one all-reduce on the current stream).
+    traj_local [counts[rank], T] and mean_part [T] (this rank's ci_predictive_mean_d) are device
+    tensors.  Returns (out [T*9 + 20] float64, mean [T]) device tensors, the same on every rank;
+    nothing is synchronised."""
+    eng = self._eng
+    torch, dev = eng._torch_dev()
+    traj_local, mean_part = traj_local.contiguous(), mean_part.contiguous().reshape(-1)
+    S, T = traj_local.shape
+    cnt = np.ascontiguousarray(counts, dtype=np.int32)
+    if cnt.shape != (self.nranks,) or int(cnt[self.rank]) != S:
+      raise ValueError("counts must be [nranks] with counts[rank] == traj_local.shape[0]")
+    obs = np.ascontiguousarray(meta.observed, dtype=np.float64)
+    per = np.ascontiguousarray(meta.period, dtype=np.uint8)
+    if obs.shape != (T,) or per.shape != (T,):
+      raise ValueError(f"observed / period must be [{T}]")
+    args = eng._impact_args(meta, S, T, traj_local.dtype)
+    out = torch.empty(T * IMPACT_SERIES_COLS + IMPACT_SUMMARY_LEN, dtype=torch.float64, device=dev)
+    mean = torch.empty(T, dtype=traj_local.dtype, device=dev)
+    part = mean_part.to(traj_local.dtype)
+    eng._check(eng._lib.ci_impact_sharded_d(
+        eng._ctx, self._h, C.byref(args), _ptr(cnt), traj_local.data_ptr() if S else None,
+        part.data_ptr(), _ptr(obs), _ptr(per), mean.data_ptr(),
+        out.data_ptr(), eng._stream(torch)))
+    return out, mean
 
   def close(self):
     if self._h:
@@ -804,6 +836,66 @@ class Engine:
     self._check(self._lib.ci_impact(self._ctx, C.byref(args), _ptr(traj), _ptr(mean_h), _ptr(obs),
                                     _ptr(per), _ptr(series), _ptr(summ)))
     return series, summ
+
+  # -- the two halves of ci_impact_d for draws sharded over GPUs ----------
+  def _impact_args(self, meta, S, T, torch_dtype):
+    import torch
+    return CiImpactArgs(S=S, T=T, dtype=F64 if torch_dtype == torch.float64 else F32, reserved=0,
+                        scale=meta.scale, offset=meta.offset, q_lo=meta.q_lo, q_hi=meta.q_hi,
+                        obs_sum=meta.obs_sum)
+
+  def impact_rows_t(self, traj, mean, meta, out=None):
+    """ci_impact_rows_d on this rank's draws: traj [S_local, T] device tensor; ``mean`` = the
+    predictive mean over ALL draws ([T] device tensor) on the one rank that writes the
+    mean-derived columns into ``out`` (float64 [T*9 + 20]), None elsewhere.  Returns device
+    tensors (trT [T,S_local], cumT [T - t_c0, S_local], stats [5, S_local]); nothing is
+    synchronised.  The
+    fourth value is the one float64 block [5 + T - t_c0, S_local] that stats and cumT are views of."""
+    torch, dev = self._torch_dev()
+    traj = traj.contiguous()
+    S, T = traj.shape
+    obs = np.ascontiguousarray(meta.observed, dtype=np.float64)
+    per = np.ascontiguousarray(meta.period, dtype=np.uint8)
+    if obs.shape != (T,) or per.shape != (T,):
+      raise ValueError(f"observed / period must be [{T}]")
+    t_c0 = int(np.argmax(per != 0)) if np.any(per != 0) else T
+    args = self._impact_args(meta, S, T, traj.dtype)
+    trT = torch.empty((T, S), dtype=traj.dtype, device=dev)
+    # one float64 block [5 + (T - t_c0), S]: the statistics ride in front of the cumulative paths
+    # so that a sharded caller exchanges both with one collective (shard.impact_sharded)
+    packed = torch.empty((5 + T - t_c0, S), dtype=torch.float64, device=dev)
+    stats, cumT = packed[:5], packed[5:]
+    if mean is not None:
+      mean = mean.to(dtype=traj.dtype).contiguous().reshape(-1)
+      if out is None or out.numel() != T * IMPACT_SERIES_COLS + IMPACT_SUMMARY_LEN:
+        raise ValueError("out (float64, T*9 + 20 elements) is required with mean")
+    self._check(self._lib.ci_impact_rows_d(
+        self._ctx, C.byref(args), traj.data_ptr(), mean.data_ptr() if mean is not None else None,
+        _ptr(obs), _ptr(per), trT.data_ptr(), cumT.data_ptr(), stats.data_ptr(),
+        out.data_ptr() if mean is not None else None,
+        out.data_ptr() + 8 * T * IMPACT_SERIES_COLS if mean is not None else None,
+        self._stream(torch)))
+    return trT, cumT, stats, packed
+
+  def impact_cols_t(self, trT, t_begin, cumT, c_begin, stats, meta, out):
+    """ci_impact_cols_d: the quantile columns of a time block.  trT [t_count, S] and cumT
+    [c_count, S] hold ALL draws of prediction steps t_begin.. / cumulative steps c_begin..;
+    ``stats`` ([5, S], all draws) on the one rank that writes summary[0..17], None elsewhere.
+    Fills this block's entries of ``out`` (float64 [T*9 + 20]); nothing is synchronised."""
+    torch, dev = self._torch_dev()
+    obs = np.ascontiguousarray(meta.observed, dtype=np.float64)
+    per = np.ascontiguousarray(meta.period, dtype=np.uint8)
+    T = obs.shape[0]
+    trT, cumT = trT.contiguous(), cumT.contiguous()
+    S = trT.shape[1] if trT.shape[0] else (cumT.shape[1] if cumT.shape[0] else stats.shape[1])
+    if stats is not None:
+      stats = stats.contiguous()
+    args = self._impact_args(meta, S, T, trT.dtype)
+    self._check(self._lib.ci_impact_cols_d(
+        self._ctx, C.byref(args), trT.data_ptr() if trT.shape[0] else None, int(t_begin),
+        trT.shape[0], cumT.data_ptr() if cumT.shape[0] else None, int(c_begin), cumT.shape[0],
+        stats.data_ptr() if stats is not None else None, _ptr(obs), _ptr(per), out.data_ptr(),
+        out.data_ptr() + 8 * T * IMPACT_SERIES_COLS, self._stream(torch)))
 
   # -- K5 --------------------------------------------------------------------
   def row_quantiles(self, a, q) -> np.ndarray:

@@ -123,6 +123,13 @@ class EngineOptions:
   return_level: False leaves ``posterior_samples.level`` (and ``seasonal_levels``) as None: the
     [S, T] level paths are then neither all-gathered across ranks nor copied to the host (they
     are the largest part of both); series and summary are unaffected.
+  exchange: what a fit sharded over several GPUs moves between them.  "draws" (default): one
+    all-gather of every rank's result rows, after which each rank holds all draws and computes the
+    impact itself -- results are bit-identical for any GPU count.  "columns": the predictive
+    trajectories stay where they were drawn; the impact stage swaps TIME BLOCKS of the transposed
+    paths (all-to-all) and each rank selects the quantiles of T/world steps (shard.impact_sharded).
+    Only theta (and the level paths if ``return_level``) are gathered.  Quantiles are identical to
+    "draws"; mean-derived columns agree to the rounding of the per-rank partial means.
   local_linear_trend: EXTENSION (the reference's model has no slope, lib.py:496; BASELINE.json
     configs[2] asks for it): the level follows a local linear trend -- state (level, slope),
     slope variance ~ InverseGamma like the level's -- sampled by batched-chain HMC over the d = 2
@@ -144,6 +151,7 @@ class EngineOptions:
   ssvs_order: str = "random"
   decorrelate_series: bool = True
   return_level: bool = True
+  exchange: str = "draws"
   profile: bool = False
   local_linear_trend: bool = False
 
@@ -344,22 +352,50 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
   ph.mark("predictive" if stats.get("sampler") == "hmc" else "sampler")
   n_local = c_local * n_per
   parts = [theta_l, level_l, traj_l] + extra_l
+  if opts.exchange not in ("draws", "columns"):
+    raise ValueError(f"EngineOptions.exchange must be draws|columns, got {opts.exchange!r}")
+  by_columns = ws > 1 and opts.exchange == "columns"
   if ws == 1:
     parts = [t[:num_results] for t in parts]
-  else:
+  elif not by_columns:
     # the ONE collective of the fit: every chain contributes n_per result rows
     import torch
     widths = [t.shape[1] for t in parts]
     rows = torch.cat([t[:n_local] for t in parts], dim=1)
     rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
     parts = [t.contiguous() for t in torch.split(rows, widths, dim=1)]
-  theta_t, level_t, traj_t = parts[:3]
-  ph.mark("all_gather")
-  # mean of the predictive mixture = average of level (+ seasonal) + X.w over the draws
-  # (causalimpact_lib.py:627); fixed summation order over the gathered draws => the same
-  # for any GPU count
-  mean_t = eng.predictive_mean_t(theta_t, parts[3] if sched is not None else level_t)
-  ph.mark("predictive_mean")
+  if not by_columns:
+    theta_t, level_t, traj_t = parts[:3]
+    ph.mark("all_gather")
+    # mean of the predictive mixture = average of level (+ seasonal) + X.w over the draws
+    # (causalimpact_lib.py:627); fixed summation order over the gathered draws => the same
+    # for any GPU count
+    mean_out = DeviceArray(eng.predictive_mean_t(theta_t, parts[3] if sched is not None else level_t))
+    ph.mark("predictive_mean")
+    traj_out = DeviceArray(traj_t)
+  else:
+    # EngineOptions.exchange == "columns": the trajectories stay sharded (the impact stage swaps
+    # time blocks instead, shard.impact_sharded); only what the result object holds is gathered
+    import torch
+    counts = []
+    for r in range(ws):
+      r0, rc = _shard.split_range(C, ws, r)
+      counts.append(max(0, min((r0 + rc) * n_per, num_results) - r0 * n_per))
+    keep = [0] + ([1] if opts.return_level else [])
+    if sched is not None:
+      keep += ([4] if opts.return_level else []) + [5]
+    widths = [parts[i].shape[1] for i in keep]
+    rows = torch.cat([parts[i][:n_local] for i in keep], dim=1)
+    rows = _shard.all_gather_rows(rows, C, rows_per_item=n_per)[:num_results]
+    got = dict(zip(keep, (t.contiguous() for t in torch.split(rows, widths, dim=1))))
+    theta_t, level_t = got[0], got.get(1)
+    parts = [got.get(i) for i in range(len(parts))]
+    ph.mark("all_gather")
+    mean_out = _shard.ShardedMean(
+        eng, _shard.predictive_mean_part(eng, theta_l, extra_l[0] if sched is not None else level_l,
+                                         counts), counts)
+    ph.mark("predictive_mean")
+    traj_out = _shard.ShardedDraws(traj_l[:counts[rank]], counts)
 
   samples = _package_samples(eng, theta_t, level_t if opts.return_level else None, p, T, np_dt, wh,
                              (parts[4] if opts.return_level else None, parts[5], K)
@@ -374,7 +410,7 @@ def _train_causalimpact_sts(*, ci_data, prior_level_sd, seed, num_results: int,
       stats["rhat_log_variances"] = split_rhat(th)
   samples.hmc_stats = stats            # pylint: disable=attribute-defined-outside-init
   samples.phases = ph                  # pylint: disable=attribute-defined-outside-init
-  return samples, DeviceArray(mean_t), DeviceArray(traj_t)
+  return samples, mean_out, traj_out
 
 
 def split_rhat(x: np.ndarray) -> np.ndarray:
@@ -456,7 +492,13 @@ def fit_causalimpact(data: pd.DataFrame,
       dtype=np_dt, seasons=model_options.seasons,
       experimental_tf_function_cache_key_addition=cache_key, engine_options=engine_options)
   eng = _resolve_engine(engine_options)
-  series, summary = _impact.compute_impact(means, trajectories, ci_data, alpha, eng.impact)
+  impact_fn = eng.impact
+  if isinstance(trajectories, _shard.ShardedDraws):
+    def impact_fn(traj, mean, meta):       # draws sharded over the ranks: swap time blocks
+      T = traj.shape[1]
+      flat = eng.to_host(_shard.impact_sharded(eng, traj.local, mean, meta, traj.counts))
+      return flat[:T * 9].reshape(T, 9), flat[T * 9:]
+  series, summary = _impact.compute_impact(means, trajectories, ci_data, alpha, impact_fn)
   ph = getattr(samples, "phases", None)
   if ph is not None and ph.on:
     ph.mark("impact_and_frames")

@@ -397,31 +397,34 @@ int ci_impact_batch_d(ci_ctx* c, const ci_impact_args* a, int n_series, const do
   const double* obs_d = reinterpret_cast<const double*>(meta);
   const uint8_t* per_d = reinterpret_cast<const uint8_t*>(meta + ob);
   const ci::ImpactSeries* ps_d = reinterpret_cast<const ci::ImpactSeries*>(meta + ob + pb);
-  const int row_ctas = (S + ci::IMP_TILE - 1) / ci::IMP_TILE + 1;
+  int row_ctas, nseg;
+  ci::impact_rows_grid(S, T, d.t_c0, true, &row_ctas, &nseg);
   size_t bytes; int in_smem, nt;
   select_launch_cfg(c, S, sizeof(double), &nt, &bytes, &in_smem);
   if (a->dtype == CI_F64) {
-    ci::k_impact_rows<double><<<dim3(row_ctas, N), 32 * ci::IMP_TILE, 0, st>>>(
+    ci::k_impact_rows<double><<<dim3(row_ctas * nseg, N), 32 * ci::IMP_WARPS, 0, st>>>(
         static_cast<const double*>(traj_d), static_cast<const double*>(mean_d), obs_d, per_d, d,
         static_cast<double*>(c->i_trT.p), static_cast<double*>(c->i_cum.p),
-        static_cast<double*>(c->i_stats.p), series_d, summ_d, ps_d);
+        static_cast<double*>(c->i_stats.p), series_d, summ_d, ps_d, row_ctas, ci::impact_seg_len(), ci::PeerDest{});
     CU_TRY(cudaGetLastError());
     auto kern = ci::k_impact_jobs<double>;
     CU_TRY(set_smem(kern, (uint32_t)bytes));
     kern<<<dim3(Tc + ci::IMP_STATS + T + 1, N), nt, bytes, st>>>(
         static_cast<const double*>(c->i_trT.p), static_cast<const double*>(c->i_cum.p),
-        static_cast<const double*>(c->i_stats.p), obs_d, d, series_d, summ_d, in_smem, ps_d);
+        static_cast<const double*>(c->i_stats.p), obs_d, d, series_d, summ_d, in_smem, ps_d,
+        ci::ImpactCols{0, T, 0, Tc, 1}, ci::ColBlocks{});
   } else {
-    ci::k_impact_rows<float><<<dim3(row_ctas, N), 32 * ci::IMP_TILE, 0, st>>>(
+    ci::k_impact_rows<float><<<dim3(row_ctas * nseg, N), 32 * ci::IMP_WARPS, 0, st>>>(
         static_cast<const float*>(traj_d), static_cast<const float*>(mean_d), obs_d, per_d, d,
         static_cast<float*>(c->i_trT.p), static_cast<double*>(c->i_cum.p),
-        static_cast<double*>(c->i_stats.p), series_d, summ_d, ps_d);
+        static_cast<double*>(c->i_stats.p), series_d, summ_d, ps_d, row_ctas, ci::impact_seg_len(), ci::PeerDest{});
     CU_TRY(cudaGetLastError());
     auto kern = ci::k_impact_jobs<float>;
     CU_TRY(set_smem(kern, (uint32_t)bytes));
     kern<<<dim3(Tc + ci::IMP_STATS + T + 1, N), nt, bytes, st>>>(
         static_cast<const float*>(c->i_trT.p), static_cast<const double*>(c->i_cum.p),
-        static_cast<const double*>(c->i_stats.p), obs_d, d, series_d, summ_d, in_smem, ps_d);
+        static_cast<const double*>(c->i_stats.p), obs_d, d, series_d, summ_d, in_smem, ps_d,
+        ci::ImpactCols{0, T, 0, Tc, 1}, ci::ColBlocks{});
   }
   CU_TRY(cudaGetLastError());
   c->launches += 2;

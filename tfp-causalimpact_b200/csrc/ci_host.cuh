@@ -121,6 +121,7 @@ struct ci_ctx {
   DevBuf i_cum, i_stats, i_meta, i_series, i_summ, i_trT;   // ci_impact workspaces
   DevBuf s_sched, s_scratch, s_series, w_latent, w_seas, w_drift;   // seasonal components
   DevBuf w_raw, w_pstats;            // ci_set_panel: the raw panel and the per-series statistics
+  DevBuf x_pack, x_recvT, x_recvC, x_allT, x_allC, x_parts;   // ci_impact_sharded_d exchange buffers
   ci::SeasDev seas{};                // seas.K == 0: no seasonal components
   // views of the CURRENT series: the context's own buffers after ci_set_data, a slice of the
   // batch buffers after ci_batch_select
@@ -142,7 +143,8 @@ struct ci_ctx {
     return {&tiles, &omega, &w_theta, &w_value, &w_grad, &w_level, &w_traj, &w_mean, &w_q, &w_draws,
             &w_stats, &w_incl, &gram, &xty0, &i_cum, &i_stats, &i_meta, &i_series, &i_summ, &i_trT,
             &s_sched, &s_scratch, &s_series, &w_latent, &w_seas, &w_drift, &b_tiles, &b_omega,
-            &b_gram, &b_xty, &b_dev, &w_raw, &w_pstats};
+            &b_gram, &b_xty, &b_dev, &w_raw, &w_pstats, &x_pack, &x_recvT, &x_recvC, &x_allT, &x_allC,
+            &x_parts};
   }
   // only from entry points that synchronise anyway (ci_set_data*, ci_ctx_destroy, host-pointer calls)
   void free_retired() {
@@ -157,6 +159,13 @@ struct ci_ctx {
   int tstream_mode = 1;              // CI_B200_TSTREAM=0 disables the long-series team kernels
   int tstream_W = 0;                 // CI_B200_TSW: warps per chain of the long-series team kernels (tuning)
 };
+
+// abi_impact.cu: argument checks, period scan and the asynchronous upload of observed / period
+// (shared by ci_impact_d, ci_impact_rows_d, ci_impact_cols_d and ci_impact_sharded_d)
+namespace ci { struct ImpactDev; }
+int cih_impact_prepare(ci_ctx* c, const ci_impact_args* a, const double* observed,
+                       const uint8_t* period, cudaStream_t st, ci::ImpactDev* d,
+                       const double** obs_d, const uint8_t** per_d);
 
 namespace {
 

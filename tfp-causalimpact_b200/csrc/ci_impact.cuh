@@ -15,7 +15,7 @@
 // column: the k-th smallest of (y_t - x) is y_t minus the k-th LARGEST x.
 //
 // Two launches:
-//   k_impact_rows  one warp per draw, 32 draws per CTA (+1 CTA for the predictive mean):
+//   k_impact_rows  32 draws per CTA, 4 per warp (+1 CTA for the predictive mean):
 //                  cumulative effect paths (warp scan over time), post-period per-draw
 //                  statistics; the raw draws and the cumulative paths leave the CTA
 //                  TRANSPOSED ([T,S], through a 32x32 shared-memory tile, coalesced on both
@@ -41,26 +41,65 @@ struct ImpactDev {
 };
 // per-series part of ImpactDev for batched launches (grid.y = series)
 struct ImpactSeries { double scale, offset, obs_sum; };
+// Which column jobs a k_impact_jobs launch runs.  One GPU: everything.  Time-sharded:
+// this rank holds prediction columns [t_begin, t_begin + t_count) and cumulative columns
+// [c_begin, c_begin + c_count) of ALL draws (trT / cumT are indexed from the block's first column);
+// only the rank with do_stats holds the per-draw statistics and writes the summary.
+struct ImpactCols { int t_begin, t_count, c_begin, c_count, do_stats; };
+// Draws held by each rank of a sharded fit (ci_impact_sharded_d).  One NVSwitch domain.
+constexpr int IMP_MAX_RANKS = 16;
+struct ShardCounts { int ws; int n[IMP_MAX_RANKS]; };
+// Column blocks as the exchange leaves them: the source ranks' blocks one after the other, block
+// r = [rows][n_r] (rowsT rows of paths, rowsC rows of cumulative paths preceded by headC rows of
+// per-draw statistics).  ws == 0: plain [rows][S] arrays.
+struct ColBlocks { int ws, rowsT, rowsC, headC; int n[IMP_MAX_RANKS]; };
+// Where k_impact_rows stores its output in a sharded fit: straight into the exchange windows of
+// the ranks that own the time blocks (peer memory over NVLink; T[g] / C[g] are rank g's windows
+// mapped into this process), in the ColBlocks layout -- this rank's block starts me_off draws in.
+// ws == 0: the local [T][S] / [T - t_c0][S] / [5][S] arrays.
+struct PeerDest {
+  int ws, me_off, n_me;
+  int T_base, T_extra, C_base, C_extra;       // balanced split of the T (T - t_c0) columns
+  void* T[IMP_MAX_RANKS];
+  void* C[IMP_MAX_RANKS];
+};
+// owner of item x under the balanced split (base = n / ws, extra = n % ws): rank, first item, count
+__device__ __forceinline__ void split_owner(int x, int base, int extra, int& g, int& start, int& cnt) {
+  const int lim = (base + 1) * extra;
+  if (x < lim) { g = x / (base + 1); start = g * (base + 1); cnt = base + 1; }
+  else { g = extra + (x - lim) / base; start = lim + (g - extra) * base; cnt = base; }
+}
 
 // standardize.py:60-64: (x * stddev) + mean, two roundings like numpy (no FMA contraction)
 __device__ __forceinline__ double imp_unscale(double x, double scale, double offset) {
   return __dadd_rn(__dmul_rn(x, scale), offset);
 }
 
-constexpr int IMP_TILE = 32;         // draws per CTA == time steps per chunk
+constexpr int IMP_TILE = 32;         // draws per CTA == draws per transposed 128-byte run
+constexpr int IMP_WARPS = 8;         // warps per CTA
+constexpr int IMP_RPW = IMP_TILE / IMP_WARPS;   // draws per warp (independent scans: ILP)
+constexpr int IMP_CH = 2;            // 32-step sub-chunks per loop iteration
+constexpr int IMP_CHUNK = IMP_CH * 32;
+constexpr int IMP_SEG = 4 * IMP_CHUNK;          // pre-period steps per transpose-only CTA
 
-// Row r < S: draw r of traj (CTA b holds draws 32b .. 32b+31, warp w <-> draw, lane <-> t);
-// the LAST CTA's warp 0 handles the predictive mean (its cumulative path and post-period
-// mean / sum are the *_mean series columns and `predicted`).
-constexpr int IMP_CH = 2;            // 32-step chunks per loop iteration (loads overlap)
-
+// CTA (rb, seg) = blockIdx.x % row_ctas, blockIdx.x / row_ctas works on draws 32 rb .. 32 rb + 31
+// (warp w <-> draws 4w .. 4w + 3, lane <-> t inside a 32-step sub-chunk):
+//   seg = 0   the steps from the 64-aligned start of the post-period to T: cumulative effect
+//             paths (warp scan over time, carried across chunks), post-period per-draw statistics,
+//             transposed copy of the raw draws and of the cumulative paths;
+//   seg >= 1  pre-period steps [(seg-1) seg_len, seg seg_len): nothing depends on them except
+//             their own quantiles, so these CTAs only transpose (and there are many of them).
+// With `mean`, CTA rb = row_ctas - 1 of seg 0 is extra: its warp 0 walks the predictive mean
+// (the *_mean series columns and `predicted`).  The next chunk's loads are issued before the
+// current one is processed.  (Run 20: the round-1 layout -- 1024 threads, 44 registers, so ONE CTA
+// per SM, every CTA walking all T steps -- took 157 us at S=10000, T=2000 for 210 MB of traffic.)
 template <typename R>
-__global__ void __launch_bounds__(32 * IMP_TILE)
+__global__ void __launch_bounds__(32 * IMP_WARPS, 4)
 k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
               const double* __restrict__ obs, const uint8_t* __restrict__ period, ImpactDev a,
               R* __restrict__ trT, double* __restrict__ cumT, double* __restrict__ statsT,
               double* __restrict__ series, double* __restrict__ summ,
-              const ImpactSeries* __restrict__ per = nullptr) {
+              const ImpactSeries* __restrict__ per, int row_ctas, int seg_len, PeerDest pd) {
   if (per) {      // batched: this CTA row works on series blockIdx.y (obs is [N,T], period shared)
     const size_t sidx = blockIdx.y;
     a.scale = per[sidx].scale; a.offset = per[sidx].offset; a.obs_sum = per[sidx].obs_sum;
@@ -69,94 +108,178 @@ k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
     statsT += sidx * (size_t)a.S * IMP_STATS;
     series += sidx * (size_t)a.T * IMP_SERIES_COLS; summ += sidx * (size_t)IMP_SUMMARY_LEN;
   }
-  __shared__ R tile_raw[IMP_TILE][IMP_CH * IMP_TILE + 1];
-  __shared__ double tile_cum[IMP_TILE][IMP_CH * IMP_TILE + 1];
+  __shared__ R tile_raw[IMP_TILE][IMP_CHUNK + 1];
+  __shared__ double tile_cum[IMP_TILE][IMP_CHUNK + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool is_mean = blockIdx.x == gridDim.x - 1;
-  const int r0 = blockIdx.x * IMP_TILE;
-  const int r = is_mean ? a.S : r0 + warp;
+  const int rb = blockIdx.x % row_ctas, seg = blockIdx.x / row_ctas;
+  const bool is_mean = mean != nullptr && rb == row_ctas - 1;
+  const int post_base = (a.t_c0 / IMP_CHUNK) * IMP_CHUNK;
+  const bool post = seg == 0;
+  int t_begin, t_end;
+  if (post) {
+    t_begin = is_mean ? 0 : post_base; t_end = a.T;
+  } else {
+    t_begin = (seg - 1) * seg_len;
+    t_end = min(t_begin + seg_len, post_base);
+    if (is_mean || t_begin >= t_end) return;
+  }
   if (is_mean && warp != 0) return;                  // (no CTA-wide barrier on this path)
-  const bool row_ok = is_mean || r < a.S;
-  const R* src = is_mean ? mean : traj + (size_t)(row_ok ? r : 0) * a.T;
-  double carry = 0.0, pred_sum = 0.0, eff_sum = 0.0;
-  int eff_cnt = 0;
-  for (int base = 0; base < a.T; base += IMP_CH * IMP_TILE) {
-    R raw[IMP_CH];
-    double ob[IMP_CH];
-    int per[IMP_CH];
+  const int r0 = rb * IMP_TILE;
+  bool ok[IMP_RPW];
+  const R* src[IMP_RPW];
 #pragma unroll
-    for (int h = 0; h < IMP_CH; ++h) {               // all loads of the iteration first
-      const int t = base + h * IMP_TILE + lane;
-      const bool valid = row_ok && t < a.T;
-      raw[h] = valid ? src[t] : (R)0;
-      ob[h] = valid ? obs[t] : CUDART_NAN;
-      per[h] = valid ? (int)period[t] : 0;
-    }
-    // nothing to accumulate before the post-period starts: cumulative effect is 0 there
-    const bool need_cum = base + IMP_CH * IMP_TILE > a.t_c0;
+  for (int k = 0; k < IMP_RPW; ++k) {
+    const int r = r0 + warp * IMP_RPW + k;
+    ok[k] = is_mean ? k == 0 : r < a.S;
+    src[k] = is_mean ? mean : traj + (size_t)(ok[k] ? r : 0) * a.T;
+  }
+  double carry[IMP_RPW], pred_sum[IMP_RPW], eff_sum[IMP_RPW];
+  int eff_cnt[IMP_RPW];
+#pragma unroll
+  for (int k = 0; k < IMP_RPW; ++k) { carry[k] = 0.0; pred_sum[k] = 0.0; eff_sum[k] = 0.0; eff_cnt[k] = 0; }
+  R nxt[IMP_RPW][IMP_CH];
+#pragma unroll
+  for (int k = 0; k < IMP_RPW; ++k)
 #pragma unroll
     for (int h = 0; h < IMP_CH; ++h) {
-      const int t = base + h * IMP_TILE + lane;
-      const bool valid = row_ok && t < a.T;
-      const double x = imp_unscale((double)raw[h], a.scale, a.offset);
-      const double pt = valid ? ob[h] - x : CUDART_NAN;            // lib.py:822-823
-      const bool isn = !(pt == pt);
-      double out = 0.0;
-      if (need_cum) {
-        // lib.py:826-831: effects before the post-period count as 0; NaNs are skipped
-        double inc = (valid && t >= a.t_c0 && !isn) ? pt : 0.0;
+      const int t = t_begin + h * 32 + lane;
+      nxt[k][h] = (ok[k] && t < t_end) ? src[k][t] : (R)0;
+    }
+  for (int base = t_begin; base < t_end; base += IMP_CHUNK) {
+    R cur[IMP_RPW][IMP_CH];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double up = __shfl_up_sync(FULL, inc, o);
-          if (lane >= o) inc += up;
-        }
-        const double cv = carry + inc;
-        carry += __shfl_sync(FULL, inc, 31);
-        out = (t >= a.t_c0 && isn) ? CUDART_NAN : cv;
+    for (int k = 0; k < IMP_RPW; ++k)
+#pragma unroll
+      for (int h = 0; h < IMP_CH; ++h) {
+        cur[k][h] = nxt[k][h];
+        const int t = base + IMP_CHUNK + h * 32 + lane;          // next chunk: loads in flight
+        nxt[k][h] = (ok[k] && t < t_end) ? src[k][t] : (R)0;
       }
-      if (valid && per[h] == 1) {                    // inside the post-period (lib.py:966-1011)
-        pred_sum += x;
-        if (!isn) { eff_sum += pt; ++eff_cnt; }
+    if (!post) {
+#pragma unroll
+      for (int k = 0; k < IMP_RPW; ++k)
+#pragma unroll
+        for (int h = 0; h < IMP_CH; ++h) tile_raw[warp * IMP_RPW + k][h * 32 + lane] = cur[k][h];
+    } else {
+      double ob[IMP_CH];
+      int pd[IMP_CH];
+#pragma unroll
+      for (int h = 0; h < IMP_CH; ++h) {             // shared by the warp's draws
+        const int t = base + h * 32 + lane;
+        ob[h] = t < a.T ? obs[t] : CUDART_NAN;
+        pd[h] = t < a.T ? (int)period[t] : 0;
       }
-      if (is_mean) {
-        if (valid) {
-          double* row = series + (size_t)t * IMP_SERIES_COLS;
-          row[0] = x; row[3] = pt; row[6] = out;
+      // nothing to accumulate before the post-period starts: cumulative effect is 0 there
+      const bool need_cum = base + IMP_CHUNK > a.t_c0;
+#pragma unroll
+      for (int k = 0; k < IMP_RPW; ++k) {
+#pragma unroll
+        for (int h = 0; h < IMP_CH; ++h) {
+          const int t = base + h * 32 + lane;
+          const bool valid = ok[k] && t < a.T;
+          const double x = imp_unscale((double)cur[k][h], a.scale, a.offset);
+          const double pt = valid ? ob[h] - x : CUDART_NAN;            // lib.py:822-823
+          const bool isn = !(pt == pt);
+          double out = 0.0;
+          if (need_cum) {
+            // lib.py:826-831: effects before the post-period count as 0; NaNs are skipped
+            double inc = (valid && t >= a.t_c0 && !isn) ? pt : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const double up = __shfl_up_sync(FULL, inc, o);
+              if (lane >= o) inc += up;
+            }
+            const double cv = carry[k] + inc;
+            carry[k] += __shfl_sync(FULL, inc, 31);
+            out = (t >= a.t_c0 && isn) ? CUDART_NAN : cv;
+          }
+          if (valid && pd[h] == 1) {                   // inside the post-period (lib.py:966-1011)
+            pred_sum[k] += x;
+            if (!isn) { eff_sum[k] += pt; ++eff_cnt[k]; }
+          }
+          if (is_mean) {
+            if (valid) {
+              double* row = series + (size_t)t * IMP_SERIES_COLS;
+              row[0] = x; row[3] = pt; row[6] = out;
+            }
+          } else {
+            tile_raw[warp * IMP_RPW + k][h * 32 + lane] = cur[k][h];
+            if (need_cum) tile_cum[warp * IMP_RPW + k][h * 32 + lane] = out;
+          }
         }
-      } else {
-        tile_raw[warp][h * IMP_TILE + lane] = raw[h];
-        if (need_cum) tile_cum[warp][h * IMP_TILE + lane] = out;
+        if (is_mean) break;                          // the mean is one row
       }
     }
     if (is_mean) continue;
-    // transpose the chunk: [draw][t] -> [t][draw]; warp <-> time step, lane <-> draw
+    // transpose the chunk: [draw][t] -> [t][draw]; warp <-> time steps w, w + 8, .., lane <-> draw
     __syncthreads();
     const int rr = r0 + lane;
-#pragma unroll
-    for (int h = 0; h < IMP_CH; ++h) {
-      const int tc = base + h * IMP_TILE + warp;
-      if (tc < a.T && rr < a.S) {
-        trT[(size_t)tc * a.S + rr] = tile_raw[lane][h * IMP_TILE + warp];
-        if (tc >= a.t_c0) cumT[(size_t)(tc - a.t_c0) * a.S + rr] = tile_cum[lane][h * IMP_TILE + warp];
+    if (rr < a.S) {
+#pragma unroll 4
+      for (int j = warp; j < IMP_CHUNK; j += IMP_WARPS) {
+        const int tc = base + j;
+        if (tc >= t_end) continue;
+        if (pd.ws == 0) {
+          trT[(size_t)tc * a.S + rr] = tile_raw[lane][j];
+          if (post && tc >= a.t_c0) cumT[(size_t)(tc - a.t_c0) * a.S + rr] = tile_cum[lane][j];
+        } else {                     // the owner's window, over NVLink: 128-byte runs per warp
+          int g, st0, cnt;
+          split_owner(tc, pd.T_base, pd.T_extra, g, st0, cnt);
+          static_cast<R*>(pd.T[g])[(size_t)cnt * pd.me_off + (size_t)(tc - st0) * pd.n_me + rr] =
+              tile_raw[lane][j];
+          if (post && tc >= a.t_c0) {
+            split_owner(tc - a.t_c0, pd.C_base, pd.C_extra, g, st0, cnt);
+            const int head = g == 0 ? IMP_STATS : 0;
+            static_cast<double*>(pd.C[g])[(size_t)(cnt + head) * pd.me_off +
+                                          (size_t)(head + tc - a.t_c0 - st0) * pd.n_me + rr] =
+                tile_cum[lane][j];
+          }
+        }
       }
     }
     __syncthreads();
   }
-  pred_sum = warp_sum(pred_sum);
-  eff_sum = warp_sum(eff_sum);
-  eff_cnt = __reduce_add_sync(FULL, eff_cnt);
-  if (lane == 0 && row_ok) {
-    const double pm = pred_sum / (double)a.n_post;
-    if (is_mean) {
-      summ[18] = pm; summ[19] = pred_sum;
-    } else {
-      statsT[0 * (size_t)a.S + r] = pm;
-      statsT[1 * (size_t)a.S + r] = pred_sum;
-      statsT[2 * (size_t)a.S + r] = eff_cnt > 0 ? eff_sum / (double)eff_cnt : CUDART_NAN;
-      statsT[3 * (size_t)a.S + r] = eff_sum;
-      statsT[4 * (size_t)a.S + r] = a.obs_sum / pred_sum - 1.0;      // lib.py:1010-1011
+  if (!post) return;
+#pragma unroll
+  for (int k = 0; k < IMP_RPW; ++k) {
+    if (is_mean && k) break;
+    const double ps = warp_sum(pred_sum[k]);
+    const double es = warp_sum(eff_sum[k]);
+    const int ec = __reduce_add_sync(FULL, eff_cnt[k]);
+    if (lane == 0 && ok[k]) {
+      const double pm = ps / (double)a.n_post;
+      if (is_mean) {
+        summ[18] = pm; summ[19] = ps;
+      } else {
+        const int r = r0 + warp * IMP_RPW + k;
+        double* sd = statsT;
+        if (pd.ws) {                 // the statistics ride in front of rank 0's cumulative block
+          const int cnt0 = pd.C_base + (pd.C_extra > 0 ? 1 : 0);
+          sd = static_cast<double*>(pd.C[0]) + (size_t)(cnt0 + IMP_STATS) * pd.me_off;
+        }
+        sd[0 * (size_t)a.S + r] = pm;
+        sd[1 * (size_t)a.S + r] = ps;
+        sd[2 * (size_t)a.S + r] = ec > 0 ? es / (double)ec : CUDART_NAN;
+        sd[3 * (size_t)a.S + r] = es;
+        sd[4 * (size_t)a.S + r] = a.obs_sum / ps - 1.0;                // lib.py:1010-1011
+      }
     }
   }
+}
+
+// Grid of k_impact_rows: (row CTAs incl. the mean's, number of segments incl. the post one).
+inline int impact_seg_len() {      // CI_B200_IMP_SEG: tuning knob (steps, rounded to whole chunks)
+  static const int v = [] {
+    const char* e = getenv("CI_B200_IMP_SEG");
+    const int n = e ? atoi(e) : 0;
+    return n > 0 ? ((n + IMP_CHUNK - 1) / IMP_CHUNK) * IMP_CHUNK : IMP_SEG;
+  }();
+  return v;
+}
+inline void impact_rows_grid(int S, int T, int t_c0, bool with_mean, int* row_ctas, int* nseg) {
+  *row_ctas = (S + IMP_TILE - 1) / IMP_TILE + (with_mean ? 1 : 0);
+  const int post_base = (t_c0 / IMP_CHUNK) * IMP_CHUNK;
+  *nseg = 1 + (post_base + impact_seg_len() - 1) / impact_seg_len();
 }
 
 // numpy.lib._function_base_impl._lerp in float64
@@ -188,6 +311,34 @@ __device__ __forceinline__ int load_contig_keys(const V* __restrict__ col, int S
   return *n_valid;
 }
 
+// Row `row` of column blocks (ColBlocks layout, `rows` rows per block) -> shared-memory keys.
+template <typename V>
+__device__ __forceinline__ int load_block_keys(const V* __restrict__ base, int rows, int row,
+                                               const ColBlocks& cb,
+                                               typename KeyOf<V>::type* keys, int* n_valid) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) *n_valid = 0;
+  __syncthreads();
+  int cnt = 0, off = 0;
+  size_t blk = 0;
+  for (int r = 0; r < cb.ws; ++r) {
+    const int nr = cb.n[r];
+    const V* col = base + blk + (size_t)row * nr;
+    for (int i = tid; i < nr; i += nt) {
+      const V v = col[i];
+      const bool ok = (v == v);
+      keys[off + i] = ok ? KeyOf<V>::enc(v) : KeyOf<V>::nan_key();
+      cnt += ok ? 1 : 0;
+    }
+    off += nr;
+    blk += (size_t)rows * nr;
+  }
+  cnt = __reduce_add_sync(FULL, cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(n_valid, cnt);
+  __syncthreads();
+  return *n_valid;
+}
+
 // (q_lo, q_hi) quantiles of one contiguous column of V; MIRROR also selects the mirrored
 // ranks: the k-th smallest of (o - x) is o minus the k-th LARGEST x.  Results (as V
 // values, not yet un-scaled) in res[iq][0..3] = lo, hi, mirrored lo, mirrored hi; g[iq] =
@@ -196,13 +347,16 @@ template <typename V, bool MIRROR>
 __device__ __forceinline__ int column_quantiles(const V* __restrict__ col, int S, double q_lo,
                                                 double q_hi, unsigned char* key_mem, int in_smem,
                                                 SelectShared<V>& sh, int* ibuf, double (&res)[2][4],
-                                                double (&g)[2]) {
+                                                double (&g)[2], const ColBlocks* cb = nullptr,
+                                                int blk_rows = 0, int blk_row = 0) {
   using Key = typename KeyOf<V>::type;
   Key* keys = reinterpret_cast<Key*>(key_mem);
   int* n_valid = ibuf;                // [0]; [1] = number of ranks; [2..9] = slots
   const GlobalKeys<V> gkeys{col, (size_t)1};
-  const int n = in_smem ? load_contig_keys<V>(col, S, keys, n_valid)
-                        : count_valid_keys<V>(gkeys, S, n_valid);
+  // column blocks (cb): `col` is the base of the blocks; always staged in shared memory
+  const int n = cb ? load_block_keys<V>(col, blk_rows, blk_row, *cb, keys, n_valid)
+                   : in_smem ? load_contig_keys<V>(col, S, keys, n_valid)
+                             : count_valid_keys<V>(gkeys, S, n_valid);
   if (n == 0) return 0;
   if (threadIdx.x == 0) {
     int nr = 0;
@@ -290,7 +444,8 @@ __global__ void __launch_bounds__(1024)
 k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
                               const double* __restrict__ statsT, const double* __restrict__ obs,
                               ImpactDev a, double* __restrict__ series, double* __restrict__ summ,
-                              int in_smem, const ImpactSeries* __restrict__ per = nullptr) {
+                              int in_smem, const ImpactSeries* __restrict__ per, ImpactCols jc,
+                              ColBlocks cb) {
   if (per) {
     const size_t sidx = blockIdx.y;
     a.scale = per[sidx].scale; a.offset = per[sidx].offset; a.obs_sum = per[sidx].obs_sum;
@@ -303,27 +458,33 @@ k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
   __shared__ __align__(16) unsigned char sel_raw[sizeof(SelectShared<double>)];
   __shared__ int ibuf[10];
   __shared__ double red[33];
-  const int Tc = a.T - a.t_c0, S = a.S;
+  const int S = a.S;
+  const int ns = jc.do_stats ? IMP_STATS : 0;
   const int b = blockIdx.x, tid = threadIdx.x;
   double res[2][4], g[2];
-  if (b < Tc + IMP_STATS) {                         // cumulative-effect / per-draw statistic column
-    const bool is_cum = b < Tc;
-    const double* col = is_cum ? cumT + (size_t)b * S : statsT + (size_t)(b - Tc) * S;
+  if (b < jc.c_count + ns) {                        // cumulative-effect / per-draw statistic column
+    const bool is_cum = b < jc.c_count;
+    // sharded: the cumulative paths are read as the exchange left them (column blocks); the
+    // per-draw statistics were laid side by side (they also feed impact_summary_block)
+    const bool blocks = is_cum && cb.ws > 0;
+    const double* col = blocks ? cumT : is_cum ? cumT + (size_t)b * S : statsT + (size_t)(b - jc.c_count) * S;
     SelectShared<double>& sh = *reinterpret_cast<SelectShared<double>*>(sel_raw);
-    const int n = column_quantiles<double, false>(col, S, a.q_lo, a.q_hi, key_mem, in_smem, sh, ibuf, res, g);
+    const int n = column_quantiles<double, false>(col, S, a.q_lo, a.q_hi, key_mem, in_smem, sh, ibuf, res, g,
+                                                  blocks ? &cb : nullptr, cb.rowsC, cb.headC + b);
     if (tid == 0) {
-      double* out = is_cum ? series + (size_t)(a.t_c0 + b) * IMP_SERIES_COLS + 7
-                           : summ + 2 * (b - Tc);
+      double* out = is_cum ? series + (size_t)(a.t_c0 + jc.c_begin + b) * IMP_SERIES_COLS + 7
+                           : summ + 2 * (b - jc.c_count);
       for (int iq = 0; iq < 2; ++iq)
         out[iq] = n ? imp_lerp(res[iq][0], res[iq][1], g[iq]) : CUDART_NAN;
     }
     return;
   }
-  if (b < Tc + IMP_STATS + a.T) {                   // prediction + point-effect column
-    const int t = b - Tc - IMP_STATS;
+  if (b < jc.c_count + ns + jc.t_count) {           // prediction + point-effect column
+    const int tl = b - jc.c_count - ns, t = jc.t_begin + tl;
     SelectShared<R>& sh = *reinterpret_cast<SelectShared<R>*>(sel_raw);
-    const int n = column_quantiles<R, true>(trT + (size_t)t * S, S, a.q_lo, a.q_hi, key_mem, in_smem,
-                                            sh, ibuf, res, g);
+    const int n = column_quantiles<R, true>(cb.ws > 0 ? trT : trT + (size_t)tl * S, S, a.q_lo, a.q_hi,
+                                            key_mem, in_smem, sh, ibuf, res, g,
+                                            cb.ws > 0 ? &cb : nullptr, cb.rowsT, tl);
     if (tid == 0) {
       double* row = series + (size_t)t * IMP_SERIES_COLS;
       if (t < a.t_c0) { row[7] = 0.0; row[8] = 0.0; }          // cumulative effect is 0 before post
@@ -339,6 +500,33 @@ k_impact_jobs(const R* __restrict__ trT, const double* __restrict__ cumT,
     return;
   }
   impact_summary_block(statsT, a, summ, red);
+}
+
+// ---- pieces of the time-sharded impact stage (ci_impact_sharded_d) ----------------
+// What the exchange leaves: the blocks of the source ranks one after the other, block r =
+// [src_rows][n_r].  Lay the first gridDim.y rows side by side: out [rows][S], draws in rank order.
+template <typename V>
+__global__ void __launch_bounds__(256)
+k_merge_blocks(const V* __restrict__ recv, V* __restrict__ out, int src_rows, ShardCounts sc, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+  if (i >= S) return;
+  int r = 0, off = 0;
+  size_t base = 0;
+  while (i >= off + sc.n[r]) { off += sc.n[r]; base += (size_t)src_rows * sc.n[r]; ++r; }
+  out[(size_t)row * S + i] = recv[base + (size_t)row * sc.n[r] + (i - off)];
+}
+
+// Predictive mean over all draws from the ranks' means of their own draws: draw-count-weighted
+// float64 sum in rank order (the same on every rank).
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_mean_combine(const R* __restrict__ parts, ShardCounts sc, int S, int T, R* __restrict__ mean) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double acc = 0.0;
+  for (int r = 0; r < sc.ws; ++r)
+    if (sc.n[r]) acc += (double)parts[(size_t)r * T + t] * ((double)sc.n[r] / (double)S);
+  mean[t] = (R)acc;
 }
 
 }  // namespace ci

@@ -17,6 +17,7 @@
 // (causalimpact/posterior_processing.py:25-60): pandas quantile(axis=1) =
 // NaN-skipping linear interpolation at q*(n-1) (numpy's _lerp, bit for bit).
 #pragma once
+#include <type_traits>
 #include "ci_kernels.cuh"
 
 namespace ci {
@@ -245,6 +246,7 @@ template <typename R> struct SelectShared {
   int gbin[QMAXR], gbelow[QMAXR];   // per group: its bin, number of values in lower bins
   int rgrp[QMAXR];             // group of each rank
   int ngroups, fallback;
+  int wsum[32];                // warp totals of the bin-count scan
   Key kmin, kmax;
 };
 
@@ -364,28 +366,37 @@ __device__ __forceinline__ bool binned_select(const KeyAt keys, int n, int nr,
     if (k != NANK) atomicAdd(&sh.hist[bin_of(k)], 1);
   }
   __syncthreads();
-  if (warp == 0) {                                    // bins of the wanted ranks
-    constexpr int per = LBINS / 32;
+  {
+    // bins of the wanted ranks: every thread owns LBINS / nt consecutive bins (CTA-wide
+    // exclusive scan of the bin counts: warp shuffles + one exchange of the warp totals).
+    // (Run 21: warp 0 alone walking 64 bins per lane -- a 32-way bank conflict per read --
+    // with the other warps parked at the barrier was 37% of the kernel's stall samples.)
+    const int per = (LBINS + nt - 1) / nt, b0 = tid * per;
     int loc = 0;
-    for (int b = 0; b < per; ++b) loc += sh.hist[lane * per + b];
+    for (int b = b0; b < b0 + per && b < LBINS; ++b) loc += sh.hist[b];
     int inc = loc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(FULL, inc, o);
       if (lane >= o) inc += t;
     }
-    const int before = inc - loc;
-    for (int r = 0; r < nr; ++r) {
-      const int rk = sh.rank[r];
-      if (rk >= before && rk < inc) {
-        int acc = before, b = lane * per;
-        while (acc + sh.hist[b] <= rk) { acc += sh.hist[b]; ++b; }
-        sh.rgrp[r] = b;                               // (bin for now; group id below)
-        sh.cnt[0][r] = acc;
+    if (lane == 31) sh.wsum[warp] = inc;
+    __syncthreads();
+    int before = inc - loc;
+    for (int w = 0; w < warp; ++w) before += sh.wsum[w];
+    if (loc > 0) {
+      for (int r = 0; r < nr; ++r) {
+        const int rk = sh.rank[r];
+        if (rk >= before && rk < before + loc) {
+          int acc = before, b = b0;
+          while (acc + sh.hist[b] <= rk) { acc += sh.hist[b]; ++b; }
+          sh.rgrp[r] = b;                             // (bin for now; group id below)
+          sh.cnt[0][r] = acc;
+        }
       }
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (tid == 0) {
       int ng = 0;
       for (int r = 0; r < nr; ++r) {
         const int b = sh.rgrp[r];
@@ -405,13 +416,23 @@ __device__ __forceinline__ bool binned_select(const KeyAt keys, int n, int nr,
   __syncthreads();
   if (sh.fallback) return false;
   const int ng = sh.ngroups;
-  for (int i = tid; i < n; i += nt) {
-    const Key k = keys(i);
-    if (k == NANK) continue;
-    const int b = bin_of(k);
-    for (int g = 0; g < ng; ++g)
-      if (sh.gbin[g] == b) sh.cand[g][atomicAdd(&sh.ccount[g], 1)] = k;
-  }
+  auto collect = [&](auto ngt) {                      // the needed bins, in registers
+    constexpr int NG = decltype(ngt)::value;
+    int gb[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) gb[g] = g < ng ? sh.gbin[g] : -1;
+    for (int i = tid; i < n; i += nt) {
+      const Key k = keys(i);
+      if (k == NANK) continue;
+      const int b = bin_of(k);
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+        if (gb[g] == b) sh.cand[g][atomicAdd(&sh.ccount[g], 1)] = k;
+    }
+  };
+  if (ng <= 2) collect(std::integral_constant<int, 2>{});
+  else if (ng <= 4) collect(std::integral_constant<int, 4>{});
+  else collect(std::integral_constant<int, QMAXR>{});
   __syncthreads();
   for (int r = warp; r < nr; r += nwarps) {           // one warp finishes one rank
     const int g = sh.rgrp[r], m = sh.ccount[g], kk = sh.rank[r] - sh.gbelow[g];
