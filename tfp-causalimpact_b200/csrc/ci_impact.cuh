@@ -77,24 +77,105 @@ __device__ __forceinline__ double imp_unscale(double x, double scale, double off
 
 constexpr int IMP_TILE = 32;         // draws per CTA == draws per transposed 128-byte run
 constexpr int IMP_WARPS = 8;         // warps per CTA
-constexpr int IMP_RPW = IMP_TILE / IMP_WARPS;   // draws per warp (independent scans: ILP)
+constexpr int IMP_LPW = IMP_TILE / IMP_WARPS;   // load phase: draws per warp (lane <-> step)
 constexpr int IMP_CH = 2;            // 32-step sub-chunks per loop iteration
 constexpr int IMP_CHUNK = IMP_CH * 32;
+constexpr int IMP_SPW = IMP_CHUNK / IMP_WARPS;  // compute phase: steps per warp (lane <-> draw)
 constexpr int IMP_SEG = 4 * IMP_CHUNK;          // pre-period steps per transpose-only CTA
 
-// CTA (rb, seg) = blockIdx.x % row_ctas, blockIdx.x / row_ctas works on draws 32 rb .. 32 rb + 31
-// (warp w <-> draws 4w .. 4w + 3, lane <-> t inside a 32-step sub-chunk):
+// where element (time column, draw) of the transposed outputs goes: the local arrays or, in a
+// sharded fit, the owner rank's window (ColBlocks layout) over NVLink
+template <typename R>
+__device__ __forceinline__ R* impact_dst_path(R* trT, const ImpactDev& a, const PeerDest& pd, int tc) {
+  if (pd.ws == 0) return trT + (size_t)tc * a.S;
+  int g, st0, cnt;
+  split_owner(tc, pd.T_base, pd.T_extra, g, st0, cnt);
+  return static_cast<R*>(pd.T[g]) + (size_t)cnt * pd.me_off + (size_t)(tc - st0) * pd.n_me;
+}
+__device__ __forceinline__ double* impact_dst_cum(double* cumT, const ImpactDev& a, const PeerDest& pd,
+                                                  int c) {
+  if (pd.ws == 0) return cumT + (size_t)c * a.S;
+  int g, st0, cnt;
+  split_owner(c, pd.C_base, pd.C_extra, g, st0, cnt);
+  const int head = g == 0 ? IMP_STATS : 0;
+  return static_cast<double*>(pd.C[g]) + (size_t)(cnt + head) * pd.me_off +
+         (size_t)(head + c - st0) * pd.n_me;
+}
+
+// The predictive mean's row (the *_mean series columns and `predicted`): one CTA, warp w takes
+// 32 steps of every 256-step round (lane <-> step, warp scan), the warps' totals are chained
+// through shared memory.
+template <typename R>
+__device__ __forceinline__ void impact_mean_row(const R* __restrict__ mean,
+                                                const double* __restrict__ obs,
+                                                const uint8_t* __restrict__ period,
+                                                const ImpactDev& a, double* __restrict__ series,
+                                                double* __restrict__ summ) {
+  __shared__ double mtot[2][IMP_WARPS];
+  __shared__ double msum[IMP_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double carry = 0.0, pred_sum = 0.0;
+  int buf = 0;
+  for (int base = 0; base < a.T; base += 32 * IMP_WARPS, buf ^= 1) {
+    const int t = base + warp * 32 + lane;
+    const bool valid = t < a.T;
+    const double x = imp_unscale(valid ? (double)mean[t] : 0.0, a.scale, a.offset);
+    const double pt = valid ? obs[t] - x : CUDART_NAN;               // lib.py:822-823
+    const bool isn = !(pt == pt);
+    // lib.py:826-831: effects before the post-period count as 0; NaNs are skipped
+    double inc = (valid && t >= a.t_c0 && !isn) ? pt : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += up;
+    }
+    if (lane == 31) mtot[buf][warp] = inc;
+    if (valid && period[t] == 1) pred_sum += x;
+    __syncthreads();
+    double off = carry, all = 0.0;
+#pragma unroll
+    for (int w = 0; w < IMP_WARPS; ++w) {
+      const double v = mtot[buf][w];
+      if (w < warp) off += v;
+      all += v;
+    }
+    carry += all;
+    if (valid) {
+      double* row = series + (size_t)t * IMP_SERIES_COLS;
+      row[0] = x; row[3] = pt;
+      row[6] = t < a.t_c0 ? 0.0 : (isn ? CUDART_NAN : off + inc);
+    }
+  }
+  pred_sum = warp_sum(pred_sum);
+  if (lane == 0) msum[warp] = pred_sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < IMP_WARPS; ++w) tot += msum[w];
+    summ[18] = tot / (double)a.n_post; summ[19] = tot;
+  }
+}
+
+// CTA (rb, seg) = blockIdx.x % row_ctas, blockIdx.x / row_ctas works on draws 32 rb .. 32 rb + 31:
 //   seg = 0   the steps from the 64-aligned start of the post-period to T: cumulative effect
-//             paths (warp scan over time, carried across chunks), post-period per-draw statistics,
-//             transposed copy of the raw draws and of the cumulative paths;
+//             paths, post-period per-draw statistics, transposed copies of the raw draws and of
+//             the cumulative paths;
 //   seg >= 1  pre-period steps [(seg-1) seg_len, seg seg_len): nothing depends on them except
 //             their own quantiles, so these CTAs only transpose (and there are many of them).
-// With `mean`, CTA rb = row_ctas - 1 of seg 0 is extra: its warp 0 walks the predictive mean
-// (the *_mean series columns and `predicted`).  The next chunk's loads are issued before the
-// current one is processed.  (Run 20: the round-1 layout -- 1024 threads, 44 registers, so ONE CTA
-// per SM, every CTA walking all T steps -- took 157 us at S=10000, T=2000 for 210 MB of traffic.)
+// Every 64-step chunk is LOADED with lane <-> step (warp w reads draws 4w .. 4w+3: coalesced 128-
+// byte runs of the [S,T] array; the next chunk's loads are issued before this one is processed)
+// into a shared-memory tile, and PROCESSED with lane <-> draw (warp w takes steps 8w .. 8w+7):
+// the running sum over time is then a plain per-thread recurrence -- no shuffles; the 8 warps'
+// partial sums are chained through shared memory -- and every store is a coalesced run of 32
+// draws of one time step, straight from registers.  With `mean`, CTA rb = row_ctas - 1 of seg 0
+// is extra and walks the predictive mean instead (impact_mean_row).
+// (History: round 1 -- 1024 threads, lane <-> step, warp-shuffle scans, every CTA walking all T
+// steps, ONE CTA per SM: 157 us at S=10000, T=2000 for 210 MB of traffic.  Run 21: 256 threads x
+// 4 draws per warp, pre-period segments as separate CTAs: 123 us, but a 1250-draw shard of an
+// 8-GPU fit still took 85-100 us -- 3400 dependent instructions per warp at 2 warps per
+// scheduler.)
 template <typename R>
-__global__ void __launch_bounds__(32 * IMP_WARPS, 4)
+__global__ void __launch_bounds__(32 * IMP_WARPS, 3)
 k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
               const double* __restrict__ obs, const uint8_t* __restrict__ period, ImpactDev a,
               R* __restrict__ trT, double* __restrict__ cumT, double* __restrict__ statsT,
@@ -108,162 +189,128 @@ k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
     statsT += sidx * (size_t)a.S * IMP_STATS;
     series += sidx * (size_t)a.T * IMP_SERIES_COLS; summ += sidx * (size_t)IMP_SUMMARY_LEN;
   }
-  __shared__ R tile_raw[IMP_TILE][IMP_CHUNK + 1];
-  __shared__ double tile_cum[IMP_TILE][IMP_CHUNK + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rb = blockIdx.x % row_ctas, seg = blockIdx.x / row_ctas;
-  const bool is_mean = mean != nullptr && rb == row_ctas - 1;
-  const int post_base = (a.t_c0 / IMP_CHUNK) * IMP_CHUNK;
   const bool post = seg == 0;
+  if (mean != nullptr && rb == row_ctas - 1) {       // the extra CTA: the predictive mean's row
+    if (post) impact_mean_row<R>(mean, obs, period, a, series, summ);
+    return;
+  }
+  __shared__ R tile[2][IMP_TILE][IMP_CHUNK + 1];     // [draw][step] of the chunk, double-buffered
+  __shared__ double wtot[2][IMP_WARPS][IMP_TILE];    // per warp: sum of its steps' effects, per draw
+  const int post_base = (a.t_c0 / IMP_CHUNK) * IMP_CHUNK;
   int t_begin, t_end;
   if (post) {
-    t_begin = is_mean ? 0 : post_base; t_end = a.T;
+    t_begin = post_base; t_end = a.T;
   } else {
     t_begin = (seg - 1) * seg_len;
     t_end = min(t_begin + seg_len, post_base);
-    if (is_mean || t_begin >= t_end) return;
+    if (t_begin >= t_end) return;
   }
-  if (is_mean && warp != 0) return;                  // (no CTA-wide barrier on this path)
   const int r0 = rb * IMP_TILE;
-  bool ok[IMP_RPW];
-  const R* src[IMP_RPW];
+  // load phase: this warp's draws
+  const R* src[IMP_LPW];
+  bool lok[IMP_LPW];
 #pragma unroll
-  for (int k = 0; k < IMP_RPW; ++k) {
-    const int r = r0 + warp * IMP_RPW + k;
-    ok[k] = is_mean ? k == 0 : r < a.S;
-    src[k] = is_mean ? mean : traj + (size_t)(ok[k] ? r : 0) * a.T;
+  for (int k = 0; k < IMP_LPW; ++k) {
+    const int r = r0 + warp * IMP_LPW + k;
+    lok[k] = r < a.S;
+    src[k] = traj + (size_t)(lok[k] ? r : 0) * a.T;
   }
-  double carry[IMP_RPW], pred_sum[IMP_RPW], eff_sum[IMP_RPW];
-  int eff_cnt[IMP_RPW];
+  // compute phase: this lane's draw
+  const int rr = r0 + lane;
+  const bool dok = rr < a.S;
+  double carry = 0.0, pred_sum = 0.0, eff_sum = 0.0;
+  int eff_cnt = 0;
+  R nxt[IMP_LPW][IMP_CH];
 #pragma unroll
-  for (int k = 0; k < IMP_RPW; ++k) { carry[k] = 0.0; pred_sum[k] = 0.0; eff_sum[k] = 0.0; eff_cnt[k] = 0; }
-  R nxt[IMP_RPW][IMP_CH];
-#pragma unroll
-  for (int k = 0; k < IMP_RPW; ++k)
+  for (int k = 0; k < IMP_LPW; ++k)
 #pragma unroll
     for (int h = 0; h < IMP_CH; ++h) {
       const int t = t_begin + h * 32 + lane;
-      nxt[k][h] = (ok[k] && t < t_end) ? src[k][t] : (R)0;
+      nxt[k][h] = (lok[k] && t < t_end) ? src[k][t] : (R)0;
     }
-  for (int base = t_begin; base < t_end; base += IMP_CHUNK) {
-    R cur[IMP_RPW][IMP_CH];
+  int buf = 0;
+  for (int base = t_begin; base < t_end; base += IMP_CHUNK, buf ^= 1) {
 #pragma unroll
-    for (int k = 0; k < IMP_RPW; ++k)
+    for (int k = 0; k < IMP_LPW; ++k)
 #pragma unroll
       for (int h = 0; h < IMP_CH; ++h) {
-        cur[k][h] = nxt[k][h];
+        tile[buf][warp * IMP_LPW + k][h * 32 + lane] = nxt[k][h];
         const int t = base + IMP_CHUNK + h * 32 + lane;          // next chunk: loads in flight
-        nxt[k][h] = (ok[k] && t < t_end) ? src[k][t] : (R)0;
+        nxt[k][h] = (lok[k] && t < t_end) ? src[k][t] : (R)0;
       }
+    __syncthreads();          // tile[buf] is whole (and everybody is done with tile[buf] of 2 chunks ago)
+    const int j0 = warp * IMP_SPW;
     if (!post) {
 #pragma unroll
-      for (int k = 0; k < IMP_RPW; ++k)
-#pragma unroll
-        for (int h = 0; h < IMP_CH; ++h) tile_raw[warp * IMP_RPW + k][h * 32 + lane] = cur[k][h];
-    } else {
-      double ob[IMP_CH];
-      int pd[IMP_CH];
-#pragma unroll
-      for (int h = 0; h < IMP_CH; ++h) {             // shared by the warp's draws
-        const int t = base + h * 32 + lane;
-        ob[h] = t < a.T ? obs[t] : CUDART_NAN;
-        pd[h] = t < a.T ? (int)period[t] : 0;
+      for (int jj = 0; jj < IMP_SPW; ++jj) {
+        const int tc = base + j0 + jj;
+        if (dok && tc < t_end) impact_dst_path<R>(trT, a, pd, tc)[rr] = tile[buf][lane][j0 + jj];
       }
-      // nothing to accumulate before the post-period starts: cumulative effect is 0 there
-      const bool need_cum = base + IMP_CHUNK > a.t_c0;
-#pragma unroll
-      for (int k = 0; k < IMP_RPW; ++k) {
-#pragma unroll
-        for (int h = 0; h < IMP_CH; ++h) {
-          const int t = base + h * 32 + lane;
-          const bool valid = ok[k] && t < a.T;
-          const double x = imp_unscale((double)cur[k][h], a.scale, a.offset);
-          const double pt = valid ? ob[h] - x : CUDART_NAN;            // lib.py:822-823
-          const bool isn = !(pt == pt);
-          double out = 0.0;
-          if (need_cum) {
-            // lib.py:826-831: effects before the post-period count as 0; NaNs are skipped
-            double inc = (valid && t >= a.t_c0 && !isn) ? pt : 0.0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const double up = __shfl_up_sync(FULL, inc, o);
-              if (lane >= o) inc += up;
-            }
-            const double cv = carry[k] + inc;
-            carry[k] += __shfl_sync(FULL, inc, 31);
-            out = (t >= a.t_c0 && isn) ? CUDART_NAN : cv;
-          }
-          if (valid && pd[h] == 1) {                   // inside the post-period (lib.py:966-1011)
-            pred_sum[k] += x;
-            if (!isn) { eff_sum[k] += pt; ++eff_cnt[k]; }
-          }
-          if (is_mean) {
-            if (valid) {
-              double* row = series + (size_t)t * IMP_SERIES_COLS;
-              row[0] = x; row[3] = pt; row[6] = out;
-            }
-          } else {
-            tile_raw[warp * IMP_RPW + k][h * 32 + lane] = cur[k][h];
-            if (need_cum) tile_cum[warp * IMP_RPW + k][h * 32 + lane] = out;
-          }
-        }
-        if (is_mean) break;                          // the mean is one row
-      }
+      continue;
     }
-    if (is_mean) continue;
-    // transpose the chunk: [draw][t] -> [t][draw]; warp <-> time steps w, w + 8, .., lane <-> draw
-    __syncthreads();
-    const int rr = r0 + lane;
-    if (rr < a.S) {
-#pragma unroll 4
-      for (int j = warp; j < IMP_CHUNK; j += IMP_WARPS) {
-        const int tc = base + j;
-        if (tc >= t_end) continue;
-        if (pd.ws == 0) {
-          trT[(size_t)tc * a.S + rr] = tile_raw[lane][j];
-          if (post && tc >= a.t_c0) cumT[(size_t)(tc - a.t_c0) * a.S + rr] = tile_cum[lane][j];
-        } else {                     // the owner's window, over NVLink: 128-byte runs per warp
-          int g, st0, cnt;
-          split_owner(tc, pd.T_base, pd.T_extra, g, st0, cnt);
-          static_cast<R*>(pd.T[g])[(size_t)cnt * pd.me_off + (size_t)(tc - st0) * pd.n_me + rr] =
-              tile_raw[lane][j];
-          if (post && tc >= a.t_c0) {
-            split_owner(tc - a.t_c0, pd.C_base, pd.C_extra, g, st0, cnt);
-            const int head = g == 0 ? IMP_STATS : 0;
-            static_cast<double*>(pd.C[g])[(size_t)(cnt + head) * pd.me_off +
-                                          (size_t)(head + tc - a.t_c0 - st0) * pd.n_me + rr] =
-                tile_cum[lane][j];
-          }
-        }
+    // post-period chunk: this thread walks draw rr over steps base + j0 .. + IMP_SPW - 1
+    double run = 0.0, s[IMP_SPW];
+    unsigned nanmask = 0;
+#pragma unroll
+    for (int jj = 0; jj < IMP_SPW; ++jj) {
+      const int t = base + j0 + jj;
+      const bool valid = dok && t < a.T;
+      const R raw = tile[buf][lane][j0 + jj];
+      const double x = imp_unscale((double)raw, a.scale, a.offset);
+      const double o = t < a.T ? obs[t] : CUDART_NAN;                // (the same for the whole warp)
+      const int pdv = t < a.T ? (int)period[t] : 0;
+      const double pt = valid ? o - x : CUDART_NAN;                  // lib.py:822-823
+      const bool isn = !(pt == pt);
+      // lib.py:826-831: effects before the post-period count as 0; NaNs are skipped
+      run += (valid && t >= a.t_c0 && !isn) ? pt : 0.0;
+      s[jj] = run;
+      nanmask |= (isn ? 1u : 0u) << jj;
+      if (valid && pdv == 1) {                       // inside the post-period (lib.py:966-1011)
+        pred_sum += x;
+        if (!isn) { eff_sum += pt; ++eff_cnt; }
       }
+      if (valid) impact_dst_path<R>(trT, a, pd, t)[rr] = raw;
     }
+    wtot[buf][warp][lane] = run;
     __syncthreads();
+    double off = carry, all = 0.0;
+#pragma unroll
+    for (int w = 0; w < IMP_WARPS; ++w) {
+      const double v = wtot[buf][w][lane];
+      if (w < warp) off += v;
+      all += v;
+    }
+    carry += all;
+#pragma unroll
+    for (int jj = 0; jj < IMP_SPW; ++jj) {
+      const int t = base + j0 + jj;
+      if (dok && t < a.T && t >= a.t_c0)
+        impact_dst_cum(cumT, a, pd, t - a.t_c0)[rr] = ((nanmask >> jj) & 1u) ? CUDART_NAN : off + s[jj];
+    }
   }
   if (!post) return;
+  // per-draw statistics: the warps' partial sums, in warp order
+  __shared__ double sred[2][IMP_WARPS][IMP_TILE];
+  __shared__ int scnt[IMP_WARPS][IMP_TILE];
+  sred[0][warp][lane] = pred_sum; sred[1][warp][lane] = eff_sum; scnt[warp][lane] = eff_cnt;
+  __syncthreads();
+  if (warp == 0 && dok) {
+    double ps = 0.0, es = 0.0;
+    int ec = 0;
 #pragma unroll
-  for (int k = 0; k < IMP_RPW; ++k) {
-    if (is_mean && k) break;
-    const double ps = warp_sum(pred_sum[k]);
-    const double es = warp_sum(eff_sum[k]);
-    const int ec = __reduce_add_sync(FULL, eff_cnt[k]);
-    if (lane == 0 && ok[k]) {
-      const double pm = ps / (double)a.n_post;
-      if (is_mean) {
-        summ[18] = pm; summ[19] = ps;
-      } else {
-        const int r = r0 + warp * IMP_RPW + k;
-        double* sd = statsT;
-        if (pd.ws) {                 // the statistics ride in front of rank 0's cumulative block
-          const int cnt0 = pd.C_base + (pd.C_extra > 0 ? 1 : 0);
-          sd = static_cast<double*>(pd.C[0]) + (size_t)(cnt0 + IMP_STATS) * pd.me_off;
-        }
-        sd[0 * (size_t)a.S + r] = pm;
-        sd[1 * (size_t)a.S + r] = ps;
-        sd[2 * (size_t)a.S + r] = ec > 0 ? es / (double)ec : CUDART_NAN;
-        sd[3 * (size_t)a.S + r] = es;
-        sd[4 * (size_t)a.S + r] = a.obs_sum / ps - 1.0;                // lib.py:1010-1011
-      }
+    for (int w = 0; w < IMP_WARPS; ++w) { ps += sred[0][w][lane]; es += sred[1][w][lane]; ec += scnt[w][lane]; }
+    double* sd = statsT;
+    if (pd.ws) {                     // the statistics ride in front of rank 0's cumulative block
+      const int cnt0 = pd.C_base + (pd.C_extra > 0 ? 1 : 0);
+      sd = static_cast<double*>(pd.C[0]) + (size_t)(cnt0 + IMP_STATS) * pd.me_off;
     }
+    sd[0 * (size_t)a.S + rr] = ps / (double)a.n_post;
+    sd[1 * (size_t)a.S + rr] = ps;
+    sd[2 * (size_t)a.S + rr] = ec > 0 ? es / (double)ec : CUDART_NAN;
+    sd[3 * (size_t)a.S + rr] = es;
+    sd[4 * (size_t)a.S + rr] = a.obs_sum / ps - 1.0;                 // lib.py:1010-1011
   }
 }
 

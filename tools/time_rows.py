@@ -18,7 +18,7 @@ meta = _imp.ImpactMeta(index=None, observed=obs, period=per, hide=None, scale=2.
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = torch.zeros(T * 9 + 20, dtype=torch.float64, device="cuda")
 print("IMP_SEG", os.environ.get("CI_B200_IMP_SEG", "default"))
-for S in (1250, 5000, 10000, 40000):
+for S in ([int(x) for x in sys.argv[1:]] or (1250, 5000, 10000, 40000)):
   traj = torch.randn(S, T, device="cuda")
   mean = traj.mean(0)
   for with_mean in (True, False):
