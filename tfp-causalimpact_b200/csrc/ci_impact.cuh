@@ -338,20 +338,40 @@ __device__ __forceinline__ double imp_lerp(double va, double vb, double g) {
   return r;
 }
 
-// Contiguous column -> shared-memory keys; returns the number of non-NaN values.
+// Fold a thread's smallest / largest valid key into sh.kmin / sh.kmax (what binned_select needs first)
+template <typename V>
+__device__ __forceinline__ void fold_minmax(typename KeyOf<V>::type mn, typename KeyOf<V>::type mx,
+                                            SelectShared<V>& sh) {
+  using Key = typename KeyOf<V>::type;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const Key a = __shfl_xor_sync(FULL, mn, o), b = __shfl_xor_sync(FULL, mx, o);
+    mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&sh.kmin, mn); atomicMax(&sh.kmax, mx); }
+}
+
+// Contiguous column -> shared-memory keys (+ their min / max in sh); returns the number of non-NaN values.
 template <typename V>
 __device__ __forceinline__ int load_contig_keys(const V* __restrict__ col, int S,
-                                                typename KeyOf<V>::type* keys, int* n_valid) {
+                                                typename KeyOf<V>::type* keys, int* n_valid,
+                                                SelectShared<V>& sh) {
+  using Key = typename KeyOf<V>::type;
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) *n_valid = 0;
+  const Key NANK = KeyOf<V>::nan_key();
+  if (tid == 0) { *n_valid = 0; sh.kmin = NANK; sh.kmax = 0; }
   __syncthreads();
   int cnt = 0;
+  Key mn = NANK, mx = 0;
   for (int i = tid; i < S; i += nt) {
     const V v = col[i];
     const bool ok = (v == v);
-    keys[i] = ok ? KeyOf<V>::enc(v) : KeyOf<V>::nan_key();
+    const Key k = ok ? KeyOf<V>::enc(v) : NANK;
+    keys[i] = k;
     cnt += ok ? 1 : 0;
+    if (ok) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
   }
+  fold_minmax<V>(mn, mx, sh);
   cnt = __reduce_add_sync(FULL, cnt);
   if ((tid & 31) == 0 && cnt) atomicAdd(n_valid, cnt);
   __syncthreads();
@@ -362,24 +382,31 @@ __device__ __forceinline__ int load_contig_keys(const V* __restrict__ col, int S
 template <typename V>
 __device__ __forceinline__ int load_block_keys(const V* __restrict__ base, int rows, int row,
                                                const ColBlocks& cb,
-                                               typename KeyOf<V>::type* keys, int* n_valid) {
+                                               typename KeyOf<V>::type* keys, int* n_valid,
+                                               SelectShared<V>& sh) {
+  using Key = typename KeyOf<V>::type;
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) *n_valid = 0;
+  const Key NANK = KeyOf<V>::nan_key();
+  if (tid == 0) { *n_valid = 0; sh.kmin = NANK; sh.kmax = 0; }
   __syncthreads();
   int cnt = 0, off = 0;
   size_t blk = 0;
+  Key mn = NANK, mx = 0;
   for (int r = 0; r < cb.ws; ++r) {
     const int nr = cb.n[r];
     const V* col = base + blk + (size_t)row * nr;
     for (int i = tid; i < nr; i += nt) {
       const V v = col[i];
       const bool ok = (v == v);
-      keys[off + i] = ok ? KeyOf<V>::enc(v) : KeyOf<V>::nan_key();
+      const Key k = ok ? KeyOf<V>::enc(v) : NANK;
+      keys[off + i] = k;
       cnt += ok ? 1 : 0;
+      if (ok) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
     }
     off += nr;
     blk += (size_t)rows * nr;
   }
+  fold_minmax<V>(mn, mx, sh);
   cnt = __reduce_add_sync(FULL, cnt);
   if ((tid & 31) == 0 && cnt) atomicAdd(n_valid, cnt);
   __syncthreads();
@@ -401,8 +428,9 @@ __device__ __forceinline__ int column_quantiles(const V* __restrict__ col, int S
   int* n_valid = ibuf;                // [0]; [1] = number of ranks; [2..9] = slots
   const GlobalKeys<V> gkeys{col, (size_t)1};
   // column blocks (cb): `col` is the base of the blocks; always staged in shared memory
-  const int n = cb ? load_block_keys<V>(col, blk_rows, blk_row, *cb, keys, n_valid)
-                   : in_smem ? load_contig_keys<V>(col, S, keys, n_valid)
+  const bool staged = cb != nullptr || in_smem;
+  const int n = cb ? load_block_keys<V>(col, blk_rows, blk_row, *cb, keys, n_valid, sh)
+                   : in_smem ? load_contig_keys<V>(col, S, keys, n_valid, sh)
                              : count_valid_keys<V>(gkeys, S, n_valid);
   if (n == 0) return 0;
   if (threadIdx.x == 0) {
@@ -422,7 +450,7 @@ __device__ __forceinline__ int column_quantiles(const V* __restrict__ col, int S
     ibuf[1] = nr;
   }
   __syncthreads();
-  if (in_smem) radix_select_multi<V>(SmemKeys<V>{keys}, S, ibuf[1], sh);
+  if (staged) radix_select_multi<V>(SmemKeys<V>{keys}, S, ibuf[1], sh, true);
   else radix_select_multi<V>(gkeys, S, ibuf[1], sh);
 #pragma unroll
   for (int iq = 0; iq < 2; ++iq) {

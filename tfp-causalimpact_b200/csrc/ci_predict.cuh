@@ -322,18 +322,23 @@ __device__ __forceinline__ void bisect_select_impl(const KeyAt keys, int n, int 
 // instructions per key instead of a pass per digit / bit.  Returns false -- nothing
 // selected -- when the column defeats the binning (infinities, a bin with more than LCAP
 // keys: heavy ties or extreme outliers); the caller then runs the bisection.
+// `have_minmax`: the loader already left the smallest / largest valid key in sh.kmin / sh.kmax
+// (load_contig_keys / load_block_keys of ci_impact.cuh fold that sweep into the load).
 template <typename R, typename KeyAt>
 __device__ __forceinline__ bool binned_select(const KeyAt keys, int n, int nr,
-                                              SelectShared<R>& sh) {
+                                              SelectShared<R>& sh, bool have_minmax = false) {
   using Key = typename KeyOf<R>::type;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = nt >> 5;
   const Key NANK = KeyOf<R>::nan_key();
-  if (tid == 0) { sh.kmin = NANK; sh.kmax = 0; sh.fallback = 0; sh.ngroups = 0; }
+  if (tid == 0) {
+    if (!have_minmax) { sh.kmin = NANK; sh.kmax = 0; }
+    sh.fallback = 0; sh.ngroups = 0;
+  }
   for (int b = tid; b < LBINS; b += nt) sh.hist[b] = 0;
   if (tid < QMAXR) sh.ccount[tid] = 0;
   __syncthreads();
-  {
+  if (!have_minmax) {
     Key mn = NANK, mx = 0;
     for (int i = tid; i < n; i += nt) {
       const Key k = keys(i);
@@ -451,8 +456,9 @@ __device__ __forceinline__ bool binned_select(const KeyAt keys, int n, int nr,
 }
 
 template <typename R, typename KeyAt>
-__device__ void radix_select_multi(const KeyAt keys, int n, int nr, SelectShared<R>& sh) {
-  if (binned_select<R>(keys, n, nr, sh)) return;
+__device__ void radix_select_multi(const KeyAt keys, int n, int nr, SelectShared<R>& sh,
+                                   bool have_minmax = false) {
+  if (binned_select<R>(keys, n, nr, sh, have_minmax)) return;
   if (nr <= 4) bisect_select_impl<R, 4>(keys, n, nr, sh);
   else if (nr <= 8) bisect_select_impl<R, 8>(keys, n, nr, sh);
   else bisect_select_impl<R, 16>(keys, n, nr, sh);
