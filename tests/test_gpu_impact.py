@@ -212,14 +212,16 @@ def test_device_entry_point_does_not_synchronise_when_workspaces_grow(engine):
   out_b = torch.empty(T * 9 + 20, dtype=torch.float64, device=dev)
   m_s, m_b = small.mean(0), big.mean(0)
   torch.cuda.synchronize()
-  torch.cuda._sleep(int(4e8))                # ~0.2 s of busy stream
+  torch.cuda._sleep(int(2e9))                # ~1 s of busy stream
   t0 = time.perf_counter()
   eng2.impact(small, m_s, meta, out=out_s)   # allocates the workspaces
   eng2.impact(big, m_b, meta, out=out_b)     # outgrows all of them
   dt = time.perf_counter() - t0
   busy = not torch.cuda.current_stream().query()
   torch.cuda.synchronize()
-  assert busy and dt < 0.1, (busy, dt)
+  # (a cudaMalloc of a grown workspace may take tens of ms on a box whose memory other tests
+  # have fragmented: the bound is "well inside the busy second", not a latency target)
+  assert busy and dt < 0.5, (busy, dt)
   got = out_s.cpu().numpy()
   np.testing.assert_array_equal(got[:T * 9].reshape(T, 9), want_small[0])
   np.testing.assert_array_equal(got[T * 9:], want_small[1])

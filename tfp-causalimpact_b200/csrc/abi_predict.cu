@@ -194,16 +194,31 @@ int ci_predictive_mean_d(ci_ctx* c, const void* theta_d, const void* level_d, in
   if (S < 1) return fail(CI_ERR_INVALID, "S must be >= 1");
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const dim3 blk(ci::MEAN_COLS, ci::MEAN_ROWS);
-  const int grid = (c->prob.T + ci::MEAN_COLS - 1) / ci::MEAN_COLS;
-  if (c->prob.dtype == CI_F64)
-    ci::k_predict_mean<double><<<grid, blk, 0, st>>>(
-        make_probdev<double>(c), static_cast<const double*>(theta_d),
-        static_cast<const double*>(level_d), S, static_cast<double*>(mean_d));
-  else
-    ci::k_predict_mean<float><<<grid, blk, 0, st>>>(
-        make_probdev<float>(c), static_cast<const float*>(theta_d),
-        static_cast<const float*>(level_d), S, static_cast<float*>(mean_d));
+  const int T = c->prob.T, p = c->prob.p, dim = c->dim;
+  // enough draw ranges for ~4 CTAs per SM, at least 64 draws each
+  const int cx = (T + ci::MEANP_COLS - 1) / ci::MEANP_COLS;
+  int SY = (4 * c->sm_count + cx - 1) / cx;
+  if (SY > ci::MEANP_MAXY) SY = ci::MEANP_MAXY;
+  if (SY > (S + 63) / 64) SY = (S + 63) / 64;
+  if (SY < 1) SY = 1;
+  CU_TRY(c->w_mpart.reserve(((size_t)SY * T + (size_t)SY * (p > 0 ? p : 1)) * sizeof(double)));
+  double* colpart = static_cast<double*>(c->w_mpart.p);
+  double* wpart = colpart + (size_t)SY * T;
+  const dim3 blk(ci::MEANP_COLS, ci::MEANP_ROWS), grid(cx, SY);
+  if (c->prob.dtype == CI_F64) {
+    ci::k_mean_partial<double><<<grid, blk, 0, st>>>(
+        static_cast<const double*>(theta_d), static_cast<const double*>(level_d), S, T, dim, p,
+        colpart, wpart);
+    ci::k_mean_final<double><<<(T + 255) / 256, 256, 0, st>>>(
+        make_probdev<double>(c), colpart, wpart, S, SY, static_cast<double*>(mean_d));
+  } else {
+    ci::k_mean_partial<float><<<grid, blk, 0, st>>>(
+        static_cast<const float*>(theta_d), static_cast<const float*>(level_d), S, T, dim, p,
+        colpart, wpart);
+    ci::k_mean_final<float><<<(T + 255) / 256, 256, 0, st>>>(
+        make_probdev<float>(c), colpart, wpart, S, SY, static_cast<float*>(mean_d));
+  }
+  c->launches++;
   CU_TRY(cudaGetLastError());
   c->launches++;
   return CI_OK;

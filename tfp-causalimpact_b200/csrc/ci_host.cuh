@@ -121,6 +121,7 @@ struct ci_ctx {
   DevBuf i_cum, i_stats, i_meta, i_series, i_summ, i_trT;   // ci_impact workspaces
   DevBuf s_sched, s_scratch, s_series, w_latent, w_seas, w_drift;   // seasonal components
   DevBuf w_raw, w_pstats;            // ci_set_panel: the raw panel and the per-series statistics
+  DevBuf w_mpart;                    // ci_predictive_mean_d: partial column / weight sums
   DevBuf x_pack, x_recvT, x_recvC, x_allT, x_allC, x_parts;   // ci_impact_sharded_d exchange buffers
   ci::SeasDev seas{};                // seas.K == 0: no seasonal components
   // views of the CURRENT series: the context's own buffers after ci_set_data, a slice of the
@@ -144,7 +145,7 @@ struct ci_ctx {
             &w_stats, &w_incl, &gram, &xty0, &i_cum, &i_stats, &i_meta, &i_series, &i_summ, &i_trT,
             &s_sched, &s_scratch, &s_series, &w_latent, &w_seas, &w_drift, &b_tiles, &b_omega,
             &b_gram, &b_xty, &b_dev, &w_raw, &w_pstats, &x_pack, &x_recvT, &x_recvC, &x_allT, &x_allC,
-            &x_parts};
+            &x_parts, &w_mpart};
   }
   // only from entry points that synchronise anyway (ci_set_data*, ci_ctx_destroy, host-pointer calls)
   void free_retired() {

@@ -187,6 +187,83 @@ k_predict_mean(ProbDev<R> pr, const R* __restrict__ theta, const R* __restrict__
   }
 }
 
+// The same mean for ONE series with many draws (ci_predictive_mean_d), split so that the whole
+// GPU reads the [S,T] level paths: (1) k_mean_partial -- grid (T/32, SY): CTA (bx, by) sums columns
+// 32 bx .. of draws [by S/SY, (by+1) S/SY) in float64 (a warp reads one 128-byte run of a row); the
+// CTAs of column block 0 also sum their draws' weights; (2) k_mean_final adds the SY partial sums
+// in order, divides, and adds x_t . wbar.  Deterministic.  (Run 25: the one-kernel version --
+// T/8 CTAs of 1024 threads, each re-deriving wbar from all S draws -- took 55 us for 80 MB.)
+constexpr int MEANP_COLS = 32, MEANP_ROWS = 8, MEANP_MAXY = 32;
+
+template <typename R>
+__global__ void __launch_bounds__(MEANP_COLS * MEANP_ROWS)
+k_mean_partial(const R* __restrict__ theta, const R* __restrict__ level, int S, int T, int dim, int p,
+               double* __restrict__ colpart /* [SY][T] */, double* __restrict__ wpart /* [SY][p] */) {
+  __shared__ double part[MEANP_ROWS][MEANP_COLS + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y, by = blockIdx.y, SY = gridDim.y;
+  const int s0 = (int)((long long)S * by / SY), s1 = (int)((long long)S * (by + 1) / SY);
+  const int t = blockIdx.x * MEANP_COLS + tx;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     // 4 loads in flight per thread
+  if (t < T) {
+    int s = s0 + ty;
+    for (; s + 3 * MEANP_ROWS < s1; s += 4 * MEANP_ROWS) {
+      a0 += (double)level[(size_t)s * T + t];
+      a1 += (double)level[(size_t)(s + MEANP_ROWS) * T + t];
+      a2 += (double)level[(size_t)(s + 2 * MEANP_ROWS) * T + t];
+      a3 += (double)level[(size_t)(s + 3 * MEANP_ROWS) * T + t];
+    }
+    for (; s < s1; s += MEANP_ROWS) a0 += (double)level[(size_t)s * T + t];
+  }
+  part[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ty == 0 && t < T) {
+    double tot = 0.0;
+#pragma unroll
+    for (int g = 0; g < MEANP_ROWS; ++g) tot += part[g][tx];
+    colpart[(size_t)by * T + t] = tot;
+  }
+  if (blockIdx.x != 0) return;
+  // weights of this draw range: thread (ty, tx) walks draws s0 + ty, + 8, ..; tx <-> covariate
+  for (int j0 = 0; j0 < p; j0 += MEANP_COLS) {
+    __syncthreads();
+    const int j = j0 + tx;
+    double acc = 0.0;
+    if (j < p)
+      for (int s = s0 + ty; s < s1; s += MEANP_ROWS) acc += (double)theta[(size_t)s * dim + j];
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && j < p) {
+      double tot = 0.0;
+#pragma unroll
+      for (int g = 0; g < MEANP_ROWS; ++g) tot += part[g][tx];
+      wpart[(size_t)by * p + j] = tot;
+    }
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_mean_final(ProbDev<R> pr, const double* __restrict__ colpart, const double* __restrict__ wpart,
+             int S, int SY, R* __restrict__ mean) {
+  __shared__ double wbar[MAX_DIM];
+  const int p = pr.p, T = pr.T;
+  for (int j = threadIdx.x; j < p; j += blockDim.x) {
+    double tot = 0.0;
+    for (int y = 0; y < SY; ++y) tot += wpart[(size_t)y * p + j];
+    wbar[j] = tot / S;
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double tot = 0.0;
+  for (int y = 0; y < SY; ++y) tot += colpart[(size_t)y * T + t];
+  tot /= S;
+  const int b = t / TB, tl = t - b * TB;
+  const R* row = pr.tiles + (size_t)b * tile_elems(p) + tile_off(tl, pr.ld);
+  for (int j = 0; j < p; ++j) tot += (double)row[j] * wbar[j];
+  mean[t] = (R)tot;
+}
+
 // ---------------------------------------------------------------------------
 // K5: one CTA per time column.  The column's S values are gathered into shared
 // memory as order-preserving integer keys; ALL needed order statistics (floor /
