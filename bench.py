@@ -481,23 +481,33 @@ def bench_forecast_config(gpu, cib, _engine, cfg, local, rank=0, world=1, with_c
 
   # N > 1, the time-sharded exchange (shard.impact_sharded): the trajectories are never gathered;
   # the ranks swap time blocks of the transposed paths and select T/N steps each
-  from causalimpact_b200 import impact as _imp
-  meta = _imp.ImpactMeta(index=None, observed=obs, period=per, hide=None, scale=2.0, offset=100.0,
-                         q_lo=0.025, q_hi=0.975, obs_mean=float(obs[t_pre:].mean()),
-                         obs_sum=float(obs[t_pre:].sum()))
   counts = cib.shard.even_counts(S, world)
 
+  comm = cib.shard.engine_comm(eng) if world > 1 else None
+  cnt32 = np.ascontiguousarray(counts, dtype=np.int32)
+  iargs_loc = _engine.CiImpactArgs(S=s_local, T=T, dtype=0, reserved=0, scale=2.0, offset=100.0,
+                                   q_lo=0.025, q_hi=0.975, obs_sum=float(obs[t_pre:].sum()))
+  mean_part = torch.empty(T, dtype=torch.float32, device=gpu.dev)
+  out_c = torch.empty(T * 9 + 20, dtype=torch.float64, device=gpu.dev)
+
   def forecast_columns(record=False):
+    """The same three C-ABI calls a non-Python host would make, on preallocated buffers (like the
+    one-GPU forecast above): draws, mean over the rank's own draws, ci_impact_sharded_d."""
     if record: marks[0].record(gpu.stream)
     rc = lib.ci_posterior_predict_d(ctx, th.data_ptr(), s_local, 11, s0, lvl.data_ptr(),
                                     trj.data_ptr(), None, st)
     assert rc == 0, lib.ci_last_error()
     if record: marks[1].record(gpu.stream)
-    mean_s = cib.shard.ShardedMean(eng, cib.shard.predictive_mean_part(eng, th, lvl, counts), counts)
+    rc = lib.ci_predictive_mean_d(ctx, th.data_ptr(), lvl.data_ptr(), s_local, mean_part.data_ptr(), st)
+    assert rc == 0, lib.ci_last_error()
     if record: marks[2].record(gpu.stream)
-    out = cib.shard.impact_sharded(eng, trj, mean_s, meta, counts)      # ci_impact_sharded_d
+    rc = lib.ci_impact_sharded_d(ctx, comm._h, ctypes.byref(iargs_loc), cnt32.ctypes.data_as(ctypes.c_void_p),
+                                 trj.data_ptr(), mean_part.data_ptr(),
+                                 obs.ctypes.data_as(ctypes.c_void_p), per.ctypes.data_as(ctypes.c_void_p),
+                                 mean_full.data_ptr(), out_c.data_ptr(), st)
+    assert rc == 0, lib.ci_last_error()
     if record: marks[3].record(gpu.stream)
-    return out
+    return out_c
 
   def timed(fn):
     for _ in range(3):
@@ -564,6 +574,10 @@ def bench_forecast_config(gpu, cib, _engine, cfg, local, rank=0, world=1, with_c
     tt = torch.tensor([t_e2e], dtype=torch.float64, device=gpu.dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_e2e = float(tt[0])
+  if comm is not None:
+    torch.cuda.synchronize()
+    comm.close()
+    eng._shard_comm = None
   eng.close()
   Bd = bytes_per_draw(T, p, T - t_pre)
   peak, peak_src = measured_peak_hbm()

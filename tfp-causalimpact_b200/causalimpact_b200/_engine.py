@@ -326,6 +326,10 @@ class Engine:
       raise EngineError(f"ci_b200 error {rc}: {msg.decode() if msg else '?'}")
 
   def close(self):
+    comm = getattr(self, "_shard_comm", None)      # shard.engine_comm: destroyed before its context
+    if comm is not None:
+      self._shard_comm = None
+      comm.close()
     if self._ctx:
       self._lib.ci_ctx_destroy(self._ctx)
       self._ctx = C.c_void_p()

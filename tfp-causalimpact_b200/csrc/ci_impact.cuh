@@ -85,21 +85,26 @@ constexpr int IMP_SEG = 4 * IMP_CHUNK;          // pre-period steps per transpos
 
 // where element (time column, draw) of the transposed outputs goes: the local arrays or, in a
 // sharded fit, the owner rank's window (ColBlocks layout) over NVLink
+// (the owner of a column is cached in `own`: a warp stores 8 consecutive columns, which cross a
+// block boundary at most once -- the two integer divisions of split_owner are paid per boundary,
+// not per store)
+struct OwnerCache { int g = 0, st0 = 0, cnt = -1; };
 template <typename R>
-__device__ __forceinline__ R* impact_dst_path(R* trT, const ImpactDev& a, const PeerDest& pd, int tc) {
+__device__ __forceinline__ R* impact_dst_path(R* trT, const ImpactDev& a, const PeerDest& pd, int tc,
+                                              OwnerCache& own) {
   if (pd.ws == 0) return trT + (size_t)tc * a.S;
-  int g, st0, cnt;
-  split_owner(tc, pd.T_base, pd.T_extra, g, st0, cnt);
-  return static_cast<R*>(pd.T[g]) + (size_t)cnt * pd.me_off + (size_t)(tc - st0) * pd.n_me;
+  if (tc < own.st0 || tc >= own.st0 + own.cnt)
+    split_owner(tc, pd.T_base, pd.T_extra, own.g, own.st0, own.cnt);
+  return static_cast<R*>(pd.T[own.g]) + (size_t)own.cnt * pd.me_off + (size_t)(tc - own.st0) * pd.n_me;
 }
 __device__ __forceinline__ double* impact_dst_cum(double* cumT, const ImpactDev& a, const PeerDest& pd,
-                                                  int c) {
+                                                  int c, OwnerCache& own) {
   if (pd.ws == 0) return cumT + (size_t)c * a.S;
-  int g, st0, cnt;
-  split_owner(c, pd.C_base, pd.C_extra, g, st0, cnt);
-  const int head = g == 0 ? IMP_STATS : 0;
-  return static_cast<double*>(pd.C[g]) + (size_t)(cnt + head) * pd.me_off +
-         (size_t)(head + c - st0) * pd.n_me;
+  if (c < own.st0 || c >= own.st0 + own.cnt)
+    split_owner(c, pd.C_base, pd.C_extra, own.g, own.st0, own.cnt);
+  const int head = own.g == 0 ? IMP_STATS : 0;
+  return static_cast<double*>(pd.C[own.g]) + (size_t)(own.cnt + head) * pd.me_off +
+         (size_t)(head + c - own.st0) * pd.n_me;
 }
 
 // The predictive mean's row (the *_mean series columns and `predicted`): one CTA, warp w takes
@@ -230,6 +235,7 @@ k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
       const int t = t_begin + h * 32 + lane;
       nxt[k][h] = (lok[k] && t < t_end) ? src[k][t] : (R)0;
     }
+  OwnerCache ownT, ownC;
   int buf = 0;
   for (int base = t_begin; base < t_end; base += IMP_CHUNK, buf ^= 1) {
 #pragma unroll
@@ -246,7 +252,7 @@ k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
 #pragma unroll
       for (int jj = 0; jj < IMP_SPW; ++jj) {
         const int tc = base + j0 + jj;
-        if (dok && tc < t_end) impact_dst_path<R>(trT, a, pd, tc)[rr] = tile[buf][lane][j0 + jj];
+        if (dok && tc < t_end) impact_dst_path<R>(trT, a, pd, tc, ownT)[rr] = tile[buf][lane][j0 + jj];
       }
       continue;
     }
@@ -271,7 +277,7 @@ k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
         pred_sum += x;
         if (!isn) { eff_sum += pt; ++eff_cnt; }
       }
-      if (valid) impact_dst_path<R>(trT, a, pd, t)[rr] = raw;
+      if (valid) impact_dst_path<R>(trT, a, pd, t, ownT)[rr] = raw;
     }
     wtot[buf][warp][lane] = run;
     __syncthreads();
@@ -287,7 +293,7 @@ k_impact_rows(const R* __restrict__ traj, const R* __restrict__ mean,
     for (int jj = 0; jj < IMP_SPW; ++jj) {
       const int t = base + j0 + jj;
       if (dok && t < a.T && t >= a.t_c0)
-        impact_dst_cum(cumT, a, pd, t - a.t_c0)[rr] = ((nanmask >> jj) & 1u) ? CUDART_NAN : off + s[jj];
+        impact_dst_cum(cumT, a, pd, t - a.t_c0, ownC)[rr] = ((nanmask >> jj) & 1u) ? CUDART_NAN : off + s[jj];
     }
   }
   if (!post) return;
@@ -389,22 +395,35 @@ __device__ __forceinline__ int load_block_keys(const V* __restrict__ base, int r
   const Key NANK = KeyOf<V>::nan_key();
   if (tid == 0) { *n_valid = 0; sh.kmin = NANK; sh.kmax = 0; }
   __syncthreads();
-  int cnt = 0, off = 0;
-  size_t blk = 0;
+  int cnt = 0;
   Key mn = NANK, mx = 0;
-  for (int r = 0; r < cb.ws; ++r) {
-    const int nr = cb.n[r];
-    const V* col = base + blk + (size_t)row * nr;
-    for (int i = tid; i < nr; i += nt) {
-      const V v = col[i];
-      const bool ok = (v == v);
-      const Key k = ok ? KeyOf<V>::enc(v) : NANK;
-      keys[off + i] = k;
-      cnt += ok ? 1 : 0;
-      if (ok) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+  // one flat sweep over the S draws, four loads in flight per thread; (seg, off, blk) = the
+  // block that holds draw i, advanced as i grows (a thread's draws are nt apart: rarely)
+  int S = 0;
+  for (int r = 0; r < cb.ws; ++r) S += cb.n[r];
+  int seg = 0, off = 0;
+  size_t blk = 0;
+  for (int i0 = tid; i0 < S; i0 += 4 * nt) {
+    V v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nt;
+      if (i < S) {
+        while (i >= off + cb.n[seg]) { off += cb.n[seg]; blk += (size_t)rows * cb.n[seg]; ++seg; }
+        v[u] = base[blk + (size_t)row * cb.n[seg] + (i - off)];
+      }
     }
-    off += nr;
-    blk += (size_t)rows * nr;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nt;
+      if (i < S) {
+        const bool ok = (v[u] == v[u]);
+        const Key k = ok ? KeyOf<V>::enc(v[u]) : NANK;
+        keys[i] = k;
+        cnt += ok ? 1 : 0;
+        if (ok) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+      }
+    }
   }
   fold_minmax<V>(mn, mx, sh);
   cnt = __reduce_add_sync(FULL, cnt);
