@@ -220,3 +220,51 @@ def test_panel_host_logic_matches_the_frame_path(monkeypatch):
     assert list(ser.columns) == list(one.series.columns) and ser.index.equals(one.series.index)
     assert list(summ.columns) == list(one.summary.columns) and list(summ.index) == list(one.summary.index)
     np.testing.assert_allclose(res.level[i], one.posterior_samples.level, rtol=1e-4, atol=1e-4)
+
+
+PIECES_WORKER = r'''
+import os, sys
+import numpy as np
+ROOT = sys.argv[1]
+for p in (ROOT, os.path.join(ROOT, "tfp-causalimpact_b200"), os.path.join(ROOT, "tests")):
+  sys.path.insert(0, p)
+import torch, torch.distributed as dist
+from causalimpact_b200 import shard
+dist.init_process_group("gloo")
+rank, ws = shard.world()
+counts = [5, 0, 3][:ws] if ws == 3 else [4, 3]
+T = 6
+full = np.arange(sum(counts) * T, dtype=np.float32).reshape(sum(counts), T)
+s0 = sum(counts[:rank])
+local = torch.from_numpy(full[s0:s0 + counts[rank]].copy())
+sd = shard.ShardedDraws(local, counts)
+assert sd.shape == (sum(counts), T)
+assert np.array_equal(np.asarray(sd), full)                      # gathered on demand, rank order
+part = local.double().mean(0).float() if counts[rank] else torch.zeros(T)
+sm = shard.ShardedMean(None, part, counts)
+np.testing.assert_allclose(np.asarray(sm), full.mean(0), rtol=1e-6)
+assert sm.shape == (T,)
+# time blocks of ragged shards: every rank ends up with all draws of ITS columns, in rank order
+splits = [shard.split_range(T, ws, r) for r in range(ws)]
+mine, head = shard._exchange_columns(local.t().contiguous(), splits, counts, rank)
+t0, tn = splits[rank]
+assert head is None and np.array_equal(mine.numpy(), full.T[t0:t0 + tn])
+dist.barrier(); dist.destroy_process_group()
+if rank == 0:
+  open(sys.argv[2], "w").write("ok")
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_containers_and_column_exchange_under_gloo(tmp_path, world):
+  """shard.ShardedDraws / ShardedMean (what a fit with exchange="columns" hands to the impact stage)
+  and the all-to-all by time block, with ragged and EMPTY shards, 2 and 3 ranks."""
+  script = tmp_path / "w.py"
+  script.write_text(PIECES_WORKER)
+  ok = tmp_path / "ok"
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29741",
+                        str(script), root, str(ok)], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
+  assert res.returncode == 0 and ok.exists(), res.stdout[-2000:] + res.stderr[-4000:]
