@@ -425,12 +425,17 @@ int ci_comm_destroy(ci_comm* comm);
 
 /* The impact stage of a fit whose draws are sharded over the ranks of `comm`, in ONE call: steps
  * 1-3 of ci_impact_rows_d / ci_impact_cols_d above with the exchange inside.  Everything is
- * enqueued on `stream` (kernels and NCCL alike; no host synchronisation):
- *   k_impact_rows on the rank's own draws -> ONE grouped ncclSend/ncclRecv exchange (time block g
- *   of the transposed float paths, and of the float64 cumulative paths with the per-draw
- *   statistics riding to rank 0, go to rank g; every rank's predictive-mean part goes to
- *   everyone) -> the received blocks side by side -> k_impact_jobs on T/nranks time steps over
- *   all draws -> ncclAllReduce of the [T*9 + 20] result (each entry written by one rank).
+ * enqueued on `stream` (kernels and NCCL alike; no host synchronisation except when the exchange
+ * windows first grow):
+ *   k_impact_rows on the rank's own draws, storing every transposed tile straight into the window
+ *   of the rank that owns its time block -- the ranks' windows are mapped into each other through
+ *   CUDA IPC (peer memory over NVLink / NVSwitch), so compute and transfer are one kernel; the
+ *   per-draw statistics go to rank 0's window -> an ncclAllGather of the ranks' predictive-mean
+ *   parts, which is also the barrier of the exchange -> k_impact_jobs on T/nranks time steps over
+ *   all draws, read as they arrived -> ncclAllReduce of the [T*9 + 20] result (each entry written
+ *   by one rank).  Where peer mapping is unavailable (agreed collectively; CI_B200_NO_PEER=1
+ *   forces it) the tiles go to local arrays and ONE grouped ncclSend/ncclRecv exchange moves the
+ *   time blocks; results are the same.  At most 16 ranks (one NVSwitch domain).
  * Time blocks: rank r owns steps start..start+count-1 with base = T / nranks, extra = T % nranks,
  * start = r*base + min(r, extra), count = base + (r < extra); likewise for the T - t_c0
  * cumulative columns.
@@ -444,7 +449,7 @@ int ci_comm_destroy(ci_comm* comm);
  *   out_d         [T*9 + CI_IMPACT_SUMMARY_LEN] float64 out, on every rank: series then summary of
  *                 ci_impact; the quantile entries are bit-identical to ci_impact_d on the gathered
  *                 draws, the mean-derived ones agree to the rounding of the parts to args->dtype.
- * comm with nranks == 1 is allowed (the exchange is a self send/receive). */
+ * comm with nranks == 1 is allowed (the window is the rank's own). */
 int ci_impact_sharded_d(ci_ctx* ctx, ci_comm* comm, const ci_impact_args* args,
                         const int32_t* counts, const void* traj_d, const void* mean_part_d,
                         const double* observed, const uint8_t* period, void* mean_d,
