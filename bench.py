@@ -791,6 +791,28 @@ def main():
         tq = time.perf_counter()
         cib.fit_causalimpact_panel(vals_p, np.arange(Tp), (0, 209), (210, Tp - 1), **kw_p)
         t_panel = (time.perf_counter() - tq) * 1e3
+        # the same panel as a list of DataFrames through fit_causalimpact_many (frames that share
+        # index and columns are stacked and take the panel route; result frames are built on first
+        # access): the call alone, and the call plus the summary frame of every series
+        many_fit = None
+        try:
+          import pandas as _pd
+          idx_p = _pd.RangeIndex(Tp)
+          dfs_p = [_pd.DataFrame(vals_p[i], index=idx_p, columns=["y", "x0", "x1"]) for i in range(Np)]
+          cib.fit_causalimpact_many(dfs_p, (0, 209), (210, Tp - 1), **kw_p)
+          torch.cuda.synchronize()             # (no barrier inside the guarded block)
+          tq = time.perf_counter()
+          res_m = cib.fit_causalimpact_many(dfs_p, (0, 209), (210, Tp - 1), **kw_p)
+          t_many = (time.perf_counter() - tq) * 1e3
+          eff = [float(r.summary.loc["average", "abs_effect"]) for r in res_m]
+          t_many_frames = (time.perf_counter() - tq) * 1e3
+          many_fit = {"series": Np, "wall_ms": t_many, "series_per_sec": Np * world / (t_many * 1e-3),
+                      "wall_ms_with_every_summary_frame": t_many_frames,
+                      "series_per_sec_with_every_summary_frame": Np * world / (t_many_frames * 1e-3),
+                      "mean_abs_effect": float(np.mean(eff)),
+                      "note": "fit_causalimpact_many on 128 DataFrames (same panel as panel_fit)"}
+        except Exception as e:               # a reported number, not a reason to lose the bench line
+          many_fit = {"error": repr(e)[:300]}
       finally:
         cib.shard.world = _w
       # ---- the product call, quickstart shape (configs[0]) and sharded at the configs[4] scale
@@ -880,6 +902,7 @@ def main():
                         "wall_ms": t_panel, "series_per_sec": Np * world / (t_panel * 1e-3),
                         "note": "fit_causalimpact_panel: the whole call for a panel of independent "
                                 "series (every rank its own panel); the reference takes ~5 s per series"},
+          "many_fit": many_fit,
           "fit_causalimpact_quickstart_ms": t_fit,
           "fit_note": "T=100, 1 covariate, 900 draws, 64 chains, 2nd call; reference publishes 5170 "
                       "ms for this call (other hardware, incl. tracing)",

@@ -107,8 +107,10 @@ def test_panel_arrays_match_the_frame_path():
   dfs = panel(5, 120, 2, 11, 90)
   idx = dfs[0].index
   pre, post = (idx[0], idx[89]), (idx[92], idx[-2])          # a gap and a tail
+  # (decorrelate_series=False keeps fit_causalimpact_many on its per-frame pandas preparation;
+  # with the default these stackable frames would take the panel route themselves)
   kw = dict(seed=7, inference_options=ci.InferenceOptions(num_results=120),
-            engine_options=ci.EngineOptions(num_chains=10))
+            engine_options=ci.EngineOptions(num_chains=10, decorrelate_series=False))
   many = ci.fit_causalimpact_many(dfs, pre, post, **kw)
   values = np.stack([d.values for d in dfs])
   res = ci.fit_causalimpact_panel(values, idx, pre, post, keep_level=True, **kw)

@@ -205,9 +205,13 @@ def test_panel_host_logic_matches_the_frame_path(monkeypatch):
       y[5] = np.nan
     dfs.append(pd.DataFrame({"y": y, "x": x}, index=idx))
   pre, post = (idx[0], idx[37]), (idx[41], idx[55])
+  # decorrelate_series=False: fit_causalimpact_many then prepares every frame with pandas (the
+  # default would route these stackable frames to the panel path itself)
   kw = dict(seed=(3, 1), inference_options=cib.InferenceOptions(num_results=10),
-            engine_options=cib.EngineOptions(num_chains=2, gibbs_min_warmup=6))
+            engine_options=cib.EngineOptions(num_chains=2, gibbs_min_warmup=6,
+                                             decorrelate_series=False))
   many = cib.fit_causalimpact_many(dfs, pre, post, **kw)
+  assert not isinstance(many[0], cib.PanelAnalysis)
   res = cib.fit_causalimpact_panel(np.stack([d.values for d in dfs]), idx, pre, post,
                                    keep_level=True, **kw)
   vals = cib.impact.SERIES_VALUE_COLUMNS
@@ -220,6 +224,62 @@ def test_panel_host_logic_matches_the_frame_path(monkeypatch):
     assert list(ser.columns) == list(one.series.columns) and ser.index.equals(one.series.index)
     assert list(summ.columns) == list(one.summary.columns) and list(summ.index) == list(one.summary.index)
     np.testing.assert_allclose(res.level[i], one.posterior_samples.level, rtol=1e-4, atol=1e-4)
+
+
+def test_many_stackable_frames_take_the_panel_route(monkeypatch):
+  """fit_causalimpact_many with frames that share index and columns (default options): ONE
+  fit_causalimpact_panel call, results behind the CausalImpactAnalysis interface with frames built
+  on first access -- equal to the panel call's arrays, same columns / index / sample shapes as the
+  per-frame results; a named outcome column that is not first is moved first; frames that do not
+  stack (another index) fall back to the per-frame path."""
+  from fake_engine import FakeEngine
+  import causalimpact_b200 as cib
+  from causalimpact_b200 import api
+  fake = FakeEngine()
+  monkeypatch.setattr(api, "_resolve_engine", lambda opts: fake)
+  rng = np.random.default_rng(18)
+  idx = pd.date_range("2021-03-01", periods=50)
+  dfs = []
+  for s in range(3):
+    x = 100 + np.cumsum(rng.normal(size=50)); y = (1 + 0.3 * s) * x + rng.normal(size=50)
+    y[35:] += 4
+    dfs.append(pd.DataFrame({"x": x, "y": y}, index=idx if s else idx.copy()))
+  pre, post = (idx[0], idx[33]), (idx[35], idx[48])
+  kw = dict(seed=(3, 1), inference_options=cib.InferenceOptions(num_results=8),
+            engine_options=cib.EngineOptions(num_chains=2, gibbs_min_warmup=5))
+  do = cib.DataOptions(outcome_column="y")
+  many = cib.fit_causalimpact_many(dfs, pre, post, data_options=do, **kw)
+  assert all(isinstance(m, cib.PanelAnalysis) and isinstance(m, cib.CausalImpactAnalysis) for m in many)
+  res = cib.fit_causalimpact_panel(np.stack([d[["y", "x"]].values for d in dfs]), idx, pre, post,
+                                   keep_level=True, **kw)
+  slow = cib.fit_causalimpact_many(dfs, pre, post, data_options=do, seed=(3, 1),
+                                   inference_options=cib.InferenceOptions(num_results=8),
+                                   engine_options=cib.EngineOptions(num_chains=2, gibbs_min_warmup=5,
+                                                                    decorrelate_series=False))
+  vals = cib.impact.SERIES_VALUE_COLUMNS
+  for i, m in enumerate(many):
+    assert m._frames is None                                        # nothing built yet
+    np.testing.assert_array_equal(m.series[vals].values, res.series[i])
+    np.testing.assert_array_equal(m.summary.values, res.summary[i])
+    assert list(m.series.columns) == list(slow[i].series.columns) and m.series.index.equals(idx)
+    assert list(m.summary.columns) == list(slow[i].summary.columns)
+    ps, qs = m.posterior_samples, slow[i].posterior_samples
+    np.testing.assert_array_equal(ps.level, res.level[i])
+    for f in ("observation_noise_scale", "level_scale", "level", "weights", "seasonal_levels"):
+      assert getattr(ps, f).shape == getattr(qs, f).shape, f
+    assert ps.seasonal_drift_scales is None and qs.seasonal_drift_scales is None
+    assert m.diagnostics["inclusion"].shape == slow[i].diagnostics["inclusion"].shape
+    assert ps.level.numpy().dtype == np.float32
+  # another index in one frame: not stackable -> the per-frame path (and its own error / result)
+  odd = [dfs[0], dfs[1].set_index(idx + pd.Timedelta(days=1))]
+  with pytest.raises(Exception):
+    cib.fit_causalimpact_many(odd, pre, (idx[35], idx[49]), data_options=do, **kw)
+  # return_level=False: no level paths in the lazy record either
+  nl = cib.fit_causalimpact_many(dfs[:2], pre, post, data_options=do, seed=1,
+                                 inference_options=cib.InferenceOptions(num_results=4),
+                                 engine_options=cib.EngineOptions(num_chains=2, gibbs_min_warmup=3,
+                                                                  return_level=False))
+  assert nl[0].posterior_samples.level is None and nl[0].posterior_samples.seasonal_levels is None
 
 
 PIECES_WORKER = r'''

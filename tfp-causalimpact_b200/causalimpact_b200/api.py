@@ -518,6 +518,69 @@ def _analysis(series, summary, samples) -> CausalImpactAnalysis:
   return CausalImpactAnalysis(series, summary, result_samples, stats)
 
 
+class PanelAnalysis(CausalImpactAnalysis):
+  """One series of a panel fit behind the ``CausalImpactAnalysis`` interface: the ``series`` /
+  ``summary`` frames and the sample record are built from the panel's arrays on first access (a
+  thousand-series call does not pay for two thousand DataFrames nobody may look at)."""
+
+  def __init__(self, panel_result, i: int, np_dt):   # pylint: disable=super-init-not-called
+    self._res, self._i, self._np_dt = panel_result, i, np_dt
+    self._frames = None
+    self._samples = None
+    self.diagnostics = {"sampler": "gibbs", "inclusion": panel_result.inclusion[i]}
+
+  def _build(self):
+    if self._frames is None:
+      self._frames = self._res.frames(self._i)
+    return self._frames
+
+  series = property(lambda self: self._build()[0])
+  summary = property(lambda self: self._build()[1])
+
+  @property
+  def posterior_samples(self) -> CausalImpactPosteriorSamples:
+    if self._samples is None:
+      r, i = self._res, self._i
+      S = r.observation_noise_scale.shape[1]
+      seasonal = r.seasonal_drift_scales is not None
+      self._samples = CausalImpactPosteriorSamples(
+          observation_noise_scale=Samples(r.observation_noise_scale[i]),
+          level_scale=Samples(r.level_scale[i]),
+          level=None if r.level is None else Samples(r.level[i]),
+          weights=None if r.weights is None else Samples(r.weights[i]),
+          seasonal_drift_scales=Samples(r.seasonal_drift_scales[i]) if seasonal else None,
+          seasonal_levels=(None if r.level is None else
+                           Samples(r.seasonal_levels[i]) if seasonal else
+                           Samples(np.zeros((S, r.level.shape[2], 0), self._np_dt))))
+    return self._samples
+
+
+def _stack_frames(datas, outcome_column):
+  """[N, T, 1 + k] float64 values (outcome first) and the common index of DataFrames that share
+  index and columns; None when they do not (or are not all-numeric frames): the caller then takes
+  the per-frame path, which raises the reference's errors."""
+  first = datas[0]
+  if not isinstance(first, pd.DataFrame) or first.shape[1] < 1:
+    return None
+  cols = list(first.columns)
+  if outcome_column is not None:
+    if outcome_column not in cols:
+      return None
+    cols = [outcome_column] + [c for c in cols if c != outcome_column]
+  order = None if cols == list(first.columns) else cols
+  vals = np.empty((len(datas),) + first.shape, dtype=np.float64)
+  for i, d in enumerate(datas):
+    if not isinstance(d, pd.DataFrame) or d.shape != first.shape or \
+        not (d.index is first.index or d.index.equals(first.index)) or \
+        not (d.columns is first.columns or d.columns.equals(first.columns)):
+      return None
+    try:
+      vals[i] = (d if order is None else d[order]).to_numpy(dtype=np.float64, copy=False)
+    except (TypeError, ValueError):
+      return None
+  return vals, first.index
+
+
 def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, seed=None,
                           data_options: Optional[DataOptions] = None,
                           model_options: Optional[ModelOptions] = None,
@@ -536,6 +599,12 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
   ``fit_causalimpact(datas[i], ..., engine_options=EngineOptions(sampler="gibbs"))`` with the
   same seed; by default every series draws from its own Philox streams.
 
+  Frames that share index and columns (the usual panel of geographies) and the default
+  ``decorrelate_series=True`` take the PANEL route: the values are stacked and handed to
+  ``fit_causalimpact_panel`` -- data prep on the device, no per-series pandas -- and every result is
+  a ``PanelAnalysis`` whose frames are built on first access.  (``decorrelate_series=False`` keeps
+  the per-frame preparation: that is what makes result i bit-identical to the single fit.)
+
   Multi-GPU: series are sharded over the ranks of an initialised process group (contiguous
   ranges, no collective: series are independent); a rank returns ``None`` for the series it
   does not own.  ``ModelOptions.seasons`` are supported (one season calendar for the panel).
@@ -550,6 +619,18 @@ def fit_causalimpact_many(datas, pre_period, post_period, alpha: float = 0.05, s
   np_dt = _np_dtype(data_options.dtype)
   seed64 = _seed_to_u64(seed)
   datas = list(datas)
+  if opts.decorrelate_series and datas:
+    stacked = _stack_frames(datas, data_options.outcome_column)
+    if stacked is not None:
+      from . import panel as _panel
+      res = _panel.fit_causalimpact_panel(
+          stacked[0], stacked[1], pre_period, post_period, alpha=alpha, seed=seed,
+          data_options=data_options, model_options=model_options,
+          inference_options=inference_options, engine_options=opts, keep_level=opts.return_level)
+      out = [None] * len(datas)
+      for j, sid in enumerate(res.series_ids):
+        out[int(sid)] = PanelAnalysis(res, j, np_dt)
+      return out
   rank, ws = _shard.world()
   s0, n_local = _shard.split_range(len(datas), ws, rank)
   out = [None] * len(datas)
