@@ -191,11 +191,25 @@ struct StepTrace {
 int ensure_windows(ci_comm* cm, NcclApi* api, size_t needT, size_t needC, cudaStream_t st) {
   if (!cm->peer_ok || (needT <= cm->capT && needC <= cm->capC)) return CI_OK;
   const int ws = cm->nranks, me = cm->rank;
+  struct Pack { cudaIpcMemHandle_t hT, hC; int status; int pad[3]; };
+  Pack mine{};
+  Pack* dev = nullptr;
+  std::vector<Pack> all(ws);
   CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaMalloc(&dev, sizeof(Pack) * (ws + 1)));
+  const bool had_windows = cm->winT != nullptr;
   for (int r = 0; r < ws; ++r) {
     if (r != me && cm->peerT[r]) cudaIpcCloseMemHandle(cm->peerT[r]);
     if (r != me && cm->peerC[r]) cudaIpcCloseMemHandle(cm->peerC[r]);
     cm->peerT[r] = cm->peerC[r] = nullptr;
+  }
+  if (had_windows) {
+    // an exported block must not be freed while another process still maps it: wait until every
+    // rank has closed its mappings (a tiny all-gather as the barrier; regrowth is rare)
+    CU_TRY(cudaMemcpyAsync(dev + ws, &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
+    const int brc = api->AllGather(dev + ws, dev, sizeof(Pack), NCCL_INT8, cm->comm, st);
+    if (brc != NCCL_SUCCESS) { cudaFree(dev); return nccl_fail(api, "ncclAllGather", brc); }
+    CU_TRY(cudaStreamSynchronize(st));
   }
   if (cm->winT) cudaFree(cm->winT);
   if (cm->winC) cudaFree(cm->winC);
@@ -203,8 +217,6 @@ int ensure_windows(ci_comm* cm, NcclApi* api, size_t needT, size_t needC, cudaSt
   auto grow = [](size_t need) { return ((need + need / 4 + (2u << 20) - 1) >> 21) << 21; };
   cm->capT = grow(needT > cm->capT ? needT : cm->capT);
   cm->capC = grow(needC > cm->capC ? needC : cm->capC);
-  struct Pack { cudaIpcMemHandle_t hT, hC; int status; int pad[3]; };
-  Pack mine{};
   mine.status = 0;
   if (cudaMalloc(&cm->winT, cm->capT) != cudaSuccess || cudaMalloc(&cm->winC, cm->capC) != cudaSuccess ||
       cudaIpcGetMemHandle(&mine.hT, cm->winT) != cudaSuccess ||
@@ -212,9 +224,6 @@ int ensure_windows(ci_comm* cm, NcclApi* api, size_t needT, size_t needC, cudaSt
     mine.status = 1;
     cudaGetLastError();
   }
-  Pack* dev = nullptr;
-  std::vector<Pack> all(ws);
-  CU_TRY(cudaMalloc(&dev, sizeof(Pack) * (ws + 1)));
   CU_TRY(cudaMemcpyAsync(dev + ws, &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
   int rc = api->AllGather(dev + ws, dev, sizeof(Pack), NCCL_INT8, cm->comm, st);
   if (rc != NCCL_SUCCESS) { cudaFree(dev); return nccl_fail(api, "ncclAllGather", rc); }
